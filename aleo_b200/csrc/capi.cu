@@ -1,0 +1,278 @@
+// capi.cu -- the C ABI of libaleo_b200.so (include/aleo_b200.h): argument checking, device
+// readiness, per-thread streams and host<->device staging.  The kernels live in ntt_lib.cu,
+// msm_lib.cu and util_lib.cu.
+//
+// No CPU fallback: if the calling thread's CUDA device is missing or is not sm_100, every entry
+// point returns ALEO_B200_ENODEVICE.
+#include "../../include/aleo_b200.h"
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include "internal.h"
+
+namespace {
+
+thread_local std::string t_last_cuda_error;
+thread_local cudaStream_t t_stream = nullptr;
+thread_local int t_stream_dev = -1;
+
+std::mutex g_dev_mu;
+bool g_dev_ready[64] = {false};
+bool g_dev_bad[64] = {false};
+
+int fail_cuda(cudaError_t e) {
+  t_last_cuda_error = cudaGetErrorString(e);
+  if (e == cudaErrorMemoryAllocation) return ALEO_B200_ENOMEM;
+  return ALEO_B200_ECUDA;
+}
+
+#define API_CK(expr)                                   \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) return fail_cuda(_e);       \
+  } while (0)
+
+// current device must be a B200-class part; constants uploaded once per device
+int ensure_ready(int* dev_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    t_last_cuda_error = (e != cudaSuccess) ? cudaGetErrorString(e) : "device index out of range";
+    return ALEO_B200_ENODEVICE;
+  }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev_bad[dev]) return ALEO_B200_ENODEVICE;
+  if (!g_dev_ready[dev]) {
+#ifndef ALEO_EMU
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+      t_last_cuda_error = cudaGetErrorString(e);
+      return ALEO_B200_ENODEVICE;
+    }
+    if (prop.major != 10) {  // the library holds sm_100a code only
+      g_dev_bad[dev] = true;
+      t_last_cuda_error =
+          std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", need sm_100 (B200)";
+      return ALEO_B200_ENODEVICE;
+    }
+#endif
+    API_CK(aleo::ntt_upload_constants());
+    API_CK(aleo::msm_upload_constants());
+    API_CK(aleo::util_upload_constants());
+    g_dev_ready[dev] = true;
+  }
+  if (dev_out) *dev_out = dev;
+  return ALEO_B200_OK;
+}
+
+int thread_stream(int dev, cudaStream_t* out) {
+  if (t_stream == nullptr || t_stream_dev != dev) {
+    API_CK(cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking));
+    t_stream_dev = dev;
+  }
+  *out = t_stream;
+  return ALEO_B200_OK;
+}
+
+bool stride_ok(size_t s) { return s == 96 || s == 104; }
+
+}  // namespace
+
+extern "C" {
+
+const char* aleo_b200_version(void) {
+#ifdef ALEO_EMU
+  return "aleo_b200 0.1.0 (EMULATOR BUILD - development tooling, not a product)";
+#else
+  return "aleo_b200 0.1.0 (sm_100a)";
+#endif
+}
+
+const char* aleo_b200_strerror(int code) {
+  switch (code) {
+    case ALEO_B200_OK: return "success";
+    case ALEO_B200_EINVAL: return "invalid argument";
+    case ALEO_B200_ETOOLARGE: return "problem too large for one call";
+    case ALEO_B200_ENODEVICE: return "no usable B200 (sm_100) device; this library has no CPU fallback";
+    case ALEO_B200_ECUDA: return "CUDA failure";
+    case ALEO_B200_ENOMEM: return "out of memory";
+  }
+  return "unknown error";
+}
+
+const char* aleo_b200_last_cuda_error(void) { return t_last_cuda_error.c_str(); }
+
+int aleo_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int aleo_b200_init(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    t_last_cuda_error = "cudaSetDevice failed";
+    return ALEO_B200_ENODEVICE;
+  }
+  return ensure_ready(nullptr);
+}
+
+int aleo_b200_shutdown(void) {
+  aleo::ntt_clear_plans();
+  return ALEO_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NTT
+int aleo_b200_ntt_launches(uint32_t log_n) { return aleo::ntt_launches(log_n); }
+
+int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, void* stream) {
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
+  if (batch == 0) return ALEO_B200_OK;
+  if (inout_dev == nullptr) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  API_CK(aleo::ntt_transform(dev, log_n, batch, direction == ALEO_B200_NTT_INVERSE, kind == ALEO_B200_NTT_COSET, inout_dev,
+                             (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) {
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (inout_host == nullptr) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  const size_t bytes = (size_t)32 << log_n;
+  void* d = nullptr;
+  API_CK(cudaMallocAsync(&d, bytes, s));
+  cudaError_t e = cudaMemcpyAsync(d, inout_host, bytes, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    rc = aleo_b200_ntt_fr_dev(d, log_n, 1, direction, kind, (void*)s);
+    if (rc == ALEO_B200_OK) e = cudaMemcpyAsync(inout_host, d, bytes, cudaMemcpyDeviceToHost, s);
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ MSM
+int aleo_b200_msm_window_bits(size_t n) { return aleo::msm_window_bits(n); }
+
+int aleo_b200_msm_launches(size_t n) {
+  int launches = 0;
+  aleo::msm_run(nullptr, 96, nullptr, n, nullptr, nullptr, true, &launches);
+  return launches;
+}
+
+int aleo_b200_msm_g1_dev(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
+                         size_t affine_stride, void* stream) {
+  if (!stride_ok(affine_stride) || out_projective_dev == nullptr) return ALEO_B200_EINVAL;
+  if (n > 0 && (bases_dev == nullptr || scalars_dev == nullptr)) return ALEO_B200_EINVAL;
+  if (!aleo::msm_size_supported(n)) return ALEO_B200_ETOOLARGE;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::msm_run(bases_dev, (u32)affine_stride, scalars_dev, n, out_projective_dev, (cudaStream_t)stream, false,
+                       nullptr));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
+                     size_t affine_stride) {
+  if (!stride_ok(affine_stride) || out_projective_host == nullptr) return ALEO_B200_EINVAL;
+  if (n > 0 && (bases_host == nullptr || scalars_host == nullptr)) return ALEO_B200_EINVAL;
+  if (!aleo::msm_size_supported(n)) return ALEO_B200_ETOOLARGE;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  unsigned char* d = nullptr;
+  const size_t bb = n * affine_stride, sb = n * 32;
+  const size_t o_s = (bb + 255) & ~(size_t)255, o_out = o_s + ((sb + 255) & ~(size_t)255);
+  API_CK(cudaMallocAsync((void**)&d, o_out + 256, s));
+  cudaError_t e = cudaSuccess;
+  if (n) e = cudaMemcpyAsync(d, bases_host, bb, cudaMemcpyHostToDevice, s);
+  if (n && e == cudaSuccess) e = cudaMemcpyAsync(d + o_s, scalars_host, sb, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    rc = aleo_b200_msm_g1_dev(d + o_out, d, n, d + o_s, affine_stride, (void*)s);
+    if (rc == ALEO_B200_OK) e = cudaMemcpyAsync(out_projective_host, d + o_out, 144, cudaMemcpyDeviceToHost, s);
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_g1_sum_dev(void* out_projective_dev, const void* points_dev, size_t count, void* stream) {
+  if (out_projective_dev == nullptr || (count && points_dev == nullptr) || count >= ((size_t)1 << 32))
+    return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::g1_sum(points_dev, (u32)count, out_projective_dev, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+// ------------------------------------------------------------------- generators / checks / bench
+int aleo_b200_gen_bases_dev(void* bases_dev, size_t n, size_t affine_stride, const void* s0_host, const void* d_host,
+                            uint64_t first_index, void* stream) {
+  if (!stride_ok(affine_stride) || s0_host == nullptr || d_host == nullptr) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  if (bases_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::gen_bases(bases_dev, n, (u32)affine_stride, s0_host, d_host, first_index, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_gen_scalars_dev(void* scalars_dev, size_t n, uint64_t seed, uint64_t first_index, int montgomery,
+                              void* stream) {
+  if (n == 0) return ALEO_B200_OK;
+  if (scalars_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::gen_scalars(scalars_dev, n, seed, first_index, montgomery != 0, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_dlog_dot_dev(void* out_scalar_dev, const void* scalars_dev, size_t n, const void* s0_host,
+                           const void* d_host, uint64_t first_index, void* stream) {
+  if (out_scalar_dev == nullptr || (n && scalars_dev == nullptr) || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  if (s0_host == nullptr || d_host == nullptr) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::dlog_dot(out_scalar_dev, scalars_dev, n, s0_host, d_host, first_index, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_check_on_curve_dev(const void* bases_dev, size_t n, size_t affine_stride, void* stream) {
+  if (!stride_ok(affine_stride)) return ALEO_B200_EINVAL;
+  if (n == 0) return 1;
+  if (bases_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  int ok = 0;
+  API_CK(aleo::check_on_curve(bases_dev, n, (u32)affine_stride, (cudaStream_t)stream, &ok));
+  return ok;
+}
+
+int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
+  if (kind < 0 || kind > 3 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::bench_imad(kind, iters, ms_out, ops_out));
+  return ALEO_B200_OK;
+}
+
+}  // extern "C"

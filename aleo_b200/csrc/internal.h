@@ -1,0 +1,28 @@
+// internal.h -- host-side seams between the translation units of libaleo_b200.so.
+// (Three kernel TUs so that nvcc/ptxas run in parallel; each TU owns a copy of the constant-bank
+// moduli and uploads it through its *_upload_constants().)
+#pragma once
+#include "platform.cuh"
+
+namespace aleo {
+// ntt_lib.cu
+cudaError_t ntt_upload_constants();
+cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s);
+int ntt_launches(u32 log_n);
+int ntt_max_log_n();
+void ntt_clear_plans();
+// msm_lib.cu
+cudaError_t msm_upload_constants();
+cudaError_t msm_run(const void* bases_dev, u32 stride, const void* scalars_dev, size_t n, void* out144_dev, cudaStream_t s,
+                    bool dry, int* launches_out);
+bool msm_size_supported(size_t n);
+int msm_window_bits(size_t n);
+cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);
+// util_lib.cu
+cudaError_t util_upload_constants();
+cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);
+cudaError_t gen_scalars(void* scalars_dev, size_t n, u64 seed, u64 first, bool montgomery, cudaStream_t s);
+cudaError_t dlog_dot(void* out_dev, const void* scalars_dev, size_t n, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);
+cudaError_t check_on_curve(const void* bases_dev, size_t n, u32 stride, cudaStream_t s, int* ok);
+cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out);
+}  // namespace aleo

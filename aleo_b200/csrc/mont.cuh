@@ -1,0 +1,247 @@
+// mont.cuh -- Montgomery-form prime-field arithmetic on 32-bit limbs for the sm_100a integer pipes.
+//
+// Number representation contract (snarkvm-fields 0.14.5 Fp256 / Fp384, SURVEY.md section 8a row 7/8,
+// App. C): a field element is the Montgomery residue a*R mod m, R = 2^(32*N), stored as
+// little-endian limbs and always fully reduced (< m).  An Fp<P> is bit-identical to the Rust
+// struct's memory image (4 or 6 little-endian u64 limbs == 8 or 12 little-endian u32 limbs).
+//
+// Multiplier: operand-scanning Montgomery product with the row products split by the parity of
+// their absolute limb position into two accumulators (E: pairs starting at even positions,
+// O: pairs starting at odd positions).  Every row is then two independent carry chains made of
+// (mad.lo.cc, madc.hi.cc) pairs, each pair = one IMAD.WIDE.U32.X in SASS.  The limb that would
+// straddle the two accumulators after the implicit one-limb shift is folded with a single add.cc
+// whose carry-out is consumed as carry-in by the next trailing chain.  fma-pipe instruction
+// count: N*(2N) IMAD.WIDE for N limbs (both moduli are == 1 mod 2^32, so the Montgomery factor
+// is a negation, not a multiplication).
+#pragma once
+#include "bls12_377_constants.cuh"
+#include "ptx_arith.cuh"
+
+// 32-byte alignment for Fr makes every element move one LDG.E.256 / STG.E.256 on sm_100a.
+template <class P>
+struct alignas((P::N % 8 == 0) ? 32 : 16) Fp {
+  u32 l[P::N];
+};
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+template <class P>
+DEV Fp<P> fp_zero() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.l[i] = 0;
+  return r;
+}
+
+// constant from a generated accessor, e.g. fp_const<FrParams, FrParams::GENERATOR_M>()
+template <class P, u32 (*F)(int)>
+DEV Fp<P> fp_const() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.l[i] = F(i);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_one() {
+  return fp_const<P, P::ONE>();
+}
+
+template <class P>
+DEV bool fp_is_zero(const Fp<P>& a) {
+  u32 acc = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) acc |= a.l[i];
+  return acc == 0;
+}
+
+template <class P>
+DEV bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
+  u32 acc = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) acc |= a.l[i] ^ b.l[i];
+  return acc == 0;
+}
+
+// r = a - m if a >= m else a      (input < 2m)
+template <class P>
+DEV void fp_reduce_once(Fp<P>& a) {
+  constexpr int N = P::N;
+  u32 s[N];
+  s[0] = ptx::sub_cc(a.l[0], P::MOD(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) s[i] = ptx::subc_cc(a.l[i], P::MOD(i));
+  u32 borrow = ptx::subc(0, 0);  // 0xffffffff when a < m
+#pragma unroll
+  for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : s[i];
+}
+
+template <class P>
+DEV Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+  r.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);  // m < 2^(32N-1): no carry out
+  fp_reduce_once(r);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+  u32 mask = ptx::subc(0, 0);  // all ones when a < b
+  r.l[0] = ptx::add_cc(r.l[0], P::MOD(0) & mask);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], P::MOD(i) & mask);
+  r.l[N - 1] = ptx::addc(r.l[N - 1], P::MOD(N - 1) & mask);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_neg(const Fp<P>& a) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  u32 nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) nz |= a.l[i];
+  r.l[0] = ptx::sub_cc(P::MOD(0), a.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::subc_cc(P::MOD(i), a.l[i]);
+  r.l[N - 1] = ptx::subc(P::MOD(N - 1), a.l[N - 1]);
+  if (nz == 0) r = a;  // -0 = 0 (keep the canonical representative)
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add(a, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery product.  Absolute-position accumulators E / O, see the header comment.
+// ---------------------------------------------------------------------------------------------
+namespace montdetail {
+// acc pairs (pos+j, pos+j+1) += x[j] * y for j = J0, J0+2, ... < N      (one carry chain)
+// CARRY_IN: first instruction consumes CF.  TOP: add the chain's carry-out into acc[pos+N'].
+// X_IS_MOD: the row operand is the modulus, read from the constant bank (uniform registers; an
+// immediate would stop ptxas from fusing the pair into IMAD.WIDE) instead of x[].
+template <class P, int POS, int J0, bool CARRY_IN, bool X_IS_MOD, int LEN>
+DEV void row_chain(u32 (&acc)[LEN], const u32* x, u32 y) {
+  constexpr int N = P::N;
+#pragma unroll
+  for (int j = J0; j < N; j += 2) {
+    const u32 xj = X_IS_MOD ? P::MODC()[j] : x[j];
+    if (j == J0 && !CARRY_IN)
+      acc[POS + j] = ptx::mad_lo_cc(xj, y, acc[POS + j]);
+    else
+      acc[POS + j] = ptx::madc_lo_cc(xj, y, acc[POS + j]);
+    if (J0 == 1 && j + 2 >= N)
+      acc[POS + j + 1] = ptx::madc_hi(xj, y, acc[POS + j + 1]);  // trailing chain: bounded, no carry out
+    else
+      acc[POS + j + 1] = ptx::madc_hi_cc(xj, y, acc[POS + j + 1]);
+  }
+  if (J0 == 0) acc[POS + N] = ptx::addc(acc[POS + N], 0);
+}
+
+template <class P, int I, int LEN>
+DEV void iter(u32 (&E)[LEN], u32 (&O)[LEN], const u32* a, u32 bi) {
+  u32(&L)[LEN] = (I & 1) ? O : E;  // leading accumulator: owns the pair that starts at position I
+  u32(&T)[LEN] = (I & 1) ? E : O;  // trailing accumulator: its limb at position I is a pair's high half
+  if (I > 0) {
+    L[I] = ptx::add_cc(L[I], T[I]);  // fold; carry-out belongs to position I+1 = first trailing pair
+    row_chain<P, I, 1, true, false>(T, a, bi);
+  } else {
+    row_chain<P, I, 1, false, false>(T, a, bi);
+  }
+  row_chain<P, I, 0, false, false>(L, a, bi);
+  u32 m = ptx::neg_opaque(L[I]);  // Montgomery factor: INV == -1 mod 2^32 for both BLS12-377 moduli
+  row_chain<P, I, 0, false, true>(L, a, m);
+  row_chain<P, I, 1, false, true>(T, a, m);
+}
+
+template <class P, int I, int LEN>
+struct Unroll {
+  static DEV void run(u32 (&E)[LEN], u32 (&O)[LEN], const u32* a, const u32* b) {
+    Unroll<P, I - 1, LEN>::run(E, O, a, b);
+    iter<P, I, LEN>(E, O, a, b[I]);
+  }
+};
+template <class P, int LEN>
+struct Unroll<P, -1, LEN> {
+  static DEV void run(u32 (&)[LEN], u32 (&)[LEN], const u32*, const u32*) {}
+};
+}  // namespace montdetail
+
+template <class P>
+DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  static_assert(P::INV == 0xffffffffu, "multiplier assumes modulus == 1 mod 2^32");
+  constexpr int LEN = 2 * N + 1;
+  u32 E[LEN], O[LEN];
+#pragma unroll
+  for (int k = 0; k < LEN; k++) E[k] = O[k] = 0;
+  montdetail::Unroll<P, N - 1, LEN>::run(E, O, a.l, b.l);
+  Fp<P> r;
+  r.l[0] = ptx::add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(E[N + k], O[N + k]);
+  r.l[N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 1]);
+  fp_reduce_once(r);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul(a, a);
+}
+
+// Montgomery -> canonical (PrimeField::to_bigint): multiply by 1.
+template <class P>
+DEV Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> one = fp_zero<P>();
+  one.l[0] = 1;
+  return fp_mul(a, one);
+}
+
+template <class P>
+DEV Fp<P> fp_to_mont(const Fp<P>& a) {
+  return fp_mul(a, fp_const<P, P::R2>());
+}
+
+// a^e for a little-endian 32-bit-limb exponent (runtime loop: used off the hot path only).
+template <class P>
+DEV Fp<P> fp_pow(const Fp<P>& a, const u32* e, int nlimbs) {
+  Fp<P> r = fp_one<P>();
+  bool started = false;
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      if (started) r = fp_sqr(r);
+      if ((e[i] >> b) & 1) {
+        r = fp_mul(r, a);
+        started = true;
+      }
+    }
+  }
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_pow_u64(const Fp<P>& a, u64 e) {
+  u32 limbs[2] = {(u32)e, (u32)(e >> 32)};
+  return fp_pow(a, limbs, 2);
+}
+
+// Fermat inversion a^(m-2); 0 -> 0.
+template <class P>
+DEV Fp<P> fp_inv(const Fp<P>& a) {
+  u32 e[P::N];
+#pragma unroll
+  for (int i = 0; i < P::N; i++) e[i] = P::MOD_MINUS_2(i);
+  return fp_pow(a, e, P::N);
+}

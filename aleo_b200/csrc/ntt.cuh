@@ -1,0 +1,359 @@
+// ntt.cuh -- radix-2 NTT over the BLS12-377 scalar field Fr for sm_100a.
+//
+// Replaces (drop-in, same numeric contract) snarkvm-algorithms 0.14.5
+//   EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place   (src/fft/domain.rs)
+// reached from the reference at rust/src/program/execute.rs:74,177 (prove_execution / vm.execute).
+// Natural order in, natural order out; omega = TWO_ADIC_ROOT^(2^(47-k)); inverse scales by n^-1;
+// coset variants shift by g = 22 (forward: c_i *= g^i before; inverse: c_i *= g^-i after).
+//
+// Design (B200 first, not a translation of any CPU loop nest):
+//   * N = 2^L is split into P = ceil(L/8) passes of K_p <= 8 bits.  One pass = one HBM round trip
+//     (64 B per element), so the algorithmic traffic is 64*P bytes per element.
+//   * A pass handles a 2048-element tile per 256-thread CTA: every thread owns 8 elements in
+//     registers, does radix-8 / radix-4 / radix-2 butterflies on them, and trades elements with
+//     the other threads of the CTA through a 64 KB shared-memory tile (two uint4 planes, so all
+//     shared accesses are 128-bit and bank-conflict free) -- at most 3 __syncthreads per pass.
+//   * Global accesses are 256-bit (LDG.E.256 / STG.E.256), each warp touching runs of >= 256
+//     contiguous bytes.  The last pass writes the digit-reversed (natural-order) positions
+//     directly, so no separate permutation pass exists.
+//   * Twiddles: the inter-pass factor w^(i2*k1) is rebuilt from two L2-resident power tables
+//     (w^lo * w^(hi<<lo_bits)); the in-tile factors come from an 8 KB table of the tile's own root.
+//     The inverse transform's n^-1 and the coset powers ride on the same two-table scheme.
+//   The transform is integer-pipe bound (about 14 Fr products per element at L = 24, 120
+//   IMAD.WIDE each), not HBM bound -- see DESIGN.md for the two rooflines.
+#pragma once
+#include "mont.cuh"
+
+namespace ntt {
+
+constexpr int TILE_LOG = 11;            // elements per CTA tile
+constexpr int TILE = 1 << TILE_LOG;     // 2048 elements = 64 KB
+constexpr int TPB = TILE / 8;           // 256 threads, 8 elements each
+constexpr int SMALL_MAX_LOG = 11;       // single-CTA kernel handles n <= 2^11
+constexpr int MAX_PASS_BITS = 8;
+constexpr int MAX_LOG_N = 32;           // memory bound, far below the field's two-adicity (47)
+
+// w^e from a two-level table: lo[e & mask] * hi[e >> lo_bits]
+struct PowTable {
+  const Fr* lo;
+  const Fr* hi;
+  u32 lo_bits;
+};
+
+DEV Fr pow_lookup(const PowTable& t, u32 e) {
+  Fr a = t.lo[e & ((1u << t.lo_bits) - 1u)];
+  Fr b = t.hi[e >> t.lo_bits];
+  return fp_mul(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2 / 4 / 8 point transforms on registers.  Natural order in, natural order out.
+// roots: w8[1], w8[2], w8[3] = powers of the primitive 8th root used by this direction
+// (w8[2] is the primitive 4th root).
+// ---------------------------------------------------------------------------------------------
+DEV void bfly(Fr& a, Fr& b) {
+  Fr s = fp_add(a, b);
+  b = fp_sub(a, b);
+  a = s;
+}
+
+DEV void ntt2(Fr* x) { bfly(x[0], x[1]); }
+
+DEV void ntt4(Fr* x, const Fr& w4) {
+  bfly(x[0], x[2]);
+  bfly(x[1], x[3]);
+  x[3] = fp_mul(x[3], w4);
+  bfly(x[0], x[1]);
+  bfly(x[2], x[3]);
+  Fr t = x[1];  // bit-reversed -> natural
+  x[1] = x[2];
+  x[2] = t;
+}
+
+DEV void ntt8(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
+  bfly(x[0], x[4]);
+  bfly(x[1], x[5]);
+  bfly(x[2], x[6]);
+  bfly(x[3], x[7]);
+  x[5] = fp_mul(x[5], w8[1]);
+  x[6] = fp_mul(x[6], w8[2]);
+  x[7] = fp_mul(x[7], w8[3]);
+  bfly(x[0], x[2]);
+  bfly(x[1], x[3]);
+  bfly(x[4], x[6]);
+  bfly(x[5], x[7]);
+  x[3] = fp_mul(x[3], w8[2]);
+  x[7] = fp_mul(x[7], w8[2]);
+  bfly(x[0], x[1]);
+  bfly(x[2], x[3]);
+  bfly(x[4], x[5]);
+  bfly(x[6], x[7]);
+  // positions hold X[bitrev3(pos)]: swap 1<->4, 3<->6
+  Fr t = x[1];
+  x[1] = x[4];
+  x[4] = t;
+  t = x[3];
+  x[3] = x[6];
+  x[6] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tile: two planes of uint4 (low / high half of an element).
+// ---------------------------------------------------------------------------------------------
+template <int K, bool LAST>
+DEV u32 tile_phys(u32 p, u32 g) {
+  constexpr u32 R = 1u << K;
+  constexpr u32 G = TILE >> K;
+  if (LAST) return g * (R + 1) + (p ^ ((p >> 3) & 7u));  // lanes run along p (loads) or g (stores)
+  return p * G + g;                                      // lanes always run along g
+}
+template <int K, bool LAST>
+CONSTFN u32 tile_plane_elems() {
+  return LAST ? (TILE >> K) * ((1u << K) + 1u) : (u32)TILE;
+}
+
+DEV void smem_put(uint4* plane0, uint4* plane1, u32 idx, const Fr& v) {
+  plane0[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  plane1[idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+DEV Fr smem_get(const uint4* plane0, const uint4* plane1, u32 idx) {
+  uint4 a = plane0[idx], b = plane1[idx];
+  Fr v;
+  v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+  v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+  return v;
+}
+
+struct PassArgs {
+  const Fr* src;
+  Fr* dst;
+  u32 log_n;        // L
+  u32 log_cur;      // log2 of the sub-problem size entering this pass
+  u32 log_r1;       // LAST only: log2 of the first pass's radix
+  u32 log_r2;       // LAST only: log2 of the second pass's radix when P >= 3, else 0
+  u32 log_r3;       // LAST only: log2 of the third pass's radix when P == 4, else 0
+  const Fr* inner;  // w_R^j, j < R, R = this pass's radix
+  PowTable tw;      // powers of w_N (inverse: hi table carries n^-1 when fold_scale)
+  PowTable pre;     // PRE : coset powers c^i applied to inputs of the first pass
+  PowTable post;    // POST: powers applied to outputs of the last pass (coset inverse, carries n^-1)
+  u32 use_pre, use_post;
+};
+
+// One pass.  K = bits handled, LAST = writes the natural-order result.  Coset scaling (use_pre on
+// the first pass, use_post on the last) is a CTA-uniform runtime branch.
+template <int K, bool LAST>
+KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
+  constexpr u32 R = 1u << K;
+  constexpr u32 LG = TILE_LOG - K;
+  constexpr u32 G = 1u << LG;
+  constexpr u32 RT = R / 8;  // threads along r
+  constexpr int S1 = 3;
+  constexpr int S2 = (K - 3 >= 3) ? 3 : (K - 3);
+  constexpr int S3 = K - S1 - S2;
+  static_assert(K >= 5 && K <= 8, "pass radix");
+  DYN_SMEM(uint4, plane0);
+  uint4* plane1 = plane0 + tile_plane_elems<K, LAST>();
+
+  const u32 tid = threadIdx.x;
+  // loads: lanes along g (strided passes) or along r (last pass, rows are contiguous)
+  const u32 tr = LAST ? (tid & (RT - 1)) : (tid >> LG);
+  const u32 tg = LAST ? (tid / RT) : (tid & (G - 1));
+
+  // ---- tile geometry -------------------------------------------------------------------------
+  const u32 log_m = a.log_cur - K;  // log2(M), M = cur / R
+  u64 in_base, out_base;
+  u64 stride_r, stride_g, ostride_r;
+  u32 i2_base = 0;
+  if (!LAST) {
+    const u32 tiles_per_blk = 1u << (log_m - LG);
+    const u32 blk = blockIdx.x / tiles_per_blk;
+    const u32 cg = blockIdx.x % tiles_per_blk;
+    i2_base = cg << LG;
+    in_base = ((u64)blk << a.log_cur) + i2_base;
+    out_base = in_base;
+    stride_r = (u64)1 << log_m;
+    stride_g = 1;
+    ostride_r = stride_r;
+  } else {
+    // blocks b = k1 * S + rest ; the tile takes G consecutive k1 for one `rest`
+    const u32 log_s = a.log_r2 + a.log_r3;  // S = product of the middle passes' radices
+    const u32 S = 1u << log_s;
+    const u32 rest = blockIdx.x & (S - 1);
+    const u32 k1_0 = (blockIdx.x >> log_s) << LG;
+    in_base = (((u64)k1_0 << log_s) + rest) << K;
+    stride_r = 1;
+    stride_g = (u64)S << K;
+    // digit reversal of the middle digits: rest = k2 * R3 + k3  ->  k2 + R2 * k3
+    const u32 k2 = rest >> a.log_r3, k3 = rest & ((1u << a.log_r3) - 1u);
+    const u64 rev_rest = k2 + ((u64)k3 << a.log_r2);
+    out_base = k1_0 + (rev_rest << a.log_r1);
+    ostride_r = (u64)1 << (a.log_n - K);
+  }
+
+  Fr x[8];
+  // ---- load + step 1 (radix 8 over the top three bits of r) ------------------------------------
+  {
+    constexpr u32 C1 = R >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const u32 p = j * C1 + tr;
+      const u64 gi = in_base + p * stride_r + tg * stride_g;
+      x[j] = a.src[gi];
+      if (!LAST && a.use_pre) x[j] = fp_mul(x[j], pow_lookup(a.pre, (u32)gi));
+    }
+    Fr w8[4];
+    w8[1] = a.inner[R / 8];
+    w8[2] = a.inner[R / 4];
+    w8[3] = a.inner[3 * (R / 8)];
+    ntt8(x, w8);
+#pragma unroll
+    for (int k = 1; k < 8; k++) x[k] = fp_mul(x[k], a.inner[tr * k]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(k * C1 + tr, tg), x[k]);
+  }
+  SYNC_THREADS();
+  // ---- step 2 ------------------------------------------------------------------------------------
+  {
+    constexpr u32 CP = R >> 3;        // sub-problem size entering the step
+    constexpr u32 C = CP >> S2;       // ... leaving it
+    constexpr int GROUPS = 8 >> S2;   // independent small transforms per thread
+    constexpr int PTS = 1 << S2;
+    Fr w8[4];
+    if (S2 == 3) {
+      w8[1] = a.inner[R / 8];
+      w8[3] = a.inner[3 * (R / 8)];
+    }
+    if (S2 >= 2) w8[2] = a.inner[R / 4];
+#pragma unroll
+    for (int h = 0; h < GROUPS; h++) {
+      const u32 gam = tr + h * RT;
+      const u32 blk = gam / C, t = gam % C;
+      const u32 bp = blk * CP + t;
+#pragma unroll
+      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j * C, tg));
+      if (S2 == 3) ntt8(x + h * PTS, w8);
+      if (S2 == 2) ntt4(x + h * PTS, w8[2]);
+      if (S2 == 1) ntt2(x + h * PTS);
+      if (C > 1) {
+#pragma unroll
+        for (int k = 1; k < PTS; k++) x[h * PTS + k] = fp_mul(x[h * PTS + k], a.inner[(R / CP) * t * k]);
+      }
+#pragma unroll
+      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k * C, tg), x[h * PTS + k]);
+    }
+  }
+  SYNC_THREADS();
+  // ---- step 3 (only when K > 6): sub-problems of size 2^S3, no twiddles afterwards ---------------
+  if (S3 > 0) {
+    constexpr u32 CP = 1u << S3;
+    constexpr int GROUPS = 8 >> S3;
+    constexpr int PTS = 1 << S3;
+    Fr w4;
+    if (S3 == 2) w4 = a.inner[R / 4];
+#pragma unroll
+    for (int h = 0; h < GROUPS; h++) {
+      const u32 gam = tr + h * RT;
+      const u32 bp = gam * CP;
+#pragma unroll
+      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j, tg));
+      if (S3 == 2) ntt4(x + h * PTS, w4);
+      if (S3 == 1) ntt2(x + h * PTS);
+#pragma unroll
+      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k, tg), x[h * PTS + k]);
+    }
+    SYNC_THREADS();
+  }
+  // ---- store: thread takes outputs kappa = j*RT + sr for its column sg (lanes along g) ------------
+  {
+    const u32 sr = tid >> LG, sg = tid & (G - 1);
+    constexpr u32 C1 = R >> S1, C2 = C1 >> S2;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const u32 kap = j * RT + sr;
+      // position of output kappa after the in-place decimation-in-frequency steps
+      const u32 d1 = kap & 7u, d2 = (kap >> S1) & ((1u << S2) - 1u), d3 = kap >> (S1 + S2);
+      const u32 pos = d1 * C1 + d2 * C2 + d3;
+      Fr v = smem_get(plane0, plane1, tile_phys<K, LAST>(pos, sg));
+      const u64 go = out_base + kap * ostride_r + sg;
+      if (!LAST) {
+        const u32 e = ((i2_base + sg) * kap) << (a.log_n - a.log_cur);
+        v = fp_mul(v, pow_lookup(a.tw, e));
+      }
+      if (LAST && a.use_post) v = fp_mul(v, pow_lookup(a.post, (u32)go));
+      a.dst[go] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// n <= 2^11: one CTA per transform, whole vector in shared memory (latency bound by nature).
+// ---------------------------------------------------------------------------------------------
+struct SmallArgs {
+  Fr* data;         // batch x n, in place
+  u32 log_n;
+  const Fr* inner;  // w_n^j, j < n
+  PowTable pre;     // coset forward: g^i on the inputs
+  PowTable post;    // coset inverse: n^-1 * g^-i on the outputs
+  Fr scale;         // plain inverse: n^-1
+  u32 use_pre, use_post, use_scale;
+};
+
+KERNEL void __launch_bounds__(TPB) small_kernel(SmallArgs a) {
+  DYN_SMEM(uint4, plane0);
+  const u32 n = 1u << a.log_n;
+  uint4* plane1 = plane0 + n;
+  Fr* x = a.data + ((u64)blockIdx.x << a.log_n);
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+    Fr v = x[i];
+    if (a.use_pre) v = fp_mul(v, pow_lookup(a.pre, i));
+    u32 r = 0;
+    for (u32 b = 0; b < a.log_n; b++) r |= ((i >> b) & 1u) << (a.log_n - 1 - b);
+    smem_put(plane0, plane1, r, v);
+  }
+  SYNC_THREADS();
+  for (u32 lm = 0; lm < a.log_n; lm++) {
+    const u32 m = 1u << lm;
+    for (u32 idx = threadIdx.x; idx < n / 2; idx += blockDim.x) {
+      const u32 k = idx & (m - 1);
+      const u32 lo = ((idx >> lm) << (lm + 1)) + k;
+      Fr u = smem_get(plane0, plane1, lo);
+      Fr t = smem_get(plane0, plane1, lo + m);
+      if (k) t = fp_mul(t, a.inner[k << (a.log_n - lm - 1)]);
+      smem_put(plane0, plane1, lo, fp_add(u, t));
+      smem_put(plane0, plane1, lo + m, fp_sub(u, t));
+    }
+    SYNC_THREADS();
+  }
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+    Fr v = smem_get(plane0, plane1, i);
+    if (a.use_post) v = fp_mul(v, pow_lookup(a.post, i));
+    if (a.use_scale) v = fp_mul(v, a.scale);
+    x[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table builders (run once per (log_n, direction, kind) and cached by the host plan).
+// ---------------------------------------------------------------------------------------------
+// out[j] = scale * base^(j << shift)      (base, scale: device scalars)
+KERNEL void pow_table_kernel(Fr* out, const Fr* base, const Fr* scale, u32 count, u32 shift) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  out[j] = fp_mul(*scale, fp_pow_u64(*base, (u64)j << shift));
+}
+
+// roots[0] = w_N (or its inverse), roots[1] = n^-1 (Montgomery), roots[2] = g or g^-1, roots[3] = 1
+KERNEL void domain_consts_kernel(Fr* roots, u32 log_n, u32 inverse) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fr w = inverse ? fp_const<FrParams, FrParams::TWO_ADIC_ROOT_INV_M>() : fp_const<FrParams, FrParams::TWO_ADIC_ROOT_M>();
+  for (u32 i = log_n; i < (u32)FR_TWO_ADICITY; i++) w = fp_sqr(w);
+  Fr ninv = fp_one<FrParams>();
+  Fr half = fp_const<FrParams, FrParams::TWO_INV_M>();
+  for (u32 i = 0; i < log_n; i++) ninv = fp_mul(ninv, half);
+  roots[0] = w;
+  roots[1] = ninv;
+  roots[2] = inverse ? fp_const<FrParams, FrParams::GENERATOR_INV_M>() : fp_const<FrParams, FrParams::GENERATOR_M>();
+  roots[3] = fp_one<FrParams>();
+}
+
+}  // namespace ntt

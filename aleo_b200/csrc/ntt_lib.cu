@@ -1,0 +1,34 @@
+// ntt_lib.cu -- translation unit holding the Fr NTT kernels and their plan cache.
+#include "internal.h"
+#include "ntt_host.cuh"
+
+namespace {
+ntt::PlanCache g_plans;
+}
+
+namespace aleo {
+cudaError_t ntt_upload_constants() { return aleo_upload_field_constants(); }
+int ntt_max_log_n() { return ntt::MAX_LOG_N; }
+void ntt_clear_plans() { g_plans.clear(); }
+
+int ntt_launches(u32 log_n) {
+  if (log_n == 0) return 0;
+  if (log_n <= (u32)ntt::SMALL_MAX_LOG) return 1;
+  int K[4];
+  return ntt::split_passes((int)log_n, K);
+}
+
+cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s) {
+  const ntt::Plan* plan = nullptr;
+  cudaError_t e = g_plans.get(device, log_n, inverse, coset, s, &plan);
+  if (e != cudaSuccess) return e;
+  Fr* scratch = nullptr;
+  if (log_n > (u32)ntt::SMALL_MAX_LOG) {
+    e = cudaMallocAsync((void**)&scratch, sizeof(Fr) << log_n, s);
+    if (e != cudaSuccess) return e;
+  }
+  e = ntt::run(*plan, (Fr*)data_dev, batch, scratch, s);
+  if (scratch) cudaFreeAsync(scratch, s);
+  return e;
+}
+}  // namespace aleo

@@ -1,0 +1,110 @@
+/* aleo_b200.h -- C ABI of libaleo_b200.so: BLS12-377 G1 MSM and Fr NTT on NVIDIA B200 (sm_100a).
+ *
+ * The reference (demox-labs/aleo = Aleo SDK 0.5.1) has no FFI of its own for this path: it reaches
+ * the arithmetic through the crates.io pin snarkvm-algorithms "=0.14.5" (reference Cargo.toml:28-53).
+ * The entry points below are what a `[patch.crates-io] snarkvm-algorithms` shim binds (see
+ * INTEGRATION.md and rust_shim/); each one names the snarkVM function it stands in for and the
+ * reference call site that reaches it.  Data contracts:
+ *   Fr element      : 32 B, Montgomery form (R = 2^256), 4 little-endian u64 limbs, fully reduced.
+ *   MSM scalar      : 32 B, canonical (non-Montgomery) BigInteger256, little-endian, < r.
+ *   G1Affine        : x (48 B) | y (48 B) Montgomery (R = 2^384) little-endian; with
+ *                     affine_stride == 104 a bool `infinity` follows at byte 96 (Rust layout,
+ *                     size_of::<G1Affine>()); with affine_stride == 96 (packed) the identity is
+ *                     encoded as x = y = 0.
+ *   G1Projective    : Jacobian x | y | z, 3 x 48 B Montgomery.  Results are returned NORMALISED:
+ *                     z = 1 (Montgomery one), or (0, 1, 0) for the identity, so that to_affine()
+ *                     on the Rust side is a copy.
+ * All functions return 0 on success and a negative ALEO_B200_E* code otherwise; nothing throws,
+ * aborts or falls back to the CPU.  Every function is re-entrant: calls may come concurrently from
+ * many host threads (snarkVM commits polynomials on a rayon ExecutionPool); host-pointer calls
+ * use an internal per-thread stream, *_dev calls run on the caller's stream.
+ */
+#ifndef ALEO_B200_H
+#define ALEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  ALEO_B200_OK = 0,
+  ALEO_B200_EINVAL = -1,     /* null pointer, bad enum value, bad stride                         */
+  ALEO_B200_ETOOLARGE = -2,  /* log_n above the supported maximum (32; the field allows 47)      */
+  ALEO_B200_ENODEVICE = -3,  /* no CUDA device, or the device is not sm_100 (B200): no fallback  */
+  ALEO_B200_ECUDA = -4,      /* a CUDA runtime call or kernel failed; see aleo_b200_last_cuda_error */
+  ALEO_B200_ENOMEM = -5      /* device or pinned-host allocation failed                          */
+};
+
+/* enums mirror upstream's optional cuda FFI so that a shim is a few lines */
+enum { ALEO_B200_NTT_FORWARD = 0, ALEO_B200_NTT_INVERSE = 1 };
+enum { ALEO_B200_NTT_STANDARD = 0, ALEO_B200_NTT_COSET = 1 };
+
+const char* aleo_b200_version(void);
+const char* aleo_b200_strerror(int code);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* aleo_b200_last_cuda_error(void);
+
+/* Selects `device` for the calling thread and prepares it (uploads field constants).  Optional:
+ * every other entry point prepares the calling thread's current device on first use. */
+int aleo_b200_init(int device);
+int aleo_b200_device_count(void);
+/* Frees cached plans / workspaces of the current device. */
+int aleo_b200_shutdown(void);
+
+/* ---- Fr NTT --------------------------------------------------------------------------------
+ * Stands in for snarkvm_algorithms::fft::EvaluationDomain::{fft_in_place, ifft_in_place,
+ * coset_fft_in_place, coset_ifft_in_place} (snarkvm-algorithms 0.14.5 src/fft/domain.rs), reached
+ * from the reference at rust/src/program/execute.rs:74,177,219 and rust/src/program/transfer.rs:99
+ * (prove_execution / vm.execute) and rust/src/program/deploy.rs:142 (vm.deploy: index polynomials).
+ * inout holds n = 2^log_n elements (the caller has already zero-padded, as Vec::resize does
+ * upstream); natural order in, natural order out.  log_n = 0 is the identity. */
+int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind);
+/* Same on device memory, asynchronous on `stream` (a cudaStream_t; NULL = default stream).
+ * `batch` transforms of the same size, contiguous, each in place. */
+int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, void* stream);
+/* kernel launches one transform of this size issues (for launch accounting) */
+int aleo_b200_ntt_launches(uint32_t log_n);
+
+/* ---- G1 MSM --------------------------------------------------------------------------------
+ * Stands in for snarkvm_algorithms::msm::VariableBase::msm::<G1Affine>(bases, scalars)
+ * (snarkvm-algorithms 0.14.5 src/msm/variable_base/mod.rs) as called by KZG10::commit /
+ * commit_lagrange / open (src/polycommit/kzg10/mod.rs), reached from the same reference call sites.
+ * Like upstream the two slices are zipped: n is the shorter length.  n = 0 gives the identity. */
+int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
+                     size_t affine_stride);
+/* Device-resident operands (bases typically stay resident: the SRS is reused by every commitment).
+ * out_projective_dev: 144 B of device memory.  Asynchronous on `stream`. */
+int aleo_b200_msm_g1_dev(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
+                         size_t affine_stride, void* stream);
+/* Sum of `count` Jacobian points (144 B each, device) -> one normalised Jacobian point (device).
+ * This is the single final combine of the point-range-sharded multi-GPU MSM. */
+int aleo_b200_g1_sum_dev(void* out_projective_dev, const void* points_dev, size_t count, void* stream);
+/* window size c (bits) the MSM uses for n points, and the kernel launches one MSM issues */
+int aleo_b200_msm_window_bits(size_t n);
+int aleo_b200_msm_launches(size_t n);
+
+/* ---- synthetic workload generation and on-device checks (bench / tests) --------------------
+ * bases[i] = (s0 + (first_index + i) * d) * G, G the G1 generator; s0, d canonical 32-byte scalars.
+ * Known discrete logs make the MSM result checkable at any size. */
+int aleo_b200_gen_bases_dev(void* bases_dev, size_t n, size_t affine_stride, const void* s0_host, const void* d_host,
+                            uint64_t first_index, void* stream);
+/* scalars[i] = splitmix-style hash of (seed, first_index + i) masked to 252 bits (< r), canonical */
+int aleo_b200_gen_scalars_dev(void* scalars_dev, size_t n, uint64_t seed, uint64_t first_index, int montgomery,
+                              void* stream);
+/* out (32 B canonical, device) = sum_i scalars[i] * (s0 + (first_index + i) * d) mod r */
+int aleo_b200_dlog_dot_dev(void* out_scalar_dev, const void* scalars_dev, size_t n, const void* s0_host,
+                           const void* d_host, uint64_t first_index, void* stream);
+/* 1 if every point is on y^2 = x^3 + 1 (or the identity), 0 if not, < 0 on error */
+int aleo_b200_check_on_curve_dev(const void* bases_dev, size_t n, size_t affine_stride, void* stream);
+/* dependent-free IMAD / IMAD.WIDE issue-rate microbenchmark: returns elapsed ms for
+ * `iters` x 64 chains per thread on a full-chip grid, and the op count through *ops_out.
+ * kind 0 = mad.lo (IMAD), 1 = mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.U32.X). */
+int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALEO_B200_H */
