@@ -139,6 +139,19 @@ int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int dire
   return ALEO_B200_OK;
 }
 
+int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4) {
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
+  if (inout_dev == nullptr || pass_ms4 == nullptr || log_n == 0) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  API_CK(aleo::ntt_transform(dev, log_n, 1, direction == ALEO_B200_NTT_INVERSE, kind == ALEO_B200_NTT_COSET, inout_dev,
+                             (cudaStream_t)stream, pass_ms4));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) {
   if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
   if (inout_host == nullptr) return ALEO_B200_EINVAL;
@@ -212,6 +225,18 @@ int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n
   if (rc) return rc;
   if (e != cudaSuccess) return fail_cuda(e);
   if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_msm_g1_dev_profile(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
+                                 size_t affine_stride, void* stream, float* phase_ms3) {
+  if (!stride_ok(affine_stride) || out_projective_dev == nullptr || phase_ms3 == nullptr || n == 0) return ALEO_B200_EINVAL;
+  if (bases_dev == nullptr || scalars_dev == nullptr) return ALEO_B200_EINVAL;
+  if (!aleo::msm_size_supported(n)) return ALEO_B200_ETOOLARGE;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::msm_run(bases_dev, (u32)affine_stride, scalars_dev, n, out_projective_dev, (cudaStream_t)stream, false,
+                       nullptr, phase_ms3));
   return ALEO_B200_OK;
 }
 

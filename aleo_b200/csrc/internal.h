@@ -7,14 +7,15 @@
 namespace aleo {
 // ntt_lib.cu
 cudaError_t ntt_upload_constants();
-cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s);
+cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s,
+                          float* pass_ms = nullptr /* >= 4 floats; synchronises the stream when given */);
 int ntt_launches(u32 log_n);
 int ntt_max_log_n();
 void ntt_clear_plans();
 // msm_lib.cu
 cudaError_t msm_upload_constants();
 cudaError_t msm_run(const void* bases_dev, u32 stride, const void* scalars_dev, size_t n, void* out144_dev, cudaStream_t s,
-                    bool dry, int* launches_out);
+                    bool dry, int* launches_out, float* phase_ms = nullptr /* 3 floats; synchronises when given */);
 bool msm_size_supported(size_t n);
 int msm_window_bits(size_t n);
 cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);

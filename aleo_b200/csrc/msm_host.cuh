@@ -71,8 +71,11 @@ struct RedLevel {
 
 // Runs (or, with dry = true, only counts the launches of) one MSM.  bases / scalars / out144 are
 // device pointers; everything is asynchronous on `s` except the workspace allocation call itself.
+// phase_ev (optional, 4 events): recorded before the sort phase, before / after the bucket
+// accumulation kernel, and after the final kernel -- bench.py's per-kernel timing.
 static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32* scalars, size_t n_sz,
-                              unsigned char* out144, cudaStream_t s, bool dry, int* launches_out) {
+                              unsigned char* out144, cudaStream_t s, bool dry, int* launches_out,
+                              cudaEvent_t* phase_ev = nullptr) {
   int launches = 0;
   if (n_sz == 0) {
     if (!dry) LAUNCH_NOSYNC(write_identity_kernel, dim3(1), dim3(1), 0, s, out144);
@@ -146,6 +149,7 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
     }                                                    \
   } while (0)
 
+  if (phase_ev && !dry) cudaEventRecord(phase_ev[0], s);
   STEP(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
   STEP(cudaMemsetAsync(meta, 0, 64, s));
   STEP(cudaMemsetAsync(buckets, 0, (size_t)NB * sizeof(G1Xyzz), s));
@@ -161,10 +165,12 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   launches++;
   if (!dry && err == cudaSuccess) err = exclusive_scan(ntasks, NB, bsums, task_off, nullptr, meta + 1, s, launches);
   else launches += 3;
+  if (phase_ev && !dry) cudaEventRecord(phase_ev[1], s);
   STEP(LAUNCH_NOSYNC(accumulate_kernel, dim3((task_ub + 127) / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
                      (const u32*)starts, (const u32*)ends, (const u32*)ntasks, (const u32*)task_off, NB, prm.T,
                      (const u32*)meta, buckets, partials));
   launches++;
+  if (phase_ev && !dry) cudaEventRecord(phase_ev[2], s);
   STEP(LAUNCH_NOSYNC(combine_small_kernel, dim3((cap_small + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
                      (const u32*)ntasks, (const u32*)task_off, (const u32*)meta, (const G1Xyzz*)partials, buckets));
   launches++;
@@ -206,6 +212,7 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   }
   STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, fa, out144));
   launches++;
+  if (phase_ev && !dry) cudaEventRecord(phase_ev[3], s);
   if (ws) cudaFreeAsync(ws, s);
 #undef STEP
 #undef WSP

@@ -130,7 +130,9 @@ static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, cuda
 static inline int launches_per_transform(const Plan& p) { return p.log_n <= (u32)SMALL_MAX_LOG ? 1 : p.npass; }
 
 // data: batch x n elements, in place.  scratch: n elements (only used when n > 2^11).
-static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch, cudaStream_t s) {
+// pass_ev (optional, npass + 1 events, batch must be 1): recorded around every pass.
+static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch, cudaStream_t s,
+                              cudaEvent_t* pass_ev = nullptr) {
   if (p.log_n == 0) return cudaSuccess;  // size-1 transform is the identity (also for coset: g^0 = 1)
   const size_t n = (size_t)1 << p.log_n;
   if (p.log_n <= (u32)SMALL_MAX_LOG) {
@@ -155,7 +157,9 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
     }
 #endif
     const u32 threads = (u32)(n / 2 < 32 ? 32 : (n / 2 > (size_t)TPB ? (size_t)TPB : n / 2));
+    if (pass_ev) cudaEventRecord(pass_ev[0], s);
     LAUNCH(small_kernel, dim3((u32)batch), dim3(threads), smem, s, a);
+    if (pass_ev) cudaEventRecord(pass_ev[1], s);
     return cudaGetLastError();
   }
   for (size_t b = 0; b < batch; b++) {
@@ -178,7 +182,9 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
       const u32 grid = (u32)(n >> TILE_LOG);
       a.use_pre = ((i == 0) && p.coset && !p.inverse) ? 1 : 0;
       a.use_post = (last && p.coset && p.inverse) ? 1 : 0;
+      if (pass_ev && i == 0) cudaEventRecord(pass_ev[0], s);
       NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, s) : launch_pass_k<false>(p.K[i], a, grid, s));
+      if (pass_ev) cudaEventRecord(pass_ev[i + 1], s);
       log_cur -= (u32)p.K[i];
     }
   }

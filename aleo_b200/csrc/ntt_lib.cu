@@ -18,7 +18,8 @@ int ntt_launches(u32 log_n) {
   return ntt::split_passes((int)log_n, K);
 }
 
-cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s) {
+cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s,
+                          float* pass_ms) {
   const ntt::Plan* plan = nullptr;
   cudaError_t e = g_plans.get(device, log_n, inverse, coset, s, &plan);
   if (e != cudaSuccess) return e;
@@ -27,8 +28,18 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
     e = cudaMallocAsync((void**)&scratch, sizeof(Fr) << log_n, s);
     if (e != cudaSuccess) return e;
   }
-  e = ntt::run(*plan, (Fr*)data_dev, batch, scratch, s);
+  cudaEvent_t ev[5];
+  const int nev = ntt_launches(log_n) + 1;
+  if (pass_ms)
+    for (int i = 0; i < nev; i++) cudaEventCreate(&ev[i]);
+  e = ntt::run(*plan, (Fr*)data_dev, batch, scratch, s, pass_ms ? ev : nullptr);
   if (scratch) cudaFreeAsync(scratch, s);
+  if (pass_ms) {
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    for (int i = 0; i < 4; i++) pass_ms[i] = 0.f;
+    for (int i = 0; i + 1 < nev && e == cudaSuccess; i++) cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+  }
   return e;
 }
 }  // namespace aleo

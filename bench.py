@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- BLS12-377 G1 MSM (headline) and Fr NTT (secondary) on B200, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 24]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...        # CPU arm: the C oracle port on the host cores
+
+A step = one G1 MSM over 2^log_n points per GPU (the rank's point range of an N*2^log_n-point MSM,
+BASELINE.json config 4's decomposition) followed, for N > 1, by the single final combine (all-gather
+of the 144-byte partials + g1_sum).  `value` = total points / max-over-ranks device time, inputs
+resident in HBM.  `e2e` = the same work through the host-pointer C-ABI entry point
+aleo_b200_msm_g1 (pinned host buffers, H2D of bases + scalars and D2H of the result inside the timed
+region).  The JSON line also carries the NTT figures, both rooflines and the CPU baseline.
+The oracle (oracle/) is used here only as the checker and as the timed CPU baseline.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MACS_PER_MIXED_ADD = 3000          # 10 Fq products x (2*12^2 + 12) 32x32->64 MACs
+NTT_BYTES_PER_ELEM_PER_PASS = 64   # 32 B read + 32 B write
+
+
+def load_c_oracle():
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "oracle"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.oracle_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    lib.oracle_gen_bases.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    lib.oracle_ntt_fr.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    return lib
+
+
+def cpu_msm_baseline(log_n_sample, steps, seed=0xA1E0B200 + 2):
+    """C oracle port (Pippenger, pthreads over windows) on all host cores; returns (Mpts/s, info)"""
+    import numpy as np
+
+    from oracle import bls12_377 as o
+
+    lib = load_c_oracle()
+    cores = os.cpu_count() or 1
+    n = 1 << log_n_sample
+    s0, d = o.base_dlogs(n, seed)
+    bases = np.zeros(n * 104, dtype=np.uint8)
+    lib.oracle_gen_bases(bases.ctypes.data, n, 104, o.int_to_le_bytes(s0, 32), o.int_to_le_bytes(d, 32), 0, cores)
+    rng = np.random.default_rng(seed)
+    scalars = rng.integers(0, 2**63, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    scalars |= rng.integers(0, 2, size=(n, 4), dtype=np.uint64) << np.uint64(63)
+    scalars[:, 3] &= np.uint64((1 << 60) - 1)          # 252 bits < r
+    out = C.create_string_buffer(144)
+    times = []
+    for _ in range(max(1, steps)):
+        t = time.perf_counter()
+        lib.oracle_msm_g1(out, bases.ctypes.data, n, scalars.ctypes.data, 104, cores)
+        times.append(time.perf_counter() - t)
+    # correctness of the timed run itself (known discrete logs)
+    sc = [int.from_bytes(scalars[i].tobytes(), "little") for i in range(min(n, 1 << 12))]
+    chk = C.create_string_buffer(144)
+    lib.oracle_msm_g1(chk, bases.ctypes.data, len(sc), scalars.ctypes.data, 104, cores)
+    assert chk.raw == o.g1_projective_to_bytes(o.msm_expected_from_dlogs(len(sc), seed, sc)), "CPU baseline produced a wrong result"
+    best = sorted(times)[len(times) // 2]
+    return n / best / 1e6, {"cores": cores, "sample": "G1 MSM n=2^%d, uniform 252-bit scalars, %d timed run(s), median" % (log_n_sample, len(times)),
+                            "seconds_per_run": best}
+
+
+def cpu_ntt_baseline(log_n_sample):
+    import numpy as np
+
+    lib = load_c_oracle()
+    cores = os.cpu_count() or 1
+    n = 1 << log_n_sample
+    data = np.random.default_rng(5).integers(0, 2**60, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    t = time.perf_counter()
+    lib.oracle_ntt_fr(data.ctypes.data, log_n_sample, 0, 0, cores)
+    dt = time.perf_counter() - t
+    return n / dt / 1e6, {"cores": cores, "sample": "Fr NTT n=2^%d forward, 1 run (includes root-table build)" % log_n_sample}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.strip().lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(args.log_n, args.cpu_log_n)
+    t0 = time.perf_counter()
+    val, info = cpu_msm_baseline(sample, args.steps + args.warmup)
+    ntt_val, ntt_info = cpu_ntt_baseline(min(args.log_n, 22))
+    line = {
+        "impl": "reference", "metric": "bls12_377_g1_msm_mpts_per_s", "value": val, "unit": "Mpts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_run"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (384-bit Montgomery Fq)", "data": "synthetic",
+        "config": {"workload": "G1 MSM, CPU arm: bounded sample n=2^%d of the n=2^%d-per-GPU workload" % (sample, args.log_n),
+                   "log_n": args.log_n, "sample_log_n": sample},
+        "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                         "note": "C restatement of the Pippenger algorithm class (oracle/oracle.c); the snarkVM Rust binary "
+                                 "cannot be built here (no Rust toolchain)"},
+        "ntt": {"value": ntt_val, "unit": "Melem/s", **ntt_info},
+        "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import aleo_b200 as ab
+    from oracle import bls12_377 as o          # checker only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ab.get_lib()                         # raises if the CUDA library was not built: no fallback
+    lib.check(lib.init(local), "aleo_b200_init")
+
+    log_n = args.log_n
+    n = 1 << log_n
+    seed = 0xA1E0B200 + 2
+    s0, d = o.base_dlogs(n * world, seed)
+    first = rank * n
+    bases = ab.gen_bases_dev(n, s0, d, first, 104, device=dev)
+    scalars = ab.gen_scalars_dev(n, seed, first, False, device=dev)
+    stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    partial = torch.empty(144, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(144 * world, dtype=torch.uint8, device=dev)
+    result = torch.empty(144, dtype=torch.uint8, device=dev)
+
+    def step():
+        ab.VariableBase.msm_dev(bases, scalars, n, 104, out=partial)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, partial)
+            ab.VariableBase.sum_partials_dev(gathered, world, out=result)
+            return result
+        return partial
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness of exactly what is timed: known discrete logs ------------------------------
+    assert ab.check_on_curve_dev(bases, n, 104), "generated bases are not on the curve"
+    k_local = ab.dlog_dot_dev(scalars, n, s0, d, first)
+    ks = [k_local]
+    if world > 1:
+        ks = [None] * world
+        dist.all_gather_object(ks, k_local)
+    got = step().cpu().numpy().tobytes()
+    want = o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, sum(ks) % o.R_MOD))
+    checked = bool(got == want)
+    assert checked, "MSM result does not match the oracle"
+
+    # ---- timed region: device-resident ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = ms_total.item() / args.steps
+    value = world * n / ms_step / 1e3               # Mpts/s, whole job
+
+    # ---- per-kernel timing for the roofline (same kernels, events around the phases) --------------
+    ph = (C.c_float * 3)()
+    acc_ms, sort_ms, tail_ms = [], [], []
+    for _ in range(max(2, args.steps)):
+        lib.check(lib.msm_g1_dev_profile(partial.data_ptr(), bases.data_ptr(), n, scalars.data_ptr(), 104, stream(), ph), "profile")
+        sort_ms.append(ph[0]); acc_ms.append(ph[1]); tail_ms.append(ph[2])
+    acc = sum(acc_ms) / len(acc_ms)
+    c_bits = ab.VariableBase.window_bits(n)
+    windows = 253 // c_bits + 1
+    macs = n * windows * MACS_PER_MIXED_ADD
+    ms_i, ops_i = C.c_double(), C.c_double()
+    lib.check(lib.bench_imad(2, 4096, C.byref(ms_i), C.byref(ops_i)), "bench_imad")
+    peak_gmac = ops_i.value / ms_i.value / 1e6          # IMAD.WIDE.U32.X issue rate, measured live
+    prof = {}
+    ppath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(ppath):
+        prof = json.load(open(ppath))
+    roofline = {"kernel": "msm::accumulate_kernel", "bound": "int", "achieved": macs / acc / 1e6, "peak": peak_gmac, "unit": "GMAC/s",
+                "frac": macs / acc / 1e6 / peak_gmac, "traffic": prof.get("msm_accumulate_dram_bytes"),
+                "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows,
+                "kernel_ms": acc, "kernel_share_of_step": acc / (sum(sort_ms) / len(sort_ms) + acc + sum(tail_ms) / len(tail_ms)),
+                "phases_ms": {"recode_sort_plan": sum(sort_ms) / len(sort_ms), "accumulate": acc, "combine_reduce_final": sum(tail_ms) / len(tail_ms)},
+                "peak_source": "measured live: carry-chained IMAD.WIDE.U32.X microbenchmark in this library (MEASURED_PEAKS.json "
+                               "has no integer-pipe figure); 32-bit MAC = one IMAD.WIDE",
+                "note": "MSM is integer-pipe bound (SURVEY.md 8d); the schema's hbm/tensor bounds do not apply to this kernel"}
+
+    # ---- e2e through the host-pointer C-ABI call, pinned host buffers ------------------------------
+    hb = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
+    hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    hb.copy_(bases)
+    hs.copy_(scalars)
+    torch.cuda.synchronize()
+    host_parts = torch.empty(144 * world, dtype=torch.uint8, device=dev)
+
+    def e2e_step():
+        raw = ab.VariableBase.msm(hb, hs, 104)              # H2D + MSM + D2H inside
+        if world > 1:
+            mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            dist.all_gather_into_tensor(host_parts, mine)
+            return ab.VariableBase.sum_partials_dev(host_parts, world).cpu().numpy().tobytes()
+        return raw
+
+    e2e_ok = e2e_step() == want
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * n * args.steps / e2e_s.item() / 1e6
+    del hb, hs
+
+    # ---- secondary: Fr NTT of the same size, resident ---------------------------------------------
+    del bases
+    torch.cuda.empty_cache()
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 77, first, True, device=dev)
+    x0 = x.clone()
+    dom.fft_in_place_dev(x)
+    dom.ifft_in_place_dev(x)
+    ntt_ok = bool(torch.equal(x, x0))
+    for _ in range(args.warmup):
+        dom.fft_in_place_dev(x)
+    barrier()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(args.steps):
+        dom.fft_in_place_dev(x)
+    n1.record()
+    barrier()
+    ntt_ms = torch.tensor([n0.elapsed_time(n1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ntt_ms, op=dist.ReduceOp.MAX)
+    ntt_step = ntt_ms.item() / args.steps
+    pm = (C.c_float * 4)()
+    passes = []
+    for _ in range(max(2, args.steps)):
+        lib.check(lib.ntt_fr_dev_profile(x.data_ptr(), log_n, 0, 0, stream(), pm), "ntt profile")
+        passes.append([pm[i] for i in range(dom.launches())])
+    pass_avg = sum(sum(p) for p in passes) / (len(passes) * dom.launches())
+    peaks = {}
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        peaks = json.load(open(mp))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ntt_bytes = NTT_BYTES_PER_ELEM_PER_PASS * n
+    mults_per_elem = 3.25 * dom.launches() + 2 * (dom.launches() - 1)     # DESIGN.md "NTT arithmetic"
+    ntt = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": world * n / ntt_step / 1e3, "unit": "Melem/s", "ms_per_step": ntt_step,
+           "log_n": log_n, "passes": dom.launches(), "round_trip_ok": ntt_ok,
+           "roofline": {"kernel": "ntt::pass_kernel", "bound": "hbm", "achieved": ntt_bytes / pass_avg / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ntt_bytes / pass_avg / 1e6 / hbm_peak, "traffic": prof.get("ntt_pass_dram_bytes"),
+                        "algorithmic_bytes_per_launch": ntt_bytes, "kernel_ms": pass_avg,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)",
+                        "int_frac": n * mults_per_elem * 120 / (ntt_step * 1e-3) / 1e9 / peak_gmac,
+                        "note": "the 253-bit NTT is integer-pipe bound (about %.1f Fr products of 120 IMAD.WIDE per element); int_frac is "
+                                "measured against the same live IMAD.WIDE peak as the MSM" % mults_per_elem}}
+
+    # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, info = cpu_msm_baseline(min(log_n, args.cpu_log_n), 1)
+        cpu = {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": "bls12_377_g1_msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (384-bit Montgomery Fq, 256-bit Fr)", "data": "synthetic",
+            "config": {"workload": "BLS12-377 G1 MSM n=2^%d points per GPU (point range of an %d*2^%d-point MSM; bases (s0+i*d)G 104-byte "
+                                   "stride, uniform 252-bit scalars), bases+scalars resident in HBM; N>1 adds the single final combine"
+                                   % (log_n, world, log_n),
+                       "log_n": log_n, "window_bits": c_bits, "cache": "inputs (%.1f GB per GPU) larger than L2" % (n * 136 / 1e9),
+                       "parallelism": "point-range shard x%d" % world},
+            "checked_against_oracle": checked and e2e_ok,
+            "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
+                    "api": "aleo_b200_msm_g1 (host pointers, pinned)"},
+            "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
+            "roofline": roofline, "ntt": ntt, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--cpu-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

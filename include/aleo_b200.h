@@ -65,6 +65,9 @@ int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind);
 /* Same on device memory, asynchronous on `stream` (a cudaStream_t; NULL = default stream).
  * `batch` transforms of the same size, contiguous, each in place. */
 int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, void* stream);
+/* One transform with CUDA events around every pass: pass_ms4[i] = device time of pass i (unused
+ * entries 0).  Synchronises `stream`.  Measurement aid for bench.py's roofline, same kernels. */
+int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4);
 /* kernel launches one transform of this size issues (for launch accounting) */
 int aleo_b200_ntt_launches(uint32_t log_n);
 
@@ -79,6 +82,10 @@ int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n
  * out_projective_dev: 144 B of device memory.  Asynchronous on `stream`. */
 int aleo_b200_msm_g1_dev(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
                          size_t affine_stride, void* stream);
+/* One MSM with CUDA events around its phases: phase_ms3 = {recode + counting sort + task plan,
+ * bucket accumulation kernel, combine + bucket reduction + final}.  Synchronises `stream`. */
+int aleo_b200_msm_g1_dev_profile(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
+                                 size_t affine_stride, void* stream, float* phase_ms3);
 /* Sum of `count` Jacobian points (144 B each, device) -> one normalised Jacobian point (device).
  * This is the single final combine of the point-range-sharded multi-GPU MSM. */
 int aleo_b200_g1_sum_dev(void* out_projective_dev, const void* points_dev, size_t count, void* stream);

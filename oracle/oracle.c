@@ -1,0 +1,438 @@
+/* oracle.c -- CPU ORACLE and CPU BASELINE (test infrastructure, NOT a product path).
+ *
+ * Plain-C restatement (64-bit limbs, unsigned __int128, pthreads) of the algorithm class snarkVM
+ * 0.14.5 runs on the CPU for the hot path of SURVEY.md section 8:
+ *   - VariableBase::msm      : Pippenger bucket method over BLS12-377 G1, windows in parallel
+ *                              (snarkvm-algorithms src/msm/variable_base/standard.rs shape; upstream's
+ *                              G1 fast path additionally batches affine additions -- not restated)
+ *   - EvaluationDomain::fft* : in-order radix-2 NTT over Fr with a precomputed root table, omega from
+ *                              the two-adic root, inverse scaled by n^-1, coset shift g = 22
+ *                              (snarkvm-algorithms src/fft/domain.rs conventions)
+ * PARITY UNPINNED at this boundary (see oracle/bls12_377.py header): the snarkVM sources are not in
+ * this environment and the reference repository holds no MSM / FFT golden vectors.  This file is
+ * validated against the independent Python big-integer oracle (tests/test_oracle_c.py) and is used
+ * (a) as the bit-exactness checker at sizes the Python oracle cannot reach and (b) as the timed
+ * "cpu_baseline" / --impl reference arm of bench.py (kind = "port").
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load it.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+/* ---- field parameters (derived from x = 0x8508c00000000001; cross-checked by the tests) ---------- */
+static const u64 FR_P[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
+static const u64 FR_ONE[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
+static const u64 FR_R2[4] = {0x25d577bab861857bull, 0xcc2c27b58860591full, 0xa7cc008fe5dc8593ull, 0x011fdae7eff1c939ull};
+static const u64 FR_INV = 0x0a117fffffffffffull;
+static const u64 FQ_P[6] = {0x8508c00000000001ull, 0x170b5d4430000000ull, 0x1ef3622fba094800ull,
+                            0x1a22d9f300f5138full, 0xc63b05c06ca1493bull, 0x01ae3a4617c510eaull};
+static const u64 FQ_ONE[6] = {0x02cdffffffffff68ull, 0x51409f837fffffb1ull, 0x9f7db3a98a7d3ff2ull,
+                              0x7b4e97b76e7c6305ull, 0x4cf495bf803c84e8ull, 0x008d6661e2fdf49aull};
+static const u64 FQ_R2[6] = {0xb786686c9400cd22ull, 0x0329fcaab00431b1ull, 0x22a5f11162d6b46dull,
+                             0xbfdf7d03827dc3acull, 0x837e92f041790bf9ull, 0x006dfccb1e914b88ull};
+static const u64 FQ_INV = 0x8508bfffffffffffull;
+/* G1 generator, canonical */
+static const u64 G1_X[6] = {0xeab9b16eb21be9efull, 0xd5481512ffcd394eull, 0x188282c8bd37cb5cull,
+                            0x85951e2caa9d41bbull, 0xc8fc6225bf87ff54ull, 0x008848defe740a67ull};
+static const u64 G1_Y[6] = {0xfd82de55559c8ea6ull, 0xc2fe3d3634a9591aull, 0x6d182ad44fb82305ull,
+                            0xbd7fb348ca3e52d9ull, 0x1f674f5d30afeec4ull, 0x01914a69c5102effull};
+
+/* ---- generic N-limb Montgomery arithmetic (N = 4, 6 instantiated through macros) ------------------ */
+#define DEFINE_FIELD(PFX, N, P, INV, ONE, R2)                                                          \
+  static inline void PFX##_copy(u64* r, const u64* a) { for (int i = 0; i < N; i++) r[i] = a[i]; }       \
+  static inline int PFX##_is_zero(const u64* a) { u64 t = 0; for (int i = 0; i < N; i++) t |= a[i]; return t == 0; } \
+  static inline int PFX##_eq(const u64* a, const u64* b) { u64 t = 0; for (int i = 0; i < N; i++) t |= a[i] ^ b[i]; return t == 0; } \
+  static inline int PFX##_geq_p(const u64* a) {                                                        \
+    for (int i = N - 1; i >= 0; i--) { if (a[i] > P[i]) return 1; if (a[i] < P[i]) return 0; }         \
+    return 1;                                                                                          \
+  }                                                                                                    \
+  static inline void PFX##_sub_p(u64* a) {                                                             \
+    u64 borrow = 0;                                                                                    \
+    for (int i = 0; i < N; i++) { u128 t = (u128)a[i] - P[i] - borrow; a[i] = (u64)t; borrow = (u64)(t >> 64) & 1; } \
+  }                                                                                                    \
+  static inline void PFX##_add(u64* r, const u64* a, const u64* b) {                                   \
+    u64 carry = 0;                                                                                     \
+    for (int i = 0; i < N; i++) { u128 t = (u128)a[i] + b[i] + carry; r[i] = (u64)t; carry = (u64)(t >> 64); } \
+    if (PFX##_geq_p(r)) PFX##_sub_p(r);                                                                \
+  }                                                                                                    \
+  static inline void PFX##_sub(u64* r, const u64* a, const u64* b) {                                   \
+    u64 borrow = 0;                                                                                    \
+    for (int i = 0; i < N; i++) { u128 t = (u128)a[i] - b[i] - borrow; r[i] = (u64)t; borrow = (u64)(t >> 64) & 1; } \
+    if (borrow) { u64 carry = 0; for (int i = 0; i < N; i++) { u128 t = (u128)r[i] + P[i] + carry; r[i] = (u64)t; carry = (u64)(t >> 64); } } \
+  }                                                                                                    \
+  static inline void PFX##_neg(u64* r, const u64* a) {                                                 \
+    if (PFX##_is_zero(a)) { PFX##_copy(r, a); return; }                                                \
+    u64 borrow = 0;                                                                                    \
+    for (int i = 0; i < N; i++) { u128 t = (u128)P[i] - a[i] - borrow; r[i] = (u64)t; borrow = (u64)(t >> 64) & 1; } \
+  }                                                                                                    \
+  static inline void PFX##_mul(u64* r, const u64* a, const u64* b) {                                   \
+    u64 t[N + 2];                                                                                      \
+    for (int i = 0; i < N + 2; i++) t[i] = 0;                                                          \
+    for (int i = 0; i < N; i++) {                                                                      \
+      u64 carry = 0;                                                                                   \
+      for (int j = 0; j < N; j++) { u128 c = (u128)a[j] * b[i] + t[j] + carry; t[j] = (u64)c; carry = (u64)(c >> 64); } \
+      u128 c = (u128)t[N] + carry; t[N] = (u64)c; t[N + 1] = (u64)(c >> 64);                           \
+      u64 m = t[0] * INV;                                                                              \
+      c = (u128)m * P[0] + t[0]; carry = (u64)(c >> 64);                                               \
+      for (int j = 1; j < N; j++) { c = (u128)m * P[j] + t[j] + carry; t[j - 1] = (u64)c; carry = (u64)(c >> 64); } \
+      c = (u128)t[N] + carry; t[N - 1] = (u64)c; t[N] = t[N + 1] + (u64)(c >> 64);                     \
+    }                                                                                                  \
+    for (int i = 0; i < N; i++) r[i] = t[i];                                                           \
+    if (t[N] || PFX##_geq_p(r)) PFX##_sub_p(r);                                                        \
+  }                                                                                                    \
+  static inline void PFX##_sqr(u64* r, const u64* a) { PFX##_mul(r, a, a); }                           \
+  static inline void PFX##_to_mont(u64* r, const u64* a) { PFX##_mul(r, a, R2); }                      \
+  static inline void PFX##_from_mont(u64* r, const u64* a) { u64 o[N]; for (int i = 0; i < N; i++) o[i] = 0; o[0] = 1; PFX##_mul(r, a, o); } \
+  static void PFX##_pow(u64* r, const u64* a, const u64* e, int elimbs) {                              \
+    u64 acc[N]; PFX##_copy(acc, ONE);                                                                  \
+    for (int i = elimbs - 1; i >= 0; i--) for (int b = 63; b >= 0; b--) {                              \
+      PFX##_sqr(acc, acc); if ((e[i] >> b) & 1) PFX##_mul(acc, acc, a); }                              \
+    PFX##_copy(r, acc);                                                                                \
+  }                                                                                                    \
+  static void PFX##_inv(u64* r, const u64* a) {                                                        \
+    u64 e[N]; PFX##_copy(e, P); e[0] -= 2; /* p - 2: p's low limb is ...0001, no borrow */             \
+    PFX##_pow(r, a, e, N);                                                                             \
+  }
+
+DEFINE_FIELD(fr, 4, FR_P, FR_INV, FR_ONE, FR_R2)
+DEFINE_FIELD(fq, 6, FQ_P, FQ_INV, FQ_ONE, FQ_R2)
+
+/* ================================================================================================= */
+/* Fr NTT                                                                                            */
+/* ================================================================================================= */
+static void fr_root_of_unity(u64* w, uint32_t log_n, int inverse) {
+  /* TWO_ADIC_ROOT = 22^((r-1)/2^47); omega_n = root^(2^(47-log_n)) */
+  u64 g[4] = {22, 0, 0, 0}, gm[4], t[4];
+  fr_to_mont(gm, g);
+  /* (r - 1) >> 47 */
+  u64 rm1[4] = {FR_P[0] - 1, FR_P[1], FR_P[2], FR_P[3]}, e[4];
+  for (int i = 0; i < 4; i++) e[i] = (rm1[i] >> 47) | (i < 3 ? rm1[i + 1] << 17 : 0);
+  fr_pow(t, gm, e, 4);
+  for (uint32_t i = log_n; i < 47; i++) fr_sqr(t, t);
+  if (inverse) fr_inv(t, t);
+  fr_copy(w, t);
+}
+
+typedef struct {
+  u64* data;
+  const u64* roots; /* n/2 powers of omega */
+  uint32_t log_n;
+  int tid, nthreads;
+  pthread_barrier_t* bar;
+  const u64* pre;   /* per-element multiplier applied before (coset fwd), or NULL */
+  const u64* post;  /* per-element multiplier applied after (inverse scale / coset inv), or NULL */
+  const u64* post_scalar;
+} ntt_job;
+
+static uint32_t bitrev32(uint32_t v, uint32_t bits) {
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+
+static void* ntt_worker(void* arg) {
+  ntt_job* j = (ntt_job*)arg;
+  const size_t n = (size_t)1 << j->log_n;
+  u64* a = j->data;
+  const size_t lo = n * j->tid / j->nthreads, hi = n * (j->tid + 1) / j->nthreads;
+  if (j->pre) for (size_t i = lo; i < hi; i++) fr_mul(a + 4 * i, a + 4 * i, j->pre + 4 * i);
+  pthread_barrier_wait(j->bar);
+  for (size_t i = lo; i < hi; i++) {
+    size_t r = bitrev32((uint32_t)i, j->log_n);
+    if (i < r) { u64 t[4]; fr_copy(t, a + 4 * i); fr_copy(a + 4 * i, a + 4 * r); fr_copy(a + 4 * r, t); }
+  }
+  pthread_barrier_wait(j->bar);
+  const size_t half = n / 2, blo = half * j->tid / j->nthreads, bhi = half * (j->tid + 1) / j->nthreads;
+  for (uint32_t s = 0; s < j->log_n; s++) {
+    const size_t m = (size_t)1 << s;
+    for (size_t idx = blo; idx < bhi; idx++) {
+      const size_t k = idx & (m - 1), base = ((idx >> s) << (s + 1)) + k;
+      u64 *u = a + 4 * base, *v = a + 4 * (base + m), t[4], x[4];
+      fr_mul(t, v, j->roots + 4 * (k << (j->log_n - s - 1)));
+      fr_add(x, u, t);
+      fr_sub(v, u, t);
+      fr_copy(u, x);
+    }
+    pthread_barrier_wait(j->bar);
+  }
+  if (j->post) for (size_t i = lo; i < hi; i++) fr_mul(a + 4 * i, a + 4 * i, j->post + 4 * i);
+  if (j->post_scalar) for (size_t i = lo; i < hi; i++) fr_mul(a + 4 * i, a + 4 * i, j->post_scalar);
+  return NULL;
+}
+
+static u64* power_table(const u64* base_m, size_t n, const u64* scale_m) {
+  u64* t = (u64*)malloc(n * 32 + 32);
+  u64 cur[4];
+  fr_copy(cur, scale_m ? scale_m : FR_ONE);
+  for (size_t i = 0; i < n; i++) { fr_copy(t + 4 * i, cur); fr_mul(cur, cur, base_m); }
+  return t;
+}
+
+/* data: n x 4 u64 Montgomery, in place.  inverse / coset as in EvaluationDomain. */
+int oracle_ntt_fr(u64* data, uint32_t log_n, int inverse, int coset, int nthreads) {
+  if (log_n > 30) return -2;
+  if (log_n == 0) return 0;
+  const size_t n = (size_t)1 << log_n;
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n / 2) nthreads = (int)(n / 2);
+  u64 w[4];
+  fr_root_of_unity(w, log_n, inverse);
+  u64* roots = power_table(w, n / 2, NULL);
+  u64 *pre = NULL, *post = NULL, ninv[4], nf[4] = {n, 0, 0, 0}, g[4] = {22, 0, 0, 0}, gm[4];
+  fr_to_mont(nf, nf);
+  fr_inv(ninv, nf);
+  fr_to_mont(gm, g);
+  if (coset && !inverse) pre = power_table(gm, n, NULL);
+  if (coset && inverse) { fr_inv(gm, gm); post = power_table(gm, n, ninv); }
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, (unsigned)nthreads);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  ntt_job* jobs = (ntt_job*)malloc(sizeof(ntt_job) * nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (ntt_job){data, roots, log_n, t, nthreads, &bar, pre, post, (inverse && !coset) ? ninv : NULL};
+    pthread_create(&th[t], NULL, ntt_worker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  pthread_barrier_destroy(&bar);
+  free(th); free(jobs); free(roots); free(pre); free(post);
+  return 0;
+}
+
+/* ================================================================================================= */
+/* G1                                                                                                */
+/* ================================================================================================= */
+typedef struct { u64 x[6], y[6], zz[6], zzz[6]; } xyzz;
+
+static void xyzz_set_identity(xyzz* p) { memset(p, 0, sizeof(*p)); }
+static int xyzz_is_identity(const xyzz* p) { return fq_is_zero(p->zz); }
+
+static void xyzz_double(xyzz* r, const xyzz* p) {
+  if (xyzz_is_identity(p) || fq_is_zero(p->y)) { xyzz_set_identity(r); return; }
+  u64 u[6], v[6], w[6], s[6], m[6], t[6], x3[6];
+  fq_add(u, p->y, p->y); fq_sqr(v, u); fq_mul(w, u, v); fq_mul(s, p->x, v);
+  fq_sqr(t, p->x); fq_add(m, t, t); fq_add(m, m, t);
+  fq_sqr(x3, m); fq_sub(x3, x3, s); fq_sub(x3, x3, s);
+  fq_sub(t, s, x3); fq_mul(t, m, t); fq_mul(u, w, p->y);
+  u64 zz[6], zzz[6];
+  fq_mul(zz, v, p->zz); fq_mul(zzz, w, p->zzz);
+  fq_sub(r->y, t, u); fq_copy(r->x, x3); fq_copy(r->zz, zz); fq_copy(r->zzz, zzz);
+}
+
+static void xyzz_add_affine(xyzz* acc, const u64* x2, const u64* y2) {
+  if (xyzz_is_identity(acc)) { fq_copy(acc->x, x2); fq_copy(acc->y, y2); fq_copy(acc->zz, FQ_ONE); fq_copy(acc->zzz, FQ_ONE); return; }
+  u64 u2[6], s2[6], p[6], r[6];
+  fq_mul(u2, x2, acc->zz); fq_mul(s2, y2, acc->zzz);
+  fq_sub(p, u2, acc->x); fq_sub(r, s2, acc->y);
+  if (fq_is_zero(p)) {
+    if (fq_is_zero(r)) { xyzz t; fq_copy(t.x, x2); fq_copy(t.y, y2); fq_copy(t.zz, FQ_ONE); fq_copy(t.zzz, FQ_ONE); xyzz_double(acc, &t); }
+    else xyzz_set_identity(acc);
+    return;
+  }
+  u64 pp[6], ppp[6], q[6], x3[6], t[6], y3[6];
+  fq_sqr(pp, p); fq_mul(ppp, p, pp); fq_mul(q, acc->x, pp);
+  fq_sqr(x3, r); fq_sub(x3, x3, ppp); fq_sub(x3, x3, q); fq_sub(x3, x3, q);
+  fq_sub(t, q, x3); fq_mul(t, r, t); fq_mul(y3, acc->y, ppp); fq_sub(y3, t, y3);
+  fq_mul(acc->zz, acc->zz, pp); fq_mul(acc->zzz, acc->zzz, ppp);
+  fq_copy(acc->x, x3); fq_copy(acc->y, y3);
+}
+
+static void xyzz_add(xyzz* acc, const xyzz* b) {
+  if (xyzz_is_identity(b)) return;
+  if (xyzz_is_identity(acc)) { *acc = *b; return; }
+  u64 u1[6], u2[6], s1[6], s2[6], p[6], r[6];
+  fq_mul(u1, acc->x, b->zz); fq_mul(u2, b->x, acc->zz);
+  fq_mul(s1, acc->y, b->zzz); fq_mul(s2, b->y, acc->zzz);
+  fq_sub(p, u2, u1); fq_sub(r, s2, s1);
+  if (fq_is_zero(p)) {
+    if (fq_is_zero(r)) { xyzz t = *acc; xyzz_double(acc, &t); } else xyzz_set_identity(acc);
+    return;
+  }
+  u64 pp[6], ppp[6], q[6], x3[6], t[6], y3[6];
+  fq_sqr(pp, p); fq_mul(ppp, p, pp); fq_mul(q, u1, pp);
+  fq_sqr(x3, r); fq_sub(x3, x3, ppp); fq_sub(x3, x3, q); fq_sub(x3, x3, q);
+  fq_sub(t, q, x3); fq_mul(t, r, t); fq_mul(y3, s1, ppp); fq_sub(y3, t, y3);
+  fq_mul(t, acc->zz, b->zz); fq_mul(acc->zz, t, pp);
+  fq_mul(t, acc->zzz, b->zzz); fq_mul(acc->zzz, t, ppp);
+  fq_copy(acc->x, x3); fq_copy(acc->y, y3);
+}
+
+/* normalised Jacobian image (x, y, 1) / (0, 1, 0) */
+static void xyzz_store_jacobian(uint8_t* out144, const xyzz* p) {
+  u64 o[18];
+  memset(o, 0, sizeof(o));
+  if (xyzz_is_identity(p)) { fq_copy(o + 6, FQ_ONE); }
+  else {
+    u64 d[6], inv[6], t[6];
+    fq_mul(d, p->zz, p->zzz); fq_inv(inv, d);
+    fq_mul(t, inv, p->zzz); fq_mul(o, p->x, t);
+    fq_mul(t, inv, p->zz); fq_mul(o + 6, p->y, t);
+    fq_copy(o + 12, FQ_ONE);
+  }
+  memcpy(out144, o, 144);
+}
+
+static int affine_load(const uint8_t* bases, size_t stride, size_t i, u64* x, u64* y) {
+  const uint8_t* p = bases + i * stride;
+  memcpy(x, p, 48); memcpy(y, p + 48, 48);
+  if (stride >= 97) return p[96] != 0;
+  return fq_is_zero(x) && fq_is_zero(y);
+}
+
+/* ================================================================================================= */
+/* Pippenger MSM: unsigned windows of c bits, windows distributed over threads                         */
+/* ================================================================================================= */
+typedef struct {
+  const uint8_t* bases; size_t stride; const u64* scalars; size_t n;
+  uint32_t c, nwin; xyzz* win_sums; int tid, nthreads;
+} msm_job;
+
+static uint32_t window_digit(const u64* s, uint32_t w, uint32_t c) {
+  const uint32_t bit = w * c, limb = bit >> 6, sh = bit & 63;
+  if (limb >= 4) return 0;
+  u64 v = s[limb] >> sh;
+  if (sh + c > 64 && limb + 1 < 4) v |= s[limb + 1] << (64 - sh);
+  return (uint32_t)(v & (((u64)1 << c) - 1));
+}
+
+static void* msm_worker(void* arg) {
+  msm_job* j = (msm_job*)arg;
+  const size_t nb = (size_t)1 << j->c;
+  xyzz* buckets = (xyzz*)malloc(nb * sizeof(xyzz));
+  for (uint32_t w = (uint32_t)j->tid; w < j->nwin; w += (uint32_t)j->nthreads) {
+    memset(buckets, 0, nb * sizeof(xyzz));
+    for (size_t i = 0; i < j->n; i++) {
+      const uint32_t d = window_digit(j->scalars + 4 * i, w, j->c);
+      if (!d) continue;
+      u64 x[6], y[6];
+      if (affine_load(j->bases, j->stride, i, x, y)) continue;
+      xyzz_add_affine(&buckets[d], x, y);
+    }
+    xyzz run, acc;
+    xyzz_set_identity(&run); xyzz_set_identity(&acc);
+    for (size_t d = nb - 1; d >= 1; d--) { xyzz_add(&run, &buckets[d]); xyzz_add(&acc, &run); }
+    j->win_sums[w] = acc;
+  }
+  free(buckets);
+  return NULL;
+}
+
+int oracle_msm_window_bits(size_t n) {
+  uint32_t l = 0;
+  while ((n >> (l + 1)) != 0) l++;
+  int c = (int)l - 3;            /* ~ ln(n) + 2, the classic CPU choice */
+  if (c < 2) c = 2;
+  if (c > 16) c = 16;
+  return c;
+}
+
+/* out144: normalised Jacobian; bases: Montgomery affine with `stride`; scalars: n x 4 u64 canonical */
+int oracle_msm_g1(uint8_t* out144, const uint8_t* bases, size_t n, const u64* scalars, size_t stride, int nthreads) {
+  xyzz total;
+  xyzz_set_identity(&total);
+  if (n > 0) {
+    const uint32_t c = (uint32_t)oracle_msm_window_bits(n), nwin = (253 + c - 1) / c;
+    if (nthreads < 1) nthreads = 1;
+    if ((uint32_t)nthreads > nwin) nthreads = (int)nwin;
+    xyzz* sums = (xyzz*)calloc(nwin, sizeof(xyzz));
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+    msm_job* jobs = (msm_job*)malloc(sizeof(msm_job) * nthreads);
+    for (int t = 0; t < nthreads; t++) {
+      jobs[t] = (msm_job){bases, stride, scalars, n, c, nwin, sums, t, nthreads};
+      pthread_create(&th[t], NULL, msm_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    for (int w = (int)nwin - 1; w >= 0; w--) {
+      for (uint32_t i = 0; i < c; i++) { xyzz t = total; xyzz_double(&total, &t); }
+      xyzz_add(&total, &sums[w]);
+    }
+    free(sums); free(th); free(jobs);
+  }
+  xyzz_store_jacobian(out144, &total);
+  return 0;
+}
+
+/* ================================================================================================= */
+/* synthetic bases P_i = (s0 + (first + i) d) G  (same definition as the Python oracle / GPU generator) */
+/* ================================================================================================= */
+static void g1_mul_generator(xyzz* r, const u64* k_canon) {
+  u64 gx[6], gy[6];
+  fq_to_mont(gx, G1_X); fq_to_mont(gy, G1_Y);
+  xyzz acc; xyzz_set_identity(&acc);
+  for (int i = 3; i >= 0; i--) for (int b = 63; b >= 0; b--) {
+    xyzz t = acc; xyzz_double(&acc, &t);
+    if ((k_canon[i] >> b) & 1) xyzz_add_affine(&acc, gx, gy);
+  }
+  *r = acc;
+}
+
+typedef struct { uint8_t* bases; size_t n, stride; const u64 *s0, *d; u64 first; int tid, nthreads; } gen_job;
+
+static void store_affine(uint8_t* bases, size_t stride, size_t i, const xyzz* p, const u64* zinv /* 1/(zz zzz) */) {
+  uint8_t* o = bases + i * stride;
+  memset(o, 0, stride);
+  if (xyzz_is_identity(p)) { if (stride >= 97) { memcpy(o + 48, FQ_ONE, 48); o[96] = 1; } return; }
+  u64 t[6], x[6], y[6];
+  fq_mul(t, zinv, p->zzz); fq_mul(x, p->x, t);
+  fq_mul(t, zinv, p->zz); fq_mul(y, p->y, t);
+  memcpy(o, x, 48); memcpy(o + 48, y, 48);
+}
+
+static void* gen_worker(void* arg) {
+  gen_job* j = (gen_job*)arg;
+  const size_t lo = j->n * j->tid / j->nthreads, hi = j->n * (j->tid + 1) / j->nthreads;
+  if (lo >= hi) return NULL;
+  u64 s0m[4], dm[4], im[4], k[4], idx[4] = {j->first + lo, 0, 0, 0};
+  fr_to_mont(s0m, j->s0); fr_to_mont(dm, j->d); fr_to_mont(im, idx);
+  fr_mul(k, im, dm); fr_add(k, k, s0m); fr_from_mont(k, k);
+  xyzz p, q;
+  g1_mul_generator(&p, k);
+  g1_mul_generator(&q, j->d);
+  u64 qx[6], qy[6], qi[6], t[6];
+  int q_inf = xyzz_is_identity(&q);
+  if (!q_inf) { fq_mul(t, q.zz, q.zzz); fq_inv(qi, t); fq_mul(t, qi, q.zzz); fq_mul(qx, q.x, t); fq_mul(t, qi, q.zz); fq_mul(qy, q.y, t); }
+  enum { CH = 64 };
+  xyzz buf[CH];
+  u64 prefix[CH][6];
+  for (size_t base = lo; base < hi; base += CH) {
+    const size_t cnt = hi - base < CH ? hi - base : CH;
+    u64 run[6]; fq_copy(run, FQ_ONE);
+    for (size_t c = 0; c < cnt; c++) {
+      buf[c] = p;
+      fq_copy(prefix[c], run);
+      if (!xyzz_is_identity(&p)) { fq_mul(t, p.zz, p.zzz); fq_mul(run, run, t); }
+      if (!q_inf) xyzz_add_affine(&p, qx, qy);
+    }
+    u64 inv[6]; fq_inv(inv, run);
+    for (size_t c = cnt; c > 0; c--) {
+      u64 zinv[6];
+      fq_mul(zinv, inv, prefix[c - 1]);
+      if (!xyzz_is_identity(&buf[c - 1])) { fq_mul(t, buf[c - 1].zz, buf[c - 1].zzz); fq_mul(inv, inv, t); }
+      store_affine(j->bases, j->stride, base + c - 1, &buf[c - 1], zinv);
+    }
+  }
+  return NULL;
+}
+
+int oracle_gen_bases(uint8_t* bases, size_t n, size_t stride, const u64* s0, const u64* d, u64 first, int nthreads) {
+  if (n == 0) return 0;
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = (int)n;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  gen_job* jobs = (gen_job*)malloc(sizeof(gen_job) * nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (gen_job){bases, n, stride, s0, d, first, t, nthreads};
+    pthread_create(&th[t], NULL, gen_worker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+  return 0;
+}
+
+/* small exported helpers so that the tests can pin the field core against Python directly */
+void oracle_fr_mul(u64* r, const u64* a, const u64* b) { fr_mul(r, a, b); }
+void oracle_fq_mul(u64* r, const u64* a, const u64* b) { fq_mul(r, a, b); }
+void oracle_fq_inv(u64* r, const u64* a) { fq_inv(r, a); }

@@ -1,0 +1,112 @@
+"""Kernel-logic checks on the development emulator (tests/emu/emu_runtime.hpp): the SAME kernel
+sources as the product, compiled by g++ and run with one OS thread per CUDA thread, compared with
+the oracle.  This is development tooling for a GPU-less container -- it proves indexing / carry-chain
+logic, not performance, and is never reachable from the aleo_b200 package.  The parity tests proper
+are the `-m gpu` tests, which call the product library through the C ABI on a B200."""
+import ctypes as C
+import json
+import os
+
+import pytest
+
+from oracle import bls12_377 as o
+
+
+def _ntt(lib, vals, log_n, direction, kind):
+    buf = C.create_string_buffer(o.fr_vec_to_bytes(vals), max(1, len(vals)) * 32)
+    lib.check(lib.ntt_fr_dev(C.cast(buf, C.c_void_p), log_n, 1, direction, kind, None), "ntt")
+    return o.fr_vec_from_bytes(buf.raw[: len(vals) * 32])
+
+
+def _msm(lib, bases, scalars, stride):
+    n = min(len(bases), len(scalars))
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(bases[:n], stride), max(1, n * stride))
+    sb = C.create_string_buffer(o.fr_vec_to_bytes(scalars[:n], mont=False), max(1, n * 32))
+    out = C.create_string_buffer(144)
+    lib.check(lib.msm_g1_dev(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), stride, None), "msm")
+    return out.raw
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 9, 11, 12, 13, 14])
+def test_emu_ntt_all_variants(emu_lib, log_n):
+    assert b"EMULATOR" in emu_lib.version()
+    n = 1 << log_n
+    v = o.random_fr_vec(n, 300 + log_n)
+    assert _ntt(emu_lib, v, log_n, 0, 0) == o.fft(v)
+    assert _ntt(emu_lib, v, log_n, 1, 0) == o.ifft(v)
+    assert _ntt(emu_lib, v, log_n, 0, 1) == o.coset_fft(v)
+    assert _ntt(emu_lib, v, log_n, 1, 1) == o.coset_ifft(v)
+
+
+def test_emu_ntt_three_passes(emu_lib):
+    log_n = 17                      # 6 + 6 + 5 bits: exercises the middle-digit reversal
+    v = o.random_fr_vec(1 << log_n, 17)
+    assert _ntt(emu_lib, v, log_n, 0, 0) == o.fft(v)
+
+
+def test_emu_msm_golden(emu_lib, golden_dir):
+    msm = json.load(open(os.path.join(golden_dir, "msm_golden.json")))
+    for name, g in msm.items():
+        raw = bytes.fromhex(g["bases104"])
+        B = [o.g1_affine_from_bytes(raw[i * 104:(i + 1) * 104]) for i in range(g["n"])]
+        s = o.fr_vec_from_bytes(bytes.fromhex(g["scalars"]), mont=False)
+        for stride in (104, 96):
+            assert _msm(emu_lib, B, s, stride).hex() == g["result"], (name, stride)
+
+
+def test_emu_msm_edge_cases(emu_lib):
+    n = 120
+    B = o.synthetic_bases(n, 5)
+    s = o.random_fr_vec(n, 6)
+    R = o.R_MOD
+
+    def ok(bases, scalars, stride=104):
+        return _msm(emu_lib, bases, scalars, stride) == o.g1_projective_to_bytes(o.msm_pippenger(bases, scalars))
+
+    assert _msm(emu_lib, [], [], 104) == o.g1_projective_to_bytes(None)          # empty
+    assert ok(B, [0] * n) and ok(B, [1] * n) and ok(B, [R - 1] * n)
+    assert ok([B[0]] * n, s)                                                     # all points equal (doubling path)
+    assert ok([B[i // 2] if i % 2 == 0 else o.g1_neg(B[i // 2]) for i in range(n)], [s[i // 2] for i in range(n)])
+    Binf = [None if i % 7 == 0 else B[i] for i in range(n)]
+    assert ok(Binf, s, 104) and ok(Binf, s, 96) and ok([None] * n, s)
+    assert ok(B, s[:50])                                                         # ragged: zip semantics
+
+
+def test_emu_msm_heavy_buckets_are_split(emu_lib):
+    n = 2000                        # all scalars equal: one bucket per window -> CTA combine path
+    B = o.synthetic_bases(n, 9)
+    k = o.random_fr_vec(1, 3)[0]
+    assert _msm(emu_lib, B, [k] * n, 104) == o.g1_projective_to_bytes(o.msm_expected_from_dlogs(n, 9, [k] * n))
+    sc = [1 if i % 4 else 0 for i in range(n)]   # witness-like 0 / 1 scalars
+    assert _msm(emu_lib, B, sc, 104) == o.g1_projective_to_bytes(o.msm_expected_from_dlogs(n, 9, sc))
+
+
+def test_emu_msm_multi_level_reduction(emu_lib):
+    n = 1 << 13                     # c = 9: two reduction levels
+    B = o.synthetic_bases(n, 21)
+    s = o.random_fr_vec(n, 22)
+    assert _msm(emu_lib, B, s, 104) == o.g1_projective_to_bytes(o.msm_expected_from_dlogs(n, 21, s))
+
+
+def test_emu_generators_and_checks(emu_lib):
+    n, seed = 70, 77
+    s0, d = o.base_dlogs(n, seed)
+    for stride in (104, 96):
+        bb = C.create_string_buffer(n * stride)
+        emu_lib.check(emu_lib.gen_bases_dev(C.cast(bb, C.c_void_p), n, stride, o.int_to_le_bytes(s0, 32),
+                                            o.int_to_le_bytes(d, 32), 5, None), "gen")
+        want = [o.g1_mul(o.G1_GEN, (s0 + (5 + i) * d) % o.R_MOD) for i in range(n)]
+        assert bb.raw == o.g1_affine_vec_to_bytes(want, stride)
+        assert emu_lib.check_on_curve_dev(C.cast(bb, C.c_void_p), n, stride, None) == 1
+        bad = bytearray(bb.raw)
+        bad[3 * stride + 5] ^= 1
+        cb = C.create_string_buffer(bytes(bad), n * stride)
+        assert emu_lib.check_on_curve_dev(C.cast(cb, C.c_void_p), n, stride, None) == 0
+    sb = C.create_string_buffer(n * 32)
+    emu_lib.check(emu_lib.gen_scalars_dev(C.cast(sb, C.c_void_p), n, 1234, 10, 0, None), "scalars")
+    sc = o.fr_vec_from_bytes(sb.raw, mont=False)
+    assert all(v < (1 << 252) for v in sc) and len(set(sc)) == n
+    out = C.create_string_buffer(32)
+    emu_lib.check(emu_lib.dlog_dot_dev(C.cast(out, C.c_void_p), C.cast(sb, C.c_void_p), n, o.int_to_le_bytes(s0, 32),
+                                       o.int_to_le_bytes(d, 32), 5, None), "dot")
+    assert o.le_bytes_to_int(out.raw) == sum(sc[i] * (s0 + (5 + i) * d) for i in range(n)) % o.R_MOD

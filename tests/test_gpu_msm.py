@@ -1,0 +1,156 @@
+"""Parity of the sm_100a MSM (through the C ABI / the VariableBase mirror) with the oracle.
+Bit-exact: the 144-byte normalised Jacobian image must equal the oracle's."""
+import ctypes as C
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import aleo_b200 as ab
+from oracle import bls12_377 as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _host(bases, scalars, stride=104):
+    return ab.VariableBase.msm(o.g1_affine_vec_to_bytes(bases, stride), o.fr_vec_to_bytes(scalars, mont=False), stride)
+
+
+def test_golden_vectors(golden_dir):
+    msm = json.load(open(os.path.join(golden_dir, "msm_golden.json")))
+    for name, g in msm.items():
+        got = ab.VariableBase.msm(bytes.fromhex(g["bases104"]), bytes.fromhex(g["scalars"]), 104)
+        assert got.hex() == g["result"], name
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 255, 1000, 4097])
+def test_parity_small_sizes_both_strides(n):
+    B = o.synthetic_bases(n, 40 + n)
+    s = o.random_fr_vec(n, 41 + n)
+    want = o.g1_projective_to_bytes(o.msm_expected_from_dlogs(n, 40 + n, s) if n else None)
+    assert _host(B, s, 104) == want
+    assert _host(B, s, 96) == want
+
+
+def test_edge_cases():
+    n = 300
+    B = o.synthetic_bases(n, 5)
+    s = o.random_fr_vec(n, 6)
+    R = o.R_MOD
+
+    def check(bases, scalars, stride=104):
+        assert _host(bases, scalars, stride) == o.g1_projective_to_bytes(o.msm_pippenger(bases, scalars))
+
+    check(B, [0] * n)
+    check(B, [1] * n)
+    check(B, [R - 1] * n)
+    check(B, [0 if i % 2 == 0 else (1 if i % 4 == 1 else s[i]) for i in range(n)])      # witness-like
+    check([B[0]] * n, s)                                                               # all points equal
+    check([B[0]] * n, [s[0]] * n)                                                      # ... and equal scalars
+    check([B[i // 2] if i % 2 == 0 else o.g1_neg(B[i // 2]) for i in range(n)], [s[i // 2] for i in range(n)])
+    Binf = [None if i % 7 == 0 else B[i] for i in range(n)]
+    check(Binf, s, 104)
+    check(Binf, s, 96)
+    check([None] * n, s)
+    # ragged inputs: upstream zips the slices (shorter length wins)
+    assert ab.VariableBase.msm(o.g1_affine_vec_to_bytes(B, 104), o.fr_vec_to_bytes(s[:77], mont=False)) == \
+        o.g1_projective_to_bytes(o.msm_pippenger(B[:77], s[:77]))
+
+
+@pytest.mark.parametrize("log_n", [14, 16, 18])
+def test_parity_with_c_oracle(c_oracle, log_n):
+    """GPU-generated bases copied to the host, C oracle as the independent checker"""
+    n = 1 << log_n
+    s0, d = o.base_dlogs(n, 5000 + log_n)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, 999 + log_n)
+    got = ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes()
+    hb, hs = bases.cpu().numpy(), sc.cpu().numpy()
+    # the generator itself is checked against the C oracle's own generator, byte for byte
+    ref_b = np.zeros(n * 104, dtype=np.uint8)
+    c_oracle.oracle_gen_bases(ref_b.ctypes.data, n, 104, o.int_to_le_bytes(s0, 32), o.int_to_le_bytes(d, 32), 0, os.cpu_count() or 1)
+    assert np.array_equal(hb, ref_b)
+    out = C.create_string_buffer(144)
+    c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, 104, os.cpu_count() or 1)
+    assert got == out.raw
+    # host-pointer entry point on the same data (numpy buffers, zero copy)
+    assert ab.VariableBase.msm(hb, hs, 104) == out.raw
+
+
+@pytest.mark.parametrize("log_n,dist", [(20, "uniform"), (20, "witness"), (22, "uniform"), (24, "uniform")])
+def test_known_discrete_logs_at_full_size(log_n, dist):
+    """bases (s0 + i d) G: the result must be (sum_i s_i (s0 + i d)) G -- checkable at any size"""
+    import torch
+
+    n = 1 << log_n
+    s0, d = o.base_dlogs(n, 7000 + log_n)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    assert ab.check_on_curve_dev(bases, n, 104)
+    raw = bases.view(-1, 104)[[0, 1, n // 3, n - 1]].cpu().numpy().tobytes()
+    for k, i in enumerate([0, 1, n // 3, n - 1]):
+        assert o.g1_affine_from_bytes(raw[k * 104:(k + 1) * 104]) == o.g1_mul(o.G1_GEN, (s0 + i * d) % o.R_MOD)
+    sc = ab.gen_scalars_dev(n, 31337 + log_n)
+    if dist == "witness":     # 50 % zero, 25 % one, 25 % uniform -- KZG witness polynomials look like this
+        idx = torch.arange(n, device="cuda")
+        sc[idx % 2 == 0] = 0
+        one = torch.tensor([1, 0, 0, 0], dtype=torch.int64, device="cuda")
+        sc[idx % 4 == 1] = one
+    k = ab.dlog_dot_dev(sc, n, s0, d)
+    # the on-device dot product is itself checked on a prefix against Python big integers
+    m = 2048
+    pref = o.fr_vec_from_bytes(sc[:m].cpu().numpy().tobytes(), mont=False)
+    assert ab.dlog_dot_dev(sc, m, s0, d) == sum(pref[i] * (s0 + i * d) for i in range(m)) % o.R_MOD
+    got = ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes()
+    assert got == o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, k))
+
+
+def test_linearity_and_point_range_sharding():
+    """msm(P, s) = sum of msm over disjoint point ranges (the multi-GPU decomposition), combined by
+    aleo_b200_g1_sum_dev"""
+    import torch
+
+    n = 1 << 16
+    s0, d = o.base_dlogs(n, 1234)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, 55)
+    full = ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes()
+    parts = torch.empty(4 * 144, dtype=torch.uint8, device="cuda")
+    q = n // 4
+    for r in range(4):
+        ab.VariableBase.msm_dev(bases[r * q * 104:], sc[r * q:], q, 104, out=parts[r * 144:(r + 1) * 144])
+    assert ab.VariableBase.sum_partials_dev(parts, 4).cpu().numpy().tobytes() == full
+
+
+def test_concurrent_host_calls_are_reentrant():
+    """snarkVM commits polynomials concurrently from a rayon pool: the ABI must be re-entrant"""
+    cases = []
+    for t in range(6):
+        n = 500 + 37 * t
+        B = o.synthetic_bases(n, 70 + t)
+        s = o.random_fr_vec(n, 80 + t)
+        cases.append((o.g1_affine_vec_to_bytes(B, 104), o.fr_vec_to_bytes(s, mont=False),
+                      o.g1_projective_to_bytes(o.msm_expected_from_dlogs(n, 70 + t, s))))
+    results = [None] * len(cases)
+
+    def work(i):
+        for _ in range(3):
+            results[i] = ab.VariableBase.msm(cases[i][0], cases[i][1], 104)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(results[i] == cases[i][2] for i in range(len(cases)))
+
+
+def test_error_codes():
+    lib = ab.get_lib()
+    buf = C.create_string_buffer(256)
+    p = C.cast(buf, C.c_void_p)
+    assert lib.msm_g1(p, p, 1, p, 100) == ab._lib.EINVAL
+    assert lib.msm_g1(None, p, 1, p, 104) == ab._lib.EINVAL
+    assert lib.msm_g1(p, None, 1, p, 104) == ab._lib.EINVAL
+    assert lib.msm_g1(p, None, 0, None, 104) == ab._lib.OK          # n = 0 -> identity
+    assert buf.raw[:144] == o.g1_projective_to_bytes(None)
+    assert lib.msm_g1_dev(p, p, 1 << 40, p, 104, None) == ab._lib.ETOOLARGE

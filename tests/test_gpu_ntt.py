@@ -1,0 +1,120 @@
+"""Parity of the sm_100a NTT (through the C ABI / the EvaluationDomain mirror) with the oracle.
+Bit-exact: every output element must equal the oracle's, as 32-byte Montgomery images."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import aleo_b200 as ab
+from oracle import bls12_377 as o
+
+pytestmark = pytest.mark.gpu
+VARIANTS = [("fft", 0, 0, o.fft), ("ifft", 1, 0, o.ifft), ("coset_fft", 0, 1, o.coset_fft), ("coset_ifft", 1, 1, o.coset_ifft)]
+
+
+def _dev_tensor(raw):
+    import torch
+    return torch.from_numpy(np.frombuffer(raw, dtype=np.int64).reshape(-1, 4).copy()).cuda()
+
+
+def test_library_is_the_cuda_build():
+    assert b"sm_100a" in ab.get_lib().version()
+    ab.get_lib().check(ab.get_lib().init(0), "init")
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 7, 10, 11, 12, 13, 14, 15, 16, 17])
+def test_parity_with_python_oracle(log_n):
+    n = 1 << log_n
+    v = o.random_fr_vec(n, 900 + log_n)
+    raw = o.fr_vec_to_bytes(v)
+    dom = ab.EvaluationDomain.new(n)
+    for name, _, _, ref in VARIANTS:
+        want = o.fr_vec_to_bytes(ref(v))
+        assert getattr(dom, name)(raw) == want, (name, "host")            # host-pointer entry point
+        t = _dev_tensor(raw)
+        getattr(dom, name + "_in_place_dev")(t)
+        assert t.cpu().numpy().tobytes() == want, (name, "device")        # device-resident entry point
+
+
+def test_golden_vectors(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ntt_golden.json")))
+    for key in ("0", "1", "3", "6", "10"):
+        dom = ab.EvaluationDomain.new(1 << int(key))
+        raw = bytes.fromhex(g[key]["input"])
+        for name, _, _, _ in VARIANTS:
+            assert getattr(dom, name)(raw).hex() == g[key][name], (key, name)
+    # fft_in_place resizes (zero-pads) to the domain first: 5 coefficients in a domain of 8
+    dom = ab.EvaluationDomain.new(5)
+    assert dom.size == 8
+    assert dom.fft(bytes.fromhex(g["pad5to8"]["input"])).hex() == g["pad5to8"]["fft"]
+
+
+@pytest.mark.parametrize("log_n", [18, 20, 23, 25])
+def test_parity_with_c_oracle_large(c_oracle, log_n):
+    """sizes the Python oracle cannot reach: 2^18 (3 passes) .. 2^25 (4 passes)"""
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 4242 + log_n, 0, True)
+    host = x.cpu().numpy()
+    for name, inv, coset, _ in (VARIANTS if log_n <= 20 else VARIANTS[:1] + VARIANTS[3:]):
+        y = x.clone()
+        getattr(dom, name + "_in_place_dev")(y)
+        ref = host.copy()
+        assert c_oracle.oracle_ntt_fr(ref.ctypes.data, log_n, inv, coset, os.cpu_count() or 1) == 0
+        assert np.array_equal(y.cpu().numpy(), ref), name
+
+
+@pytest.mark.parametrize("log_n", [22, 24, 26])
+def test_round_trip_and_linearity_at_full_size(log_n):
+    import torch
+
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 7, 0, True)
+    y = x.clone()
+    dom.fft_in_place_dev(y)
+    assert not torch.equal(x, y)
+    dom.ifft_in_place_dev(y)
+    assert torch.equal(x, y)                      # ifft(fft(x)) == x, bit for bit
+    dom.coset_fft_in_place_dev(y)
+    dom.coset_ifft_in_place_dev(y)
+    assert torch.equal(x, y)
+    # a delta at index 1 transforms to the powers of omega: X[k] = w^k  (checks the output ORDER)
+    z = torch.zeros_like(x)
+    one = np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64)
+    z[1] = torch.from_numpy(one.copy()).cuda()
+    dom.fft_in_place_dev(z)
+    w = o.fr_root_of_unity(log_n)
+    zs = z.cpu().numpy()
+    for k in (0, 1, 2, 3, 5, n // 2 + 1, n - 1, 12345 % n):
+        assert zs[k].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, k, o.R_MOD)), 32), k
+
+
+def test_batch_of_transforms():
+    log_n, batch = 12, 5
+    n = 1 << log_n
+    vs = [o.random_fr_vec(n, 60 + b) for b in range(batch)]
+    t = _dev_tensor(b"".join(o.fr_vec_to_bytes(v) for v in vs))
+    ab.EvaluationDomain.new(n).fft_in_place_dev(t, batch=batch)
+    got = t.cpu().numpy().tobytes()
+    for b in range(batch):
+        assert got[b * n * 32:(b + 1) * n * 32] == o.fr_vec_to_bytes(o.fft(vs[b]))
+    # small-kernel batch path (n <= 2^11)
+    n = 1 << 6
+    vs = [o.random_fr_vec(n, 80 + b) for b in range(7)]
+    t = _dev_tensor(b"".join(o.fr_vec_to_bytes(v) for v in vs))
+    ab.EvaluationDomain.new(n).coset_ifft_in_place_dev(t, batch=7)
+    got = t.cpu().numpy().tobytes()
+    for b in range(7):
+        assert got[b * n * 32:(b + 1) * n * 32] == o.fr_vec_to_bytes(o.coset_ifft(vs[b]))
+
+
+def test_error_codes():
+    lib = ab.get_lib()
+    assert lib.ntt_fr(None, 4, 0, 0) == ab._lib.EINVAL
+    buf = C.create_string_buffer(64)
+    assert lib.ntt_fr(C.cast(buf, C.c_void_p), 33, 0, 0) == ab._lib.ETOOLARGE
+    assert lib.ntt_fr_dev(C.cast(buf, C.c_void_p), 1, 1, 2, 0, None) == ab._lib.EINVAL
+    assert ab.EvaluationDomain.new((1 << 47) + 1) is None
