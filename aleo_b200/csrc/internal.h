@@ -9,6 +9,8 @@ namespace aleo {
 cudaError_t ntt_upload_constants();
 cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s,
                           float* pass_ms = nullptr /* >= 4 floats; synchronises the stream when given */);
+cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void* data_dev, u32 rows, u32 cols, u32 row0, u32 col0,
+                               cudaStream_t s);
 int ntt_launches(u32 log_n);
 int ntt_max_log_n();
 void ntt_clear_plans();

@@ -16,7 +16,7 @@
 //               -- this is >95 % of the work: n * W additions of 8M + 2S in Fq
 //   6 combine   partial sums of split buckets are added (thread per bucket, or CTA per bucket)
 //   7 reduce    per window sum_b (b+1) * bucket[b] by chunked running sums, recursively
-//   8 final     Horner over windows (c doublings each) + one inversion -> normalised Jacobian
+//   8 final     per window 2^(c w) * S_w (windows in parallel), sum, one inversion -> normalised Jacobian
 #pragma once
 #include "g1.cuh"
 
@@ -289,19 +289,25 @@ struct FinalArgs {
   u32 W, c;
 };
 
-// S_w = f0 + Kc (f1 + Kc (f2 + ...));  result = sum_w 2^(c w) S_w;  one thread (tail of the MSM)
-KERNEL void final_kernel(FinalArgs a, unsigned char* out144) {
+// Tail, step 1 (one thread per window): S_w = f0 + Kc (f1 + Kc (f2 + ...)), then D_w = 2^(c w) S_w.
+// The c*w doublings of the different windows run in parallel; the critical path is the top window's.
+KERNEL void window_weigh_kernel(FinalArgs a, G1Xyzz* D) {
+  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.W) return;
+  G1Xyzz s = xyzz_identity();
+  for (int l = a.levels - 1; l >= 0; l--) {
+    for (u32 i = 0; i < RED_LOG_KC; i++) s = xyzz_double(s);
+    xyzz_add_ni(s, a.f[l][(size_t)w * a.stride[l]]);
+  }
+  for (u32 i = 0; i < a.c * w; i++) s = xyzz_double(s);
+  D[w] = s;
+}
+
+// Tail, step 2 (one thread): result = sum_w D_w, normalised (one inversion).
+KERNEL void final_kernel(const G1Xyzz* D, u32 W, unsigned char* out144) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   G1Xyzz total = xyzz_identity();
-  for (int w = (int)a.W - 1; w >= 0; w--) {
-    for (u32 i = 0; i < a.c; i++) total = xyzz_double(total);
-    G1Xyzz s = xyzz_identity();
-    for (int l = a.levels - 1; l >= 0; l--) {
-      for (u32 i = 0; i < RED_LOG_KC; i++) s = xyzz_double(s);
-      xyzz_add_ni(s, a.f[l][(size_t)w * a.stride[l]]);
-    }
-    xyzz_add_ni(total, s);
-  }
+  for (u32 w = 0; w < W; w++) xyzz_add_ni(total, D[w]);
   jacobian_store_normalised(out144, total);
 }
 

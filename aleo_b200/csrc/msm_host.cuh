@@ -123,6 +123,7 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   std::vector<size_t> o_PSfinal(lv.size());
   const size_t o_psA = cv.take(ps_elems * sizeof(G1Xyzz)), o_psB = cv.take(ps_elems * sizeof(G1Xyzz));
   for (size_t l = 0; l < lv.size(); l++) o_PSfinal[l] = cv.take((size_t)prm.W * sizeof(G1Xyzz));
+  const size_t o_D = cv.take((size_t)prm.W * sizeof(G1Xyzz));
 
   unsigned char* ws = nullptr;
   if (!dry) MSM_CK(cudaMallocAsync((void**)&ws, cv.off, s));
@@ -210,7 +211,10 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
     fa.f[l] = cur;
     fa.stride[l] = 1;
   }
-  STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, fa, out144));
+  G1Xyzz* D = WSP(G1Xyzz, o_D);
+  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((prm.W + 31) / 32), dim3(32), 0, s, fa, D));
+  launches++;
+  STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, prm.W, out144));
   launches++;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[3], s);
   if (ws) cudaFreeAsync(ws, s);

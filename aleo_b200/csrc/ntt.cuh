@@ -155,6 +155,9 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
   uint4* plane1 = plane0 + tile_plane_elems<K, LAST>();
 
   const u32 tid = threadIdx.x;
+  // gridDim.y = batch of independent transforms laid out back to back
+  const Fr* src = a.src + ((u64)blockIdx.y << a.log_n);
+  Fr* dst = a.dst + ((u64)blockIdx.y << a.log_n);
   // loads: lanes along g (strided passes) or along r (last pass, rows are contiguous)
   const u32 tr = LAST ? (tid & (RT - 1)) : (tid >> LG);
   const u32 tg = LAST ? (tid / RT) : (tid & (G - 1));
@@ -198,7 +201,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
     for (int j = 0; j < 8; j++) {
       const u32 p = j * C1 + tr;
       const u64 gi = in_base + p * stride_r + tg * stride_g;
-      x[j] = a.src[gi];
+      x[j] = src[gi];
       if (!LAST && a.use_pre) x[j] = fp_mul(x[j], pow_lookup(a.pre, (u32)gi));
     }
     Fr w8[4];
@@ -280,7 +283,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
         v = fp_mul(v, pow_lookup(a.tw, e));
       }
       if (LAST && a.use_post) v = fp_mul(v, pow_lookup(a.post, (u32)go));
-      a.dst[go] = v;
+      dst[go] = v;
     }
   }
 }
@@ -330,6 +333,18 @@ KERNEL void __launch_bounds__(TPB) small_kernel(SmallArgs a) {
     if (a.use_scale) v = fp_mul(v, a.scale);
     x[i] = v;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// data[r][c] *= w^((r + row0) * (c + col0)) for a rows x cols matrix: the twiddle step between the two
+// local transform stages of the multi-GPU four-step NTT (w = root of the GLOBAL domain).
+// ---------------------------------------------------------------------------------------------
+KERNEL void twiddle_matrix_kernel(Fr* data, u32 rows, u32 cols, u32 row0, u32 col0, PowTable tw, u32 log_n_global) {
+  const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (u64)rows * cols) return;
+  const u32 r = (u32)(idx / cols), c = (u32)(idx % cols);
+  const u64 e = ((u64)(r + row0) * (u64)(c + col0)) & (((u64)1 << log_n_global) - 1);
+  data[idx] = fp_mul(data[idx], pow_lookup(tw, (u32)e));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ static inline void destroy_plan(Plan& p) {
 }
 
 template <int K, bool LAST>
-static inline cudaError_t launch_pass(const PassArgs& a, u32 grid, cudaStream_t s) {
+static inline cudaError_t launch_pass(const PassArgs& a, u32 grid, u32 batch, cudaStream_t s) {
   const size_t smem = 2 * sizeof(uint4) * tile_plane_elems<K, LAST>();
 #ifndef ALEO_EMU
   static thread_local int attr_done_dev = -1;  // per instantiation, per thread: cheap and race free
@@ -111,17 +111,17 @@ static inline cudaError_t launch_pass(const PassArgs& a, u32 grid, cudaStream_t 
     attr_done_dev = dev;
   }
 #endif
-  LAUNCH((pass_kernel<K, LAST>), dim3(grid), dim3(TPB), smem, s, a);
+  LAUNCH((pass_kernel<K, LAST>), dim3(grid, batch), dim3(TPB), smem, s, a);
   return cudaGetLastError();
 }
 
 template <bool LAST>
-static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, cudaStream_t s) {
+static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, u32 batch, cudaStream_t s) {
   switch (K) {
-    case 5: return launch_pass<5, LAST>(a, grid, s);
-    case 6: return launch_pass<6, LAST>(a, grid, s);
-    case 7: return launch_pass<7, LAST>(a, grid, s);
-    case 8: return launch_pass<8, LAST>(a, grid, s);
+    case 5: return launch_pass<5, LAST>(a, grid, batch, s);
+    case 6: return launch_pass<6, LAST>(a, grid, batch, s);
+    case 7: return launch_pass<7, LAST>(a, grid, batch, s);
+    case 8: return launch_pass<8, LAST>(a, grid, batch, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -129,7 +129,16 @@ static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, cuda
 // number of kernel launches one transform of this plan issues (bench.py's gpu_launches)
 static inline int launches_per_transform(const Plan& p) { return p.log_n <= (u32)SMALL_MAX_LOG ? 1 : p.npass; }
 
-// data: batch x n elements, in place.  scratch: n elements (only used when n > 2^11).
+// scratch elements run() needs for `batch` transforms of 2^log_n (0 for the single-CTA sizes)
+static inline size_t scratch_batch(u32 log_n, size_t batch) {
+  if (log_n <= (u32)SMALL_MAX_LOG) return 0;
+  size_t cap = ((size_t)1 << 25) >> log_n;  // <= 2^25 elements (1 GiB) of scratch per launch group
+  if (cap < 1) cap = 1;
+  if (cap > 65535) cap = 65535;             // gridDim.y limit
+  return batch < cap ? batch : cap;
+}
+
+// data: batch x n elements, in place.  scratch: scratch_batch(log_n, batch) x n elements.
 // pass_ev (optional, npass + 1 events, batch must be 1): recorded around every pass.
 static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch, cudaStream_t s,
                               cudaEvent_t* pass_ev = nullptr) {
@@ -162,8 +171,10 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
     if (pass_ev) cudaEventRecord(pass_ev[1], s);
     return cudaGetLastError();
   }
-  for (size_t b = 0; b < batch; b++) {
+  const size_t group = scratch_batch(p.log_n, batch);
+  for (size_t b = 0; b < batch; b += group) {
     Fr* x = data + b * n;
+    const u32 nb = (u32)(batch - b < group ? batch - b : group);
     u32 log_cur = p.log_n;
     for (int i = 0; i < p.npass; i++) {
       const bool last = (i == p.npass - 1);
@@ -183,7 +194,7 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
       a.use_pre = ((i == 0) && p.coset && !p.inverse) ? 1 : 0;
       a.use_post = (last && p.coset && p.inverse) ? 1 : 0;
       if (pass_ev && i == 0) cudaEventRecord(pass_ev[0], s);
-      NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, s) : launch_pass_k<false>(p.K[i], a, grid, s));
+      NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, nb, s) : launch_pass_k<false>(p.K[i], a, grid, nb, s));
       if (pass_ev) cudaEventRecord(pass_ev[i + 1], s);
       log_cur -= (u32)p.K[i];
     }

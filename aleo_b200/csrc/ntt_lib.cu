@@ -25,7 +25,7 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
   if (e != cudaSuccess) return e;
   Fr* scratch = nullptr;
   if (log_n > (u32)ntt::SMALL_MAX_LOG) {
-    e = cudaMallocAsync((void**)&scratch, sizeof(Fr) << log_n, s);
+    e = cudaMallocAsync((void**)&scratch, (sizeof(Fr) << log_n) * ntt::scratch_batch(log_n, batch), s);
     if (e != cudaSuccess) return e;
   }
   cudaEvent_t ev[5];
@@ -41,5 +41,19 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
     for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
   }
   return e;
+}
+
+// data[r][c] *= w_N^(+-(r + row0)(c + col0)), N = 2^log_n_global (multi-GPU four-step twiddle step)
+cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void* data_dev, u32 rows, u32 cols, u32 row0, u32 col0,
+                               cudaStream_t s) {
+  if (log_n_global <= (u32)ntt::SMALL_MAX_LOG) return cudaErrorInvalidValue;
+  const ntt::Plan* plan = nullptr;
+  cudaError_t e = g_plans.get(device, log_n_global, inverse, false, s, &plan);
+  if (e != cudaSuccess) return e;
+  const u64 total = (u64)rows * cols;
+  if (total == 0) return cudaSuccess;
+  LAUNCH_NOSYNC(ntt::twiddle_matrix_kernel, dim3((u32)((total + 255) / 256)), dim3(256), 0, s, (Fr*)data_dev, rows, cols, row0, col0,
+                (ntt::PowTable{plan->tw_lo, plan->tw_hi, plan->lo_bits}), log_n_global);
+  return cudaGetLastError();
 }
 }  // namespace aleo

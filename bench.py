@@ -239,7 +239,8 @@ def run_ours(args):
     if os.path.exists(ppath):
         prof = json.load(open(ppath))
     roofline = {"kernel": "msm::accumulate_kernel", "bound": "int", "achieved": macs / acc / 1e6, "peak": peak_gmac, "unit": "GMAC/s",
-                "frac": macs / acc / 1e6 / peak_gmac, "traffic": prof.get("msm_accumulate_dram_bytes"),
+                "frac": macs / acc / 1e6 / peak_gmac, "traffic": (prof["msm_accumulate_dram_bytes_at_2p22"] * n / (1 << 22)) if "msm_accumulate_dram_bytes_at_2p22" in prof else None,
+                "traffic_source": "ncu --set full at n=2^22 (profiles/r01_ncu_hot_kernels.md), scaled linearly to this n",
                 "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows,
                 "kernel_ms": acc, "kernel_share_of_step": acc / (sum(sort_ms) / len(sort_ms) + acc + sum(tail_ms) / len(tail_ms)),
                 "phases_ms": {"recode_sort_plan": sum(sort_ms) / len(sort_ms), "accumulate": acc, "combine_reduce_final": sum(tail_ms) / len(tail_ms)},
@@ -313,12 +314,51 @@ def run_ours(args):
     ntt = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": world * n / ntt_step / 1e3, "unit": "Melem/s", "ms_per_step": ntt_step,
            "log_n": log_n, "passes": dom.launches(), "round_trip_ok": ntt_ok,
            "roofline": {"kernel": "ntt::pass_kernel", "bound": "hbm", "achieved": ntt_bytes / pass_avg / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ntt_bytes / pass_avg / 1e6 / hbm_peak, "traffic": prof.get("ntt_pass_dram_bytes"),
+                        "frac": ntt_bytes / pass_avg / 1e6 / hbm_peak, "traffic": (prof["ntt_pass_dram_bytes_at_2p22"] * n / (1 << 22)) if "ntt_pass_dram_bytes_at_2p22" in prof else None,
                         "algorithmic_bytes_per_launch": ntt_bytes, "kernel_ms": pass_avg,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)",
                         "int_frac": n * mults_per_elem * 120 / (ntt_step * 1e-3) / 1e9 / peak_gmac,
                         "note": "the 253-bit NTT is integer-pipe bound (about %.1f Fr products of 120 IMAD.WIDE per element); int_frac is "
                                 "measured against the same live IMAD.WIDE peak as the MSM" % mults_per_elem}}
+
+    # ---- N > 1: one NTT of 2^(log_n + log2 N) sharded four-step with a single NCCL all-to-all ---------
+    ntt_dist = None
+    if world > 1 and (world & (world - 1)) == 0:
+        from aleo_b200 import dist as adist
+
+        glog = log_n + world.bit_length() - 1
+        l1, l2 = adist.four_step_shape(glog)
+        g1, g2 = 1 << l1, 1 << l2
+        wc, wr = g2 // world, g1 // world
+        # order / twiddle / transpose check: a delta at index 1 must transform to the powers of omega
+        blk = torch.zeros((g1, wc, 4), dtype=torch.int64, device=dev)
+        if rank == 1 // wc:
+            one = np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64)
+            blk[0, 1 % wc] = torch.from_numpy(one.copy()).to(dev)
+        outb = adist.ntt_four_step(blk, glog).cpu().numpy()
+        w = o.fr_root_of_unity(glog)
+        dist_ok = all(outb[k, k2].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, rank * wr + k + g1 * k2, o.R_MOD)), 32)
+                      for k, k2 in ((0, 0), (1, 0), (wr - 1, 1), (wr // 2, g2 - 1), (3, g2 // 2)))
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(dist_ok))
+        del blk, outb
+        xb = x.reshape(g1, wc, 4) if x.numel() == g1 * wc * 4 else ab.gen_scalars_dev(g1 * wc, 78, first, True, device=dev).reshape(g1, wc, 4)
+        for _ in range(args.warmup):
+            adist.ntt_four_step(xb, glog)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            adist.ntt_four_step(xb, glog)
+        d1.record()
+        barrier()
+        dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
+        dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        dstep = dms.item() / args.steps
+        ntt_dist = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": (1 << glog) / dstep / 1e3, "unit": "Melem/s", "ms_per_step": dstep,
+                    "log_n_global": glog, "schedule": "four-step %dx%d, column blocks in, transposed row blocks out" % (g1, g2),
+                    "collective": "one all_to_all_single (NCCL) of %d bytes per rank" % (g1 * wc * 32 * (world - 1) // world),
+                    "scaling": "weak", "delta_impulse_check": all(flags)}
 
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------
     cpu = None
@@ -340,7 +380,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
                     "api": "aleo_b200_msm_g1 (host pointers, pinned)"},
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
-            "roofline": roofline, "ntt": ntt, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "ntt": ntt, "ntt_distributed": ntt_dist, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -68,6 +68,11 @@ int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int dire
 /* One transform with CUDA events around every pass: pass_ms4[i] = device time of pass i (unused
  * entries 0).  Synchronises `stream`.  Measurement aid for bench.py's roofline, same kernels. */
 int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4);
+/* Multi-GPU four-step NTT, twiddle step between the two local stages: for a rows x cols row-major
+ * matrix of Fr on the device, data[r][c] *= w^((r + row0) * (c + col0)) with w the root of the GLOBAL
+ * domain of size 2^log_n_global (its inverse for ALEO_B200_NTT_INVERSE).  12 <= log_n_global <= 32. */
+int aleo_b200_ntt_twiddle_dev(void* data_dev, uint32_t log_n_global, int direction, uint32_t rows, uint32_t cols,
+                              uint32_t row0, uint32_t col0, void* stream);
 /* kernel launches one transform of this size issues (for launch accounting) */
 int aleo_b200_ntt_launches(uint32_t log_n);
 

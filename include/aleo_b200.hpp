@@ -1,0 +1,84 @@
+// aleo_b200.hpp -- C++ host-side mirror of the snarkVM 0.14.5 interface for the hot path, above the C ABI
+// (include/aleo_b200.h).  The reference's host language is Rust and this image has no Rust toolchain, so the
+// compiled-language mirror is C++: same names, argument meaning and error behaviour as
+//   snarkvm_algorithms::msm::VariableBase::msm                      (src/msm/variable_base/mod.rs)
+//   snarkvm_algorithms::fft::EvaluationDomain::{new, fft, ifft, coset_fft, coset_ifft, *_in_place}
+//                                                                    (src/fft/domain.rs)
+// reached from the reference at rust/src/program/execute.rs:74,177.  Struct layouts are the Rust memory images
+// the FFI receives; the static_asserts below are the layout contract the Rust shim relies on.
+// Errors: the Rust shim panics on a non-zero return code (no CPU fallback); here that is a std::runtime_error.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "aleo_b200.h"
+
+namespace aleo_b200 {
+
+struct BigInteger256 { uint64_t v[4]; };                 // canonical little-endian
+struct Fr { uint64_t v[4]; };                            // Fp256<FrParameters>: Montgomery residue
+struct Fq { uint64_t v[6]; };                            // Fp384<FqParameters>: Montgomery residue
+struct G1Affine { Fq x, y; bool infinity; };             // short_weierstrass_jacobian::Affine<Bls12_377G1Parameters>
+struct G1Projective { Fq x, y, z; };                     // Jacobian; identity: z == 0
+
+static_assert(sizeof(BigInteger256) == 32 && sizeof(Fr) == 32 && sizeof(Fq) == 48, "field element images");
+static_assert(sizeof(G1Affine) == 104 && offsetof(G1Affine, y) == 48 && offsetof(G1Affine, infinity) == 96,
+              "size_of::<G1Affine>() == 104: x | y | infinity | 7 bytes padding");
+static_assert(sizeof(G1Projective) == 144, "G1Projective image");
+
+inline void check(int rc, const char* what) {
+  if (rc != ALEO_B200_OK)
+    throw std::runtime_error(std::string(what) + ": " + aleo_b200_strerror(rc) + " [" + aleo_b200_last_cuda_error() + "]");
+}
+
+struct VariableBase {
+  // VariableBase::msm(bases, scalars) -> G::Projective; the two slices are zipped (shorter length wins)
+  static G1Projective msm(const G1Affine* bases, size_t n_bases, const BigInteger256* scalars, size_t n_scalars) {
+    G1Projective out;
+    const size_t n = n_bases < n_scalars ? n_bases : n_scalars;
+    check(aleo_b200_msm_g1(&out, bases, n, scalars, sizeof(G1Affine)), "VariableBase::msm");
+    return out;
+  }
+  static G1Projective msm(const std::vector<G1Affine>& bases, const std::vector<BigInteger256>& scalars) {
+    return msm(bases.data(), bases.size(), scalars.data(), scalars.size());
+  }
+};
+
+class EvaluationDomain {
+ public:
+  static constexpr uint32_t TWO_ADICITY = 47;
+  uint64_t size = 1;
+  uint32_t log_size_of_group = 0;
+
+  // EvaluationDomain::new(num_coeffs): next power of two; None when log2(size) > two-adicity
+  static std::optional<EvaluationDomain> new_(size_t num_coeffs) {
+    EvaluationDomain d;
+    while (d.size < num_coeffs) {
+      d.size <<= 1;
+      d.log_size_of_group++;
+      if (d.log_size_of_group > TWO_ADICITY) return std::nullopt;
+    }
+    return d;
+  }
+  // *_in_place first resize the vector to the domain size with zeros (a longer input is truncated)
+  void fft_in_place(std::vector<Fr>& v) const { run(v, ALEO_B200_NTT_FORWARD, ALEO_B200_NTT_STANDARD); }
+  void ifft_in_place(std::vector<Fr>& v) const { run(v, ALEO_B200_NTT_INVERSE, ALEO_B200_NTT_STANDARD); }
+  void coset_fft_in_place(std::vector<Fr>& v) const { run(v, ALEO_B200_NTT_FORWARD, ALEO_B200_NTT_COSET); }
+  void coset_ifft_in_place(std::vector<Fr>& v) const { run(v, ALEO_B200_NTT_INVERSE, ALEO_B200_NTT_COSET); }
+  std::vector<Fr> fft(const std::vector<Fr>& c) const { auto v = c; fft_in_place(v); return v; }
+  std::vector<Fr> ifft(const std::vector<Fr>& e) const { auto v = e; ifft_in_place(v); return v; }
+  std::vector<Fr> coset_fft(const std::vector<Fr>& c) const { auto v = c; coset_fft_in_place(v); return v; }
+  std::vector<Fr> coset_ifft(const std::vector<Fr>& e) const { auto v = e; coset_ifft_in_place(v); return v; }
+
+ private:
+  void run(std::vector<Fr>& v, int direction, int kind) const {
+    v.resize(size, Fr{{0, 0, 0, 0}});
+    check(aleo_b200_ntt_fr(v.data(), log_size_of_group, direction, kind), "EvaluationDomain::fft");
+  }
+};
+
+}  // namespace aleo_b200

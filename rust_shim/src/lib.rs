@@ -1,0 +1,71 @@
+//! aleo-b200-sys: FFI declarations for libaleo_b200.so (include/aleo_b200.h) and the two call-site
+//! replacements inside a patched snarkvm-algorithms 0.14.5.  NOT compiled in this environment (no
+//! Rust toolchain); the layouts it assumes are asserted on the C++ side in include/aleo_b200.hpp.
+use std::os::raw::{c_char, c_int, c_void};
+
+extern "C" {
+    pub fn aleo_b200_strerror(code: c_int) -> *const c_char;
+    pub fn aleo_b200_ntt_fr(inout_host: *mut c_void, log_n: u32, direction: c_int, kind: c_int) -> c_int;
+    pub fn aleo_b200_msm_g1(
+        out_projective_host: *mut c_void,
+        bases_host: *const c_void,
+        n: usize,
+        scalars_host: *const c_void,
+        affine_stride: usize,
+    ) -> c_int;
+}
+
+pub const NTT_FORWARD: c_int = 0;
+pub const NTT_INVERSE: c_int = 1;
+pub const NTT_STANDARD: c_int = 0;
+pub const NTT_COSET: c_int = 1;
+
+#[cold]
+fn die(what: &str, rc: c_int) -> ! {
+    let msg = unsafe { std::ffi::CStr::from_ptr(aleo_b200_strerror(rc)) }.to_string_lossy().into_owned();
+    // north_star: no CPU fallback -- a failed device call is fatal
+    panic!("{what}: aleo_b200 error {rc}: {msg}");
+}
+
+/// Body of `VariableBase::msm` for `G == bls12_377::G1Affine` (src/msm/variable_base/mod.rs):
+/// ```ignore
+/// pub fn msm<G: AffineCurve>(bases: &[G], scalars: &[<G::ScalarField as PrimeField>::BigInteger]) -> G::Projective {
+///     if TypeId::of::<G>() == TypeId::of::<G1Affine>() {
+///         return unsafe { aleo_b200_sys::msm_g1(bases, scalars) };
+///     }
+///     unimplemented!("only BLS12-377 G1 is on the proving path")
+/// }
+/// ```
+/// # Safety
+/// `A` must be the 104-byte `G1Affine`, `S` the 32-byte `BigInteger256`, `P` the 144-byte `G1Projective`.
+pub unsafe fn msm_g1<A, S, P>(bases: &[A], scalars: &[S]) -> P {
+    assert_eq!(std::mem::size_of::<A>(), 104);
+    assert_eq!(std::mem::size_of::<S>(), 32);
+    assert_eq!(std::mem::size_of::<P>(), 144);
+    let n = bases.len().min(scalars.len());
+    let mut out = std::mem::MaybeUninit::<P>::uninit();
+    let rc = aleo_b200_msm_g1(
+        out.as_mut_ptr() as *mut c_void,
+        bases.as_ptr() as *const c_void,
+        n,
+        scalars.as_ptr() as *const c_void,
+        std::mem::size_of::<A>(),
+    );
+    if rc != 0 {
+        die("VariableBase::msm", rc);
+    }
+    out.assume_init()
+}
+
+/// Body of `EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place` when `size_of::<T>() == 32`
+/// (src/fft/domain.rs): the caller has already done `x_s.resize(self.size(), T::zero())`.
+/// # Safety
+/// `T` must be `Fp256<FrParameters>` (32-byte Montgomery residue).
+pub unsafe fn ntt_fr<T>(x_s: &mut [T], log_size_of_group: u32, direction: c_int, kind: c_int) {
+    assert_eq!(std::mem::size_of::<T>(), 32);
+    assert_eq!(x_s.len(), 1usize << log_size_of_group);
+    let rc = aleo_b200_ntt_fr(x_s.as_mut_ptr() as *mut c_void, log_size_of_group, direction, kind);
+    if rc != 0 {
+        die("EvaluationDomain::fft", rc);
+    }
+}

@@ -118,3 +118,37 @@ def test_error_codes():
     assert lib.ntt_fr(C.cast(buf, C.c_void_p), 33, 0, 0) == ab._lib.ETOOLARGE
     assert lib.ntt_fr_dev(C.cast(buf, C.c_void_p), 1, 1, 2, 0, None) == ab._lib.EINVAL
     assert ab.EvaluationDomain.new((1 << 47) + 1) is None
+
+
+def test_twiddle_matrix_step():
+    """aleo_b200_ntt_twiddle_dev: data[r][c] *= w_N^((r + row0)(c + col0)), forward and inverse roots"""
+    from aleo_b200.dist import CudaBackend
+
+    log_n, rows, cols, row0, col0 = 14, 6, 10, 37, 3
+    v = o.random_fr_vec(rows * cols, 31)
+    for inverse in (False, True):
+        w = o.fr_root_of_unity(log_n)
+        if inverse:
+            w = pow(w, -1, o.R_MOD)
+        t = _dev_tensor(o.fr_vec_to_bytes(v))
+        CudaBackend().twiddle(t, log_n, inverse, rows, cols, row0, col0)
+        want = [v[r * cols + c] * pow(w, (r + row0) * (c + col0), o.R_MOD) % o.R_MOD for r in range(rows) for c in range(cols)]
+        assert t.cpu().numpy().tobytes() == o.fr_vec_to_bytes(want)
+
+
+@pytest.mark.parametrize("log_n", [16, 17, 24])
+def test_four_step_schedule_matches_single_kernel_path(log_n):
+    """the multi-GPU schedule (aleo_b200/dist.py) run on one GPU must reproduce the direct transform bit
+    for bit -- batched local transforms, twiddle step, transposes and output ordering"""
+    import torch
+
+    from aleo_b200 import dist as adist
+
+    n = 1 << log_n
+    x = ab.gen_scalars_dev(n, 606 + log_n, 0, True)
+    for inverse in (False, True):
+        direct = x.clone()
+        dom = ab.EvaluationDomain.new(n)
+        (dom.ifft_in_place_dev if inverse else dom.fft_in_place_dev)(direct)
+        out = adist.ntt_four_step(adist.column_block(x, log_n, 0, 1), log_n, inverse=inverse)
+        assert torch.equal(adist.gather_natural([out], log_n), direct)
