@@ -10,12 +10,12 @@
 //   2 scan      exclusive scan of the histogram -> bucket start offsets                 [tiny]
 //   3 scatter   recode again, claim a slot per (window, bucket) with an atomic cursor, write
 //               point index | sign<<31   (order inside a bucket is irrelevant: + commutes) [HBM]
-//   4 tasks     buckets longer than T entries are cut into tasks of <= T entries (skewed
-//               scalar distributions: KZG witnesses are full of 0 / 1) + scan of task counts
-//   5 accumulate one thread per task: XYZZ mixed additions of gathered affine bases      [IMAD]
+//   4 plan      the sorted entry list is cut into equal runs, one per thread; buckets cut by a run
+//               boundary are listed for the combine step (skew-proof: KZG witnesses are full of 0 / 1)
+//   5 accumulate one thread per run: XYZZ mixed additions of gathered affine bases       [IMAD]
 //               -- this is >95 % of the work: n * W additions of 8M + 2S in Fq
-//   6 combine   partial sums of split buckets are added (thread per bucket, or CTA per bucket)
-//   7 reduce    per window sum_b (b+1) * bucket[b] by chunked running sums, recursively
+//   6 combine   the pieces of cut buckets are added (thread per bucket, or CTA per bucket)
+//   7 reduce    per window sum_b (b+1) * bucket[b] by chunked running sums, one launch per level
 //   8 final     per window 2^(c w) * S_w (windows in parallel), sum, one inversion -> normalised Jacobian
 #pragma once
 #include "g1.cuh"
@@ -23,7 +23,7 @@
 namespace msm {
 
 constexpr u32 SCALAR_BITS = 253;
-constexpr u32 RED_LOG_KC = 5;            // bucket-reduction chunk: 32 buckets per thread
+constexpr u32 RED_LOG_KC = 4;            // bucket-reduction chunk: 16 buckets per thread
 constexpr u32 RED_KC = 1u << RED_LOG_KC;
 constexpr u32 SMALL_SPLIT_MAX = 64;      // split buckets with <= 64 tasks are combined by one thread
 constexpr u32 COMBINE_TPB = 128;
@@ -32,7 +32,7 @@ struct Params {
   u32 c;       // window bits
   u32 W;       // number of windows = 253 / c + 1 (always absorbs the recoding carry)
   u32 B;       // buckets per window = 2^(c-1)
-  u32 T;       // longest run of entries one accumulation task handles
+  u32 nlanes;  // threads of the accumulation kernel = equal runs the sorted entry list is cut into
 };
 
 // signed digit of window w given the carry from window w-1; returns |digit| and updates carry/neg
@@ -152,85 +152,128 @@ KERNEL void scan_apply_kernel(const u32* in, u32 n, const u32* block_sums, u32* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// task planning
+// Bucket accumulation, "flat" scheme: the sorted entry list (all windows, all buckets, back to back)
+// is cut into `nlanes` equal runs of L = ceil(total / nlanes) entries and every thread (lane) sums
+// exactly one run -- all lanes of a warp execute the same number of mixed additions no matter how
+// the scalars are distributed (uniform: bucket sizes fluctuate; KZG witnesses: a few huge buckets of
+// 0 / 1 digits).  A bucket that lies inside one run is written straight to buckets[]; a bucket cut
+// by run boundaries leaves one PIECE per run it touches (a run has at most two cut buckets: the one
+// it starts in and the one it ends in) and the pieces are added by the combine kernels.
 // ---------------------------------------------------------------------------------------------
-// meta[0] = total entries, meta[1] = total tasks, meta[2] = #small split buckets, meta[3] = #large
-KERNEL void plan_tasks_kernel(const u32* starts, const u32* ends, u32 nb, u32 T, u32* ntasks, u32* small_list,
-                              u32* large_list, u32 list_cap_small, u32 list_cap_large, u32* meta) {
-  const u32 wb = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wb >= nb) return;
-  const u32 cnt = ends[wb] - starts[wb];
-  const u32 nt = (cnt + T - 1) / T;
-  ntasks[wb] = nt;
-  if (nt > 1) {
-    if (nt <= SMALL_SPLIT_MAX) {
-      const u32 k = atomic_add_u32(&meta[2], 1u);
-      if (k < list_cap_small) small_list[k] = wb;
-    } else {
-      const u32 k = atomic_add_u32(&meta[3], 1u);
-      if (k < list_cap_large) large_list[k] = wb;
-    }
-  }
-}
+constexpr u32 NO_BUCKET = 0xffffffffu;
 
-// ---------------------------------------------------------------------------------------------
-// bucket accumulation: one thread per task
-// ---------------------------------------------------------------------------------------------
-KERNEL void __launch_bounds__(128) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
-                                                      const u32* starts, const u32* ends, const u32* ntasks,
-                                                      const u32* task_off, u32 nb, u32 T, const u32* meta,
-                                                      G1Xyzz* buckets, G1Xyzz* partials) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= meta[1]) return;
-  u32 lo = 0, hi = nb - 1;  // last bucket whose first task id is <= t
+DEV u32 run_length(u32 total, u32 nlanes) { return (total + nlanes - 1) / nlanes; }
+
+// last bucket whose start offset is <= pos: the non-empty bucket that contains entry `pos`
+DEV u32 bucket_of_entry(const u32* starts, u32 nb, u32 pos) {
+  u32 lo = 0, hi = nb - 1;
   while (lo < hi) {
     const u32 mid = (lo + hi + 1) >> 1;
-    if (task_off[mid] <= t)
+    if (starts[mid] <= pos)
       lo = mid;
     else
       hi = mid - 1;
   }
-  const u32 wb = lo;
-  const u32 k = t - task_off[wb];
-  const u32 begin = starts[wb] + k * T;
-  u32 end = begin + T;
-  const u32 bend = ends[wb];
-  if (end > bend) end = bend;
+  return lo;
+}
+
+// meta[0] = total entries, meta[2] = #buckets cut into 2..64 pieces, meta[3] = #buckets cut into more
+KERNEL void plan_pieces_kernel(const u32* starts, const u32* ends, u32 nb, u32 nlanes, u32* small_list, u32* large_list,
+                               u32 cap_small, u32 cap_large, u32* meta) {
+  const u32 wb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wb >= nb) return;
+  const u32 s = starts[wb], e = ends[wb];
+  if (e == s) return;
+  const u32 L = run_length(meta[0], nlanes);
+  const u32 span = (e - 1) / L - s / L + 1;
+  if (span > 1) {
+    if (span <= SMALL_SPLIT_MAX) {
+      const u32 k = atomic_add_u32(&meta[2], 1u);
+      if (k < cap_small) small_list[k] = wb;
+    } else {
+      const u32 k = atomic_add_u32(&meta[3], 1u);
+      if (k < cap_large) large_list[k] = wb;
+    }
+  }
+}
+
+KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
+                                                      const u32* starts, const u32* ends, u32 nb, u32 nlanes,
+                                                      const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
+                                                      u32* piece_bucket) {
+  const u32 lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= nlanes) return;
+  piece_bucket[2 * lane] = NO_BUCKET;
+  piece_bucket[2 * lane + 1] = NO_BUCKET;
+  const u32 total = meta[0];
+  if (total == 0) return;
+  const u32 L = run_length(total, nlanes);
+  const u32 begin = lane * L;
+  if (begin >= total) return;
+  const u32 end = (begin + L < total) ? begin + L : total;
+  u32 wb = bucket_of_entry(starts, nb, begin);
+  u32 cur_end = ends[wb];
+  bool cut_at_start = starts[wb] < begin;  // the bucket began in an earlier run: what we sum is a piece
   G1Xyzz acc = xyzz_identity();
   for (u32 pos = begin; pos < end; pos++) {
+    if (pos == cur_end) {  // bucket wb ends inside this run (rare, short, divergent)
+      if (cut_at_start) {
+        pieces[2 * lane] = acc;
+        piece_bucket[2 * lane] = wb;
+      } else {
+        buckets[wb] = acc;
+      }
+      cut_at_start = false;
+      acc = xyzz_identity();
+      wb = bucket_of_entry(starts, nb, pos);
+      cur_end = ends[wb];
+    }
     const u32 e = sorted[pos];
     G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
     if (p.inf) continue;
     if (e >> 31) p.y = fp_neg(p.y);
     xyzz_add_affine(acc, p.x, p.y);
   }
-  if (ntasks[wb] == 1)
-    buckets[wb] = acc;
-  else
-    partials[t] = acc;
+  if (cur_end == end && !cut_at_start) {
+    buckets[wb] = acc;  // the bucket ends exactly with the run and began inside it
+  } else {
+    const u32 slot = cut_at_start ? 0u : 1u;
+    pieces[2 * lane + slot] = acc;
+    piece_bucket[2 * lane + slot] = wb;
+  }
 }
 
-KERNEL void __launch_bounds__(128) combine_small_kernel(const u32* small_list, const u32* ntasks, const u32* task_off,
-                                                         const u32* meta, const G1Xyzz* partials, G1Xyzz* buckets) {
+// adds the pieces of bucket wb held by runs first_run .. last_run (strided by `step` from `offset`)
+DEV void gather_pieces(G1Xyzz& acc, u32 wb, u32 first_run, u32 last_run, u32 offset, u32 step, const G1Xyzz* pieces,
+                       const u32* piece_bucket) {
+  for (u32 r = first_run + offset; r <= last_run; r += step) {
+    if (piece_bucket[2 * r] == wb) xyzz_add_ni(acc, pieces[2 * r]);
+    if (piece_bucket[2 * r + 1] == wb) xyzz_add_ni(acc, pieces[2 * r + 1]);
+  }
+}
+
+KERNEL void __launch_bounds__(128) combine_small_kernel(const u32* small_list, const u32* starts, const u32* ends,
+                                                         u32 nlanes, const u32* meta, const G1Xyzz* pieces,
+                                                         const u32* piece_bucket, G1Xyzz* buckets) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= meta[2]) return;
   const u32 wb = small_list[j];
-  const u32 first = task_off[wb], nt = ntasks[wb];
-  G1Xyzz acc = partials[first];
-  for (u32 k = 1; k < nt; k++) xyzz_add_ni(acc, partials[first + k]);
+  const u32 L = run_length(meta[0], nlanes);
+  G1Xyzz acc = xyzz_identity();
+  gather_pieces(acc, wb, starts[wb] / L, (ends[wb] - 1) / L, 0, 1, pieces, piece_bucket);
   buckets[wb] = acc;
 }
 
-// one CTA per heavily split bucket: strided partial sums, then a shared-memory tree
-KERNEL void __launch_bounds__(COMBINE_TPB) combine_large_kernel(const u32* large_list, const u32* ntasks,
-                                                                 const u32* task_off, const u32* meta,
-                                                                 const G1Xyzz* partials, G1Xyzz* buckets) {
+// one CTA per bucket that was cut into many pieces: strided partial sums, then a shared-memory tree
+KERNEL void __launch_bounds__(COMBINE_TPB) combine_large_kernel(const u32* large_list, const u32* starts, const u32* ends,
+                                                                 u32 nlanes, const u32* meta, const G1Xyzz* pieces,
+                                                                 const u32* piece_bucket, G1Xyzz* buckets) {
   DYN_SMEM(G1Xyzz, sh);
+  const u32 L = run_length(meta[0], nlanes);
   for (u32 j = blockIdx.x; j < meta[3]; j += gridDim.x) {
     const u32 wb = large_list[j];
-    const u32 first = task_off[wb], nt = ntasks[wb];
     G1Xyzz acc = xyzz_identity();
-    for (u32 k = threadIdx.x; k < nt; k += blockDim.x) xyzz_add_ni(acc, partials[first + k]);
+    gather_pieces(acc, wb, starts[wb] / L, (ends[wb] - 1) / L, threadIdx.x, blockDim.x, pieces, piece_bucket);
     sh[threadIdx.x] = acc;
     SYNC_THREADS();
     for (u32 off = blockDim.x >> 1; off > 0; off >>= 1) {
@@ -247,59 +290,55 @@ KERNEL void __launch_bounds__(COMBINE_TPB) combine_large_kernel(const u32* large
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction:  f(X[0..m)) = sum_i (i+1) * X[i]  =  sum_t WS_t + Kc * f(R[1..T))
-//   with chunk sums R_t = sum X[tKc .. tKc+Kc) and WS_t = sum (local index + 1) * X[...]
+// bucket reduction, per window:  f(X[0..m)) = sum_i (i+1) * X[i].
+//   With chunks of Kc:  f(X) = sum_t WS_t + Kc * f(R[1..T)),  R_t = sum of chunk t,
+//   WS_t = sum (local index + 1) * X[..] (running sums).  One launch per level l computes, for chunk t,
+//     R'_t = sum of its chunk of the weighted input (X at level 0, R[1..) above),
+//     P'_t = Kc^l * WS_t + sum of its chunk of the previous level's P        (plain partial sums)
+//   so that after the last level (one chunk left) P[0] = f(buckets): no separate plain-sum launches.
 // ---------------------------------------------------------------------------------------------
-KERNEL void __launch_bounds__(128) wsum_kernel(const G1Xyzz* X, u32 x_stride, u32 m, u32 nwin, u32 T, G1Xyzz* R,
-                                                G1Xyzz* WS) {
+struct ReduceArgs {
+  const G1Xyzz* X;   // weighted input, per window `x_stride` apart, first element at X[x_off]
+  u32 x_stride, x_off, m;
+  const G1Xyzz* P;   // plain input of the previous level (T_in per window) or nullptr at level 0
+  u32 T_in;
+  u32 level;         // scale of this level's WS: Kc^level
+  G1Xyzz* R_out;     // T_out per window
+  G1Xyzz* P_out;
+  u32 T_out, nwin;
+};
+
+KERNEL void __launch_bounds__(128) reduce_level_kernel(ReduceArgs a) {
   const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nwin * T) return;
-  const u32 w = id / T, t = id % T;
-  const G1Xyzz* x = X + (size_t)w * x_stride;
+  if (id >= a.nwin * a.T_out) return;
+  const u32 w = id / a.T_out, t = id % a.T_out;
+  const G1Xyzz* x = a.X + (size_t)w * a.x_stride + a.x_off;
   const u32 lo = t * RED_KC;
   u32 hi = lo + RED_KC;
-  if (hi > m) hi = m;
+  if (hi > a.m) hi = a.m;
   G1Xyzz run = xyzz_identity(), acc = xyzz_identity();
   for (u32 i = hi; i > lo; i--) {
     xyzz_add_ni(run, x[i - 1]);
     xyzz_add_ni(acc, run);
   }
-  R[(size_t)w * T + t] = run;
-  WS[(size_t)w * T + t] = acc;
-}
-
-KERNEL void __launch_bounds__(128) psum_kernel(const G1Xyzz* X, u32 x_stride, u32 m, u32 nwin, u32 T, G1Xyzz* PS) {
-  const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nwin * T) return;
-  const u32 w = id / T, t = id % T;
-  const G1Xyzz* x = X + (size_t)w * x_stride;
-  const u32 lo = t * RED_KC;
-  u32 hi = lo + RED_KC;
-  if (hi > m) hi = m;
-  G1Xyzz acc = xyzz_identity();
-  for (u32 i = lo; i < hi; i++) xyzz_add_ni(acc, x[i]);
-  PS[(size_t)w * T + t] = acc;
-}
-
-constexpr int MAX_RED_LEVELS = 6;
-struct FinalArgs {
-  const G1Xyzz* f[MAX_RED_LEVELS];  // f[l][w * stride[l]] = per-window plain sum of level l's WS
-  u32 stride[MAX_RED_LEVELS];
-  int levels;
-  u32 W, c;
-};
-
-// Tail, step 1 (one thread per window): S_w = f0 + Kc (f1 + Kc (f2 + ...)), then D_w = 2^(c w) S_w.
-// The c*w doublings of the different windows run in parallel; the critical path is the top window's.
-KERNEL void window_weigh_kernel(FinalArgs a, G1Xyzz* D) {
-  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= a.W) return;
-  G1Xyzz s = xyzz_identity();
-  for (int l = a.levels - 1; l >= 0; l--) {
-    for (u32 i = 0; i < RED_LOG_KC; i++) s = xyzz_double(s);
-    xyzz_add_ni(s, a.f[l][(size_t)w * a.stride[l]]);
+  a.R_out[(size_t)w * a.T_out + t] = run;
+  for (u32 i = 0; i < a.level * RED_LOG_KC; i++) acc = xyzz_double(acc);
+  if (a.P) {
+    const G1Xyzz* p = a.P + (size_t)w * a.T_in;
+    u32 phi = lo + RED_KC;
+    if (phi > a.T_in) phi = a.T_in;
+    for (u32 i = lo; i < phi; i++) xyzz_add_ni(acc, p[i]);
   }
-  for (u32 i = 0; i < a.c * w; i++) s = xyzz_double(s);
+  a.P_out[(size_t)w * a.T_out + t] = acc;
+}
+
+// Tail, step 1 (one thread per window): D_w = 2^(c w) * S_w, S_w = f(buckets of window w) = P[w].
+// The c*w doublings of the different windows run in parallel; the critical path is the top window's.
+KERNEL void window_weigh_kernel(const G1Xyzz* S, u32 s_stride, u32 W, u32 c, G1Xyzz* D) {
+  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  G1Xyzz s = S[(size_t)w * s_stride];
+  for (u32 i = 0; i < c * w; i++) s = xyzz_double(s);
   D[w] = s;
 }
 

@@ -32,10 +32,12 @@ static inline Params make_params(size_t n) {
   p.c = choose_window(n);
   p.W = SCALAR_BITS / p.c + 1;
   p.B = 1u << (p.c - 1);
-  size_t t = ((size_t)n * p.W + 149999) / 150000;  // ~1000 tasks per SM keeps 148 SMs busy
-  if (t < 16) t = 16;
-  if (t > 1024) t = 1024;
-  p.T = (u32)t;
+  // accumulation threads: 4 waves of (148 SMs x 3 CTAs x 128 threads), but at least ~32 entries per run
+  size_t lanes = ((size_t)n * p.W + 31) / 32;
+  const size_t full = (size_t)148 * 384 * 4;
+  if (lanes > full) lanes = full;
+  lanes = (lanes + 127) / 128 * 128;
+  p.nlanes = (u32)lanes;
   return p;
 }
 
@@ -87,42 +89,42 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   const Params prm = make_params(n_sz);
   const u32 NB = prm.W * prm.B;
   const size_t entries_ub = (size_t)n * prm.W;
-  const u32 task_ub = (u32)(NB + entries_ub / prm.T + 1);
-  const u32 cap_small = (u32)(entries_ub / prm.T + 1);
-  const u32 cap_large = (u32)(entries_ub / ((size_t)prm.T * SMALL_SPLIT_MAX) + 1);
+  const u32 cap_small = prm.nlanes + 1;                   // every run boundary cuts at most one bucket
+  const u32 cap_large = prm.nlanes / SMALL_SPLIT_MAX + 1;
   const u32 scan_blocks = (NB + SCAN_BLOCK - 1) / SCAN_BLOCK;
 
   // reduction level structure
   std::vector<RedLevel> lv;
   {
-    u32 m = prm.B;
-    while (m > 0 && (int)lv.size() < MAX_RED_LEVELS) {
+    // level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out;
+    // the plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too
+    u32 m = prm.B, t_prev = 0;
+    for (;;) {
       RedLevel l;
       l.m = m;
-      l.T = (m + RED_KC - 1) / RED_KC;
+      const u32 need = t_prev > m ? t_prev : m;
+      l.T = (need + RED_KC - 1) / RED_KC;
+      if (l.T == 0) l.T = 1;
       lv.push_back(l);
+      if (l.T == 1) break;
+      t_prev = l.T;
       m = l.T - 1;
     }
   }
 
   Carver cv;
   const size_t o_counts = cv.take((size_t)NB * 4), o_starts = cv.take((size_t)NB * 4), o_ends = cv.take((size_t)NB * 4);
-  const size_t o_ntasks = cv.take((size_t)NB * 4), o_taskoff = cv.take((size_t)NB * 4);
+  const size_t o_piece_bucket = cv.take((size_t)prm.nlanes * 2 * 4);
   const size_t o_bsums = cv.take((size_t)(scan_blocks + 1) * 4), o_meta = cv.take(64);
   const size_t o_sorted = cv.take(entries_ub * 4);
   const size_t o_small = cv.take((size_t)cap_small * 4), o_large = cv.take((size_t)cap_large * 4);
   const size_t o_buckets = cv.take((size_t)NB * sizeof(G1Xyzz));
-  const size_t o_partials = cv.take((size_t)task_ub * sizeof(G1Xyzz));
-  std::vector<size_t> o_R(lv.size()), o_WS(lv.size());
+  const size_t o_pieces = cv.take((size_t)prm.nlanes * 2 * sizeof(G1Xyzz));
+  std::vector<size_t> o_R(lv.size()), o_P(lv.size());
   for (size_t l = 0; l < lv.size(); l++) {
     o_R[l] = cv.take((size_t)prm.W * lv[l].T * sizeof(G1Xyzz));
-    o_WS[l] = cv.take((size_t)prm.W * lv[l].T * sizeof(G1Xyzz));
+    o_P[l] = cv.take((size_t)prm.W * lv[l].T * sizeof(G1Xyzz));
   }
-  // ping-pong buffers for the plain sums of WS (largest needed: W * ceil(T0 / Kc))
-  const size_t ps_elems = (size_t)prm.W * ((lv[0].T + RED_KC - 1) / RED_KC);
-  std::vector<size_t> o_PSfinal(lv.size());
-  const size_t o_psA = cv.take(ps_elems * sizeof(G1Xyzz)), o_psB = cv.take(ps_elems * sizeof(G1Xyzz));
-  for (size_t l = 0; l < lv.size(); l++) o_PSfinal[l] = cv.take((size_t)prm.W * sizeof(G1Xyzz));
   const size_t o_D = cv.take((size_t)prm.W * sizeof(G1Xyzz));
 
   unsigned char* ws = nullptr;
@@ -131,15 +133,14 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   u32* counts = WSP(u32, o_counts);
   u32* starts = WSP(u32, o_starts);
   u32* ends = WSP(u32, o_ends);
-  u32* ntasks = WSP(u32, o_ntasks);
-  u32* task_off = WSP(u32, o_taskoff);
+  u32* piece_bucket = WSP(u32, o_piece_bucket);
   u32* bsums = WSP(u32, o_bsums);
   u32* meta = WSP(u32, o_meta);
   u32* sorted = WSP(u32, o_sorted);
   u32* small_list = WSP(u32, o_small);
   u32* large_list = WSP(u32, o_large);
   G1Xyzz* buckets = WSP(G1Xyzz, o_buckets);
-  G1Xyzz* partials = WSP(G1Xyzz, o_partials);
+  G1Xyzz* pieces = WSP(G1Xyzz, o_pieces);
 
   cudaError_t err = cudaSuccess;
 #define STEP(stmt)                                       \
@@ -161,58 +162,46 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   else launches += 3;
   STEP(LAUNCH_NOSYNC(scatter_kernel, dim3(g_n), dim3(256), 0, s, scalars, n, prm, ends, sorted));
   launches++;
-  STEP(LAUNCH_NOSYNC(plan_tasks_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB,
-                     prm.T, ntasks, small_list, large_list, cap_small, cap_large, meta));
+  STEP(LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB,
+                     prm.nlanes, small_list, large_list, cap_small, cap_large, meta));
   launches++;
-  if (!dry && err == cudaSuccess) err = exclusive_scan(ntasks, NB, bsums, task_off, nullptr, meta + 1, s, launches);
-  else launches += 3;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[1], s);
-  STEP(LAUNCH_NOSYNC(accumulate_kernel, dim3((task_ub + 127) / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                     (const u32*)starts, (const u32*)ends, (const u32*)ntasks, (const u32*)task_off, NB, prm.T,
-                     (const u32*)meta, buckets, partials));
+  STEP(LAUNCH_NOSYNC(accumulate_kernel, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                     (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
   launches++;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[2], s);
   STEP(LAUNCH_NOSYNC(combine_small_kernel, dim3((cap_small + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
-                     (const u32*)ntasks, (const u32*)task_off, (const u32*)meta, (const G1Xyzz*)partials, buckets));
+                     (const u32*)starts, (const u32*)ends, prm.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
+                     (const u32*)piece_bucket, buckets));
   launches++;
   {
     const u32 g = cap_large < 592 ? cap_large : 592;  // 4 CTAs per SM; the kernel strides over the list
     STEP(LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), COMBINE_TPB * sizeof(G1Xyzz), s, (const u32*)large_list,
-                (const u32*)ntasks, (const u32*)task_off, (const u32*)meta, (const G1Xyzz*)partials, buckets));
+                (const u32*)starts, (const u32*)ends, prm.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
+                (const u32*)piece_bucket, buckets));
     launches++;
   }
-  // bucket reduction
-  FinalArgs fa;
-  fa.levels = (int)lv.size();
-  fa.W = prm.W;
-  fa.c = prm.c;
+  // bucket reduction: one launch per level until a single chunk per window is left
   for (size_t l = 0; l < lv.size(); l++) {
-    const G1Xyzz* X = (l == 0) ? buckets : (WSP(G1Xyzz, o_R[l - 1]) + 1);
-    const u32 xs = (l == 0) ? prm.B : lv[l - 1].T;
-    G1Xyzz* R = WSP(G1Xyzz, o_R[l]);
-    G1Xyzz* WS = WSP(G1Xyzz, o_WS[l]);
+    ReduceArgs ra;
+    ra.X = (l == 0) ? buckets : WSP(G1Xyzz, o_R[l - 1]);
+    ra.x_stride = (l == 0) ? prm.B : lv[l - 1].T;
+    ra.x_off = (l == 0) ? 0 : 1;
+    ra.m = lv[l].m;
+    ra.P = (l == 0) ? nullptr : WSP(G1Xyzz, o_P[l - 1]);
+    ra.T_in = (l == 0) ? 0 : lv[l - 1].T;
+    ra.level = (u32)l;
+    ra.R_out = WSP(G1Xyzz, o_R[l]);
+    ra.P_out = WSP(G1Xyzz, o_P[l]);
+    ra.T_out = lv[l].T;
+    ra.nwin = prm.W;
     const u32 threads = prm.W * lv[l].T;
-    STEP(LAUNCH_NOSYNC(wsum_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, X, xs, lv[l].m, prm.W, lv[l].T, R, WS));
+    STEP(LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra));
     launches++;
-    // plain sum of WS[l] (T entries per window) down to one entry per window
-    const G1Xyzz* cur = WS;
-    u32 cur_n = lv[l].T;
-    int flip = 0;
-    while (cur_n > 1) {
-      const u32 t = (cur_n + RED_KC - 1) / RED_KC;
-      G1Xyzz* dst = (t == 1) ? WSP(G1Xyzz, o_PSfinal[l]) : WSP(G1Xyzz, flip ? o_psB : o_psA);
-      const u32 th = prm.W * t;
-      STEP(LAUNCH_NOSYNC(psum_kernel, dim3((th + 127) / 128), dim3(128), 0, s, cur, cur_n, cur_n, prm.W, t, dst));
-      launches++;
-      cur = dst;
-      cur_n = t;
-      flip ^= 1;
-    }
-    fa.f[l] = cur;
-    fa.stride[l] = 1;
   }
+  const G1Xyzz* S = WSP(G1Xyzz, o_P[lv.size() - 1]);
   G1Xyzz* D = WSP(G1Xyzz, o_D);
-  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((prm.W + 31) / 32), dim3(32), 0, s, fa, D));
+  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((prm.W + 31) / 32), dim3(32), 0, s, S, lv.back().T, prm.W, prm.c, D));
   launches++;
   STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, prm.W, out144));
   launches++;
