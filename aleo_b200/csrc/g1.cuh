@@ -119,8 +119,26 @@ DEV_NOINLINE G1Xyzz xyzz_double(const G1Xyzz& p) {
   return r;
 }
 
+// Out-of-line Fq product with by-value operands: ptxas passes them in registers (no stack), so a call
+// costs ~36 MOVs on the ALU pipe while the loop body that uses it shrinks ~10x and stays resident in
+// the instruction cache (the fully inlined accumulation loop is ~115 KB of SASS and was stalled on
+// instruction fetch for 10-40 % of its issue slots, profiles/r01_ncu_hot_kernels.md).
+DEV_NOINLINE Fq fq_mul_v(Fq a, Fq b) { return fp_mul(a, b); }
+
+template <bool CALL>
+DEV Fq fq_mul_sel(const Fq& a, const Fq& b) {
+  if (CALL) return fq_mul_v(a, b);
+  return fp_mul(a, b);
+}
+
 // acc += (x2, y2)   (madd-2008-s; the affine operand is not the identity)
-DEV void xyzz_add_affine(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
+template <bool CALL>
+DEV void xyzz_add_affine_t(G1Xyzz& acc, const Fq& x2, const Fq& y2);
+
+DEV void xyzz_add_affine(G1Xyzz& acc, const Fq& x2, const Fq& y2) { xyzz_add_affine_t<false>(acc, x2, y2); }
+
+template <bool CALL>
+DEV void xyzz_add_affine_t(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
   if (xyzz_is_identity(acc)) {
     acc.x = x2;
     acc.y = y2;
@@ -128,8 +146,8 @@ DEV void xyzz_add_affine(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
     acc.zzz = acc.zz;
     return;
   }
-  Fq u2 = fp_mul(x2, acc.zz);
-  Fq s2 = fp_mul(y2, acc.zzz);
+  Fq u2 = fq_mul_sel<CALL>(x2, acc.zz);
+  Fq s2 = fq_mul_sel<CALL>(y2, acc.zzz);
   Fq p = fp_sub(u2, acc.x);
   Fq r = fp_sub(s2, acc.y);
   if (fp_is_zero(p)) {  // same x: doubling or cancellation (rare; the reference's edge-case tests hit it)
@@ -139,13 +157,13 @@ DEV void xyzz_add_affine(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
       acc = xyzz_identity();
     return;
   }
-  Fq pp = fp_sqr(p);
-  Fq ppp = fp_mul(p, pp);
-  Fq q = fp_mul(acc.x, pp);
-  Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-  Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
-  acc.zz = fp_mul(acc.zz, pp);
-  acc.zzz = fp_mul(acc.zzz, ppp);
+  Fq pp = fq_mul_sel<CALL>(p, p);
+  Fq ppp = fq_mul_sel<CALL>(p, pp);
+  Fq q = fq_mul_sel<CALL>(acc.x, pp);
+  Fq x3 = fp_sub(fp_sub(fq_mul_sel<CALL>(r, r), ppp), fp_dbl(q));
+  Fq y3 = fp_sub(fq_mul_sel<CALL>(r, fp_sub(q, x3)), fq_mul_sel<CALL>(acc.y, ppp));
+  acc.zz = fq_mul_sel<CALL>(acc.zz, pp);
+  acc.zzz = fq_mul_sel<CALL>(acc.zzz, ppp);
   acc.x = x3;
   acc.y = y3;
 }

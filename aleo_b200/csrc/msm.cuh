@@ -197,6 +197,7 @@ KERNEL void plan_pieces_kernel(const u32* starts, const u32* ends, u32 nb, u32 n
   }
 }
 
+template <bool CALL>
 KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
@@ -232,7 +233,7 @@ KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bas
     G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
     if (p.inf) continue;
     if (e >> 31) p.y = fp_neg(p.y);
-    xyzz_add_affine(acc, p.x, p.y);
+    xyzz_add_affine_t<CALL>(acc, p.x, p.y);
   }
   if (cur_end == end && !cut_at_start) {
     buckets[wb] = acc;  // the bucket ends exactly with the run and began inside it

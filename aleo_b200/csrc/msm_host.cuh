@@ -1,5 +1,6 @@
 // msm_host.cuh -- host-side driver of msm.cuh: window choice, workspace carving, launch sequence.
 #pragma once
+#include <cstdlib>
 #include <vector>
 #include "msm.cuh"
 
@@ -32,9 +33,11 @@ static inline Params make_params(size_t n) {
   p.c = choose_window(n);
   p.W = SCALAR_BITS / p.c + 1;
   p.B = 1u << (p.c - 1);
-  // accumulation threads: 4 waves of (148 SMs x 3 CTAs x 128 threads), but at least ~32 entries per run
+  // accumulation threads: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on B200: 4 waves
+  // 96.1 ms, 16 waves 93.4 ms at n = 2^24 -- but at least ~32 entries per run
   size_t lanes = ((size_t)n * p.W + 31) / 32;
-  const size_t full = (size_t)148 * 384 * 4;
+  static const long waves_env = []() { const char* e = getenv("ALEO_B200_MSM_WAVES"); return e ? atol(e) : 0L; }();
+  const size_t full = (size_t)148 * 384 * (waves_env > 0 ? (size_t)waves_env : 16);
   if (lanes > full) lanes = full;
   lanes = (lanes + 127) / 128 * 128;
   p.nlanes = (u32)lanes;
@@ -166,8 +169,13 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
                      prm.nlanes, small_list, large_list, cap_small, cap_large, meta));
   launches++;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[1], s);
-  STEP(LAUNCH_NOSYNC(accumulate_kernel, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                     (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
+  static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
+  if (acc_inline)
+    STEP(LAUNCH_NOSYNC(accumulate_kernel<false>, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                       (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
+  else
+    STEP(LAUNCH_NOSYNC(accumulate_kernel<true>, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                       (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
   launches++;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[2], s);
   STEP(LAUNCH_NOSYNC(combine_small_kernel, dim3((cap_small + 127) / 128), dim3(128), 0, s, (const u32*)small_list,

@@ -33,6 +33,19 @@ constexpr int SMALL_MAX_LOG = 11;       // single-CTA kernel handles n <= 2^11
 constexpr int MAX_PASS_BITS = 8;
 constexpr int MAX_LOG_N = 32;           // memory bound, far below the field's two-adicity (47)
 
+// Fr product used by the transform kernels.  Inlined by default: the out-of-line variant (by-value
+// operands in registers, ~20 KB of SASS per pass kernel instead of > 200 KB) measured 5-7 % SLOWER on
+// B200 -- a pass kernel is straight-line code executed once per tile, so unlike the MSM accumulation
+// loop it gains nothing from instruction-cache residency and pays ~24 MOVs per 120-IMAD product.
+#ifndef ALEO_NTT_CALL_MUL
+#define ALEO_NTT_CALL_MUL 0
+#endif
+#if ALEO_NTT_CALL_MUL
+DEV_NOINLINE Fr fr_mul_v(Fr a, Fr b) { return fp_mul(a, b); }
+#else
+DEV Fr fr_mul_v(const Fr& a, const Fr& b) { return fp_mul(a, b); }
+#endif
+
 // w^e from a two-level table: lo[e & mask] * hi[e >> lo_bits]
 struct PowTable {
   const Fr* lo;
@@ -43,7 +56,7 @@ struct PowTable {
 DEV Fr pow_lookup(const PowTable& t, u32 e) {
   Fr a = t.lo[e & ((1u << t.lo_bits) - 1u)];
   Fr b = t.hi[e >> t.lo_bits];
-  return fp_mul(a, b);
+  return fr_mul_v(a, b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -62,7 +75,7 @@ DEV void ntt2(Fr* x) { bfly(x[0], x[1]); }
 DEV void ntt4(Fr* x, const Fr& w4) {
   bfly(x[0], x[2]);
   bfly(x[1], x[3]);
-  x[3] = fp_mul(x[3], w4);
+  x[3] = fr_mul_v(x[3], w4);
   bfly(x[0], x[1]);
   bfly(x[2], x[3]);
   Fr t = x[1];  // bit-reversed -> natural
@@ -75,15 +88,15 @@ DEV void ntt8(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
   bfly(x[1], x[5]);
   bfly(x[2], x[6]);
   bfly(x[3], x[7]);
-  x[5] = fp_mul(x[5], w8[1]);
-  x[6] = fp_mul(x[6], w8[2]);
-  x[7] = fp_mul(x[7], w8[3]);
+  x[5] = fr_mul_v(x[5], w8[1]);
+  x[6] = fr_mul_v(x[6], w8[2]);
+  x[7] = fr_mul_v(x[7], w8[3]);
   bfly(x[0], x[2]);
   bfly(x[1], x[3]);
   bfly(x[4], x[6]);
   bfly(x[5], x[7]);
-  x[3] = fp_mul(x[3], w8[2]);
-  x[7] = fp_mul(x[7], w8[2]);
+  x[3] = fr_mul_v(x[3], w8[2]);
+  x[7] = fr_mul_v(x[7], w8[2]);
   bfly(x[0], x[1]);
   bfly(x[2], x[3]);
   bfly(x[4], x[5]);
@@ -202,7 +215,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u32 p = j * C1 + tr;
       const u64 gi = in_base + p * stride_r + tg * stride_g;
       x[j] = src[gi];
-      if (!LAST && a.use_pre) x[j] = fp_mul(x[j], pow_lookup(a.pre, (u32)gi));
+      if (!LAST && a.use_pre) x[j] = fr_mul_v(x[j], pow_lookup(a.pre, (u32)gi));
     }
     Fr w8[4];
     w8[1] = a.inner[R / 8];
@@ -210,7 +223,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
     w8[3] = a.inner[3 * (R / 8)];
     ntt8(x, w8);
 #pragma unroll
-    for (int k = 1; k < 8; k++) x[k] = fp_mul(x[k], a.inner[tr * k]);
+    for (int k = 1; k < 8; k++) x[k] = fr_mul_v(x[k], a.inner[tr * k]);
 #pragma unroll
     for (int k = 0; k < 8; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(k * C1 + tr, tg), x[k]);
   }
@@ -239,7 +252,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       if (S2 == 1) ntt2(x + h * PTS);
       if (C > 1) {
 #pragma unroll
-        for (int k = 1; k < PTS; k++) x[h * PTS + k] = fp_mul(x[h * PTS + k], a.inner[(R / CP) * t * k]);
+        for (int k = 1; k < PTS; k++) x[h * PTS + k] = fr_mul_v(x[h * PTS + k], a.inner[(R / CP) * t * k]);
       }
 #pragma unroll
       for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k * C, tg), x[h * PTS + k]);
@@ -280,9 +293,9 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u64 go = out_base + kap * ostride_r + sg;
       if (!LAST) {
         const u32 e = ((i2_base + sg) * kap) << (a.log_n - a.log_cur);
-        v = fp_mul(v, pow_lookup(a.tw, e));
+        v = fr_mul_v(v, pow_lookup(a.tw, e));
       }
-      if (LAST && a.use_post) v = fp_mul(v, pow_lookup(a.post, (u32)go));
+      if (LAST && a.use_post) v = fr_mul_v(v, pow_lookup(a.post, (u32)go));
       dst[go] = v;
     }
   }
@@ -308,7 +321,7 @@ KERNEL void __launch_bounds__(TPB) small_kernel(SmallArgs a) {
   Fr* x = a.data + ((u64)blockIdx.x << a.log_n);
   for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
     Fr v = x[i];
-    if (a.use_pre) v = fp_mul(v, pow_lookup(a.pre, i));
+    if (a.use_pre) v = fr_mul_v(v, pow_lookup(a.pre, i));
     u32 r = 0;
     for (u32 b = 0; b < a.log_n; b++) r |= ((i >> b) & 1u) << (a.log_n - 1 - b);
     smem_put(plane0, plane1, r, v);
@@ -321,7 +334,7 @@ KERNEL void __launch_bounds__(TPB) small_kernel(SmallArgs a) {
       const u32 lo = ((idx >> lm) << (lm + 1)) + k;
       Fr u = smem_get(plane0, plane1, lo);
       Fr t = smem_get(plane0, plane1, lo + m);
-      if (k) t = fp_mul(t, a.inner[k << (a.log_n - lm - 1)]);
+      if (k) t = fr_mul_v(t, a.inner[k << (a.log_n - lm - 1)]);
       smem_put(plane0, plane1, lo, fp_add(u, t));
       smem_put(plane0, plane1, lo + m, fp_sub(u, t));
     }
@@ -329,8 +342,8 @@ KERNEL void __launch_bounds__(TPB) small_kernel(SmallArgs a) {
   }
   for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
     Fr v = smem_get(plane0, plane1, i);
-    if (a.use_post) v = fp_mul(v, pow_lookup(a.post, i));
-    if (a.use_scale) v = fp_mul(v, a.scale);
+    if (a.use_post) v = fr_mul_v(v, pow_lookup(a.post, i));
+    if (a.use_scale) v = fr_mul_v(v, a.scale);
     x[i] = v;
   }
 }
@@ -344,7 +357,7 @@ KERNEL void twiddle_matrix_kernel(Fr* data, u32 rows, u32 cols, u32 row0, u32 co
   if (idx >= (u64)rows * cols) return;
   const u32 r = (u32)(idx / cols), c = (u32)(idx % cols);
   const u64 e = ((u64)(r + row0) * (u64)(c + col0)) & (((u64)1 << log_n_global) - 1);
-  data[idx] = fp_mul(data[idx], pow_lookup(tw, (u32)e));
+  data[idx] = fr_mul_v(data[idx], pow_lookup(tw, (u32)e));
 }
 
 // ---------------------------------------------------------------------------------------------
