@@ -8,4 +8,6 @@ from .domain import EvaluationDomain  # noqa: F401
 from .msm import (VariableBase, gen_bases_dev, gen_scalars_dev, dlog_dot_dev, check_on_curve_dev,  # noqa: F401
                   AFFINE_STRIDE_RUST, AFFINE_STRIDE_PACKED, PROJECTIVE_BYTES)
 
+from .kzg import ResidentSRS, KZG10  # noqa: F401,E402
+
 __version__ = "0.1.0"

@@ -34,6 +34,16 @@ SYMBOLS = [
     ("aleo_b200_msm_g1_dev", _int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_msm_g1_dev_profile", _int, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(C.c_float)]),
     ("aleo_b200_g1_sum_dev", _int, [_vp, _vp, _sz, _vp]),
+    ("aleo_b200_srs_create", _int, [C.POINTER(_vp), _vp, _sz, _sz]),
+    ("aleo_b200_srs_create_dev", _int, [C.POINTER(_vp), _vp, _sz, _sz, _vp]),
+    ("aleo_b200_srs_destroy", _int, [_vp]),
+    ("aleo_b200_srs_info", _int, [_vp, C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int), C.POINTER(_sz)]),
+    ("aleo_b200_srs_msm", _int, [_vp, _vp, _vp, _sz]),
+    ("aleo_b200_srs_msm_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
+    ("aleo_b200_srs_msm_dev_profile", _int, [_vp, _vp, _vp, _sz, _vp, C.POINTER(C.c_float)]),
+    ("aleo_b200_srs_msm_launches", _int, [_vp, _sz]),
+    ("aleo_b200_kzg_commit", _int, [_vp, _vp, _vp, _sz]),
+    ("aleo_b200_kzg_commit_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
     ("aleo_b200_gen_bases_dev", _int, [_vp, _sz, _sz, _vp, _vp, _u64, _vp]),

@@ -332,3 +332,126 @@ int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------- resident SRS / KZG commit
+extern "C" {
+
+int aleo_b200_srs_create_dev(void** handle_out, const void* bases_dev, size_t n, size_t affine_stride, void* stream) {
+  if (handle_out == nullptr || bases_dev == nullptr || n == 0 || !stride_ok(affine_stride)) return ALEO_B200_EINVAL;
+  if (n >= ((size_t)1 << 28)) return ALEO_B200_ETOOLARGE;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::srs_create(bases_dev, (u32)affine_stride, n, (cudaStream_t)stream, handle_out));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_create(void** handle_out, const void* bases_host, size_t n, size_t affine_stride) {
+  if (handle_out == nullptr || bases_host == nullptr || n == 0 || !stride_ok(affine_stride)) return ALEO_B200_EINVAL;
+  if (n >= ((size_t)1 << 28)) return ALEO_B200_ETOOLARGE;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  void* d = nullptr;
+  API_CK(cudaMallocAsync(&d, n * affine_stride, s));
+  cudaError_t e = cudaMemcpyAsync(d, bases_host, n * affine_stride, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = aleo::srs_create(d, (u32)affine_stride, n, s, handle_out);
+  cudaFreeAsync(d, s);
+  cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_destroy(void* handle) {
+  aleo::srs_destroy(handle);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_info(const void* handle, size_t* n_out, int* window_bits_out, int* windows_out, size_t* bytes_out) {
+  if (handle == nullptr) return ALEO_B200_EINVAL;
+  aleo::srs_info(handle, n_out, window_bits_out, windows_out, bytes_out);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_msm_launches(const void* handle, size_t n_used) {
+  if (handle == nullptr) return ALEO_B200_EINVAL;
+  int launches = 0;
+  if (aleo::srs_msm(handle, nullptr, n_used, nullptr, nullptr, true, &launches, nullptr) != cudaSuccess) return ALEO_B200_EINVAL;
+  return launches;
+}
+
+int aleo_b200_srs_msm_dev(const void* handle, void* out_projective_dev, const void* scalars_dev, size_t n_used, void* stream) {
+  if (handle == nullptr || out_projective_dev == nullptr || (n_used && scalars_dev == nullptr)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::srs_msm(handle, scalars_dev, n_used, out_projective_dev, (cudaStream_t)stream, false, nullptr, nullptr));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_msm_dev_profile(const void* handle, void* out_projective_dev, const void* scalars_dev, size_t n_used,
+                                  void* stream, float* phase_ms3) {
+  if (handle == nullptr || out_projective_dev == nullptr || scalars_dev == nullptr || n_used == 0 || phase_ms3 == nullptr)
+    return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::srs_msm(handle, scalars_dev, n_used, out_projective_dev, (cudaStream_t)stream, false, nullptr, phase_ms3));
+  return ALEO_B200_OK;
+}
+
+// host scalars -> device, run `body` on the staged copy, copy `out_bytes` of result back
+static int srs_host_call(const void* handle, void* out_host, size_t out_bytes, const void* in_host, size_t n, bool montgomery_in) {
+  if (handle == nullptr || out_host == nullptr || (n && in_host == nullptr)) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  unsigned char* d = nullptr;
+  const size_t sb = (n * 32 + 255) & ~(size_t)255;
+  API_CK(cudaMallocAsync((void**)&d, sb + 512, s));
+  cudaError_t e = cudaSuccess;
+  if (n) e = cudaMemcpyAsync(d, in_host, n * 32, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && montgomery_in) e = aleo::fr_to_bigint(d, d, n, s);
+  if (e == cudaSuccess) e = aleo::srs_msm(handle, d, n, d + sb, s, false, nullptr, nullptr);
+  if (e == cudaSuccess && out_bytes == 48) {
+    e = aleo::g1_compress(d + sb, d + sb + 256, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d + sb + 256, 48, cudaMemcpyDeviceToHost, s);
+  } else if (e == cudaSuccess) {
+    e = cudaMemcpyAsync(out_host, d + sb, 144, cudaMemcpyDeviceToHost, s);
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_srs_msm(const void* handle, void* out_projective_host, const void* scalars_host, size_t n_used) {
+  return srs_host_call(handle, out_projective_host, 144, scalars_host, n_used, false);
+}
+
+int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs) {
+  return srs_host_call(handle, out_compressed48_host, 48, coeffs_montgomery_host, n_coeffs, true);
+}
+
+int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
+                             void* stream) {
+  if (handle == nullptr || out_compressed48_dev == nullptr || (n_coeffs && coeffs_montgomery_dev == nullptr)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* d = nullptr;
+  const size_t sb = (n_coeffs * 32 + 255) & ~(size_t)255;
+  API_CK(cudaMallocAsync((void**)&d, sb + 256, s));
+  cudaError_t e = aleo::fr_to_bigint(coeffs_montgomery_dev, d, n_coeffs, s);
+  if (e == cudaSuccess) e = aleo::srs_msm(handle, d, n_coeffs, d + sb, s, false, nullptr, nullptr);
+  if (e == cudaSuccess) e = aleo::g1_compress(d + sb, out_compressed48_dev, s);
+  cudaFreeAsync(d, s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return ALEO_B200_OK;
+}
+
+}  // extern "C"

@@ -21,6 +21,13 @@ cudaError_t msm_run(const void* bases_dev, u32 stride, const void* scalars_dev, 
 bool msm_size_supported(size_t n);
 int msm_window_bits(size_t n);
 cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);
+cudaError_t srs_create(const void* bases_dev, u32 stride, size_t n, cudaStream_t s, void** handle_out);
+void srs_destroy(void* handle);
+void srs_info(const void* handle, size_t* n, int* c, int* W, size_t* bytes);
+cudaError_t srs_msm(const void* handle, const void* scalars_dev, size_t n_used, void* out144_dev, cudaStream_t s, bool dry,
+                    int* launches_out, float* phase_ms);
+cudaError_t fr_to_bigint(const void* in_dev, void* out_dev, size_t n, cudaStream_t s);
+cudaError_t g1_compress(const void* jac144_dev, void* out48_dev, cudaStream_t s);
 // util_lib.cu
 cudaError_t util_upload_constants();
 cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);

@@ -33,7 +33,13 @@ struct Params {
   u32 W;       // number of windows = 253 / c + 1 (always absorbs the recoding carry)
   u32 B;       // buckets per window = 2^(c-1)
   u32 nlanes;  // threads of the accumulation kernel = equal runs the sorted entry list is cut into
+  // Resident-SRS mode (n_stride != 0): bases were expanded once to P[w][i] = 2^(c w) * P_i, so every
+  // window shares ONE set of 2^(c-1) buckets and the entry for (point i, window w) is w * n_stride + i.
+  u32 n_stride;
 };
+
+DEV u32 bucket_slot(const Params& prm, u32 w, u32 mag) { return prm.n_stride ? (mag - 1) : (w * prm.B + (mag - 1)); }
+DEV u32 entry_index(const Params& prm, u32 w, u32 i) { return prm.n_stride ? (w * prm.n_stride + i) : i; }
 
 // signed digit of window w given the carry from window w-1; returns |digit| and updates carry/neg
 DEV u32 recode_digit(const u32* s /* 8 limbs in global memory */, u32 w, u32 c, u32& carry, u32& neg) {
@@ -63,7 +69,7 @@ KERNEL void count_kernel(const u32* scalars, u32 n, Params prm, u32* counts) {
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
     const u32 mag = recode_digit(s, w, prm.c, carry, neg);
-    if (mag) atomic_add_u32(&counts[w * prm.B + (mag - 1)], 1u);
+    if (mag) atomic_add_u32(&counts[bucket_slot(prm, w, mag)], 1u);
   }
 }
 
@@ -75,8 +81,8 @@ KERNEL void scatter_kernel(const u32* scalars, u32 n, Params prm, u32* cursor, u
   for (u32 w = 0; w < prm.W; w++) {
     const u32 mag = recode_digit(s, w, prm.c, carry, neg);
     if (mag) {
-      const u32 pos = atomic_add_u32(&cursor[w * prm.B + (mag - 1)], 1u);
-      sorted[pos] = i | (neg << 31);
+      const u32 pos = atomic_add_u32(&cursor[bucket_slot(prm, w, mag)], 1u);
+      sorted[pos] = entry_index(prm, w, i) | (neg << 31);
     }
   }
 }
@@ -360,6 +366,81 @@ KERNEL void g1_sum_kernel(const unsigned char* pts144, u32 count, unsigned char*
     xyzz_add_ni(total, xyzz_from_jacobian(fq_load8(p), fq_load8(p + 48), fq_load8(p + 96)));
   }
   jacobian_store_normalised(out144, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident SRS: one thread per point expands P_i into W packed affine copies 2^(c w) * P_i
+// (window-major: pre[(w * n + i) * 96]).  c doublings per window in XYZZ, then ONE inversion per
+// point normalises all windows (Montgomery's trick).  Runs once per SRS; every later commitment
+// then needs neither per-window buckets nor the 253 final doublings.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 SRS_MAX_WINDOWS = 32;
+
+KERNEL void __launch_bounds__(128) srs_expand_kernel(const unsigned char* bases, u32 stride, u32 n, u32 c, u32 W,
+                                                      unsigned char* pre) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = affine_load(bases, stride, i);
+  affine_store(pre, 96, i, p);
+  G1Xyzz pts[SRS_MAX_WINDOWS - 1];
+  Fq prefix[SRS_MAX_WINDOWS - 1];
+  G1Xyzz cur = xyzz_from_affine(p);
+  Fq run = fp_one<FqParams>();
+  for (u32 w = 1; w < W; w++) {
+    for (u32 k = 0; k < c; k++) cur = xyzz_double(cur);
+    pts[w - 1] = cur;
+    prefix[w - 1] = run;
+    if (!xyzz_is_identity(cur)) run = fq_mul_ni(run, fq_mul_ni(cur.zz, cur.zzz));
+  }
+  Fq inv = fq_inv_ni(run);
+  for (u32 w = W - 1; w >= 1; w--) {
+    const G1Xyzz q = pts[w - 1];
+    G1Affine a;
+    if (xyzz_is_identity(q)) {
+      a.inf = true;
+      a.x = fp_zero<FqParams>();
+      a.y = fp_zero<FqParams>();
+    } else {
+      const Fq zinv = fq_mul_ni(inv, prefix[w - 1]);
+      inv = fq_mul_ni(inv, fq_mul_ni(q.zz, q.zzz));
+      a.inf = false;
+      a.x = fq_mul_ni(q.x, fq_mul_ni(zinv, q.zzz));
+      a.y = fq_mul_ni(q.y, fq_mul_ni(zinv, q.zz));
+    }
+    affine_store(pre, 96, (size_t)w * n + i, a);
+  }
+}
+
+// Montgomery Fr -> canonical BigInteger256 (PrimeField::to_bigint), the first step of KZG10::commit
+KERNEL void fr_to_bigint_kernel(const Fr* in, Fr* out, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fp_from_mont(in[i]);
+}
+
+// normalised Jacobian (144 B, Montgomery) -> 48-byte compressed G1 (snarkVM wire format, pinned by the
+// reference's proof fixture: x little-endian canonical, bit 383 = y is the larger root, bit 382 = infinity)
+KERNEL void g1_compress_kernel(const unsigned char* jac144, unsigned char* out48) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const Fq z = fq_load8(jac144 + 96);
+  Fq x = fp_zero<FqParams>();
+  u32 flags = 0;
+  if (fp_is_zero(z)) {
+    flags = 1u << 30;
+  } else {
+    x = fp_from_mont(fq_load8(jac144));
+    const Fq y = fp_from_mont(fq_load8(jac144 + 48));
+    const Fq ny = fp_neg(y);
+    bool larger = false;  // y > p - y  <=>  y > (p - 1) / 2
+    for (int k = FqParams::N - 1; k >= 0; k--) {
+      if (y.l[k] != ny.l[k]) {
+        larger = y.l[k] > ny.l[k];
+        break;
+      }
+    }
+    if (larger) flags = 1u << 31;
+  }
+  x.l[FqParams::N - 1] |= flags;
+  fq_store8(out48, x);
 }
 
 KERNEL void write_identity_kernel(unsigned char* out144) {

@@ -28,11 +28,29 @@ static inline u32 choose_window(size_t n) {
   return (u32)c;
 }
 
-static inline Params make_params(size_t n) {
+// a resident SRS expanded by srs_expand_kernel: pre[w][i] = 2^(c w) * P_i, packed 96-byte affine
+struct SrsView {
+  const unsigned char* pre;
+  u32 n_total;  // points per window block
+  u32 c, W;
+};
+
+// window bits of a resident SRS of n points: the doubling tail and the per-window buckets are gone, so
+// the optimum moves up (n * W(c) mixed additions against 2 * 2^(c-1) reduction additions)
+static inline u32 choose_window_srs(size_t n) {
+  if (n < 2) return 8;
+  long c = (long)floor_log2(n) - 2;
+  if (c < 8) c = 8;
+  if (c > 22) c = 22;
+  return (u32)c;
+}
+
+static inline Params make_params(size_t n, const SrsView* srs = nullptr) {
   Params p;
-  p.c = choose_window(n);
+  p.c = srs ? srs->c : choose_window(n);
   p.W = SCALAR_BITS / p.c + 1;
   p.B = 1u << (p.c - 1);
+  p.n_stride = srs ? srs->n_total : 0;
   // accumulation threads: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on B200: 4 waves
   // 96.1 ms, 16 waves 93.4 ms at n = 2^24 -- but at least ~32 entries per run
   size_t lanes = ((size_t)n * p.W + 31) / 32;
@@ -80,7 +98,7 @@ struct RedLevel {
 // accumulation kernel, and after the final kernel -- bench.py's per-kernel timing.
 static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32* scalars, size_t n_sz,
                               unsigned char* out144, cudaStream_t s, bool dry, int* launches_out,
-                              cudaEvent_t* phase_ev = nullptr) {
+                              cudaEvent_t* phase_ev = nullptr, const SrsView* srs = nullptr) {
   int launches = 0;
   if (n_sz == 0) {
     if (!dry) LAUNCH_NOSYNC(write_identity_kernel, dim3(1), dim3(1), 0, s, out144);
@@ -89,8 +107,13 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
     return dry ? cudaSuccess : cudaGetLastError();
   }
   const u32 n = (u32)n_sz;
-  const Params prm = make_params(n_sz);
-  const u32 NB = prm.W * prm.B;
+  const Params prm = make_params(n_sz, srs);
+  if (srs) {
+    bases = srs->pre;
+    stride = 96;
+  }
+  const u32 nwin = srs ? 1u : prm.W;  // bucket sets (the resident SRS shares one across all windows)
+  const u32 NB = nwin * prm.B;
   const size_t entries_ub = (size_t)n * prm.W;
   const u32 cap_small = prm.nlanes + 1;                   // every run boundary cuts at most one bucket
   const u32 cap_large = prm.nlanes / SMALL_SPLIT_MAX + 1;
@@ -125,10 +148,10 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
   const size_t o_pieces = cv.take((size_t)prm.nlanes * 2 * sizeof(G1Xyzz));
   std::vector<size_t> o_R(lv.size()), o_P(lv.size());
   for (size_t l = 0; l < lv.size(); l++) {
-    o_R[l] = cv.take((size_t)prm.W * lv[l].T * sizeof(G1Xyzz));
-    o_P[l] = cv.take((size_t)prm.W * lv[l].T * sizeof(G1Xyzz));
+    o_R[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
+    o_P[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
   }
-  const size_t o_D = cv.take((size_t)prm.W * sizeof(G1Xyzz));
+  const size_t o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));
 
   unsigned char* ws = nullptr;
   if (!dry) MSM_CK(cudaMallocAsync((void**)&ws, cv.off, s));
@@ -202,16 +225,17 @@ static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32*
     ra.R_out = WSP(G1Xyzz, o_R[l]);
     ra.P_out = WSP(G1Xyzz, o_P[l]);
     ra.T_out = lv[l].T;
-    ra.nwin = prm.W;
-    const u32 threads = prm.W * lv[l].T;
+    ra.nwin = nwin;
+    const u32 threads = nwin * lv[l].T;
     STEP(LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra));
     launches++;
   }
   const G1Xyzz* S = WSP(G1Xyzz, o_P[lv.size() - 1]);
   G1Xyzz* D = WSP(G1Xyzz, o_D);
-  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((prm.W + 31) / 32), dim3(32), 0, s, S, lv.back().T, prm.W, prm.c, D));
+  // per-window weights 2^(c w): not needed for a resident SRS (they are baked into the expanded bases)
+  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((nwin + 31) / 32), dim3(32), 0, s, S, lv.back().T, nwin, prm.c, D));
   launches++;
-  STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, prm.W, out144));
+  STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, nwin, out144));
   launches++;
   if (phase_ev && !dry) cudaEventRecord(phase_ev[3], s);
   if (ws) cudaFreeAsync(ws, s);

@@ -1,0 +1,98 @@
+"""Resident SRS and the KZG10 commitment path.
+
+snarkVM's ``KZG10::commit(powers, polynomial, hiding_bound, rng)`` (snarkvm-algorithms 0.14.5
+src/polycommit/kzg10/mod.rs) is ``VariableBase::msm(&powers.powers_of_beta_g[..d + 1], coeffs.to_bigint())``
+with the SAME bases for every commitment.  ``ResidentSRS`` keeps those bases on the GPU, expanded once
+(``aleo_b200_srs_create``); ``KZG10.commit`` mirrors the non-hiding commitment and returns the 48-byte
+compressed G1 the proof serialises.  (The hiding term is a second, small MSM over
+``powers_of_beta_times_gamma_g`` with a random polynomial -- a second ResidentSRS and a point addition on the
+caller's side; the randomness belongs to snarkVM's prover and is out of this path.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from .msm import _host_ptr, PROJECTIVE_BYTES, AFFINE_STRIDE_RUST
+
+
+class ResidentSRS:
+    def __init__(self, handle, lib):
+        self._h = handle
+        self._lib = lib
+
+    @classmethod
+    def from_host(cls, bases, affine_stride: int = AFFINE_STRIDE_RUST):
+        lib = _lib.get_lib()
+        ptr, nbytes, _keep = _host_ptr(bases)
+        h = C.c_void_p()
+        lib.check(lib.srs_create(C.byref(h), ptr, nbytes // affine_stride, affine_stride), "aleo_b200_srs_create")
+        return cls(h, lib)
+
+    @classmethod
+    def from_device(cls, bases_t, n: int, affine_stride: int = AFFINE_STRIDE_RUST):
+        import torch
+
+        lib = _lib.get_lib()
+        h = C.c_void_p()
+        with torch.cuda.device(bases_t.device):
+            lib.check(lib.srs_create_dev(C.byref(h), bases_t.data_ptr(), n, affine_stride, torch.cuda.current_stream().cuda_stream),
+                      "aleo_b200_srs_create_dev")
+        return cls(h, lib)
+
+    def info(self) -> dict:
+        n, c, w, b = C.c_size_t(), C.c_int(), C.c_int(), C.c_size_t()
+        self._lib.check(self._lib.srs_info(self._h, C.byref(n), C.byref(c), C.byref(w), C.byref(b)), "aleo_b200_srs_info")
+        return {"n": n.value, "window_bits": c.value, "windows": w.value, "device_bytes": b.value}
+
+    def msm(self, scalars) -> bytes:
+        """sum_i s_i P_i over the first len(scalars) bases; canonical 32-byte scalars on the host"""
+        sp, sbytes, _keep = _host_ptr(scalars)
+        out = C.create_string_buffer(PROJECTIVE_BYTES)
+        self._lib.check(self._lib.srs_msm(self._h, C.cast(out, C.c_void_p), sp, sbytes // 32), "aleo_b200_srs_msm")
+        return out.raw
+
+    def msm_dev(self, scalars_t, n_used: int, out=None):
+        import torch
+
+        if out is None:
+            out = torch.empty(PROJECTIVE_BYTES, dtype=torch.uint8, device=scalars_t.device)
+        with torch.cuda.device(scalars_t.device):
+            self._lib.check(self._lib.srs_msm_dev(self._h, out.data_ptr(), scalars_t.data_ptr(), n_used,
+                                                  torch.cuda.current_stream().cuda_stream), "aleo_b200_srs_msm_dev")
+        return out
+
+    def launches(self, n_used: int) -> int:
+        return self._lib.srs_msm_launches(self._h, n_used)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.srs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class KZG10:
+    @staticmethod
+    def commit(srs: ResidentSRS, coeffs_montgomery) -> bytes:
+        """non-hiding KZG10::commit: Montgomery-form Fr coefficients (host) -> 48-byte compressed G1"""
+        cp, cbytes, _keep = _host_ptr(coeffs_montgomery)
+        out = C.create_string_buffer(48)
+        srs._lib.check(srs._lib.kzg_commit(srs._h, C.cast(out, C.c_void_p), cp, cbytes // 32), "aleo_b200_kzg_commit")
+        return out.raw
+
+    @staticmethod
+    def commit_dev(srs: ResidentSRS, coeffs_t, n_coeffs: int, out=None):
+        import torch
+
+        if out is None:
+            out = torch.empty(48, dtype=torch.uint8, device=coeffs_t.device)
+        with torch.cuda.device(coeffs_t.device):
+            srs._lib.check(srs._lib.kzg_commit_dev(srs._h, out.data_ptr(), coeffs_t.data_ptr(), n_coeffs,
+                                                   torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_dev")
+        return out

@@ -248,6 +248,57 @@ def run_ours(args):
                                "has no integer-pipe figure); 32-bit MAC = one IMAD.WIDE",
                 "note": "MSM is integer-pipe bound (SURVEY.md 8d); the schema's hbm/tensor bounds do not apply to this kernel"}
 
+    # ---- resident SRS (KZG10::commit shape): bases expanded once, one shared bucket set ----------------
+    srs_obj = None
+    if not args.no_srs:
+        t_exp = time.perf_counter()
+        srs = ab.ResidentSRS.from_device(bases, n, 104)
+        torch.cuda.synchronize()
+        t_exp = time.perf_counter() - t_exp
+        sinfo = srs.info()
+        srs_ok = srs.msm_dev(scalars, n).cpu().numpy().tobytes() == o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, k_local))
+        for _ in range(args.warmup):
+            srs.msm_dev(scalars, n, out=partial)
+        barrier()
+        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0e.record()
+        for _ in range(args.steps):
+            srs.msm_dev(scalars, n, out=partial)
+        s1e.record()
+        barrier()
+        sms = torch.tensor([s0e.elapsed_time(s1e)], device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sstep = sms.item() / args.steps
+        sph = (C.c_float * 3)()
+        lib.check(lib.srs_msm_dev_profile(srs._h, partial.data_ptr(), scalars.data_ptr(), n, stream(), sph), "srs profile")
+        hs_pin = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+        hs_pin.copy_(scalars)
+        torch.cuda.synchronize()
+        srs.msm(hs_pin)
+        barrier()
+        t0s = time.perf_counter()
+        for _ in range(args.steps):
+            srs.msm(hs_pin)                      # H2D of the scalars + MSM + D2H, bases stay resident
+        barrier()
+        e2e_srs = torch.tensor([time.perf_counter() - t0s], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_srs, op=dist.ReduceOp.MAX)
+        wins = sinfo["windows"]
+        srs_obj = {"what": "same MSM over a resident SRS handle (aleo_b200_srs_*): bases expanded once to 2^(cw)P_i, shared buckets; "
+                           "this is KZG10::commit's shape (fixed powers_of_beta_g)", "value": world * n / sstep / 1e3, "unit": "Mpts/s",
+                   "ms_per_step": sstep, "window_bits": sinfo["window_bits"], "windows": wins, "device_bytes": sinfo["device_bytes"],
+                   "expand_seconds_once": t_exp, "checked_against_oracle": bool(srs_ok),
+                   "phases_ms": {"recode_sort_plan": sph[0], "accumulate": sph[1], "combine_reduce_final": sph[2]},
+                   "accumulate_int_frac": n * wins * MACS_PER_MIXED_ADD / sph[1] / 1e6 / peak_gmac,
+                   "e2e_scalars_only": {"value": world * n * args.steps / e2e_srs.item() / 1e6, "unit": "Mpts/s",
+                                        "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * 144,
+                                        "api": "aleo_b200_srs_msm (host scalars, pinned)"},
+                   "gpu_launches_per_step": srs.launches(n)}
+        srs.close()
+        del srs, hs_pin
+        torch.cuda.empty_cache()
+
     # ---- e2e through the host-pointer C-ABI call, pinned host buffers ------------------------------
     hb = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
     hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
@@ -380,7 +431,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
                     "api": "aleo_b200_msm_g1 (host pointers, pinned)"},
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
-            "roofline": roofline, "ntt": ntt, "ntt_distributed": ntt_dist, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -396,6 +447,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cpu-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-srs", action="store_true", help="skip the resident-SRS (KZG commit) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

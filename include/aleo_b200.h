@@ -94,6 +94,30 @@ int aleo_b200_msm_g1_dev_profile(void* out_projective_dev, const void* bases_dev
 /* Sum of `count` Jacobian points (144 B each, device) -> one normalised Jacobian point (device).
  * This is the single final combine of the point-range-sharded multi-GPU MSM. */
 int aleo_b200_g1_sum_dev(void* out_projective_dev, const void* points_dev, size_t count, void* stream);
+/* ---- resident SRS / KZG10::commit ---------------------------------------------------------------
+ * snarkVM commits every polynomial against the SAME bases (`powers_of_beta_g`, or its Lagrange form):
+ * KZG10::commit(powers, polynomial, ..) = VariableBase::msm(&powers.powers_of_beta_g[..d+1], coeffs.to_bigint())
+ * (snarkvm-algorithms 0.14.5 src/polycommit/kzg10/mod.rs).  An SRS
+ * handle keeps the bases on the device, expanded once to 2^(c w) * P_i for every window w, so that a
+ * commitment needs one shared bucket set, ~25 % fewer additions (larger windows) and no doubling tail.
+ * Device memory: n * (253 / c + 1) * 96 bytes (c = clamp(log2 n - 2, 8, 22)).  A handle belongs to the
+ * device that was current when it was created; MSMs over any PREFIX of the bases are supported. */
+int aleo_b200_srs_create(void** handle_out, const void* bases_host, size_t n, size_t affine_stride);
+int aleo_b200_srs_create_dev(void** handle_out, const void* bases_dev, size_t n, size_t affine_stride, void* stream);
+int aleo_b200_srs_destroy(void* handle);
+int aleo_b200_srs_info(const void* handle, size_t* n_out, int* window_bits_out, int* windows_out, size_t* bytes_out);
+/* sum_i scalars[i] * P_i over the first n_used bases; scalars canonical 32-byte LE */
+int aleo_b200_srs_msm(const void* handle, void* out_projective_host, const void* scalars_host, size_t n_used);
+int aleo_b200_srs_msm_dev(const void* handle, void* out_projective_dev, const void* scalars_dev, size_t n_used, void* stream);
+int aleo_b200_srs_msm_dev_profile(const void* handle, void* out_projective_dev, const void* scalars_dev, size_t n_used,
+                                  void* stream, float* phase_ms3);
+int aleo_b200_srs_msm_launches(const void* handle, size_t n_used);
+/* KZG10::commit without hiding: coefficients are Fr in MONTGOMERY form (the polynomial as snarkVM holds
+ * it); converts them to canonical integers on the device (to_bigint), runs the MSM and returns the
+ * commitment as the 48-byte compressed G1 wire format (x LE | bit 383: larger y | bit 382: infinity). */
+int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs);
+int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
+                             void* stream);
 /* window size c (bits) the MSM uses for n points, and the kernel launches one MSM issues */
 int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);

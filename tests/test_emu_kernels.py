@@ -110,3 +110,35 @@ def test_emu_generators_and_checks(emu_lib):
     emu_lib.check(emu_lib.dlog_dot_dev(C.cast(out, C.c_void_p), C.cast(sb, C.c_void_p), n, o.int_to_le_bytes(s0, 32),
                                        o.int_to_le_bytes(d, 32), 5, None), "dot")
     assert o.le_bytes_to_int(out.raw) == sum(sc[i] * (s0 + (5 + i) * d) for i in range(n)) % o.R_MOD
+
+
+def test_emu_resident_srs_and_kzg_commit(emu_lib):
+    """resident-SRS mode (bases expanded to 2^(cw) P_i, one shared bucket set) and the KZG commit path"""
+    n = 700
+    B = o.synthetic_bases(n, 61)
+    B[5] = None
+    for stride in (104, 96):
+        bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, stride), n * stride)
+        h = C.c_void_p()
+        emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, stride, None), "srs_create")
+        nn, c, w, by = C.c_size_t(), C.c_int(), C.c_int(), C.c_size_t()
+        emu_lib.check(emu_lib.srs_info(h, C.byref(nn), C.byref(c), C.byref(w), C.byref(by)), "info")
+        assert nn.value == n and c.value == 8 and w.value == 32 and by.value == n * 32 * 96
+        for n_used, seed in ((n, 1), (n // 3, 2), (1, 3), (0, 4)):       # any prefix of the SRS
+            s = o.random_fr_vec(n_used, 70 + seed)
+            if n_used > 10:
+                s[3], s[4], s[7] = 0, 1, o.R_MOD - 1
+            sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), max(1, n_used * 32))
+            out = C.create_string_buffer(144)
+            emu_lib.check(emu_lib.srs_msm_dev(h, C.cast(out, C.c_void_p), C.cast(sb, C.c_void_p), n_used, None), "srs_msm")
+            want = o.msm_pippenger(B[:n_used], s) if n_used else None
+            assert out.raw == o.g1_projective_to_bytes(want), (stride, n_used)
+        # KZG10::commit: Montgomery coefficients in, compressed G1 out
+        coeffs = o.random_fr_vec(200, 99)
+        cb = C.create_string_buffer(o.fr_vec_to_bytes(coeffs, mont=True), 200 * 32)
+        out48 = C.create_string_buffer(48)
+        emu_lib.check(emu_lib.kzg_commit_dev(h, C.cast(out48, C.c_void_p), C.cast(cb, C.c_void_p), 200, None), "commit")
+        assert out48.raw == o.g1_compress(o.msm_pippenger(B[:200], coeffs))
+        emu_lib.check(emu_lib.kzg_commit_dev(h, C.cast(out48, C.c_void_p), C.cast(cb, C.c_void_p), 0, None), "commit0")
+        assert out48.raw == o.g1_compress(None)
+        emu_lib.check(emu_lib.srs_destroy(h), "destroy")

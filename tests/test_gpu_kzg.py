@@ -1,0 +1,57 @@
+"""Resident SRS + KZG10::commit path on the GPU against the oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+import aleo_b200 as ab
+from oracle import bls12_377 as o
+
+pytestmark = pytest.mark.gpu
+
+
+def test_srs_from_host_prefix_msm_and_commit():
+    n = 3000
+    B = o.synthetic_bases(n, 61)
+    B[5] = None
+    for stride in (104, 96):
+        srs = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(B, stride), stride)
+        info = srs.info()
+        assert info["n"] == n and info["windows"] == 253 // info["window_bits"] + 1
+        for n_used, seed in ((n, 1), (n // 3, 2), (1, 3), (0, 4)):
+            s = o.random_fr_vec(n_used, 70 + seed)
+            if n_used > 10:
+                s[3], s[4], s[7] = 0, 1, o.R_MOD - 1
+            want = o.msm_pippenger(B[:n_used], s) if n_used else None
+            assert srs.msm(o.fr_vec_to_bytes(s, mont=False)) == o.g1_projective_to_bytes(want)
+        coeffs = o.random_fr_vec(500, 99)
+        got = ab.KZG10.commit(srs, o.fr_vec_to_bytes(coeffs, mont=True))
+        want = o.msm_pippenger(B[:500], coeffs)
+        assert got == o.g1_compress(want)
+        assert o.g1_decompress(got) == want                       # wire format round trip (fixture-pinned codec)
+        srs.close()
+
+
+@pytest.mark.parametrize("log_n", [16, 20, 22])
+def test_srs_matches_plain_msm_and_known_dlogs(log_n):
+    n = 1 << log_n
+    s0, d = o.base_dlogs(n, 8100 + log_n)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    srs = ab.ResidentSRS.from_device(bases, n, 104)
+    for n_used, dist in ((n, "uniform"), (n - 12345 % n, "witness"), (n // 2 + 1, "uniform")):
+        import torch
+        sc = ab.gen_scalars_dev(n_used, 4000 + log_n)
+        if dist == "witness":
+            idx = torch.arange(n_used, device="cuda")
+            sc[idx % 2 == 0] = 0
+            sc[idx % 4 == 1] = torch.tensor([1, 0, 0, 0], dtype=torch.int64, device="cuda")
+        got = srs.msm_dev(sc, n_used).cpu().numpy().tobytes()
+        k = ab.dlog_dot_dev(sc, n_used, s0, d)
+        assert got == o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, k))
+        assert got == ab.VariableBase.msm_dev(bases, sc, n_used, 104).cpu().numpy().tobytes()
+    # commit on device: Montgomery coefficients
+    m = 1 << (log_n - 1)
+    cm = ab.gen_scalars_dev(m, 77, 0, True)
+    cc = ab.gen_scalars_dev(m, 77, 0, False)          # same values, canonical
+    got48 = ab.KZG10.commit_dev(srs, cm, m).cpu().numpy().tobytes()
+    want = o.g1_mul(o.G1_GEN, ab.dlog_dot_dev(cc, m, s0, d))
+    assert got48 == o.g1_compress(want)
+    srs.close()
