@@ -240,22 +240,7 @@ int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n
   cudaStream_t s;
   rc = thread_stream(dev, &s);
   if (rc) return rc;
-  unsigned char* d = nullptr;
-  const size_t bb = n * affine_stride, sb = n * 32;
-  const size_t o_s = (bb + 255) & ~(size_t)255, o_out = o_s + ((sb + 255) & ~(size_t)255);
-  API_CK(cudaMallocAsync((void**)&d, o_out + 256, s));
-  cudaError_t e = cudaSuccess;
-  if (n) e = cudaMemcpyAsync(d, bases_host, bb, cudaMemcpyHostToDevice, s);
-  if (n && e == cudaSuccess) e = cudaMemcpyAsync(d + o_s, scalars_host, sb, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) {
-    rc = aleo_b200_msm_g1_dev(d + o_out, d, n, d + o_s, affine_stride, (void*)s);
-    if (rc == ALEO_B200_OK) e = cudaMemcpyAsync(out_projective_host, d + o_out, 144, cudaMemcpyDeviceToHost, s);
-  }
-  cudaFreeAsync(d, s);
-  cudaError_t e2 = cudaStreamSynchronize(s);
-  if (rc) return rc;
-  if (e != cudaSuccess) return fail_cuda(e);
-  if (e2 != cudaSuccess) return fail_cuda(e2);
+  API_CK(aleo::msm_run_host(bases_host, (u32)affine_stride, scalars_host, n, out_projective_host, s));
   return ALEO_B200_OK;
 }
 
@@ -409,23 +394,7 @@ static int srs_host_call(const void* handle, void* out_host, size_t out_bytes, c
   cudaStream_t s;
   rc = thread_stream(dev, &s);
   if (rc) return rc;
-  unsigned char* d = nullptr;
-  const size_t sb = (n * 32 + 255) & ~(size_t)255;
-  API_CK(cudaMallocAsync((void**)&d, sb + 512, s));
-  cudaError_t e = cudaSuccess;
-  if (n) e = cudaMemcpyAsync(d, in_host, n * 32, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess && montgomery_in) e = aleo::fr_to_bigint(d, d, n, s);
-  if (e == cudaSuccess) e = aleo::srs_msm(handle, d, n, d + sb, s, false, nullptr, nullptr);
-  if (e == cudaSuccess && out_bytes == 48) {
-    e = aleo::g1_compress(d + sb, d + sb + 256, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d + sb + 256, 48, cudaMemcpyDeviceToHost, s);
-  } else if (e == cudaSuccess) {
-    e = cudaMemcpyAsync(out_host, d + sb, 144, cudaMemcpyDeviceToHost, s);
-  }
-  cudaFreeAsync(d, s);
-  cudaError_t e2 = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return fail_cuda(e);
-  if (e2 != cudaSuccess) return fail_cuda(e2);
+  API_CK(aleo::srs_msm_host(handle, in_host, n, montgomery_in, out_host, out_bytes, s));
   return ALEO_B200_OK;
 }
 

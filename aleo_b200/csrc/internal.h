@@ -18,6 +18,12 @@ void ntt_clear_plans();
 cudaError_t msm_upload_constants();
 cudaError_t msm_run(const void* bases_dev, u32 stride, const void* scalars_dev, size_t n, void* out144_dev, cudaStream_t s,
                     bool dry, int* launches_out, float* phase_ms = nullptr /* 3 floats; synchronises when given */);
+// host-pointer MSM: copies and accumulates point range by point range (overlapped); synchronises s
+cudaError_t msm_run_host(const void* bases_host, u32 stride, const void* scalars_host, size_t n, void* out144_host, cudaStream_t s);
+int msm_host_chunks(size_t n);
+int msm_host_window_bits(size_t n);
+cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool montgomery_in, void* out_host, size_t out_bytes,
+                         cudaStream_t s);
 bool msm_size_supported(size_t n);
 int msm_window_bits(size_t n);
 cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);

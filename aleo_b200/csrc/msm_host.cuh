@@ -18,14 +18,30 @@ static inline u32 floor_log2(size_t n) {
   return l;
 }
 
-// window bits: about n / 2^(c-1) >= 32 entries per bucket, capped so that the bucket reduction
-// (2 * 2^(c-1) full additions per window) stays a small fraction of the n mixed additions per window
-static inline u32 choose_window(size_t n) {
+// windows of c bits: W(c) = 253 / c + 1 (the +1 absorbs the signed-recoding carry)
+static inline u32 windows_for(u32 c) { return SCALAR_BITS / c + 1; }
+
+// Window bits by cost model, in Fq products: n * W(c) mixed additions (10 each) of bucket accumulation
+// against W(c) * 2^(c-1) buckets * 2 full additions (14 each, x1.5: the reduction runs at lower
+// occupancy).  2^16 -> 12, 2^20 -> 16, 2^24 -> 20, 2^26 -> 20.  ALEO_B200_MSM_C overrides (sweeps).
+static inline u32 choose_window(size_t n, u32 chunks = 1) {
+  const char* env = getenv("ALEO_B200_MSM_C");  // read per call: sweeps switch it
+  const long c_env = env ? atol(env) : 0L;
+  if (c_env >= 4 && c_env <= 22) return (u32)c_env;
   if (n < 2) return 4;
-  long c = (long)floor_log2(n) - 4;
-  if (c < 4) c = 4;
-  if (c > 16) c = 16;
-  return (u32)c;
+  u32 best_c = 4;
+  double best = 0;
+  for (u32 c = 4; c <= 22; c++) {
+    const double W = (double)windows_for(c);
+    // an MSM that arrives in `chunks` point ranges re-opens every bucket once per extra range: one more
+    // mixed addition per bucket and range (the first addition into an empty bucket is a copy)
+    const double cost = (double)n * W * 10.0 + W * (double)(1u << (c - 1)) * (2.0 * 14.0 * 1.5 + 10.0 * (chunks - 1));
+    if (c == 4 || cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
 }
 
 // a resident SRS expanded by srs_expand_kernel: pre[w][i] = 2^(c w) * P_i, packed 96-byte affine
@@ -45,20 +61,26 @@ static inline u32 choose_window_srs(size_t n) {
   return (u32)c;
 }
 
-static inline Params make_params(size_t n, const SrsView* srs = nullptr) {
-  Params p;
-  p.c = srs ? srs->c : choose_window(n);
-  p.W = SCALAR_BITS / p.c + 1;
-  p.B = 1u << (p.c - 1);
-  p.n_stride = srs ? srs->n_total : 0;
-  // accumulation threads: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on B200: 4 waves
-  // 96.1 ms, 16 waves 93.4 ms at n = 2^24 -- but at least ~32 entries per run
-  size_t lanes = ((size_t)n * p.W + 31) / 32;
+// accumulation threads for `n_chunk` points: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on
+// B200: 4 waves 96.1 ms, 16 waves 93.4 ms at n = 2^24 -- but at least ~32 entries per run
+static inline u32 lanes_for(size_t n_chunk, u32 W) {
+  size_t lanes = ((size_t)n_chunk * W + 31) / 32;
   static const long waves_env = []() { const char* e = getenv("ALEO_B200_MSM_WAVES"); return e ? atol(e) : 0L; }();
   const size_t full = (size_t)148 * 384 * (waves_env > 0 ? (size_t)waves_env : 16);
   if (lanes > full) lanes = full;
-  lanes = (lanes + 127) / 128 * 128;
-  p.nlanes = (u32)lanes;
+  if (lanes < 128) lanes = 128;
+  return (u32)((lanes + 127) / 128 * 128);
+}
+
+// n: points of the whole MSM (decides the window); chunks: how many point ranges it arrives in
+static inline Params make_params(size_t n, const SrsView* srs = nullptr, u32 chunks = 1) {
+  Params p;
+  p.c = srs ? srs->c : choose_window(n, chunks);
+  p.W = windows_for(p.c);
+  p.B = 1u << (p.c - 1);
+  p.n_stride = srs ? srs->n_total : 0;
+  p.first = 0;
+  p.nlanes = lanes_for(n, p.W);
   return p;
 }
 
@@ -92,157 +114,204 @@ struct RedLevel {
   u32 m, T;  // input length per window, chunks per window
 };
 
-// Runs (or, with dry = true, only counts the launches of) one MSM.  bases / scalars / out144 are
-// device pointers; everything is asynchronous on `s` except the workspace allocation call itself.
+// One MSM = begin() + add_chunk() per point range + finish().  The bucket set lives in the session's
+// workspace across chunks: a chunk is sorted on its own and its bucket sums are ADDED to what the earlier
+// chunks left, so that the host-pointer entry points can overlap the host->device copy of chunk k + 1
+// with the accumulation of chunk k (capi.cu).  Device-resident callers use a single chunk.
+// With dry = true nothing is allocated or launched; only the launch count is kept.
+struct Session {
+  Params prm;
+  const SrsView* srs = nullptr;
+  u32 nwin = 0, NB = 0, max_lanes = 0, cap_small = 0, cap_large = 0, scan_blocks = 0;
+  size_t max_chunk = 0;
+  std::vector<RedLevel> lv;
+  size_t o_counts = 0, o_starts = 0, o_ends = 0, o_piece_bucket = 0, o_bsums = 0, o_meta = 0, o_sorted = 0, o_small = 0,
+         o_large = 0, o_buckets = 0, o_pieces = 0, o_D = 0, bytes = 0;
+  std::vector<size_t> o_R, o_P;
+  unsigned char* ws = nullptr;
+  bool dry = false;
+  int launches = 0;
+  u32 chunks_done = 0;
+
+  template <class T>
+  T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+
+  // n_total: points of the whole MSM; max_chunk: largest point range add_chunk() will see; chunks: how many
+  cudaError_t begin(size_t n_total, size_t max_chunk_, u32 chunks, const SrsView* srs_, cudaStream_t s, bool dry_) {
+    srs = srs_;
+    dry = dry_;
+    max_chunk = max_chunk_;
+    prm = make_params(n_total, srs, chunks);
+    nwin = srs ? 1u : prm.W;  // bucket sets (the resident SRS shares one across all windows)
+    NB = nwin * prm.B;
+    max_lanes = lanes_for(max_chunk, prm.W);
+    cap_small = max_lanes + 1;  // every run boundary cuts at most one bucket
+    cap_large = max_lanes / SMALL_SPLIT_MAX + 1;
+    scan_blocks = (NB + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    {
+      // level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out;
+      // the plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too
+      u32 m = prm.B, t_prev = 0;
+      for (;;) {
+        RedLevel l;
+        l.m = m;
+        const u32 need = t_prev > m ? t_prev : m;
+        l.T = (need + RED_KC - 1) / RED_KC;
+        if (l.T == 0) l.T = 1;
+        lv.push_back(l);
+        if (l.T == 1) break;
+        t_prev = l.T;
+        m = l.T - 1;
+      }
+    }
+    Carver cv;
+    o_counts = cv.take((size_t)NB * 4);
+    o_starts = cv.take((size_t)NB * 4);
+    o_ends = cv.take((size_t)NB * 4);
+    o_piece_bucket = cv.take((size_t)max_lanes * 2 * 4);
+    o_bsums = cv.take((size_t)(scan_blocks + 1) * 4);
+    o_meta = cv.take(64);
+    o_sorted = cv.take((size_t)max_chunk * prm.W * 4);
+    o_small = cv.take((size_t)cap_small * 4);
+    o_large = cv.take((size_t)cap_large * 4);
+    o_buckets = cv.take((size_t)NB * sizeof(G1Xyzz));
+    o_pieces = cv.take((size_t)max_lanes * 2 * sizeof(G1Xyzz));
+    o_R.resize(lv.size());
+    o_P.resize(lv.size());
+    for (size_t l = 0; l < lv.size(); l++) {
+      o_R[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
+      o_P[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
+    }
+    o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));
+    bytes = cv.off;
+    if (dry) return cudaSuccess;
+    MSM_CK(cudaMallocAsync((void**)&ws, bytes, s));
+    MSM_CK(cudaMemsetAsync(at<G1Xyzz>(o_buckets), 0, (size_t)NB * sizeof(G1Xyzz), s));
+    return cudaSuccess;
+  }
+
+  // Sorts one point range by (window, bucket) and adds its bucket sums into the session's buckets.
+  // bases: the range's own base array (entry indices are range-local), or ignored for a resident SRS,
+  // where `first` is the range's offset into the SRS.  phase_ev (optional, 3 events): before the sort,
+  // before and after the accumulation kernel.
+  cudaError_t add_chunk(const unsigned char* bases, u32 stride, const u32* scalars, size_t n_chunk, size_t first,
+                        cudaStream_t s, cudaEvent_t* phase_ev = nullptr) {
+    if (n_chunk == 0) return cudaSuccess;
+    if (n_chunk > max_chunk) return cudaErrorInvalidValue;
+    const u32 n = (u32)n_chunk;
+    Params p = prm;
+    p.first = (u32)first;
+    p.nlanes = lanes_for(n_chunk, p.W);
+    if (srs) {
+      bases = srs->pre;
+      stride = 96;
+    }
+    const u32 into = chunks_done > 0 ? 1u : 0u;  // later chunks start every bucket from its stored sum
+    chunks_done++;
+    launches += 9;
+    if (dry) return cudaSuccess;
+    u32* counts = at<u32>(o_counts);
+    u32* starts = at<u32>(o_starts);
+    u32* ends = at<u32>(o_ends);
+    u32* piece_bucket = at<u32>(o_piece_bucket);
+    u32* meta = at<u32>(o_meta);
+    u32* sorted = at<u32>(o_sorted);
+    u32* small_list = at<u32>(o_small);
+    u32* large_list = at<u32>(o_large);
+    G1Xyzz* buckets = at<G1Xyzz>(o_buckets);
+    G1Xyzz* pieces = at<G1Xyzz>(o_pieces);
+    const u32 NB = this->NB, cap_small = this->cap_small, cap_large = this->cap_large;  // plain values for the launch macros
+    if (phase_ev) cudaEventRecord(phase_ev[0], s);
+    MSM_CK(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
+    MSM_CK(cudaMemsetAsync(meta, 0, 64, s));
+    const u32 g_n = (n + 255) / 256;
+    LAUNCH_NOSYNC(count_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, counts);
+    int scan_launches = 0;
+    MSM_CK(exclusive_scan(counts, NB, at<u32>(o_bsums), starts, ends, meta + 0, s, scan_launches));
+    LAUNCH_NOSYNC(scatter_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB, p.nlanes,
+                  small_list, large_list, cap_small, cap_large, meta);
+    if (phase_ev) cudaEventRecord(phase_ev[1], s);
+    static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
+    if (acc_inline)
+      LAUNCH_NOSYNC(accumulate_kernel<false>, dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
+    else
+      LAUNCH_NOSYNC(accumulate_kernel<true>, dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
+    if (phase_ev) cudaEventRecord(phase_ev[2], s);
+    LAUNCH_NOSYNC(combine_small_kernel, dim3((p.nlanes + 1 + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
+                  (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
+                  (const u32*)piece_bucket, buckets);
+    {
+      const u32 cl = p.nlanes / SMALL_SPLIT_MAX + 1;
+      const u32 g = cl < 592 ? cl : 592;  // 4 CTAs per SM; the kernel strides over the list
+      LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), COMBINE_TPB * sizeof(G1Xyzz), s, (const u32*)large_list,
+             (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces, (const u32*)piece_bucket,
+             buckets);
+    }
+    return cudaGetLastError();
+  }
+
+  // bucket reduction + window combination + normalisation -> 144-byte Jacobian; frees the workspace
+  cudaError_t finish(unsigned char* out144, cudaStream_t s, cudaEvent_t* done_ev = nullptr) {
+    launches += (int)lv.size() + 2;
+    if (dry) return cudaSuccess;
+    G1Xyzz* buckets = at<G1Xyzz>(o_buckets);
+    // bucket reduction: one launch per level until a single chunk per window is left
+    for (size_t l = 0; l < lv.size(); l++) {
+      ReduceArgs ra;
+      ra.X = (l == 0) ? buckets : at<G1Xyzz>(o_R[l - 1]);
+      ra.x_stride = (l == 0) ? prm.B : lv[l - 1].T;
+      ra.x_off = (l == 0) ? 0 : 1;
+      ra.m = lv[l].m;
+      ra.P = (l == 0) ? nullptr : at<G1Xyzz>(o_P[l - 1]);
+      ra.T_in = (l == 0) ? 0 : lv[l - 1].T;
+      ra.level = (u32)l;
+      ra.R_out = at<G1Xyzz>(o_R[l]);
+      ra.P_out = at<G1Xyzz>(o_P[l]);
+      ra.T_out = lv[l].T;
+      ra.nwin = nwin;
+      const u32 threads = nwin * lv[l].T;
+      LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra);
+    }
+    const G1Xyzz* S = at<G1Xyzz>(o_P[lv.size() - 1]);
+    G1Xyzz* D = at<G1Xyzz>(o_D);
+    const u32 nwin = this->nwin, c = prm.c, s_stride = lv.back().T;
+    // per-window weights 2^(c w): not needed for a resident SRS (they are baked into the expanded bases)
+    LAUNCH_NOSYNC(window_weigh_kernel, dim3((nwin + 31) / 32), dim3(32), 0, s, S, s_stride, nwin, c, D);
+    LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, nwin, out144);
+    if (done_ev) cudaEventRecord(*done_ev, s);
+    cudaError_t e = cudaGetLastError();
+    release(s);
+    return e;
+  }
+
+  void release(cudaStream_t s) {
+    if (ws) cudaFreeAsync(ws, s);
+    ws = nullptr;
+  }
+};
+
+// Runs (or, with dry = true, only counts the launches of) one MSM over device-resident operands.
+// Everything is asynchronous on `s` except the workspace allocation call itself.
 // phase_ev (optional, 4 events): recorded before the sort phase, before / after the bucket
 // accumulation kernel, and after the final kernel -- bench.py's per-kernel timing.
 static inline cudaError_t run(const unsigned char* bases, u32 stride, const u32* scalars, size_t n_sz,
                               unsigned char* out144, cudaStream_t s, bool dry, int* launches_out,
                               cudaEvent_t* phase_ev = nullptr, const SrsView* srs = nullptr) {
-  int launches = 0;
   if (n_sz == 0) {
     if (!dry) LAUNCH_NOSYNC(write_identity_kernel, dim3(1), dim3(1), 0, s, out144);
-    launches = 1;
-    if (launches_out) *launches_out = launches;
+    if (launches_out) *launches_out = 1;
     return dry ? cudaSuccess : cudaGetLastError();
   }
-  const u32 n = (u32)n_sz;
-  const Params prm = make_params(n_sz, srs);
-  if (srs) {
-    bases = srs->pre;
-    stride = 96;
-  }
-  const u32 nwin = srs ? 1u : prm.W;  // bucket sets (the resident SRS shares one across all windows)
-  const u32 NB = nwin * prm.B;
-  const size_t entries_ub = (size_t)n * prm.W;
-  const u32 cap_small = prm.nlanes + 1;                   // every run boundary cuts at most one bucket
-  const u32 cap_large = prm.nlanes / SMALL_SPLIT_MAX + 1;
-  const u32 scan_blocks = (NB + SCAN_BLOCK - 1) / SCAN_BLOCK;
-
-  // reduction level structure
-  std::vector<RedLevel> lv;
-  {
-    // level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out;
-    // the plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too
-    u32 m = prm.B, t_prev = 0;
-    for (;;) {
-      RedLevel l;
-      l.m = m;
-      const u32 need = t_prev > m ? t_prev : m;
-      l.T = (need + RED_KC - 1) / RED_KC;
-      if (l.T == 0) l.T = 1;
-      lv.push_back(l);
-      if (l.T == 1) break;
-      t_prev = l.T;
-      m = l.T - 1;
-    }
-  }
-
-  Carver cv;
-  const size_t o_counts = cv.take((size_t)NB * 4), o_starts = cv.take((size_t)NB * 4), o_ends = cv.take((size_t)NB * 4);
-  const size_t o_piece_bucket = cv.take((size_t)prm.nlanes * 2 * 4);
-  const size_t o_bsums = cv.take((size_t)(scan_blocks + 1) * 4), o_meta = cv.take(64);
-  const size_t o_sorted = cv.take(entries_ub * 4);
-  const size_t o_small = cv.take((size_t)cap_small * 4), o_large = cv.take((size_t)cap_large * 4);
-  const size_t o_buckets = cv.take((size_t)NB * sizeof(G1Xyzz));
-  const size_t o_pieces = cv.take((size_t)prm.nlanes * 2 * sizeof(G1Xyzz));
-  std::vector<size_t> o_R(lv.size()), o_P(lv.size());
-  for (size_t l = 0; l < lv.size(); l++) {
-    o_R[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
-    o_P[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
-  }
-  const size_t o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));
-
-  unsigned char* ws = nullptr;
-  if (!dry) MSM_CK(cudaMallocAsync((void**)&ws, cv.off, s));
-#define WSP(type, off) reinterpret_cast<type*>(ws + (off))
-  u32* counts = WSP(u32, o_counts);
-  u32* starts = WSP(u32, o_starts);
-  u32* ends = WSP(u32, o_ends);
-  u32* piece_bucket = WSP(u32, o_piece_bucket);
-  u32* bsums = WSP(u32, o_bsums);
-  u32* meta = WSP(u32, o_meta);
-  u32* sorted = WSP(u32, o_sorted);
-  u32* small_list = WSP(u32, o_small);
-  u32* large_list = WSP(u32, o_large);
-  G1Xyzz* buckets = WSP(G1Xyzz, o_buckets);
-  G1Xyzz* pieces = WSP(G1Xyzz, o_pieces);
-
-  cudaError_t err = cudaSuccess;
-#define STEP(stmt)                                       \
-  do {                                                   \
-    if (!dry && err == cudaSuccess) {                    \
-      stmt;                                              \
-      err = cudaGetLastError();                          \
-    }                                                    \
-  } while (0)
-
-  if (phase_ev && !dry) cudaEventRecord(phase_ev[0], s);
-  STEP(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
-  STEP(cudaMemsetAsync(meta, 0, 64, s));
-  STEP(cudaMemsetAsync(buckets, 0, (size_t)NB * sizeof(G1Xyzz), s));
-  const u32 g_n = (n + 255) / 256;
-  STEP(LAUNCH_NOSYNC(count_kernel, dim3(g_n), dim3(256), 0, s, scalars, n, prm, counts));
-  launches++;
-  if (!dry && err == cudaSuccess) err = exclusive_scan(counts, NB, bsums, starts, ends, meta + 0, s, launches);
-  else launches += 3;
-  STEP(LAUNCH_NOSYNC(scatter_kernel, dim3(g_n), dim3(256), 0, s, scalars, n, prm, ends, sorted));
-  launches++;
-  STEP(LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB,
-                     prm.nlanes, small_list, large_list, cap_small, cap_large, meta));
-  launches++;
-  if (phase_ev && !dry) cudaEventRecord(phase_ev[1], s);
-  static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
-  if (acc_inline)
-    STEP(LAUNCH_NOSYNC(accumulate_kernel<false>, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                       (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
-  else
-    STEP(LAUNCH_NOSYNC(accumulate_kernel<true>, dim3(prm.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                       (const u32*)starts, (const u32*)ends, NB, prm.nlanes, (const u32*)meta, buckets, pieces, piece_bucket));
-  launches++;
-  if (phase_ev && !dry) cudaEventRecord(phase_ev[2], s);
-  STEP(LAUNCH_NOSYNC(combine_small_kernel, dim3((cap_small + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
-                     (const u32*)starts, (const u32*)ends, prm.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
-                     (const u32*)piece_bucket, buckets));
-  launches++;
-  {
-    const u32 g = cap_large < 592 ? cap_large : 592;  // 4 CTAs per SM; the kernel strides over the list
-    STEP(LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), COMBINE_TPB * sizeof(G1Xyzz), s, (const u32*)large_list,
-                (const u32*)starts, (const u32*)ends, prm.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
-                (const u32*)piece_bucket, buckets));
-    launches++;
-  }
-  // bucket reduction: one launch per level until a single chunk per window is left
-  for (size_t l = 0; l < lv.size(); l++) {
-    ReduceArgs ra;
-    ra.X = (l == 0) ? buckets : WSP(G1Xyzz, o_R[l - 1]);
-    ra.x_stride = (l == 0) ? prm.B : lv[l - 1].T;
-    ra.x_off = (l == 0) ? 0 : 1;
-    ra.m = lv[l].m;
-    ra.P = (l == 0) ? nullptr : WSP(G1Xyzz, o_P[l - 1]);
-    ra.T_in = (l == 0) ? 0 : lv[l - 1].T;
-    ra.level = (u32)l;
-    ra.R_out = WSP(G1Xyzz, o_R[l]);
-    ra.P_out = WSP(G1Xyzz, o_P[l]);
-    ra.T_out = lv[l].T;
-    ra.nwin = nwin;
-    const u32 threads = nwin * lv[l].T;
-    STEP(LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra));
-    launches++;
-  }
-  const G1Xyzz* S = WSP(G1Xyzz, o_P[lv.size() - 1]);
-  G1Xyzz* D = WSP(G1Xyzz, o_D);
-  // per-window weights 2^(c w): not needed for a resident SRS (they are baked into the expanded bases)
-  STEP(LAUNCH_NOSYNC(window_weigh_kernel, dim3((nwin + 31) / 32), dim3(32), 0, s, S, lv.back().T, nwin, prm.c, D));
-  launches++;
-  STEP(LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, nwin, out144));
-  launches++;
-  if (phase_ev && !dry) cudaEventRecord(phase_ev[3], s);
-  if (ws) cudaFreeAsync(ws, s);
-#undef STEP
-#undef WSP
-  if (launches_out) *launches_out = launches;
-  return err;
+  Session ss;
+  cudaError_t e = ss.begin(n_sz, n_sz, 1, srs, s, dry);
+  if (e == cudaSuccess) e = ss.add_chunk(bases, stride, scalars, n_sz, 0, s, phase_ev);
+  if (e == cudaSuccess) e = ss.finish(out144, s, phase_ev ? &phase_ev[3] : nullptr);
+  else ss.release(s);
+  if (launches_out) *launches_out = ss.launches;
+  return e;
 }
 
 }  // namespace msm

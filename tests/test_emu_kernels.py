@@ -142,3 +142,47 @@ def test_emu_resident_srs_and_kzg_commit(emu_lib):
         emu_lib.check(emu_lib.kzg_commit_dev(h, C.cast(out48, C.c_void_p), C.cast(cb, C.c_void_p), 0, None), "commit0")
         assert out48.raw == o.g1_compress(None)
         emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+@pytest.mark.parametrize("chunks", [2, 3])
+def test_emu_host_calls_stream_point_ranges(emu_lib, chunks, monkeypatch):
+    """host-pointer entry points: the MSM arrives in point ranges whose bucket sums are added up
+    (Session::add_chunk) -- same result as one range, for the plain MSM, the resident SRS and KZG commit"""
+    monkeypatch.setenv("ALEO_B200_MSM_CHUNKS", str(chunks))
+    n = 900
+    B = o.synthetic_bases(n, 31)
+    B[17] = None
+    s = o.random_fr_vec(n, 32)
+    s[0], s[1], s[2] = 0, 1, o.R_MOD - 1
+    s[400:440] = [s[400]] * 40                                   # a bucket that every range re-opens
+    want = o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+    for stride in (104, 96):
+        bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, stride), n * stride)
+        sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), n * 32)
+        out = C.create_string_buffer(144)
+        emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), stride), "msm_g1")
+        assert out.raw == want, stride
+    # all points equal / cancelling pairs across range boundaries
+    Beq = [B[3]] * n
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(Beq, 104), n * 104)
+    ones = C.create_string_buffer(o.fr_vec_to_bytes([5] * n, mont=False), n * 32)
+    out = C.create_string_buffer(144)
+    emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(ones, C.c_void_p), 104), "msm_g1 eq")
+    assert out.raw == o.g1_projective_to_bytes(o.g1_mul(B[3], 5 * n))
+    Bpm = [B[3] if i < n // 2 else o.g1_neg(B[3]) for i in range(n)]
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(Bpm, 104), n * 104)
+    emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(ones, C.c_void_p), 104), "msm_g1 pm")
+    assert out.raw == o.g1_projective_to_bytes(None)
+    # resident SRS + commit through the host entry points
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    h = C.c_void_p()
+    emu_lib.check(emu_lib.srs_create(C.byref(h), C.cast(bb, C.c_void_p), n, 104), "srs_create")
+    for n_used in (n, 601, 9):
+        sb = C.create_string_buffer(o.fr_vec_to_bytes(s[:n_used], mont=False), n_used * 32)
+        emu_lib.check(emu_lib.srs_msm(h, C.cast(out, C.c_void_p), C.cast(sb, C.c_void_p), n_used), "srs_msm")
+        assert out.raw == o.g1_projective_to_bytes(o.msm_pippenger(B[:n_used], s[:n_used])), n_used
+        cb = C.create_string_buffer(o.fr_vec_to_bytes(s[:n_used], mont=True), n_used * 32)
+        out48 = C.create_string_buffer(48)
+        emu_lib.check(emu_lib.kzg_commit(h, C.cast(out48, C.c_void_p), C.cast(cb, C.c_void_p), n_used), "kzg_commit")
+        assert out48.raw == o.g1_compress(o.msm_pippenger(B[:n_used], s[:n_used])), n_used
+    emu_lib.check(emu_lib.srs_destroy(h), "destroy")
