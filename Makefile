@@ -8,7 +8,7 @@ CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2 -Xptxas -v
 CSRC      := aleo_b200/csrc
-TUS       := capi ntt_lib msm_lib util_lib
+TUS       := capi ntt_lib msm_lib util_lib poly_lib
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/internal.h include/aleo_b200.h
 OBJ       := $(patsubst %,build/%.o,$(TUS))
 EMUOBJ    := $(patsubst %,build/emu_%.o,$(TUS))

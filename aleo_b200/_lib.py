@@ -44,6 +44,7 @@ SYMBOLS = [
     ("aleo_b200_srs_msm_launches", _int, [_vp, _sz]),
     ("aleo_b200_kzg_commit", _int, [_vp, _vp, _vp, _sz]),
     ("aleo_b200_kzg_commit_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
+    ("aleo_b200_field_op_dev", _int, [_int, _int, _vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
     ("aleo_b200_gen_bases_dev", _int, [_vp, _sz, _sz, _vp, _vp, _u64, _vp]),

@@ -70,6 +70,7 @@ int ensure_ready(int* dev_out) {
     API_CK(aleo::ntt_upload_constants());
     API_CK(aleo::msm_upload_constants());
     API_CK(aleo::util_upload_constants());
+    API_CK(aleo::poly_upload_constants());
     g_dev_ready[dev] = true;
   }
   if (dev_out) *dev_out = dev;
@@ -306,6 +307,18 @@ int aleo_b200_check_on_curve_dev(const void* bases_dev, size_t n, size_t affine_
   int ok = 0;
   API_CK(aleo::check_on_curve(bases_dev, n, (u32)affine_stride, (cudaStream_t)stream, &ok));
   return ok;
+}
+
+int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, void* stream) {
+  if (field != ALEO_B200_FIELD_FR && field != ALEO_B200_FIELD_FQ) return ALEO_B200_EINVAL;
+  if (op < ALEO_B200_OP_ADD || op > ALEO_B200_OP_NEG) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  const bool binary = op == ALEO_B200_OP_ADD || op == ALEO_B200_OP_SUB || op == ALEO_B200_OP_MUL;
+  if (out_dev == nullptr || a_dev == nullptr || (binary && b_dev == nullptr)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::field_op(field, op, out_dev, a_dev, b_dev, n, (cudaStream_t)stream));
+  return ALEO_B200_OK;
 }
 
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {

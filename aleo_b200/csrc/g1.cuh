@@ -85,8 +85,18 @@ DEV void affine_store(unsigned char* bases, size_t stride, size_t idx, const G1A
   }
 }
 
+// Out-of-line Fq product with by-value operands: ptxas passes them in registers (no stack), so a call
+// costs ~36 MOVs on the ALU pipe while the loop body that uses it shrinks ~10x and stays resident in
+// the instruction cache (the fully inlined accumulation loop is ~115 KB of SASS and was stalled on
+// instruction fetch for 10-40 % of its issue slots, profiles/r01_ncu_hot_kernels.md).
+DEV_NOINLINE Fq fq_mul_v(Fq a, Fq b) { return fp_mul(a, b); }
+// dedicated square (mont.cuh fp_sqr: 222 wide MACs instead of 288), same calling convention
+DEV_NOINLINE Fq fq_sqr_v(Fq a) { return fp_sqr(a); }
+
 // 2 * (x, y) for an affine point that is not the identity (mdbl-2008-s-1, a = 0).
 // Out of line: only reached when a bucket receives the same point twice.
+// (Inlined products on purpose: routing them through fq_mul_v changes the register assignment around the
+// call sites of the accumulation loop and cost 4 % of its throughput on B200.)
 DEV_NOINLINE G1Xyzz xyzz_double_affine(const Fq& x, const Fq& y) {
   G1Xyzz r;
   Fq u = fp_dbl(y);
@@ -107,28 +117,27 @@ DEV_NOINLINE G1Xyzz xyzz_double(const G1Xyzz& p) {
   if (xyzz_is_identity(p) || fp_is_zero(p.y)) return xyzz_identity();
   G1Xyzz r;
   Fq u = fp_dbl(p.y);
-  Fq v = fp_sqr(u);
-  Fq w = fp_mul(u, v);
-  Fq s = fp_mul(p.x, v);
-  Fq xx = fp_sqr(p.x);
+  Fq v = fq_sqr_v(u);
+  Fq w = fq_mul_v(u, v);
+  Fq s = fq_mul_v(p.x, v);
+  Fq xx = fq_sqr_v(p.x);
   Fq m = fp_add(fp_dbl(xx), xx);
-  r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-  r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
-  r.zz = fp_mul(v, p.zz);
-  r.zzz = fp_mul(w, p.zzz);
+  r.x = fp_sub(fq_sqr_v(m), fp_dbl(s));
+  r.y = fp_sub(fq_mul_v(m, fp_sub(s, r.x)), fq_mul_v(w, p.y));
+  r.zz = fq_mul_v(v, p.zz);
+  r.zzz = fq_mul_v(w, p.zzz);
   return r;
 }
-
-// Out-of-line Fq product with by-value operands: ptxas passes them in registers (no stack), so a call
-// costs ~36 MOVs on the ALU pipe while the loop body that uses it shrinks ~10x and stays resident in
-// the instruction cache (the fully inlined accumulation loop is ~115 KB of SASS and was stalled on
-// instruction fetch for 10-40 % of its issue slots, profiles/r01_ncu_hot_kernels.md).
-DEV_NOINLINE Fq fq_mul_v(Fq a, Fq b) { return fp_mul(a, b); }
 
 template <bool CALL>
 DEV Fq fq_mul_sel(const Fq& a, const Fq& b) {
   if (CALL) return fq_mul_v(a, b);
   return fp_mul(a, b);
+}
+template <bool CALL>
+DEV Fq fq_sqr_sel(const Fq& a) {
+  if (CALL) return fq_sqr_v(a);
+  return fp_sqr(a);
 }
 
 // acc += (x2, y2)   (madd-2008-s; the affine operand is not the identity)
@@ -157,10 +166,10 @@ DEV void xyzz_add_affine_t(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
       acc = xyzz_identity();
     return;
   }
-  Fq pp = fq_mul_sel<CALL>(p, p);
+  Fq pp = fq_sqr_sel<CALL>(p);
   Fq ppp = fq_mul_sel<CALL>(p, pp);
   Fq q = fq_mul_sel<CALL>(acc.x, pp);
-  Fq x3 = fp_sub(fp_sub(fq_mul_sel<CALL>(r, r), ppp), fp_dbl(q));
+  Fq x3 = fp_sub(fp_sub(fq_sqr_sel<CALL>(r), ppp), fp_dbl(q));
   Fq y3 = fp_sub(fq_mul_sel<CALL>(r, fp_sub(q, x3)), fq_mul_sel<CALL>(acc.y, ppp));
   acc.zz = fq_mul_sel<CALL>(acc.zz, pp);
   acc.zzz = fq_mul_sel<CALL>(acc.zzz, ppp);
@@ -168,17 +177,18 @@ DEV void xyzz_add_affine_t(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
   acc.y = y3;
 }
 
-// acc += b   (add-2008-s)
+// acc += b   (add-2008-s).  All products go through the out-of-line multiplier: the tail kernels run a handful of
+// warps, and 14 inlined products (~80 KB of SASS per addition) made them instruction-fetch bound.
 DEV void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
   if (xyzz_is_identity(b)) return;
   if (xyzz_is_identity(acc)) {
     acc = b;
     return;
   }
-  Fq u1 = fp_mul(acc.x, b.zz);
-  Fq u2 = fp_mul(b.x, acc.zz);
-  Fq s1 = fp_mul(acc.y, b.zzz);
-  Fq s2 = fp_mul(b.y, acc.zzz);
+  Fq u1 = fq_mul_v(acc.x, b.zz);
+  Fq u2 = fq_mul_v(b.x, acc.zz);
+  Fq s1 = fq_mul_v(acc.y, b.zzz);
+  Fq s2 = fq_mul_v(b.y, acc.zzz);
   Fq p = fp_sub(u2, u1);
   Fq r = fp_sub(s2, s1);
   if (fp_is_zero(p)) {
@@ -188,13 +198,13 @@ DEV void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
       acc = xyzz_identity();
     return;
   }
-  Fq pp = fp_sqr(p);
-  Fq ppp = fp_mul(p, pp);
-  Fq q = fp_mul(u1, pp);
-  Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-  Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(s1, ppp));
-  acc.zz = fp_mul(fp_mul(acc.zz, b.zz), pp);
-  acc.zzz = fp_mul(fp_mul(acc.zzz, b.zzz), ppp);
+  Fq pp = fq_sqr_v(p);
+  Fq ppp = fq_mul_v(p, pp);
+  Fq q = fq_mul_v(u1, pp);
+  Fq x3 = fp_sub(fp_sub(fq_sqr_v(r), ppp), fp_dbl(q));
+  Fq y3 = fp_sub(fq_mul_v(r, fp_sub(q, x3)), fq_mul_v(s1, ppp));
+  acc.zz = fq_mul_v(fq_mul_v(acc.zz, b.zz), pp);
+  acc.zzz = fq_mul_v(fq_mul_v(acc.zzz, b.zzz), ppp);
   acc.x = x3;
   acc.y = y3;
 }
@@ -208,8 +218,8 @@ DEV G1Xyzz xyzz_from_jacobian(const Fq& X, const Fq& Y, const Fq& Z) {
   G1Xyzz r;
   r.x = X;
   r.y = Y;
-  r.zz = fp_sqr(Z);
-  r.zzz = fp_mul(r.zz, Z);
+  r.zz = fq_sqr_v(Z);
+  r.zzz = fq_mul_v(r.zz, Z);
   return r;
 }
 
@@ -240,19 +250,5 @@ DEV void jacobian_store_normalised(unsigned char* out, const G1Xyzz& p) {
 // size and ptxas time small; the bucket-accumulation loop uses the inlined xyzz_add_affine above.
 DEV_NOINLINE void xyzz_add_ni(G1Xyzz& acc, const G1Xyzz& b) { xyzz_add(acc, b); }
 DEV_NOINLINE void xyzz_add_affine_ni(G1Xyzz& acc, const Fq& x2, const Fq& y2) { xyzz_add_affine(acc, x2, y2); }
-DEV_NOINLINE Fq fq_mul_ni(const Fq& a, const Fq& b) { return fp_mul(a, b); }
-DEV_NOINLINE Fq fq_inv_ni(const Fq& a) {
-  Fq r = fp_one<FqParams>();
-  bool started = false;
-  for (int i = FqParams::N - 1; i >= 0; i--) {
-    const u32 e = FqParams::MOD_MINUS_2(i);
-    for (int b = 31; b >= 0; b--) {
-      if (started) r = fq_mul_ni(r, r);
-      if ((e >> b) & 1u) {
-        r = fq_mul_ni(r, a);
-        started = true;
-      }
-    }
-  }
-  return r;
-}
+DEV_NOINLINE Fq fq_mul_ni(const Fq& a, const Fq& b) { return fq_mul_v(a, b); }
+DEV_NOINLINE Fq fq_inv_ni(const Fq& a) { return fq_mul_v(fp_inv_bingcd_raw(a), fp_const<FqParams, FqParams::R3>()); }

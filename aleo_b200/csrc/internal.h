@@ -34,6 +34,9 @@ cudaError_t srs_msm(const void* handle, const void* scalars_dev, size_t n_used, 
                     int* launches_out, float* phase_ms);
 cudaError_t fr_to_bigint(const void* in_dev, void* out_dev, size_t n, cudaStream_t s);
 cudaError_t g1_compress(const void* jac144_dev, void* out48_dev, cudaStream_t s);
+// poly_lib.cu
+cudaError_t poly_upload_constants();
+cudaError_t field_op(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, cudaStream_t s);
 // util_lib.cu
 cudaError_t util_upload_constants();
 cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);

@@ -196,9 +196,124 @@ DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Montgomery square.  The 2N x N multiplier rows of fp_mul become N(N-1)/2 off-diagonal products
+// a_i * (2a)_j (i < j), N diagonal squares and N reduction rows: N(N+1)/2 + N^2 wide MACs instead of 2N^2
+// (Fq: 222 instead of 288).  Same two-accumulator layout (E: pairs starting at even limb positions,
+// O: odd), every row again two carry chains of IMAD.WIDE pairs.
+//   phase 1  T = a^2 into E + O (2N limbs).  A row chain ends with one addc into the next limb: that limb has
+//            so far only received carry bits of earlier rows (rows i' < i end below position i + N), so it
+//            cannot overflow; the diagonal chain runs last and propagates through all 2N limbs.
+//   phase 2  Montgomery-reduce the LOW halves only (upper limbs start at zero, exactly the situation the
+//            fp_mul rows are bounded for) and add the high halves at the end:
+//            (T + M q) / R = T_hi + (T_lo + M q) / R < 2q.
+// ---------------------------------------------------------------------------------------------
+namespace montdetail {
+// acc pairs (POS+j, POS+j+1) += x[j] * y for j = JS, JS+2, ... < N (x[JS] replaced by `first`), carry-out into
+// the limb above
+template <class P, int POS, int JS, int LEN>
+DEV void sqr_row_chain(u32 (&acc)[LEN], const u32* x, u32 first, u32 y) {
+  constexpr int N = P::N;
+  if (JS < N) {
+#pragma unroll
+    for (int j = JS; j < N; j += 2) {
+      const u32 xj = (j == JS) ? first : x[j];
+      if (j == JS)
+        acc[POS + j] = ptx::mad_lo_cc(xj, y, acc[POS + j]);
+      else
+        acc[POS + j] = ptx::madc_lo_cc(xj, y, acc[POS + j]);
+      acc[POS + j + 1] = ptx::madc_hi_cc(xj, y, acc[POS + j + 1]);
+    }
+    constexpr int LAST = JS + 2 * ((N - 1 - JS) / 2);
+    acc[POS + LAST + 2] = ptx::addc(acc[POS + LAST + 2], 0);
+  }
+}
+
+template <class P, int I, int LEN>
+struct SqrRows {
+  static DEV void run(u32 (&E)[LEN], u32 (&O)[LEN], const u32* a, const u32* b2) {
+    SqrRows<P, I - 1, LEN>::run(E, O, a, b2);
+    // row I multiplies a_I by the limbs of 2 * (a >> 32 (I+1)): limb I+1 of 2a without the bit that a_I shifts in
+    sqr_row_chain<P, I, I + 1, LEN>(O, b2, a[I + 1] << 1, a[I]);                            // positions 2I+1, 2I+3, ...: odd
+    sqr_row_chain<P, I, I + 2, LEN>(E, b2, (I + 2 < P::N) ? b2[(I + 2 < P::N) ? I + 2 : 0] : 0u, a[I]);  // 2I+2, 2I+4, ...: even
+  }
+};
+template <class P, int LEN>
+struct SqrRows<P, -1, LEN> {
+  static DEV void run(u32 (&)[LEN], u32 (&)[LEN], const u32*, const u32*) {}
+};
+
+// reduction step I on the low halves: fold position I, m = -L[I], add m * modulus at positions I .. I+N
+template <class P, int I, int LEN>
+DEV void red_iter(u32 (&E)[LEN], u32 (&O)[LEN]) {
+  u32(&L)[LEN] = (I & 1) ? O : E;
+  u32(&T)[LEN] = (I & 1) ? E : O;
+  if (I > 0) L[I] = ptx::add_cc(L[I], T[I]);  // carry-out belongs to position I+1 = first trailing pair
+  const u32 m = ptx::neg_opaque(L[I]);
+  if (I > 0)
+    row_chain<P, I, 1, true, true>(T, (const u32*)nullptr, m);
+  else
+    row_chain<P, I, 1, false, true>(T, (const u32*)nullptr, m);
+  row_chain<P, I, 0, false, true>(L, (const u32*)nullptr, m);
+}
+template <class P, int I, int LEN>
+struct RedRows {
+  static DEV void run(u32 (&E)[LEN], u32 (&O)[LEN]) {
+    RedRows<P, I - 1, LEN>::run(E, O);
+    red_iter<P, I, LEN>(E, O);
+  }
+};
+template <class P, int LEN>
+struct RedRows<P, -1, LEN> {
+  static DEV void run(u32 (&)[LEN], u32 (&)[LEN]) {}
+};
+}  // namespace montdetail
+
 template <class P>
 DEV Fp<P> fp_sqr(const Fp<P>& a) {
-  return fp_mul(a, a);
+  constexpr int N = P::N;
+  static_assert(P::INV == 0xffffffffu, "multiplier assumes modulus == 1 mod 2^32");
+  static_assert(P::BITS + 1 <= 32 * N, "2a must fit N limbs");
+  constexpr int LEN = 2 * N + 1;
+  u32 E[LEN], O[LEN], b2[N];
+#pragma unroll
+  for (int k = 0; k < LEN; k++) E[k] = O[k] = 0;
+  b2[0] = a.l[0] << 1;
+#pragma unroll
+  for (int k = 1; k < N; k++) b2[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
+  // phase 1: off-diagonal rows, then the diagonal chain through all 2N limbs of E
+  montdetail::SqrRows<P, N - 2, LEN>::run(E, O, a.l, b2);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (i == 0)
+      E[0] = ptx::mad_lo_cc(a.l[0], a.l[0], E[0]);
+    else
+      E[2 * i] = ptx::madc_lo_cc(a.l[i], a.l[i], E[2 * i]);
+    if (i == N - 1)
+      E[2 * i + 1] = ptx::madc_hi(a.l[i], a.l[i], E[2 * i + 1]);  // a^2 < 2^(64N): no carry out
+    else
+      E[2 * i + 1] = ptx::madc_hi_cc(a.l[i], a.l[i], E[2 * i + 1]);
+  }
+  // high halves aside (H = E_hi + O_hi < 2^(32N)), low halves reduced with fresh upper limbs
+  u32 H[N];
+  H[0] = ptx::add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) H[k] = ptx::addc_cc(E[N + k], O[N + k]);
+  H[N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 1]);
+#pragma unroll
+  for (int k = N; k < LEN; k++) E[k] = O[k] = 0;
+  montdetail::RedRows<P, N - 1, LEN>::run(E, O);
+  Fp<P> r;
+  r.l[0] = ptx::add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(E[N + k], O[N + k]);
+  r.l[N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 1]);
+  r.l[0] = ptx::add_cc(r.l[0], H[0]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(r.l[k], H[k]);
+  r.l[N - 1] = ptx::addc(r.l[N - 1], H[N - 1]);
+  fp_reduce_once(r);
+  return r;
 }
 
 // Montgomery -> canonical (PrimeField::to_bigint): multiply by 1.
@@ -244,4 +359,83 @@ DEV Fp<P> fp_inv(const Fp<P>& a) {
 #pragma unroll
   for (int i = 0; i < P::N; i++) e[i] = P::MOD_MINUS_2(i);
   return fp_pow(a, e, P::N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inversion by the binary extended Euclid algorithm (shifts and subtractions only).  One inversion ends
+// every MSM (normalisation of the result) and sits on its latency path: Fermat costs ~570 dependent
+// products (~0.45 ms on one B200 thread), this ~750 short carry chains (< 0.1 ms).
+// Invariants: x1 * a == u, x2 * a == v (mod m); u, v odd after the halving loops; ends with u == 1 or v == 1.
+// a is a Montgomery residue A*R; the loop yields (A*R)^-1 as a plain residue, and a Montgomery product with R^3
+// (done by the caller, so that it can use its out-of-line multiplier) turns that into A^-1 * R.  0 -> 0.
+// ---------------------------------------------------------------------------------------------
+namespace bingcd {
+template <int N>
+DEV bool is_one(const u32* a) {
+  u32 acc = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < N; i++) acc |= a[i];
+  return acc == 0;
+}
+template <int N>
+DEV void shr1(u32* a, u32 top) {
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+  a[N - 1] = (a[N - 1] >> 1) | (top << 31);
+}
+// x <- x / 2 mod m
+template <class P>
+DEV void halve(u32* x) {
+  constexpr int N = P::N;
+  u32 carry = 0;
+  if (x[0] & 1u) {
+    x[0] = ptx::add_cc(x[0], P::MOD(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) x[i] = ptx::addc_cc(x[i], P::MOD(i));
+    carry = ptx::addc(0, 0);
+  }
+  shr1<N>(x, carry);
+}
+template <int N>
+DEV bool geq(const u32* a, const u32* b) {
+  ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) ptx::subc_cc(a[i], b[i]);
+  return ptx::subc(0, 0) == 0;  // no borrow
+}
+template <int N>
+DEV void sub(u32* a, const u32* b) {
+  a[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) a[i] = ptx::subc_cc(a[i], b[i]);
+  a[N - 1] = ptx::subc(a[N - 1], b[N - 1]);
+}
+}  // namespace bingcd
+
+template <class P>
+DEV Fp<P> fp_inv_bingcd_raw(const Fp<P>& a) {
+  constexpr int N = P::N;
+  if (fp_is_zero(a)) return a;
+  Fp<P> u = a, v, x1 = fp_zero<P>(), x2 = fp_zero<P>();
+#pragma unroll
+  for (int i = 0; i < N; i++) v.l[i] = P::MOD(i);
+  x1.l[0] = 1;
+  while (!bingcd::is_one<N>(u.l) && !bingcd::is_one<N>(v.l)) {
+    while (!(u.l[0] & 1u)) {
+      bingcd::shr1<N>(u.l, 0);
+      bingcd::halve<P>(x1.l);
+    }
+    while (!(v.l[0] & 1u)) {
+      bingcd::shr1<N>(v.l, 0);
+      bingcd::halve<P>(x2.l);
+    }
+    if (bingcd::geq<N>(u.l, v.l)) {
+      bingcd::sub<N>(u.l, v.l);
+      x1 = fp_sub(x1, x2);
+    } else {
+      bingcd::sub<N>(v.l, u.l);
+      x2 = fp_sub(x2, x1);
+    }
+  }
+  return bingcd::is_one<N>(u.l) ? x1 : x2;  // (A*R)^-1 as a plain residue; the caller multiplies by R^3
 }

@@ -96,21 +96,51 @@ DEV u32 warp_aggregated_inc(u32* counters, u32 slot, bool active) {
 // Both sort kernels run window-major (blockIdx.y = window): the CTAs in flight then write to the 2^(c-1)
 // bucket heads of ONE window (16 MB of 32-byte sectors at c = 20, L2 resident) instead of W * 2^(c-1)
 // heads at once, which at c >= 18 overflowed L2 and turned every 4-byte entry into a DRAM sector write.
+// gridDim.x CTAs per window stride over the scalars (a CTA per 256 scalars and window was launch bound:
+// 2^20 short CTAs at n = 2^24).
 KERNEL void count_kernel(const u32* scalars, u32 n, Params prm, u32* counts) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 w = blockIdx.y;
-  u32 neg = 0, mag = 0;
-  if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
-  warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+  for (u32 base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // uniform trip count per CTA
+    const u32 i = base + threadIdx.x;
+    u32 neg = 0, mag = 0;
+    if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
+    warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+  }
 }
 
 KERNEL void scatter_kernel(const u32* scalars, u32 n, Params prm, u32* cursor, u32* sorted) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 w = blockIdx.y;
-  u32 neg = 0, mag = 0;
-  if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
-  const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
-  if (mag) sorted[pos] = entry_index(prm, w, i) | (neg << 31);
+  for (u32 base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const u32 i = base + threadIdx.x;
+    u32 neg = 0, mag = 0;
+    if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
+    const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+    if (mag) sorted[pos] = entry_index(prm, w, i) | (neg << 31);
+  }
+}
+
+// scalar-major variants: one thread per scalar walks all windows (the carry is free), the warp's 32 atomics of an
+// iteration go to 32 different counters of ONE window, and consecutive iterations move on to the next window's
+// counter region
+KERNEL void count_kernel_sm(const u32* scalars, u32 n, Params prm, u32* counts) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32* s = scalars + (size_t)(i < n ? i : 0) * 8;
+  u32 carry = 0, neg = 0;
+  for (u32 w = 0; w < prm.W; w++) {
+    const u32 mag = (i < n) ? recode_digit(s, w, prm.c, carry, neg) : 0u;
+    warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+  }
+}
+
+KERNEL void scatter_kernel_sm(const u32* scalars, u32 n, Params prm, u32* cursor, u32* sorted) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32* s = scalars + (size_t)(i < n ? i : 0) * 8;
+  u32 carry = 0, neg = 0;
+  for (u32 w = 0; w < prm.W; w++) {
+    const u32 mag = (i < n) ? recode_digit(s, w, prm.c, carry, neg) : 0u;
+    const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+    if (mag) sorted[pos] = entry_index(prm, w, i) | (neg << 31);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -309,7 +339,7 @@ KERNEL void __launch_bounds__(128) combine_small_kernel(const u32* small_list, c
 KERNEL void __launch_bounds__(COMBINE_TPB) combine_large_kernel(const u32* large_list, const u32* starts, const u32* ends,
                                                                  u32 nlanes, const u32* meta, const G1Xyzz* pieces,
                                                                  const u32* piece_bucket, G1Xyzz* buckets) {
-  DYN_SMEM(G1Xyzz, sh);
+  SHARED G1Xyzz sh[COMBINE_TPB];
   const u32 L = run_length(meta[0], nlanes);
   for (u32 j = blockIdx.x; j < meta[3]; j += gridDim.x) {
     const u32 wb = large_list[j];
@@ -334,17 +364,23 @@ KERNEL void __launch_bounds__(COMBINE_TPB) combine_large_kernel(const u32* large
 // ---------------------------------------------------------------------------------------------
 // bucket reduction, per window:  f(X[0..m)) = sum_i (i+1) * X[i].
 //   With chunks of Kc:  f(X) = sum_t WS_t + Kc * f(R[1..T)),  R_t = sum of chunk t,
-//   WS_t = sum (local index + 1) * X[..] (running sums).  One launch per level l computes, for chunk t,
+//   WS_t = sum (local index + 1) * X[..] (running sums).  A CHUNK LEVEL (reduce_level_kernel) computes, for chunk t,
 //     R'_t = sum of its chunk of the weighted input (X at level 0, R[1..) above),
-//     P'_t = Kc^l * WS_t + sum of its chunk of the previous level's P        (plain partial sums)
-//   so that after the last level (one chunk left) P[0] = f(buckets): no separate plain-sum launches.
+//     P'_t = scale * WS_t + sum of its chunk of the previous level's P        (plain partial sums)
+//   with scale = product of the earlier levels' chunk sizes.  Chunk levels are work efficient (2 additions
+//   per element) but serial inside a thread, so they only run until <= SCAN_MAX elements per window are
+//   left; the rest is one CTA per window (reduce_scan_kernel): f = sum of all suffix sums, a log-depth
+//   suffix scan plus a log-depth tree -- 17 dependent additions instead of ~50 per level.
 // ---------------------------------------------------------------------------------------------
+constexpr u32 SCAN_MAX = 256;  // elements per window the scan stage takes (256 x 192 B = 48 KB of shared memory)
+
 struct ReduceArgs {
   const G1Xyzz* X;   // weighted input, per window `x_stride` apart, first element at X[x_off]
   u32 x_stride, x_off, m;
   const G1Xyzz* P;   // plain input of the previous level (T_in per window) or nullptr at level 0
   u32 T_in;
-  u32 level;         // scale of this level's WS: Kc^level
+  u32 log_kc;        // chunk size of this level = 2^log_kc
+  u32 scale_log;     // log2 of the product of the earlier levels' chunk sizes: weight of this level's WS
   G1Xyzz* R_out;     // T_out per window
   G1Xyzz* P_out;
   u32 T_out, nwin;
@@ -355,8 +391,9 @@ KERNEL void __launch_bounds__(128) reduce_level_kernel(ReduceArgs a) {
   if (id >= a.nwin * a.T_out) return;
   const u32 w = id / a.T_out, t = id % a.T_out;
   const G1Xyzz* x = a.X + (size_t)w * a.x_stride + a.x_off;
-  const u32 lo = t * RED_KC;
-  u32 hi = lo + RED_KC;
+  const u32 kc = 1u << a.log_kc;
+  const u32 lo = t * kc;
+  u32 hi = lo + kc;
   if (hi > a.m) hi = a.m;
   G1Xyzz run = xyzz_identity(), acc = xyzz_identity();
   for (u32 i = hi; i > lo; i--) {
@@ -364,32 +401,177 @@ KERNEL void __launch_bounds__(128) reduce_level_kernel(ReduceArgs a) {
     xyzz_add_ni(acc, run);
   }
   a.R_out[(size_t)w * a.T_out + t] = run;
-  for (u32 i = 0; i < a.level * RED_LOG_KC; i++) acc = xyzz_double(acc);
+  for (u32 i = 0; i < a.scale_log; i++) acc = xyzz_double(acc);
   if (a.P) {
     const G1Xyzz* p = a.P + (size_t)w * a.T_in;
-    u32 phi = lo + RED_KC;
+    u32 phi = lo + kc;
     if (phi > a.T_in) phi = a.T_in;
     for (u32 i = lo; i < phi; i++) xyzz_add_ni(acc, p[i]);
   }
   a.P_out[(size_t)w * a.T_out + t] = acc;
 }
 
-// Tail, step 1 (one thread per window): D_w = 2^(c w) * S_w, S_w = f(buckets of window w) = P[w].
-// The c*w doublings of the different windows run in parallel; the critical path is the top window's.
-KERNEL void window_weigh_kernel(const G1Xyzz* S, u32 s_stride, u32 W, u32 c, G1Xyzz* D) {
-  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= W) return;
-  G1Xyzz s = S[(size_t)w * s_stride];
-  for (u32 i = 0; i < c * w; i++) s = xyzz_double(s);
-  D[w] = s;
+// Last reduction stage, one CTA per window: S_w = 2^scale_log * f(X[0..m)) + sum P[0..T_in), m, T_in <= blockDim.x.
+struct ScanArgs {
+  const G1Xyzz* X;
+  u32 x_stride, x_off, m;
+  const G1Xyzz* P;
+  u32 T_in, scale_log;
+  G1Xyzz* S;  // one per window
+};
+
+KERNEL void __launch_bounds__(SCAN_MAX) reduce_scan_kernel(ScanArgs a) {
+  DYN_SMEM(G1Xyzz, sh);
+  const u32 w = blockIdx.x, i = threadIdx.x, span = blockDim.x;
+  G1Xyzz mine = xyzz_identity();
+  if (i < a.m) {
+    mine = a.X[(size_t)w * a.x_stride + a.x_off + i];
+    for (u32 k = 0; k < a.scale_log; k++) mine = xyzz_double(mine);
+  }
+  sh[i] = mine;
+  SYNC_THREADS();
+  // suffix scan (Hillis-Steele): after the loop mine = sum_{j >= i} X[j]
+  for (u32 off = 1; off < span; off <<= 1) {
+    const bool take = (i + off < a.m);
+    G1Xyzz other;
+    if (take) other = sh[i + off];
+    SYNC_THREADS();
+    if (take) {
+      xyzz_add_ni(mine, other);
+      sh[i] = mine;
+    }
+    SYNC_THREADS();
+  }
+  // f(X) = sum of all suffix sums; the plain partial sums of the chunk levels join the same tree
+  if (a.P && i < a.T_in) {
+    xyzz_add_ni(mine, a.P[(size_t)w * a.T_in + i]);
+    sh[i] = mine;
+  }
+  SYNC_THREADS();
+  for (u32 off = span >> 1; off > 0; off >>= 1) {
+    if (i < off) {
+      xyzz_add_ni(mine, sh[i + off]);
+      sh[i] = mine;
+    }
+    SYNC_THREADS();
+  }
+  if (i == 0) a.S[w] = mine;
 }
 
-// Tail, step 2 (one thread): result = sum_w D_w, normalised (one inversion).
-KERNEL void final_kernel(const G1Xyzz* D, u32 W, unsigned char* out144) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  G1Xyzz total = xyzz_identity();
-  for (u32 w = 0; w < W; w++) xyzz_add_ni(total, D[w]);
-  jacobian_store_normalised(out144, total);
+// ---------------------------------------------------------------------------------------------
+// Tail: result = sum_w 2^(c w) * S_w, normalised.  The c * (W - 1) doublings of the top window are a
+// dependency chain no schedule removes, so the kernel shortens each link instead: a QUAD of lanes owns one
+// window and computes the independent Fq products of a doubling side by side (XYZZ dbl-2008-s-1 has
+// 9 products in 3 dependent levels of 2 / 4 / 3), exchanging them with warp shuffles.  Every lane of a
+// warp runs the same multiplier code on its own operands, so there is no divergence.  One CTA, 4 lanes
+// per window (W <= 64).  Then a tree over the windows and ONE inversion (binary GCD).
+// ---------------------------------------------------------------------------------------------
+constexpr u32 TAIL_TPB = 256;
+
+// operand of the calling lane: x_r for role r, chosen with bit masks (a ternary per limb compiles to divergent
+// branches here: measured 4400 clocks per product level instead of ~1700)
+DEV Fq role_select(u32 role, const Fq& x0, const Fq& x1, const Fq& x2, const Fq& x3) {
+  const u32 m0 = 0u - (u32)(role == 0), m1 = 0u - (u32)(role == 1), m2 = 0u - (u32)(role == 2), m3 = 0u - (u32)(role == 3);
+  Fq r;
+#pragma unroll
+  for (int k = 0; k < FqParams::N; k++) r.l[k] = (x0.l[k] & m0) | (x1.l[k] & m1) | (x2.l[k] & m2) | (x3.l[k] & m3);
+  return r;
+}
+
+// out[r] = a_r * b_r for the four roles of a quad, delivered to every lane of the quad
+DEV void quad_products(u32 role, const Fq& a0, const Fq& b0, const Fq& a1, const Fq& b1, const Fq& a2, const Fq& b2,
+                       const Fq& a3, const Fq& b3, Fq& o0, Fq& o1, Fq& o2, Fq& o3) {
+#ifndef ALEO_EMU
+  const Fq mine = fp_mul(role_select(role, a0, a1, a2, a3), role_select(role, b0, b1, b2, b3));  // inlined: 3 per loop body
+  const unsigned base = (threadIdx.x & 31u) & ~3u;
+#pragma unroll
+  for (int k = 0; k < FqParams::N; k++) {
+    o0.l[k] = __shfl_sync(0xffffffffu, mine.l[k], base + 0);
+    o1.l[k] = __shfl_sync(0xffffffffu, mine.l[k], base + 1);
+    o2.l[k] = __shfl_sync(0xffffffffu, mine.l[k], base + 2);
+    o3.l[k] = __shfl_sync(0xffffffffu, mine.l[k], base + 3);
+  }
+#else
+  (void)role;  // the emulator runs CUDA threads one after the other: role 0 computes all four products
+  o0 = fq_mul_v(a0, b0);
+  o1 = fq_mul_v(a1, b1);
+  o2 = fq_mul_v(a2, b2);
+  o3 = fq_mul_v(a3, b3);
+#endif
+}
+
+// p <- 2 p, all four lanes of the quad hold (and update) the whole point
+DEV void quad_double(u32 role, G1Xyzz& p) {
+  const Fq u = fp_dbl(p.y);
+  Fq v, xx, t2, t3;
+  quad_products(role, u, u, p.x, p.x, u, u, p.x, p.x, v, xx, t2, t3);                     // level 1: V = U^2, X^2
+  const Fq m = fp_add(fp_dbl(xx), xx);
+  Fq w, mm, s, zz3;
+  quad_products(role, u, v, m, m, p.x, v, p.zz, v, w, mm, s, zz3);                        // level 2: W, M^2, S, ZZ3
+  const Fq x3 = fp_sub(mm, fp_dbl(s));
+  const Fq d = fp_sub(s, x3);
+  Fq t, wy, zzz3, t4;
+  quad_products(role, m, d, w, p.y, w, p.zzz, m, d, t, wy, zzz3, t4);                     // level 3: M (S - X3), W Y, ZZZ3
+  p.x = x3;
+  p.y = fp_sub(t, wy);
+  p.zz = zz3;    // identity (zz = 0) and y = 0 (u = 0 => v = 0) both give zz3 = 0: the identity, as xyzz_double does
+  p.zzz = zzz3;
+}
+
+#ifndef ALEO_EMU
+#define TAIL_CLOCK(slot) \
+  if (dbg && threadIdx.x == ((nwin - 1) << 2)) dbg[slot] = (unsigned long long)clock64()
+#else
+#define TAIL_CLOCK(slot) ((void)0)
+#endif
+
+// dbg (optional, 4 x u64): clock64 of the top window's lane before / after the doubling chain, after the tree,
+// after the normalisation (tuning aid, ALEO_B200_MSM_TRACE)
+KERNEL void __launch_bounds__(TAIL_TPB, 1) weigh_sum_kernel(const G1Xyzz* S, u32 nwin, u32 c, unsigned char* out144,
+                                                            unsigned long long* dbg) {
+  SHARED G1Xyzz D[TAIL_TPB / 4];
+  const u32 tid = threadIdx.x;
+  TAIL_CLOCK(0);
+  const u32 w = tid >> 2, role = tid & 3u;
+  G1Xyzz p = xyzz_identity();
+  if (w < nwin) p = S[w];
+  // every lane of a warp iterates to the warp's largest count (shuffles need the whole warp); a quad that is
+  // done keeps its point
+  const u32 my_count = (w < nwin) ? c * w : 0u;
+#ifndef ALEO_EMU
+  const u32 w_first = (tid & ~31u) >> 2, w_last = (tid | 31u) >> 2;  // windows of this warp's quads
+  const u32 warp_count = (w_first < nwin) ? c * (w_last < nwin ? w_last : nwin - 1) : 0u;
+  for (u32 it = 0; it < warp_count; it++) {
+    G1Xyzz q = p;
+    quad_double(role, q);
+    const u32 keep = 0u - (u32)(it >= my_count);  // all ones: this quad is done, its point stays
+#pragma unroll
+    for (int k = 0; k < FqParams::N; k++) {
+      p.x.l[k] = (p.x.l[k] & keep) | (q.x.l[k] & ~keep);
+      p.y.l[k] = (p.y.l[k] & keep) | (q.y.l[k] & ~keep);
+      p.zz.l[k] = (p.zz.l[k] & keep) | (q.zz.l[k] & ~keep);
+      p.zzz.l[k] = (p.zzz.l[k] & keep) | (q.zzz.l[k] & ~keep);
+    }
+  }
+#else
+  if (role == 0)
+    for (u32 it = 0; it < my_count; it++) quad_double(role, p);
+#endif
+  TAIL_CLOCK(1);
+  if (role == 0) D[w] = p;
+  SYNC_THREADS();
+  for (u32 off = TAIL_TPB / 8; off > 0; off >>= 1) {
+    if (tid < off && tid + off < nwin) {
+      G1Xyzz a = D[tid];
+      xyzz_add_ni(a, D[tid + off]);
+      D[tid] = a;
+    }
+    SYNC_THREADS();
+  }
+  TAIL_CLOCK(2);
+  if (tid == 0) jacobian_store_normalised(out144, D[0]);
+  SYNC_THREADS();
+  TAIL_CLOCK(3);
 }
 
 // sum of `count` Jacobian points -> normalised Jacobian (multi-GPU combine; count is tiny)

@@ -1,5 +1,6 @@
 // msm_host.cuh -- host-side driver of msm.cuh: window choice, workspace carving, launch sequence.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "msm.cuh"
@@ -110,9 +111,40 @@ static inline cudaError_t exclusive_scan(const u32* in, u32 n, u32* block_sums, 
   return cudaGetLastError();
 }
 
-struct RedLevel {
-  u32 m, T;  // input length per window, chunks per window
+// ALEO_B200_MSM_TRACE=1: finish() times its launches with events and prints them to stderr (tuning aid; synchronises)
+struct TailTrace {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  void mark(const char* name, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    names.push_back(name);
+  }
+  void report(cudaStream_t s) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "[msm tail] %-14s %.3f ms\n", names[i], ms);
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+  }
 };
+
+struct RedLevel {
+  u32 m, T, log_kc, scale_log;  // weighted input length per window, chunks out per window, chunk size, weight of WS
+};
+
+static inline u32 ceil_log2(u32 v) {
+  u32 l = 0;
+  while ((1u << l) < v) l++;
+  return l;
+}
 
 // One MSM = begin() + add_chunk() per point range + finish().  The bucket set lives in the session's
 // workspace across chunks: a chunk is sorted on its own and its bucket sums are ADDED to what the earlier
@@ -125,6 +157,7 @@ struct Session {
   u32 nwin = 0, NB = 0, max_lanes = 0, cap_small = 0, cap_large = 0, scan_blocks = 0;
   size_t max_chunk = 0;
   std::vector<RedLevel> lv;
+  u32 scan_m = 0, scan_t_in = 0, scan_scale_log = 0, scan_span = 32;  // last reduction stage (one CTA per window)
   size_t o_counts = 0, o_starts = 0, o_ends = 0, o_piece_bucket = 0, o_bsums = 0, o_meta = 0, o_sorted = 0, o_small = 0,
          o_large = 0, o_buckets = 0, o_pieces = 0, o_D = 0, bytes = 0;
   std::vector<size_t> o_R, o_P;
@@ -149,20 +182,29 @@ struct Session {
     cap_large = max_lanes / SMALL_SPLIT_MAX + 1;
     scan_blocks = (NB + SCAN_BLOCK - 1) / SCAN_BLOCK;
     {
-      // level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out;
-      // the plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too
-      u32 m = prm.B, t_prev = 0;
+      // chunk level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out; the
+      // plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too.  Chunk
+      // levels run until the scan stage (<= SCAN_MAX elements per window) can take over.
+      u32 m = prm.B, t_prev = 0, scale_log = 0;
       for (;;) {
+        const u32 need = t_prev > m ? t_prev : m;
+        if (need <= SCAN_MAX) break;
         RedLevel l;
         l.m = m;
-        const u32 need = t_prev > m ? t_prev : m;
-        l.T = (need + RED_KC - 1) / RED_KC;
-        if (l.T == 0) l.T = 1;
+        l.log_kc = ceil_log2((need + SCAN_MAX - 1) / SCAN_MAX);
+        if (l.log_kc > 4) l.log_kc = 4;
+        l.scale_log = scale_log;
+        l.T = (need + (1u << l.log_kc) - 1) >> l.log_kc;
         lv.push_back(l);
-        if (l.T == 1) break;
+        scale_log += l.log_kc;
         t_prev = l.T;
         m = l.T - 1;
       }
+      scan_m = m;
+      scan_t_in = t_prev;
+      scan_scale_log = scale_log;
+      scan_span = 32;
+      while (scan_span < (scan_m > scan_t_in ? scan_m : scan_t_in)) scan_span <<= 1;
     }
     Carver cv;
     o_counts = cv.take((size_t)NB * 4);
@@ -182,7 +224,7 @@ struct Session {
       o_R[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
       o_P[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
     }
-    o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));
+    o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));  // S_w: one sum per window
     bytes = cv.off;
     if (dry) return cudaSuccess;
     MSM_CK(cudaMallocAsync((void**)&ws, bytes, s));
@@ -224,13 +266,35 @@ struct Session {
     if (phase_ev) cudaEventRecord(phase_ev[0], s);
     MSM_CK(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
     MSM_CK(cudaMemsetAsync(meta, 0, 64, s));
-    const u32 g_n = (n + 255) / 256;
-    LAUNCH_NOSYNC(count_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, counts);
+    const u32 g_all = (n + 255) / 256, g_n = g_all < 1184 ? g_all : 1184;  // <= 8 CTAs of 256 per SM and window
+    // count: scalar-major (every warp iteration spreads its 32 atomics over one window's counters and moves on);
+    // scatter: window-major once the bucket heads of all windows (W * 2^(c-1) sectors of 32 B) outgrow L2 --
+    // measured on B200 at n = 2^24, c = 20: count 3.3 (scalar) / 4.5 (window) ms, scatter 9.2 / 5.3 ms;
+    // at c = 16: count 4.0 / 5.6, scatter 4.2 / 5.8.  ALEO_B200_MSM_SORT = s | w forces one order for both.
+    const char* sort_env = getenv("ALEO_B200_MSM_SORT");
+    const bool heads_fit_l2 = (size_t)NB * 32 <= ((size_t)48 << 20);
+    const bool count_wm = sort_env && sort_env[0] == 'w';
+    const bool scatter_wm = sort_env ? sort_env[0] == 'w' : !heads_fit_l2;
+    TailTrace st;
+    st.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
+    st.mark("start", s);
+    if (count_wm)
+      LAUNCH_NOSYNC(count_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, counts);
+    else
+      LAUNCH_NOSYNC(count_kernel_sm, dim3(g_all), dim3(256), 0, s, scalars, n, p, counts);
+    st.mark("count", s);
     int scan_launches = 0;
     MSM_CK(exclusive_scan(counts, NB, at<u32>(o_bsums), starts, ends, meta + 0, s, scan_launches));
-    LAUNCH_NOSYNC(scatter_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    st.mark("scan", s);
+    if (scatter_wm)
+      LAUNCH_NOSYNC(scatter_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    else
+      LAUNCH_NOSYNC(scatter_kernel_sm, dim3(g_all), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    st.mark("scatter", s);
     LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB, p.nlanes,
                   small_list, large_list, cap_small, cap_large, meta);
+    st.mark("plan", s);
+    st.report(s);
     if (phase_ev) cudaEventRecord(phase_ev[1], s);
     static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
     if (acc_inline)
@@ -240,16 +304,22 @@ struct Session {
       LAUNCH_NOSYNC(accumulate_kernel<true>, dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
                     (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
     if (phase_ev) cudaEventRecord(phase_ev[2], s);
+    TailTrace tr;
+    tr.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
+    tr.mark("start", s);
     LAUNCH_NOSYNC(combine_small_kernel, dim3((p.nlanes + 1 + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
                   (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
                   (const u32*)piece_bucket, buckets);
+    tr.mark("combine small", s);
     {
       const u32 cl = p.nlanes / SMALL_SPLIT_MAX + 1;
       const u32 g = cl < 592 ? cl : 592;  // 4 CTAs per SM; the kernel strides over the list
-      LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), COMBINE_TPB * sizeof(G1Xyzz), s, (const u32*)large_list,
+      LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), 0, s, (const u32*)large_list,
              (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces, (const u32*)piece_bucket,
              buckets);
+      tr.mark("combine large", s);
     }
+    tr.report(s);
     return cudaGetLastError();
   }
 
@@ -258,7 +328,10 @@ struct Session {
     launches += (int)lv.size() + 2;
     if (dry) return cudaSuccess;
     G1Xyzz* buckets = at<G1Xyzz>(o_buckets);
-    // bucket reduction: one launch per level until a single chunk per window is left
+    const u32 nwin = this->nwin, c = prm.c;  // plain values for the launch macros
+    TailTrace tr;
+    tr.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
+    tr.mark("start", s);
     for (size_t l = 0; l < lv.size(); l++) {
       ReduceArgs ra;
       ra.X = (l == 0) ? buckets : at<G1Xyzz>(o_R[l - 1]);
@@ -267,20 +340,45 @@ struct Session {
       ra.m = lv[l].m;
       ra.P = (l == 0) ? nullptr : at<G1Xyzz>(o_P[l - 1]);
       ra.T_in = (l == 0) ? 0 : lv[l - 1].T;
-      ra.level = (u32)l;
+      ra.log_kc = lv[l].log_kc;
+      ra.scale_log = lv[l].scale_log;
       ra.R_out = at<G1Xyzz>(o_R[l]);
       ra.P_out = at<G1Xyzz>(o_P[l]);
       ra.T_out = lv[l].T;
       ra.nwin = nwin;
       const u32 threads = nwin * lv[l].T;
       LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra);
+      tr.mark("chunk level", s);
     }
-    const G1Xyzz* S = at<G1Xyzz>(o_P[lv.size() - 1]);
-    G1Xyzz* D = at<G1Xyzz>(o_D);
-    const u32 nwin = this->nwin, c = prm.c, s_stride = lv.back().T;
-    // per-window weights 2^(c w): not needed for a resident SRS (they are baked into the expanded bases)
-    LAUNCH_NOSYNC(window_weigh_kernel, dim3((nwin + 31) / 32), dim3(32), 0, s, S, s_stride, nwin, c, D);
-    LAUNCH_NOSYNC(final_kernel, dim3(1), dim3(1), 0, s, (const G1Xyzz*)D, nwin, out144);
+    G1Xyzz* S = at<G1Xyzz>(o_D);
+    {
+      const size_t L = lv.size();
+      ScanArgs sa;
+      sa.X = L ? at<G1Xyzz>(o_R[L - 1]) : buckets;
+      sa.x_stride = L ? lv[L - 1].T : prm.B;
+      sa.x_off = L ? 1 : 0;
+      sa.m = scan_m;
+      sa.P = L ? at<G1Xyzz>(o_P[L - 1]) : nullptr;
+      sa.T_in = scan_t_in;
+      sa.scale_log = scan_scale_log;
+      sa.S = S;
+      const u32 span = scan_span;
+      LAUNCH(reduce_scan_kernel, dim3(nwin), dim3(span), span * sizeof(G1Xyzz), s, sa);
+      tr.mark("scan", s);
+    }
+    // per-window weights 2^(c w) (none for a resident SRS: they are baked into the expanded bases), sum, normalise
+    unsigned long long* dbg = nullptr;
+    if (tr.on && cudaMalloc((void**)&dbg, 32) != cudaSuccess) dbg = nullptr;
+    LAUNCH(weigh_sum_kernel, dim3(1), dim3(TAIL_TPB), 0, s, (const G1Xyzz*)S, nwin, c, out144, dbg);
+    tr.mark("weigh+sum+inv", s);
+    tr.report(s);
+    if (dbg) {
+      unsigned long long h[4] = {0, 0, 0, 0};
+      cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[msm tail] clocks: doubling chain %llu (%u doublings), window tree %llu, normalise %llu\n", h[1] - h[0],
+              c * (nwin - 1), h[2] - h[1], h[3] - h[2]);
+      cudaFree(dbg);
+    }
     if (done_ev) cudaEventRecord(*done_ev, s);
     cudaError_t e = cudaGetLastError();
     release(s);

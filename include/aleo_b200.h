@@ -122,6 +122,18 @@ int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, con
 int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);
 
+/* ---- elementwise field arithmetic on device vectors ------------------------------------------------
+ * out[i] = a[i] op b[i] over n elements in Montgomery form (Fr: 32 B, Fq: 48 B; in-place allowed).  Stands in
+ * for the pointwise arithmetic snarkVM's prover does on evaluation vectors between its FFTs
+ * (snarkvm-algorithms 0.14.5 src/fft/evaluations.rs Mul / Sub / Add, snarkvm-fields batch_inversion;
+ * SURVEY.md 8f rank 2), reached from the reference at rust/src/program/execute.rs:74,219, so that prover
+ * rounds can stay on the device between transforms.  b is ignored for SQR / INV / NEG; INV maps 0 to 0
+ * (batch_inversion leaves zeros untouched).  Also what the parity tests use to pin the field core. */
+enum { ALEO_B200_FIELD_FR = 0, ALEO_B200_FIELD_FQ = 1 };
+enum { ALEO_B200_OP_ADD = 0, ALEO_B200_OP_SUB = 1, ALEO_B200_OP_MUL = 2, ALEO_B200_OP_SQR = 3, ALEO_B200_OP_INV = 4,
+       ALEO_B200_OP_NEG = 5 };
+int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, void* stream);
+
 /* ---- synthetic workload generation and on-device checks (bench / tests) --------------------
  * bases[i] = (s0 + (first_index + i) * d) * G, G the G1 generator; s0, d canonical 32-byte scalars.
  * Known discrete logs make the MSM result checkable at any size. */

@@ -186,3 +186,56 @@ def test_emu_host_calls_stream_point_ranges(emu_lib, chunks, monkeypatch):
         emu_lib.check(emu_lib.kzg_commit(h, C.cast(out48, C.c_void_p), C.cast(cb, C.c_void_p), n_used), "kzg_commit")
         assert out48.raw == o.g1_compress(o.msm_pippenger(B[:n_used], s[:n_used])), n_used
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+@pytest.mark.parametrize("c", [5, 12, 14])
+def test_emu_msm_reduction_stages(emu_lib, c, monkeypatch):
+    """forced window sizes: c = 5 -> scan stage only, 12 -> one chunk level + scan, 14 -> two chunk levels + scan;
+    also exercises the quad-cooperative doubling tail over 51 / 22 / 19 windows and the binary-GCD inversion"""
+    monkeypatch.setenv("ALEO_B200_MSM_C", str(c))
+    n = 200
+    assert emu_lib.msm_window_bits(n) == c
+    B = o.synthetic_bases(n, 41)
+    s = o.random_fr_vec(n, 42)
+    s[0], s[1] = o.R_MOD - 1, 1
+    assert _msm(emu_lib, B, s, 104) == o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+
+
+def _field_op(lib, field, op, a, b=None):
+    size = 32 if field == 0 else 48
+    n = len(a)
+    enc = (lambda v: o.fr_vec_to_bytes(v)) if field == 0 else (lambda v: b"".join(o.int_to_le_bytes(o.fq_to_mont(x), 48) for x in v))
+    ab = C.create_string_buffer(enc(a), n * size)
+    bb = C.create_string_buffer(enc(b), n * size) if b is not None else None
+    out = C.create_string_buffer(n * size)
+    lib.check(lib.field_op_dev(field, op, C.cast(out, C.c_void_p), C.cast(ab, C.c_void_p),
+                               C.cast(bb, C.c_void_p) if bb is not None else None, n, None), "field_op")
+    if field == 0:
+        return o.fr_vec_from_bytes(out.raw)
+    return [o.fq_from_mont(o.le_bytes_to_int(out.raw[i * 48:(i + 1) * 48])) for i in range(n)]
+
+
+def field_edge_values(mod, nlimbs):
+    """values that stress the carry chains: 0, 1, m-1, all-ones limbs, single high bits, R mod m ..."""
+    R = 1 << (32 * nlimbs)
+    vals = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, R % mod, (R * R) % mod, pow(R, -1, mod)]
+    vals += [((1 << k) - 1) % mod for k in (31, 32, 33, 63, 64, 65, 32 * nlimbs - 8)]
+    vals += [(1 << k) % mod for k in range(0, mod.bit_length(), 29)]
+    vals += [v for x in list(vals) for v in ((x * pow(R, -1, mod)) % mod,)]   # Montgomery images with the same shapes
+    return vals
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_emu_field_ops(emu_lib, field):
+    """add / sub / mul / dedicated square / binary-GCD inverse / neg against big-integer arithmetic"""
+    import random
+    mod, nl = (o.R_MOD, 8) if field == 0 else (o.P_MOD, 12)
+    rng = random.Random(1234 + field)
+    a = field_edge_values(mod, nl) + [rng.randrange(mod) for _ in range(120)]
+    b = list(reversed(field_edge_values(mod, nl))) + [rng.randrange(mod) for _ in range(120)]
+    assert _field_op(emu_lib, field, 0, a, b) == [(x + y) % mod for x, y in zip(a, b)]
+    assert _field_op(emu_lib, field, 1, a, b) == [(x - y) % mod for x, y in zip(a, b)]
+    assert _field_op(emu_lib, field, 2, a, b) == [(x * y) % mod for x, y in zip(a, b)]
+    assert _field_op(emu_lib, field, 3, a) == [(x * x) % mod for x in a]
+    assert _field_op(emu_lib, field, 4, a) == [pow(x, -1, mod) if x else 0 for x in a]
+    assert _field_op(emu_lib, field, 5, a) == [(-x) % mod for x in a]
