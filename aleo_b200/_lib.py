@@ -47,6 +47,7 @@ SYMBOLS = [
     ("aleo_b200_field_op_dev", _int, [_int, _int, _vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
+    ("aleo_b200_msm_host_plan", _int, [_sz, C.POINTER(_int), C.POINTER(_int)]),
     ("aleo_b200_gen_bases_dev", _int, [_vp, _sz, _sz, _vp, _vp, _u64, _vp]),
     ("aleo_b200_gen_scalars_dev", _int, [_vp, _sz, _u64, _u64, _int, _vp]),
     ("aleo_b200_dlog_dot_dev", _int, [_vp, _vp, _sz, _vp, _vp, _u64, _vp]),

@@ -218,6 +218,13 @@ int aleo_b200_msm_launches(size_t n) {
   return launches;
 }
 
+int aleo_b200_msm_host_plan(size_t n, int* ranges_out, int* window_bits_out) {
+  if (!aleo::msm_size_supported(n)) return ALEO_B200_ETOOLARGE;
+  if (ranges_out) *ranges_out = n ? aleo::msm_host_chunks(n) : 1;
+  if (window_bits_out) *window_bits_out = aleo::msm_host_window_bits(n);
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_msm_g1_dev(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,
                          size_t affine_stride, void* stream) {
   if (!stride_ok(affine_stride) || out_projective_dev == nullptr) return ALEO_B200_EINVAL;

@@ -37,13 +37,36 @@ struct Params {
   // window shares ONE set of 2^(c-1) buckets and the entry for (point i, window w) is w * n_stride + i.
   u32 n_stride;
   u32 first;   // resident-SRS mode: offset of this point range into the SRS (scalar i belongs to P_(first + i))
+  // Half-range recoding: a scalar s > (r-1)/2 is replaced by r - s and all its digits change sign
+  // (s P = (r - s)(-P)).  The recoded scalars have 252 bits, which is what lets c = 23 cover them with 11
+  // windows instead of 12 (253 = 11 * 23 leaves no room for the recoding carry).  Used by the resident SRS.
+  u32 half_range;
 };
 
 DEV u32 bucket_slot(const Params& prm, u32 w, u32 mag) { return prm.n_stride ? (mag - 1) : (w * prm.B + (mag - 1)); }
 DEV u32 entry_index(const Params& prm, u32 w, u32 i) { return prm.n_stride ? (w * prm.n_stride + prm.first + i) : i; }
 
+// scalar i -> t (local copy, indexed by window position); returns 1 when half-range recoding replaced it by r - s
+DEV u32 load_scalar(const u32* s, u32 (&t)[8], u32 half_range) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) t[k] = s[k];
+  if (!half_range) return 0;
+  // s > (r-1)/2  <=>  2s >= r  <=>  2s - r does not borrow   (2s < 2^254 fits 8 limbs)
+  u32 d[8];
+  d[0] = ptx::sub_cc(t[0] << 1, FrParams::MOD(0));
+#pragma unroll
+  for (int k = 1; k < 8; k++) d[k] = ptx::subc_cc((t[k] << 1) | (t[k - 1] >> 31), FrParams::MOD(k));
+  const u32 borrow = ptx::subc(0, 0);
+  if (borrow) return 0;
+  t[0] = ptx::sub_cc(FrParams::MOD(0), t[0]);
+#pragma unroll
+  for (int k = 1; k < 7; k++) t[k] = ptx::subc_cc(FrParams::MOD(k), t[k]);
+  t[7] = ptx::subc(FrParams::MOD(7), t[7]);
+  return 1;
+}
+
 // signed digit of window w given the carry from window w-1; returns |digit| and updates carry/neg
-DEV u32 recode_digit(const u32* s /* 8 limbs in global memory */, u32 w, u32 c, u32& carry, u32& neg) {
+DEV u32 recode_digit(const u32* s /* 8 limbs */, u32 w, u32 c, u32& carry, u32& neg) {
   const u32 bit = w * c;
   const u32 limb = bit >> 5, sh = bit & 31u;
   u32 raw = 0;
@@ -102,8 +125,11 @@ KERNEL void count_kernel(const u32* scalars, u32 n, Params prm, u32* counts) {
   const u32 w = blockIdx.y;
   for (u32 base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // uniform trip count per CTA
     const u32 i = base + threadIdx.x;
-    u32 neg = 0, mag = 0;
-    if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
+    u32 neg = 0, mag = 0, t[8];
+    if (i < n) {
+      load_scalar(scalars + (size_t)i * 8, t, prm.half_range);
+      mag = digit_of_window(t, w, prm.c, neg);
+    }
     warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
   }
 }
@@ -112,10 +138,13 @@ KERNEL void scatter_kernel(const u32* scalars, u32 n, Params prm, u32* cursor, u
   const u32 w = blockIdx.y;
   for (u32 base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const u32 i = base + threadIdx.x;
-    u32 neg = 0, mag = 0;
-    if (i < n) mag = digit_of_window(scalars + (size_t)i * 8, w, prm.c, neg);
+    u32 neg = 0, mag = 0, flip = 0, t[8];
+    if (i < n) {
+      flip = load_scalar(scalars + (size_t)i * 8, t, prm.half_range);
+      mag = digit_of_window(t, w, prm.c, neg);
+    }
     const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
-    if (mag) sorted[pos] = entry_index(prm, w, i) | (neg << 31);
+    if (mag) sorted[pos] = entry_index(prm, w, i) | ((neg ^ flip) << 31);
   }
 }
 
@@ -124,22 +153,24 @@ KERNEL void scatter_kernel(const u32* scalars, u32 n, Params prm, u32* cursor, u
 // counter region
 KERNEL void count_kernel_sm(const u32* scalars, u32 n, Params prm, u32* counts) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32* s = scalars + (size_t)(i < n ? i : 0) * 8;
+  u32 t[8];
+  load_scalar(scalars + (size_t)(i < n ? i : 0) * 8, t, prm.half_range);
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
-    const u32 mag = (i < n) ? recode_digit(s, w, prm.c, carry, neg) : 0u;
+    const u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
     warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
   }
 }
 
 KERNEL void scatter_kernel_sm(const u32* scalars, u32 n, Params prm, u32* cursor, u32* sorted) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32* s = scalars + (size_t)(i < n ? i : 0) * 8;
+  u32 t[8];
+  const u32 flip = load_scalar(scalars + (size_t)(i < n ? i : 0) * 8, t, prm.half_range);
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
-    const u32 mag = (i < n) ? recode_digit(s, w, prm.c, carry, neg) : 0u;
+    const u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
     const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
-    if (mag) sorted[pos] = entry_index(prm, w, i) | (neg << 31);
+    if (mag) sorted[pos] = entry_index(prm, w, i) | ((neg ^ flip) << 31);
   }
 }
 

@@ -52,14 +52,22 @@ struct SrsView {
   u32 c, W;
 };
 
-// window bits of a resident SRS of n points: the doubling tail and the per-window buckets are gone, so
-// the optimum moves up (n * W(c) mixed additions against 2 * 2^(c-1) reduction additions)
+// Resident SRS: the doubling tail and the per-window bucket sets are gone (n * W mixed additions against ONE set of
+// 2^(c-1) buckets), and the scalars are recoded half-range (252 bits), so W(c) = ceil(253 / c): c = 23 needs 11 windows.
+static inline u32 windows_for_srs(u32 c) { return (SCALAR_BITS + c - 1) / c; }
+
 static inline u32 choose_window_srs(size_t n) {
   if (n < 2) return 8;
-  long c = (long)floor_log2(n) - 2;
-  if (c < 8) c = 8;
-  if (c > 22) c = 22;
-  return (u32)c;
+  u32 best_c = 8;
+  double best = 0;
+  for (u32 c = 8; c <= 23; c++) {
+    const double cost = (double)n * windows_for_srs(c) * 10.0 + (double)(1u << (c - 1)) * 2.0 * 14.0 * 1.5;
+    if (c == 8 || cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
 }
 
 // accumulation threads for `n_chunk` points: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on
@@ -77,7 +85,8 @@ static inline u32 lanes_for(size_t n_chunk, u32 W) {
 static inline Params make_params(size_t n, const SrsView* srs = nullptr, u32 chunks = 1) {
   Params p;
   p.c = srs ? srs->c : choose_window(n, chunks);
-  p.W = windows_for(p.c);
+  p.W = srs ? srs->W : windows_for(p.c);
+  p.half_range = srs ? 1u : 0u;
   p.B = 1u << (p.c - 1);
   p.n_stride = srs ? srs->n_total : 0;
   p.first = 0;
@@ -274,7 +283,7 @@ struct Session {
     const char* sort_env = getenv("ALEO_B200_MSM_SORT");
     const bool heads_fit_l2 = (size_t)NB * 32 <= ((size_t)48 << 20);
     const bool count_wm = sort_env && sort_env[0] == 'w';
-    const bool scatter_wm = sort_env ? sort_env[0] == 'w' : !heads_fit_l2;
+    const bool scatter_wm = sort_env ? sort_env[0] == 'w' : (!heads_fit_l2 && !srs);  // a resident SRS shares one bucket set: nothing to gain
     TailTrace st;
     st.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
     st.mark("start", s);

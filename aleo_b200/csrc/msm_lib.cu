@@ -150,7 +150,7 @@ cudaError_t srs_create(const void* bases_dev, u32 stride, size_t n, cudaStream_t
   cudaGetDevice(&h->device);
   h->n = n;
   h->c = msm::choose_window_srs(n);
-  h->W = msm::SCALAR_BITS / h->c + 1;
+  h->W = msm::windows_for_srs(h->c);
   if (h->W > msm::SRS_MAX_WINDOWS || (unsigned long long)n * h->W >= (1ull << 31)) {
     delete h;
     return cudaErrorInvalidValue;

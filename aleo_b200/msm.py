@@ -82,6 +82,14 @@ class VariableBase:
     def launches(n: int) -> int:
         return _lib.get_lib().msm_launches(n)
 
+    @staticmethod
+    def host_plan(n: int) -> dict:
+        """how the host-pointer entry point cuts n points into overlapped point ranges, and its window size"""
+        lib = _lib.get_lib()
+        k, c = C.c_int(), C.c_int()
+        lib.check(lib.msm_host_plan(n, C.byref(k), C.byref(c)), "aleo_b200_msm_host_plan")
+        return {"ranges": k.value, "window_bits": c.value}
+
 
 # ---- synthetic workloads (BASELINE.md section 3) and on-device checks ---------------------------------
 def gen_bases_dev(n: int, s0: int, d: int, first_index: int = 0, affine_stride: int = AFFINE_STRIDE_RUST, device=None):

@@ -25,7 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MACS_PER_MIXED_ADD = 3000          # 10 Fq products x (2*12^2 + 12) 32x32->64 MACs
+MACS_PER_MIXED_ADD = 3000          # 10 Fq products x (2*12^2 + 12) 32x32->64 MACs (algorithmic)
+ISSUED_MACS_PER_MIXED_ADD = 8 * 276 + 2 * 210   # IMAD.WIDE actually issued: 8 products + 2 dedicated squares (cuobjdump)
 NTT_BYTES_PER_ELEM_PER_PASS = 64   # 32 B read + 32 B write
 
 
@@ -239,14 +240,18 @@ def run_ours(args):
     if os.path.exists(ppath):
         prof = json.load(open(ppath))
     roofline = {"kernel": "msm::accumulate_kernel", "bound": "int", "achieved": macs / acc / 1e6, "peak": peak_gmac, "unit": "GMAC/s",
-                "frac": macs / acc / 1e6 / peak_gmac, "traffic": (prof["msm_accumulate_dram_bytes_at_2p22"] * n / (1 << 22)) if "msm_accumulate_dram_bytes_at_2p22" in prof else None,
+                "frac": macs / acc / 1e6 / peak_gmac,
+                "pipe_frac": n * windows * ISSUED_MACS_PER_MIXED_ADD / acc / 1e6 / peak_gmac,
+                "issued_macs_per_mixed_add": ISSUED_MACS_PER_MIXED_ADD, "traffic": (prof["msm_accumulate_dram_bytes_at_2p22"] * n / (1 << 22)) if "msm_accumulate_dram_bytes_at_2p22" in prof else None,
                 "traffic_source": "ncu --set full at n=2^22 (profiles/r01_ncu_hot_kernels.md), scaled linearly to this n",
                 "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows,
                 "kernel_ms": acc, "kernel_share_of_step": acc / (sum(sort_ms) / len(sort_ms) + acc + sum(tail_ms) / len(tail_ms)),
                 "phases_ms": {"recode_sort_plan": sum(sort_ms) / len(sort_ms), "accumulate": acc, "combine_reduce_final": sum(tail_ms) / len(tail_ms)},
                 "peak_source": "measured live: carry-chained IMAD.WIDE.U32.X microbenchmark in this library (MEASURED_PEAKS.json "
                                "has no integer-pipe figure); 32-bit MAC = one IMAD.WIDE",
-                "note": "MSM is integer-pipe bound (SURVEY.md 8d); the schema's hbm/tensor bounds do not apply to this kernel"}
+                "note": "MSM is integer-pipe bound (SURVEY.md 8d); the schema's hbm/tensor bounds do not apply to this kernel. "
+                        "frac counts SURVEY's ALGORITHMIC 3000 MACs per mixed addition; the kernel issues fewer (dedicated "
+                        "squaring, modulus limb 0 = 1), so frac can exceed the share of the pipe it occupies: pipe_frac"}
 
     # ---- resident SRS (KZG10::commit shape): bases expanded once, one shared bucket set ----------------
     srs_obj = None
@@ -325,6 +330,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = world * n * args.steps / e2e_s.item() / 1e6
+    host_plan = ab.VariableBase.host_plan(n)
     del hb, hs
 
     # ---- secondary: Fr NTT of the same size, resident ---------------------------------------------
@@ -411,6 +417,41 @@ def run_ours(args):
                     "collective": "one all_to_all_single (NCCL) of %d bytes per rank" % (g1 * wc * 32 * (world - 1) // world),
                     "scaling": "weak", "delta_impulse_check": all(flags)}
 
+    # ---- size sweep 2^16 .. 2^22 (BASELINE.json metric range / config 2), single-GPU run only -----------------
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        del x, x0
+        torch.cuda.empty_cache()
+        sweep = []
+        for ln in range(16, min(log_n, 23), 2):
+            m = 1 << ln
+            sb = ab.gen_bases_dev(m, s0, d, 0, 104, device=dev)
+            ss = ab.gen_scalars_dev(m, seed + ln, 0, False, device=dev)
+            want_s = o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, ab.dlog_dot_dev(ss, m, s0, d, 0)))
+            ok_s = ab.VariableBase.msm_dev(sb, ss, m, 104).cpu().numpy().tobytes() == want_s
+            reps = 10
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                ab.VariableBase.msm_dev(sb, ss, m, 104, out=partial)
+            a1.record()
+            torch.cuda.synchronize()
+            msm_ms = a0.elapsed_time(a1) / reps
+            sd = ab.EvaluationDomain.new(m)
+            sx = ab.gen_scalars_dev(m, 5 + ln, 0, True, device=dev)
+            sd.fft_in_place_dev(sx)
+            torch.cuda.synchronize()
+            a0.record()
+            for _ in range(reps):
+                sd.fft_in_place_dev(sx)
+            a1.record()
+            torch.cuda.synchronize()
+            ntt_ms_s = a0.elapsed_time(a1) / reps
+            sweep.append({"log_n": ln, "msm_ms": msm_ms, "msm_mpts_per_s": m / msm_ms / 1e3, "msm_window_bits": ab.VariableBase.window_bits(m),
+                          "msm_checked_against_oracle": bool(ok_s), "ntt_ms": ntt_ms_s, "ntt_melem_per_s": m / ntt_ms_s / 1e3})
+            del sb, ss, sx
+
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -429,9 +470,11 @@ def run_ours(args):
                        "parallelism": "point-range shard x%d" % world},
             "checked_against_oracle": checked and e2e_ok,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
-                    "api": "aleo_b200_msm_g1 (host pointers, pinned)"},
+                    "api": "aleo_b200_msm_g1 (host pointers, pinned)", "point_ranges": host_plan["ranges"],
+                    "window_bits": host_plan["window_bits"],
+                    "note": "the call copies and accumulates point range by point range: H2D of range k+1 overlaps range k"},
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
-            "roofline": roofline, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "sweep": sweep, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -448,6 +491,7 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-srs", action="store_true", help="skip the resident-SRS (KZG commit) measurement")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^22 size sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -99,8 +99,9 @@ int aleo_b200_g1_sum_dev(void* out_projective_dev, const void* points_dev, size_
  * KZG10::commit(powers, polynomial, ..) = VariableBase::msm(&powers.powers_of_beta_g[..d+1], coeffs.to_bigint())
  * (snarkvm-algorithms 0.14.5 src/polycommit/kzg10/mod.rs).  An SRS
  * handle keeps the bases on the device, expanded once to 2^(c w) * P_i for every window w, so that a
- * commitment needs one shared bucket set, ~25 % fewer additions (larger windows) and no doubling tail.
- * Device memory: n * (253 / c + 1) * 96 bytes (c = clamp(log2 n - 2, 8, 22)).  A handle belongs to the
+ * commitment needs one shared bucket set, ~30 % fewer additions (larger windows; scalars above (r-1)/2 are
+ * recoded as r - s on the negated point, so 2^24 points need 11 windows of 23 bits) and no doubling tail.
+ * Device memory: n * ceil(253 / c) * 96 bytes (c by cost model, 8..23: 2^16 -> 15, 2^24 -> 23).  A handle belongs to the
  * device that was current when it was created; MSMs over any PREFIX of the bases are supported. */
 int aleo_b200_srs_create(void** handle_out, const void* bases_host, size_t n, size_t affine_stride);
 int aleo_b200_srs_create_dev(void** handle_out, const void* bases_dev, size_t n, size_t affine_stride, void* stream);
@@ -118,9 +119,13 @@ int aleo_b200_srs_msm_launches(const void* handle, size_t n_used);
 int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs);
 int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                              void* stream);
-/* window size c (bits) the MSM uses for n points, and the kernel launches one MSM issues */
+/* window size c (bits) the MSM uses for n device-resident points, and the kernel launches one MSM issues */
 int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);
+/* The host-pointer entry points (aleo_b200_msm_g1, aleo_b200_srs_msm, aleo_b200_kzg_commit) copy and accumulate
+ * the MSM in point ranges so that the host->device copy of range k+1 overlaps the accumulation of range k:
+ * how many ranges n points are cut into, and the window size that goes with it. */
+int aleo_b200_msm_host_plan(size_t n, int* ranges_out, int* window_bits_out);
 
 /* ---- elementwise field arithmetic on device vectors ------------------------------------------------
  * out[i] = a[i] op b[i] over n elements in Montgomery form (Fr: 32 B, Fq: 48 B; in-place allowed).  Stands in

@@ -123,7 +123,7 @@ def test_emu_resident_srs_and_kzg_commit(emu_lib):
         emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, stride, None), "srs_create")
         nn, c, w, by = C.c_size_t(), C.c_int(), C.c_int(), C.c_size_t()
         emu_lib.check(emu_lib.srs_info(h, C.byref(nn), C.byref(c), C.byref(w), C.byref(by)), "info")
-        assert nn.value == n and c.value == 8 and w.value == 32 and by.value == n * 32 * 96
+        assert nn.value == n and c.value == 10 and w.value == 26 and by.value == n * 26 * 96
         for n_used, seed in ((n, 1), (n // 3, 2), (1, 3), (0, 4)):       # any prefix of the SRS
             s = o.random_fr_vec(n_used, 70 + seed)
             if n_used > 10:

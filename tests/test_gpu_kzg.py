@@ -15,7 +15,7 @@ def test_srs_from_host_prefix_msm_and_commit():
     for stride in (104, 96):
         srs = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(B, stride), stride)
         info = srs.info()
-        assert info["n"] == n and info["windows"] == 253 // info["window_bits"] + 1
+        assert info["n"] == n and info["windows"] == -(-253 // info["window_bits"])
         for n_used, seed in ((n, 1), (n // 3, 2), (1, 3), (0, 4)):
             s = o.random_fr_vec(n_used, 70 + seed)
             if n_used > 10:

@@ -154,3 +154,26 @@ def test_error_codes():
     assert lib.msm_g1(p, None, 0, None, 104) == ab._lib.OK          # n = 0 -> identity
     assert buf.raw[:144] == o.g1_projective_to_bytes(None)
     assert lib.msm_g1_dev(p, p, 1 << 40, p, 104, None) == ab._lib.ETOOLARGE
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 3])
+def test_host_call_streams_point_ranges(chunks, monkeypatch):
+    """aleo_b200_msm_g1 copies and accumulates point range by point range (H2D overlapped); the result must
+    not depend on the number of ranges.  2^20 points, known discrete logs, witness-like scalars mixed in."""
+    monkeypatch.setenv("ALEO_B200_MSM_CHUNKS", str(chunks))
+    n = (1 << 20) + 12345
+    seed = 4242
+    s0, d = o.base_dlogs(n, seed)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, seed)
+    sc[::3] = 0                                  # a third zero, a sixth one: the hot buckets of a witness
+    sc[1::6, 0] = 1
+    sc[1::6, 1:] = 0
+    k = ab.dlog_dot_dev(sc, n, s0, d, 0)
+    want = o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, k))
+    assert ab.VariableBase.msm(bases.cpu().numpy(), sc.cpu().numpy(), 104) == want
+    srs = ab.ResidentSRS.from_device(bases, n, 104)
+    try:
+        assert srs.msm(sc.cpu().numpy()) == want
+    finally:
+        srs.close()
