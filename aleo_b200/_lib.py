@@ -15,6 +15,7 @@ PRODUCT_LIB = os.path.join(_HERE, "libaleo_b200.so")
 OK, EINVAL, ETOOLARGE, ENODEVICE, ECUDA, ENOMEM = 0, -1, -2, -3, -4, -5
 NTT_FORWARD, NTT_INVERSE = 0, 1
 NTT_STANDARD, NTT_COSET = 0, 1
+NTT_ORDER_II, NTT_ORDER_IO, NTT_ORDER_OI = 0, 1, 2
 
 # every symbol include/aleo_b200.h declares: (name, restype, argtypes)
 _vp, _sz, _u32, _u64, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
@@ -27,6 +28,7 @@ SYMBOLS = [
     ("aleo_b200_shutdown", _int, []),
     ("aleo_b200_ntt_fr", _int, [_vp, _u32, _int, _int]),
     ("aleo_b200_ntt_fr_dev", _int, [_vp, _u32, _sz, _int, _int, _vp]),
+    ("aleo_b200_ntt_fr_ordered_dev", _int, [_vp, _u32, _sz, _int, _int, _int, _vp]),
     ("aleo_b200_ntt_fr_dev_profile", _int, [_vp, _u32, _int, _int, _vp, C.POINTER(C.c_float)]),
     ("aleo_b200_ntt_twiddle_dev", _int, [_vp, _u32, _int, _u32, _u32, _u32, _u32, _vp]),
     ("aleo_b200_ntt_launches", _int, [_u32]),
@@ -45,6 +47,10 @@ SYMBOLS = [
     ("aleo_b200_kzg_commit", _int, [_vp, _vp, _vp, _sz]),
     ("aleo_b200_kzg_commit_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_field_op_dev", _int, [_int, _int, _vp, _vp, _vp, _sz, _vp]),
+    ("aleo_b200_fr_distribute_powers_dev", _int, [_vp, _sz, _vp, _vp, _vp]),
+    ("aleo_b200_fr_poly_eval_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
+    ("aleo_b200_fr_divide_by_linear_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
+    ("aleo_b200_kzg_open_dev", _int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
     ("aleo_b200_msm_host_plan", _int, [_sz, C.POINTER(_int), C.POINTER(_int)]),

@@ -158,6 +158,22 @@ int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int dire
   return ALEO_B200_OK;
 }
 
+int aleo_b200_ntt_fr_ordered_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, int order, void* stream) {
+  if (order != ALEO_B200_NTT_ORDER_II && order != ALEO_B200_NTT_ORDER_IO && order != ALEO_B200_NTT_ORDER_OI) return ALEO_B200_EINVAL;
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (batch == 0) return ALEO_B200_OK;
+  if (inout_dev == nullptr) return ALEO_B200_EINVAL;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
+  int rc0 = ensure_ready(nullptr);
+  if (rc0) return rc0;
+  if (order == ALEO_B200_NTT_ORDER_OI) API_CK(aleo::ntt_bitrev(log_n, batch, inout_dev, (cudaStream_t)stream));
+  int rc = aleo_b200_ntt_fr_dev(inout_dev, log_n, batch, direction, kind, stream);
+  if (rc) return rc;
+  if (order == ALEO_B200_NTT_ORDER_IO) API_CK(aleo::ntt_bitrev(log_n, batch, inout_dev, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4) {
   if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
   if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
@@ -326,6 +342,52 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
   if (rc) return rc;
   API_CK(aleo::field_op(field, op, out_dev, a_dev, b_dev, n, (cudaStream_t)stream));
   return ALEO_B200_OK;
+}
+
+int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream) {
+  if (g_host == nullptr) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  if (inout_dev == nullptr) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_distribute_powers(inout_dev, n, g_host, k_host, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream) {
+  if (out_dev == nullptr || z_host == nullptr || (n && coeffs_dev == nullptr)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_poly_eval(out_dev, coeffs_dev, n, z_host, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_fr_divide_by_linear_dev(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream) {
+  if (z_host == nullptr) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  if (quotient_dev == nullptr || coeffs_dev == nullptr || quotient_dev == coeffs_dev) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_divide_by_linear(quotient_dev, coeffs_dev, n, z_host, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
+                           const void* z_host, void* stream) {
+  if (handle == nullptr || out_compressed48_dev == nullptr || z_host == nullptr || (n_coeffs && coeffs_montgomery_dev == nullptr))
+    return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_coeffs <= 1) return aleo_b200_kzg_commit_dev(handle, out_compressed48_dev, coeffs_montgomery_dev, 0, stream);  // q = 0
+  unsigned char* q = nullptr;
+  API_CK(cudaMallocAsync((void**)&q, n_coeffs * 32, s));
+  cudaError_t e = aleo::fr_divide_by_linear(q, coeffs_montgomery_dev, n_coeffs, z_host, s);
+  int rc2 = ALEO_B200_OK;
+  if (e == cudaSuccess) rc2 = aleo_b200_kzg_commit_dev(handle, out_compressed48_dev, q, n_coeffs - 1, stream);
+  cudaFreeAsync(q, s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return rc2;
 }
 
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {

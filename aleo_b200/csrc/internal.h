@@ -11,6 +11,7 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
                           float* pass_ms = nullptr /* >= 4 floats; synchronises the stream when given */);
 cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void* data_dev, u32 rows, u32 cols, u32 row0, u32 col0,
                                cudaStream_t s);
+cudaError_t ntt_bitrev(u32 log_n, size_t batch, void* data_dev, cudaStream_t s);
 int ntt_launches(u32 log_n);
 int ntt_max_log_n();
 void ntt_clear_plans();
@@ -37,6 +38,9 @@ cudaError_t g1_compress(const void* jac144_dev, void* out48_dev, cudaStream_t s)
 // poly_lib.cu
 cudaError_t poly_upload_constants();
 cudaError_t field_op(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, cudaStream_t s);
+cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s);
+cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
+cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
 // util_lib.cu
 cudaError_t util_upload_constants();
 cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);

@@ -39,7 +39,9 @@ struct Params {
   u32 first;   // resident-SRS mode: offset of this point range into the SRS (scalar i belongs to P_(first + i))
   // Half-range recoding: a scalar s > (r-1)/2 is replaced by r - s and all its digits change sign
   // (s P = (r - s)(-P)).  The recoded scalars have 252 bits, which is what lets c = 23 cover them with 11
-  // windows instead of 12 (253 = 11 * 23 leaves no room for the recoding carry).  Used by the resident SRS.
+  // windows instead of 12 (253 = 11 * 23 leaves no room for the recoding carry) for the resident SRS.  Always on:
+  // it also turns the "negative small" scalars of a witness (r - k) into k, whose digits are zero above window 0,
+  // instead of one crowded bucket in every window.
   u32 half_range;
 };
 
@@ -93,14 +95,24 @@ DEV u32 digit_of_window(const u32* s, u32 w, u32 c, u32& neg) {
   return mag;
 }
 
-// slot += 1 for every active lane, one atomic per distinct slot of the warp; returns the lane's position.
-// KZG scalars are full of 0 / 1 / small values and the top window of some (c, 253) pairs has one or two
-// bits: without aggregation millions of atomics serialise on a handful of counters (measured on B200 at
-// n = 2^24: c = 21 -> 41 ms of "sort" against 10 ms for c = 20).
+// slot += 1 for every active lane; returns the lane's position.  When lanes of the warp share a slot the warp
+// issues ONE atomic per distinct slot: KZG scalars are full of 0 / 1 / small values and the top window of some
+// (c, 253) pairs has one or two bits, and without aggregation millions of atomics serialise on a handful of
+// counters (measured on B200 at n = 2^24: c = 21 -> 41 ms of "sort" against 10 ms for c = 20).  MATCH is slow
+// (one per ~64 clocks per SM: unconditional use cost 1.5 ms per sort kernel at 2^24), so it only runs when a
+// cheap test -- some lane holds the same slot as its neighbour -- says the warp has duplicates; hot slots put
+// duplicates next to each other with near certainty, uniform scalars almost never do.
 DEV u32 warp_aggregated_inc(u32* counters, u32 slot, bool active) {
 #ifndef ALEO_EMU
   const unsigned act = __ballot_sync(0xffffffffu, active);
+  const u32 key = active ? slot : (0xffffff00u | (threadIdx.x & 31u));  // inactive lanes never match anybody
+  const u32 next = __shfl_down_sync(0xffffffffu, key, 1);
+  const bool dup = __any_sync(0xffffffffu, (threadIdx.x & 31u) != 31u && next == key);
   u32 pos = 0;
+  if (!dup) {
+    if (active) pos = atomicAdd(&counters[slot], 1u);
+    return pos;
+  }
   if (active) {
     const unsigned peers = __match_any_sync(act, slot);
     const unsigned lane = threadIdx.x & 31u;

@@ -86,7 +86,7 @@ static inline Params make_params(size_t n, const SrsView* srs = nullptr, u32 chu
   Params p;
   p.c = srs ? srs->c : choose_window(n, chunks);
   p.W = srs ? srs->W : windows_for(p.c);
-  p.half_range = srs ? 1u : 0u;
+  p.half_range = 1u;
   p.B = 1u << (p.c - 1);
   p.n_stride = srs ? srs->n_total : 0;
   p.first = 0;

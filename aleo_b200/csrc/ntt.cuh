@@ -361,6 +361,30 @@ KERNEL void twiddle_matrix_kernel(Fr* data, u32 rows, u32 cols, u32 row0, u32 co
 }
 
 // ---------------------------------------------------------------------------------------------
+// In-place bit-reversal permutation of 2^log_n elements (blockIdx.y = transform of a batch): the out-of-order
+// variants of upstream's transforms (FFTOrder::IO / OI in snarkvm-algorithms 0.14.5 src/fft/domain.rs, used by
+// the prover with its FFTPrecomputation) are the in-order transform plus this pass.
+// ---------------------------------------------------------------------------------------------
+DEV u32 bit_reverse(u32 v, u32 bits) {
+  u32 r = 0;
+  for (u32 b = 0; b < bits; b++) r |= ((v >> b) & 1u) << (bits - 1 - b);
+  return r;
+}
+
+KERNEL void bitrev_permute_kernel(Fr* data, u32 log_n) {
+  Fr* x = data + ((u64)blockIdx.y << log_n);
+  const u64 n = (u64)1 << log_n;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 j = bit_reverse((u32)i, log_n);
+    if (i < j) {
+      const Fr a = x[i], b = x[j];
+      x[i] = b;
+      x[j] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Table builders (run once per (log_n, direction, kind) and cached by the host plan).
 // ---------------------------------------------------------------------------------------------
 // out[j] = scale * base^(j << shift)      (base, scale: device scalars)

@@ -43,6 +43,19 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
   return e;
 }
 
+// in-place bit-reversal permutation of `batch` vectors of 2^log_n elements
+cudaError_t ntt_bitrev(u32 log_n, size_t batch, void* data_dev, cudaStream_t s) {
+  if (log_n < 2 || batch == 0) return cudaSuccess;  // sizes 1 and 2 are their own reversal
+  const u64 n = (u64)1 << log_n;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  for (size_t b0 = 0; b0 < batch; b0 += 65535) {
+    const u32 nb = (u32)(batch - b0 < 65535 ? batch - b0 : 65535);
+    LAUNCH_NOSYNC(ntt::bitrev_permute_kernel, dim3((u32)blocks, nb), dim3(256), 0, s, (Fr*)data_dev + (b0 << log_n), log_n);
+  }
+  return cudaGetLastError();
+}
+
 // data[r][c] *= w_N^(+-(r + row0)(c + col0)), N = 2^log_n_global (multi-GPU four-step twiddle step)
 cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void* data_dev, u32 rows, u32 cols, u32 row0, u32 col0,
                                cudaStream_t s) {

@@ -61,3 +61,183 @@ KERNEL void __launch_bounds__(256) field_op_kernel(void* out, const void* a, con
 }
 
 }  // namespace poly
+
+// =============================================================================================
+// Polynomial helpers of the KZG / Varuna call sites (Fr only; all vectors in Montgomery form).
+// =============================================================================================
+namespace poly {
+
+constexpr u32 PW_TPB = 256;   // threads per CTA
+constexpr u32 PW_RUN = 32;    // elements per thread, strided by PW_TPB: a CTA covers 8192 contiguous elements
+
+// scalars every kernel below needs, computed once per call by setup_kernel:
+//   s[0] = k (or 1), s[1] = g, s[2] = g^PW_TPB, s[3] = g^-1 (0 if g = 0), s[4] = g^-PW_TPB
+KERNEL void setup_kernel(Fr* s, Fr g, Fr k, u32 have_k) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  s[0] = have_k ? k : fp_one<FrParams>();
+  s[1] = g;
+  Fr p = g;
+  for (u32 i = 1; i < PW_TPB; i <<= 1) p = fp_sqr(p);
+  s[2] = p;
+  const Fr gi = inv_elem<FrParams>(g);
+  s[3] = gi;
+  p = gi;
+  for (u32 i = 1; i < PW_TPB; i <<= 1) p = fp_sqr(p);
+  s[4] = p;
+}
+
+// first index of this thread and the power base^(first + shift), times `scale`
+DEV Fr thread_power(const Fr& base, const Fr& scale, u64 first, u64 shift) {
+  return fp_mul(scale, fp_pow_u64(base, first + shift));
+}
+
+// a[i] <- a[i] * k * g^i      (EvaluationDomain::distribute_powers / distribute_powers_and_mul_by_const)
+KERNEL void __launch_bounds__(PW_TPB) distribute_powers_kernel(Fr* a, u64 n, const Fr* s) {
+  const u64 cta_base = (u64)blockIdx.x * PW_TPB * PW_RUN;
+  const u64 first = cta_base + threadIdx.x;
+  if (first >= n) return;
+  Fr p = thread_power(s[1], s[0], first, 0);
+  const Fr step = s[2];
+#pragma unroll 4
+  for (u32 j = 0; j < PW_RUN; j++) {
+    const u64 i = first + (u64)j * PW_TPB;
+    if (i >= n) break;
+    a[i] = fp_mul(a[i], p);
+    p = fp_mul(p, step);
+  }
+}
+
+// block-wide sum of one Fr per thread (blockDim.x = PW_TPB), result valid in thread 0
+DEV Fr block_sum(Fr v, Fr* sh) {
+  sh[threadIdx.x] = v;
+  SYNC_THREADS();
+  for (u32 off = PW_TPB / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] = fp_add(sh[threadIdx.x], sh[threadIdx.x + off]);
+    SYNC_THREADS();
+  }
+  return sh[0];
+}
+
+// partial[cta] = sum over the CTA's 8192 elements of c[i] * z^i      (DensePolynomial::evaluate, first stage)
+KERNEL void __launch_bounds__(PW_TPB) eval_partial_kernel(const Fr* c, u64 n, const Fr* s, Fr* partial) {
+  SHARED Fr sh[PW_TPB];
+  const u64 first = (u64)blockIdx.x * PW_TPB * PW_RUN + threadIdx.x;
+  Fr acc = fp_zero<FrParams>();
+  if (first < n) {
+    Fr p = thread_power(s[1], fp_one<FrParams>(), first, 0);
+    const Fr step = s[2];
+    for (u32 j = 0; j < PW_RUN; j++) {
+      const u64 i = first + (u64)j * PW_TPB;
+      if (i >= n) break;
+      acc = fp_add(acc, fp_mul(c[i], p));
+      p = fp_mul(p, step);
+    }
+  }
+  const Fr tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// out = sum of `count` partials (single CTA)
+KERNEL void __launch_bounds__(PW_TPB) sum_partials_kernel(const Fr* partial, u32 count, Fr* out) {
+  SHARED Fr sh[PW_TPB];
+  Fr acc = fp_zero<FrParams>();
+  for (u32 i = threadIdx.x; i < count; i += PW_TPB) acc = fp_add(acc, partial[i]);
+  const Fr tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) *out = tot;
+}
+
+// ---- witness polynomial of KZG10::open: q(x) = (p(x) - p(z)) / (x - z), q_j = sum_{i > j} p_i z^(i-j-1) ----------
+// With t_i = p_i z^i and the suffix sums S_j = sum_{i >= j} t_i:  q_j = S_(j+1) * z^-(j+1).  Three stages:
+//   suffix_local : t_i and the suffix sums inside a CTA's 8192-element slab (thread-strided layout turned into
+//                  a contiguous one through the scan), slab totals out
+//   suffix_carry : exclusive suffix scan of the slab totals (single CTA; <= 2^19 slabs for 2^32 coefficients)
+//   witness_fix  : q_j = (local S_(j+1) + carry of the slab) * z^-(j+1)
+// z = 0 needs no arithmetic (q_j = p_(j+1)) and is handled by the host.
+constexpr u32 SLAB = PW_TPB * 8;  // 2048 contiguous elements per CTA for the scan kernels, 8 consecutive per thread
+
+KERNEL void __launch_bounds__(PW_TPB) suffix_local_kernel(const Fr* p, u64 n, const Fr* s, Fr* S, Fr* slab_total) {
+  SHARED Fr sh[PW_TPB];
+  const u64 base = (u64)blockIdx.x * SLAB + (u64)threadIdx.x * 8;
+  // t_i for this thread's 8 consecutive elements, then their local suffix sums
+  Fr t[8];
+  Fr pw = (base < n) ? thread_power(s[1], fp_one<FrParams>(), base, 0) : fp_zero<FrParams>();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const u64 i = base + k;
+    t[k] = (i < n) ? fp_mul(p[i], pw) : fp_zero<FrParams>();
+    pw = fp_mul(pw, s[1]);
+  }
+#pragma unroll
+  for (int k = 6; k >= 0; k--) t[k] = fp_add(t[k], t[k + 1]);
+  // exclusive suffix scan of the per-thread totals across the CTA (Hillis-Steele on 256 values)
+  sh[threadIdx.x] = t[0];
+  SYNC_THREADS();
+  for (u32 off = 1; off < PW_TPB; off <<= 1) {
+    Fr add = fp_zero<FrParams>();
+    const bool take = threadIdx.x + off < PW_TPB;
+    if (take) add = sh[threadIdx.x + off];
+    SYNC_THREADS();
+    if (take) sh[threadIdx.x] = fp_add(sh[threadIdx.x], add);
+    SYNC_THREADS();
+  }
+  const Fr after = (threadIdx.x + 1 < PW_TPB) ? sh[threadIdx.x + 1] : fp_zero<FrParams>();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const u64 i = base + k;
+    if (i < n) S[i] = fp_add(t[k], after);
+  }
+  if (threadIdx.x == 0) slab_total[blockIdx.x] = sh[0];
+}
+
+// carry[b] = sum of slab totals of the slabs after b (single CTA, walks the slabs from the top down)
+KERNEL void __launch_bounds__(PW_TPB) suffix_carry_kernel(const Fr* slab_total, u32 nslabs, Fr* carry) {
+  SHARED Fr sh[PW_TPB];
+  SHARED Fr running;
+  if (threadIdx.x == 0) running = fp_zero<FrParams>();
+  SYNC_THREADS();
+  const u32 rounds = (nslabs + PW_TPB - 1) / PW_TPB;
+  for (u32 r = 0; r < rounds; r++) {
+    // this round covers slabs hi-1 .. hi-256 (descending); thread t takes slab hi-1-t
+    const long long idx = (long long)nslabs - 1 - (long long)r * PW_TPB - threadIdx.x;
+    const Fr v = (idx >= 0) ? slab_total[idx] : fp_zero<FrParams>();
+    // inclusive prefix scan over t (= suffix over slabs)
+    sh[threadIdx.x] = v;
+    SYNC_THREADS();
+    for (u32 off = 1; off < PW_TPB; off <<= 1) {
+      Fr add = fp_zero<FrParams>();
+      const bool take = threadIdx.x >= off;
+      if (take) add = sh[threadIdx.x - off];
+      SYNC_THREADS();
+      if (take) sh[threadIdx.x] = fp_add(sh[threadIdx.x], add);
+      SYNC_THREADS();
+    }
+    const Fr incl = sh[threadIdx.x];
+    const Fr run = running;
+    if (idx >= 0) carry[idx] = fp_add(run, fp_sub(incl, v));  // slabs strictly after idx
+    SYNC_THREADS();
+    if (threadIdx.x == PW_TPB - 1) running = fp_add(run, incl);
+    SYNC_THREADS();
+  }
+}
+
+// q[j] = (S[j+1] + carry of slab(j+1)) * z^-(j+1), j < n-1
+KERNEL void __launch_bounds__(PW_TPB) witness_fix_kernel(const Fr* S, const Fr* carry, u64 n, const Fr* s, Fr* q) {
+  const u64 first = (u64)blockIdx.x * PW_TPB * PW_RUN + threadIdx.x;  // j
+  if (first + 1 >= n) return;
+  Fr pw = thread_power(s[3], fp_one<FrParams>(), first, 1);  // z^-(j+1)
+  const Fr step = s[4];
+  for (u32 k = 0; k < PW_RUN; k++) {
+    const u64 j = first + (u64)k * PW_TPB;
+    if (j + 1 >= n) break;
+    const Fr full = fp_add(S[j + 1], carry[(j + 1) / SLAB]);
+    q[j] = fp_mul(full, pw);
+    pw = fp_mul(pw, step);
+  }
+}
+
+// z = 0: q_j = p_(j+1)
+KERNEL void shift_down_kernel(const Fr* p, u64 n, Fr* q) {
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j + 1 < n; j += (u64)gridDim.x * blockDim.x) q[j] = p[j + 1];
+}
+
+}  // namespace poly

@@ -22,6 +22,93 @@ static cudaError_t field_op_t(int op, void* out, const void* a, const void* b, s
   return cudaGetLastError();
 }
 
+#define PL_CK(expr)                       \
+  do {                                    \
+    cudaError_t _e = (expr);              \
+    if (_e != cudaSuccess) return _e;     \
+  } while (0)
+
+static Fr host_fr(const void* p) {
+  Fr v;
+  std::memcpy(v.l, p, 32);
+  return v;
+}
+
+// the per-call scalars (k, g, g^256, g^-1, g^-256) on the device
+static cudaError_t make_setup(Fr** s_out, const void* g32, const void* k32, cudaStream_t s) {
+  Fr* d = nullptr;
+  PL_CK(cudaMallocAsync((void**)&d, 8 * sizeof(Fr), s));
+  Fr k = host_fr(g32);
+  if (k32) k = host_fr(k32);
+  LAUNCH_NOSYNC(poly::setup_kernel, dim3(1), dim3(1), 0, s, d, host_fr(g32), k, (u32)(k32 ? 1 : 0));
+  *s_out = d;
+  return cudaGetLastError();
+}
+
+static inline u32 pw_grid(size_t n) { return (u32)((n + (size_t)poly::PW_TPB * poly::PW_RUN - 1) / ((size_t)poly::PW_TPB * poly::PW_RUN)); }
+
+cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  Fr* sc = nullptr;
+  PL_CK(make_setup(&sc, g32, k32, s));
+  LAUNCH_NOSYNC(poly::distribute_powers_kernel, dim3(pw_grid(n)), dim3(poly::PW_TPB), 0, s, (Fr*)inout_dev, (u64)n, (const Fr*)sc);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(sc, s);
+  return e;
+}
+
+cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s) {
+  if (n == 0) return cudaMemsetAsync(out_dev, 0, sizeof(Fr), s);
+  Fr* sc = nullptr;
+  Fr* partial = nullptr;
+  PL_CK(make_setup(&sc, z32, nullptr, s));
+  const u32 g = pw_grid(n);
+  cudaError_t e = cudaMallocAsync((void**)&partial, (size_t)g * sizeof(Fr), s);
+  if (e == cudaSuccess) {
+    LAUNCH(poly::eval_partial_kernel, dim3(g), dim3(poly::PW_TPB), 0, s, (const Fr*)coeffs_dev, (u64)n, (const Fr*)sc, partial);
+    LAUNCH(poly::sum_partials_kernel, dim3(1), dim3(poly::PW_TPB), 0, s, (const Fr*)partial, g, (Fr*)out_dev);
+    e = cudaGetLastError();
+    cudaFreeAsync(partial, s);
+  }
+  cudaFreeAsync(sc, s);
+  return e;
+}
+
+// quotient_dev: n elements; q[n-1] = 0 (the witness polynomial has one coefficient less)
+cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  Fr* q = (Fr*)quotient_dev;
+  PL_CK(cudaMemsetAsync(q + (n - 1), 0, sizeof(Fr), s));
+  if (n == 1) return cudaSuccess;
+  const Fr z = host_fr(z32);
+  bool z_is_zero = true;
+  for (int i = 0; i < 8; i++) z_is_zero = z_is_zero && z.l[i] == 0;
+  if (z_is_zero) {
+    u32 blocks = (u32)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    LAUNCH_NOSYNC(poly::shift_down_kernel, dim3(blocks), dim3(256), 0, s, (const Fr*)coeffs_dev, (u64)n, q);
+    return cudaGetLastError();
+  }
+  const u32 nslabs = (u32)((n + poly::SLAB - 1) / poly::SLAB);
+  Fr* sc = nullptr;
+  Fr* S = nullptr;
+  Fr* totals = nullptr;
+  PL_CK(make_setup(&sc, z32, nullptr, s));
+  cudaError_t e = cudaMallocAsync((void**)&S, n * sizeof(Fr), s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&totals, (size_t)2 * nslabs * sizeof(Fr), s);
+  if (e == cudaSuccess) {
+    Fr* carry = totals + nslabs;
+    LAUNCH(poly::suffix_local_kernel, dim3(nslabs), dim3(poly::PW_TPB), 0, s, (const Fr*)coeffs_dev, (u64)n, (const Fr*)sc, S, totals);
+    LAUNCH(poly::suffix_carry_kernel, dim3(1), dim3(poly::PW_TPB), 0, s, (const Fr*)totals, nslabs, carry);
+    LAUNCH_NOSYNC(poly::witness_fix_kernel, dim3(pw_grid(n)), dim3(poly::PW_TPB), 0, s, (const Fr*)S, (const Fr*)carry, (u64)n,
+                  (const Fr*)sc, q);
+    e = cudaGetLastError();
+  }
+  if (totals) cudaFreeAsync(totals, s);
+  if (S) cudaFreeAsync(S, s);
+  cudaFreeAsync(sc, s);
+  return e;
+}
+
 cudaError_t field_op(int field, int op, void* out, const void* a, const void* b, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   return field == 0 ? field_op_t<FrParams>(op, out, a, b, n, s) : field_op_t<FqParams>(op, out, a, b, n, s);

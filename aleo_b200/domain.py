@@ -133,6 +133,37 @@ class EvaluationDomain:
     def coset_ifft_in_place_dev(self, t, batch: int = 1):
         return self._run_dev(t, _lib.NTT_INVERSE, _lib.NTT_COSET, batch)
 
+    # -- upstream's FFTOrder variants (fft_helper_in_place_with_pc & co.; the precomputation argument is accepted
+    #    and ignored: twiddle tables are cached per size inside the library) ---------------------------------------
+    def _run_dev_ordered(self, t, direction: int, kind: int, order: int, batch: int = 1):
+        import torch
+
+        lib = _lib.get_lib()
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("expected a contiguous CUDA tensor")
+        if t.numel() * t.element_size() != batch * self.size * 32:
+            raise ValueError("tensor holds %d bytes, domain needs %d" % (t.numel() * t.element_size(), batch * self.size * 32))
+        with torch.cuda.device(t.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            lib.check(lib.ntt_fr_ordered_dev(t.data_ptr(), self.log_size_of_group, batch, direction, kind, order, stream),
+                      "aleo_b200_ntt_fr_ordered_dev")
+        return t
+
+    def fft_helper_in_place_with_pc_dev(self, t, order: int, pc=None, batch: int = 1):
+        return self._run_dev_ordered(t, _lib.NTT_FORWARD, _lib.NTT_STANDARD, order, batch)
+
+    def ifft_helper_in_place_with_pc_dev(self, t, order: int, pc=None, batch: int = 1):
+        return self._run_dev_ordered(t, _lib.NTT_INVERSE, _lib.NTT_STANDARD, order, batch)
+
+    def out_order_fft_in_place_with_pc_dev(self, t, pc=None, batch: int = 1):
+        return self._run_dev_ordered(t, _lib.NTT_FORWARD, _lib.NTT_STANDARD, _lib.NTT_ORDER_IO, batch)
+
+    def in_order_ifft_in_place_with_pc_dev(self, t, pc=None, batch: int = 1):
+        return self._run_dev_ordered(t, _lib.NTT_INVERSE, _lib.NTT_STANDARD, _lib.NTT_ORDER_II, batch)
+
+    def in_order_coset_ifft_in_place_with_pc_dev(self, t, pc=None, batch: int = 1):
+        return self._run_dev_ordered(t, _lib.NTT_INVERSE, _lib.NTT_COSET, _lib.NTT_ORDER_II, batch)
+
     def ntt_host_buffer(self, buf, direction: int, kind: int):
         """in-place transform of a host buffer that already holds `size` elements (numpy array or
         torch CPU tensor, pinned or pageable) -- the zero-copy form of aleo_b200_ntt_fr"""

@@ -55,3 +55,52 @@ class Evaluations:
     @staticmethod
     def neg(a, out=None):
         return field_op_dev(FR, NEG, a, None, out)
+
+
+def _fr_host(v) -> bytes:
+    """32-byte Montgomery image of a canonical integer (or pass 32 bytes through)"""
+    if isinstance(v, (bytes, bytearray)):
+        assert len(v) == 32
+        return bytes(v)
+    r = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
+    return ((int(v) % r) * (1 << 256) % r).to_bytes(32, "little")
+
+
+def distribute_powers_dev(t, g, k=None):
+    """t[i] *= k * g^i in place (EvaluationDomain::distribute_powers[_and_mul_by_const]); g, k canonical ints"""
+    import torch
+
+    lib = _lib.get_lib()
+    n = t.numel() * t.element_size() // 32
+    with torch.cuda.device(t.device):
+        lib.check(lib.fr_distribute_powers_dev(t.data_ptr(), n, _fr_host(g), _fr_host(k) if k is not None else None,
+                                               torch.cuda.current_stream().cuda_stream), "aleo_b200_fr_distribute_powers_dev")
+    return t
+
+
+def evaluate_dev(coeffs_t, z) -> int:
+    """DensePolynomial::evaluate: sum_i c_i z^i as a canonical integer (synchronises)"""
+    import torch
+
+    lib = _lib.get_lib()
+    n = coeffs_t.numel() * coeffs_t.element_size() // 32
+    out = torch.empty(4, dtype=torch.int64, device=coeffs_t.device)
+    with torch.cuda.device(coeffs_t.device):
+        lib.check(lib.fr_poly_eval_dev(out.data_ptr(), coeffs_t.data_ptr(), n, _fr_host(z), torch.cuda.current_stream().cuda_stream),
+                  "aleo_b200_fr_poly_eval_dev")
+    r = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
+    return int.from_bytes(out.cpu().numpy().tobytes(), "little") * pow(1 << 256, -1, r) % r
+
+
+def divide_by_linear_dev(coeffs_t, z, out=None):
+    """KZG10::compute_witness_polynomial: (p(x) - p(z)) / (x - z), same length as p with a trailing zero"""
+    import torch
+
+    lib = _lib.get_lib()
+    n = coeffs_t.numel() * coeffs_t.element_size() // 32
+    if out is None:
+        out = torch.empty_like(coeffs_t)
+    with torch.cuda.device(coeffs_t.device):
+        lib.check(lib.fr_divide_by_linear_dev(out.data_ptr(), coeffs_t.data_ptr(), n, _fr_host(z),
+                                              torch.cuda.current_stream().cuda_stream), "aleo_b200_fr_divide_by_linear_dev")
+    return out

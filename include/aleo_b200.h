@@ -65,6 +65,13 @@ int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind);
 /* Same on device memory, asynchronous on `stream` (a cudaStream_t; NULL = default stream).
  * `batch` transforms of the same size, contiguous, each in place. */
 int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, void* stream);
+/* Out-of-order variants (snarkVM's FFTOrder, src/fft/domain.rs: fft_helper_in_place_with_pc / ifft_helper_in_place_with_pc /
+ * out_order_fft_in_place_with_pc, which the Varuna prover calls with its cached FFTPrecomputation; SURVEY.md 8a
+ * row 11 -- the precomputation itself is not needed here: twiddle tables are cached per size inside the library).
+ *   II: natural order in, natural order out (= aleo_b200_ntt_fr_dev);  IO: natural in, bit-reversed out
+ *   (out[bitrev(i)] = X[i]);  OI: bit-reversed in, natural out.  Coset scaling always refers to the natural index. */
+enum { ALEO_B200_NTT_ORDER_II = 0, ALEO_B200_NTT_ORDER_IO = 1, ALEO_B200_NTT_ORDER_OI = 2 };
+int aleo_b200_ntt_fr_ordered_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, int order, void* stream);
 /* One transform with CUDA events around every pass: pass_ms4[i] = device time of pass i (unused
  * entries 0).  Synchronises `stream`.  Measurement aid for bench.py's roofline, same kernels. */
 int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4);
@@ -138,6 +145,22 @@ enum { ALEO_B200_FIELD_FR = 0, ALEO_B200_FIELD_FQ = 1 };
 enum { ALEO_B200_OP_ADD = 0, ALEO_B200_OP_SUB = 1, ALEO_B200_OP_MUL = 2, ALEO_B200_OP_SQR = 3, ALEO_B200_OP_INV = 4,
        ALEO_B200_OP_NEG = 5 };
 int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, void* stream);
+
+/* Polynomial helpers of the KZG / Varuna call sites; Fr vectors in Montgomery form on the device, the scalar
+ * arguments (g, k, z) are 32-byte Montgomery Fr on the HOST.
+ *   distribute_powers : a[i] *= k * g^i   (EvaluationDomain::distribute_powers[_and_mul_by_const], src/fft/domain.rs;
+ *                       k_host NULL = 1) -- the coset shift of a polynomial by an arbitrary generator
+ *   poly_eval         : out = sum_i c[i] z^i   (DensePolynomial::evaluate, src/fft/polynomial/dense.rs), 32 bytes
+ *   divide_by_linear  : q(x) = (p(x) - p(z)) / (x - z), the witness polynomial of KZG10::open
+ *                       (KZG10::compute_witness_polynomial, src/polycommit/kzg10/mod.rs); quotient_dev holds n
+ *                       elements, q[n-1] = 0; must not alias coeffs_dev
+ *   kzg_open          : commitment (48-byte compressed G1) to that witness polynomial against the resident SRS =
+ *                       the non-hiding part of KZG10::open */
+int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream);
+int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);
+int aleo_b200_fr_divide_by_linear_dev(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);
+int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
+                           const void* z_host, void* stream);
 
 /* ---- synthetic workload generation and on-device checks (bench / tests) --------------------
  * bases[i] = (s0 + (first_index + i) * d) * G, G the G1 generator; s0, d canonical 32-byte scalars.

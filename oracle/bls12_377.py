@@ -223,6 +223,29 @@ def poly_eval(coeffs, x: int) -> int:
     return acc
 
 
+def distribute_powers(coeffs, g: int, k: int = 1):
+    """c_i <- c_i * k * g^i: EvaluationDomain::distribute_powers / distribute_powers_and_mul_by_const
+    (snarkvm-algorithms 0.14.5 src/fft/domain.rs [U])."""
+    out, p = [], k % R_MOD
+    for c in coeffs:
+        out.append(c * p % R_MOD)
+        p = p * g % R_MOD
+    return out
+
+
+def divide_by_linear(coeffs, z: int):
+    """witness polynomial of KZG10::open: q(x) = (p(x) - p(z)) / (x - z) by synthetic division, returned with
+    len(coeffs) entries (the last one 0) (KZG10::compute_witness_polynomial, src/polycommit/kzg10/mod.rs [U];
+    SURVEY.md 8a row 13)."""
+    n = len(coeffs)
+    q = [0] * n
+    carry = 0
+    for i in range(n - 1, 0, -1):
+        carry = (coeffs[i] + carry * z) % R_MOD
+        q[i - 1] = carry
+    return q
+
+
 # ----------------------------------------------------------------------------------------------
 # G1: y^2 = x^3 + 1 over Fq.  Affine points are (x, y) tuples; None is the identity.
 # ----------------------------------------------------------------------------------------------

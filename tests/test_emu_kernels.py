@@ -239,3 +239,67 @@ def test_emu_field_ops(emu_lib, field):
     assert _field_op(emu_lib, field, 3, a) == [(x * x) % mod for x in a]
     assert _field_op(emu_lib, field, 4, a) == [pow(x, -1, mod) if x else 0 for x in a]
     assert _field_op(emu_lib, field, 5, a) == [(-x) % mod for x in a]
+
+
+def _bitrev_list(v):
+    n = len(v)
+    bits = n.bit_length() - 1
+    return [v[int(format(i, "0%db" % bits)[::-1], 2)] if bits else v[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 3, 8, 12])
+def test_emu_ntt_orders(emu_lib, log_n):
+    """FFTOrder IO / OI (bit-reversed output / input) around the in-order transform"""
+    n = 1 << log_n
+    v = o.random_fr_vec(n, 500 + log_n)
+
+    def run(vals, direction, kind, order):
+        buf = C.create_string_buffer(o.fr_vec_to_bytes(vals), n * 32)
+        emu_lib.check(emu_lib.ntt_fr_ordered_dev(C.cast(buf, C.c_void_p), log_n, 1, direction, kind, order, None), "ordered")
+        return o.fr_vec_from_bytes(buf.raw)
+
+    assert run(v, 0, 0, 0) == o.fft(v)
+    assert run(v, 0, 0, 1) == _bitrev_list(o.fft(v))                   # IO
+    assert run(_bitrev_list(v), 0, 0, 2) == o.fft(v)                   # OI
+    assert run(_bitrev_list(v), 1, 1, 2) == o.coset_ifft(v)            # OI, coset inverse
+    assert run(v, 0, 1, 1) == _bitrev_list(o.coset_fft(v))             # IO, coset forward
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 256, 2049, 8193, 20000])
+def test_emu_poly_helpers(emu_lib, n):
+    """distribute_powers, polynomial evaluation and the KZG witness polynomial against the oracle"""
+    c = o.random_fr_vec(n, 700 + n)
+    g, k, z = o.random_fr_vec(3, 800 + n)
+    mont = lambda v: o.int_to_le_bytes(o.fr_to_mont(v), 32)  # noqa: E731
+    buf = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
+    emu_lib.check(emu_lib.fr_distribute_powers_dev(C.cast(buf, C.c_void_p), n, mont(g), mont(k), None), "distribute")
+    assert o.fr_vec_from_bytes(buf.raw) == o.distribute_powers(c, g, k)
+    buf = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
+    emu_lib.check(emu_lib.fr_distribute_powers_dev(C.cast(buf, C.c_void_p), n, mont(g), None, None), "distribute k=1")
+    assert o.fr_vec_from_bytes(buf.raw) == o.distribute_powers(c, g)
+    src = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
+    out = C.create_string_buffer(32)
+    emu_lib.check(emu_lib.fr_poly_eval_dev(C.cast(out, C.c_void_p), C.cast(src, C.c_void_p), n, mont(z), None), "eval")
+    assert o.fr_vec_from_bytes(out.raw) == [o.poly_eval(c, z)]
+    for zz in (z, 0, 1):
+        q = C.create_string_buffer(n * 32)
+        emu_lib.check(emu_lib.fr_divide_by_linear_dev(C.cast(q, C.c_void_p), C.cast(src, C.c_void_p), n, mont(zz), None), "divide")
+        assert o.fr_vec_from_bytes(q.raw) == o.divide_by_linear(c, zz), zz
+
+
+def test_emu_kzg_open(emu_lib):
+    n = 300
+    B = o.synthetic_bases(n, 91)
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    h = C.c_void_p()
+    emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, 104, None), "srs_create")
+    c = o.random_fr_vec(n, 92)
+    z = o.random_fr_vec(1, 93)[0]
+    src = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
+    out48 = C.create_string_buffer(48)
+    emu_lib.check(emu_lib.kzg_open_dev(h, C.cast(out48, C.c_void_p), C.cast(src, C.c_void_p), n, o.int_to_le_bytes(o.fr_to_mont(z), 32), None), "open")
+    q = o.divide_by_linear(c, z)
+    assert out48.raw == o.g1_compress(o.msm_pippenger(B[:n - 1], q[:n - 1]))
+    emu_lib.check(emu_lib.kzg_open_dev(h, C.cast(out48, C.c_void_p), C.cast(src, C.c_void_p), 1, o.int_to_le_bytes(o.fr_to_mont(z), 32), None), "open1")
+    assert out48.raw == o.g1_compress(None)          # a constant polynomial has the zero witness
+    emu_lib.check(emu_lib.srs_destroy(h), "destroy")

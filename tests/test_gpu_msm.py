@@ -79,7 +79,7 @@ def test_parity_with_c_oracle(c_oracle, log_n):
     assert ab.VariableBase.msm(hb, hs, 104) == out.raw
 
 
-@pytest.mark.parametrize("log_n,dist", [(20, "uniform"), (20, "witness"), (22, "uniform"), (24, "uniform")])
+@pytest.mark.parametrize("log_n,dist", [(20, "uniform"), (20, "witness"), (22, "witness-signed"), (22, "uniform"), (24, "uniform")])
 def test_known_discrete_logs_at_full_size(log_n, dist):
     """bases (s0 + i d) G: the result must be (sum_i s_i (s0 + i d)) G -- checkable at any size"""
     import torch
@@ -92,11 +92,16 @@ def test_known_discrete_logs_at_full_size(log_n, dist):
     for k, i in enumerate([0, 1, n // 3, n - 1]):
         assert o.g1_affine_from_bytes(raw[k * 104:(k + 1) * 104]) == o.g1_mul(o.G1_GEN, (s0 + i * d) % o.R_MOD)
     sc = ab.gen_scalars_dev(n, 31337 + log_n)
-    if dist == "witness":     # 50 % zero, 25 % one, 25 % uniform -- KZG witness polynomials look like this
+    if dist.startswith("witness"):     # 50 % zero, 25 % one, 25 % uniform -- KZG witness polynomials look like this
         idx = torch.arange(n, device="cuda")
         sc[idx % 2 == 0] = 0
         one = torch.tensor([1, 0, 0, 0], dtype=torch.int64, device="cuda")
         sc[idx % 4 == 1] = one
+    if dist == "witness-signed":       # ... plus "negative" small values r - 1, r - 2, r - 3 (half-range recoding)
+        rm = [o.R_MOD - k for k in (1, 2, 3)]
+        for j, v in enumerate(rm):
+            limbs = np.frombuffer(o.int_to_le_bytes(v, 32), dtype=np.int64).copy()
+            sc[idx % 16 == 2 * j + 2] = torch.from_numpy(limbs).cuda()
     k = ab.dlog_dot_dev(sc, n, s0, d)
     # the on-device dot product is itself checked on a prefix against Python big integers
     m = 2048

@@ -152,3 +152,35 @@ def test_four_step_schedule_matches_single_kernel_path(log_n):
         (dom.ifft_in_place_dev if inverse else dom.fft_in_place_dev)(direct)
         out = adist.ntt_four_step(adist.column_block(x, log_n, 0, 1), log_n, inverse=inverse)
         assert torch.equal(adist.gather_natural([out], log_n), direct)
+
+
+def _bitrev_perm(log_n):
+    n = 1 << log_n
+    idx = np.arange(n, dtype=np.uint64)
+    rev = np.zeros(n, dtype=np.uint64)
+    for b in range(log_n):
+        rev |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(log_n - 1 - b)
+    return rev.astype(np.int64)
+
+
+@pytest.mark.parametrize("log_n", [1, 4, 11, 12, 16, 20])
+def test_fft_order_variants(log_n):
+    """FFTOrder::IO / OI (snarkVM fft_helper_in_place_with_pc & co., SURVEY 8a row 11): bit-reversed output /
+    input around the in-order transform, all four transform kinds, batch of 2 at the small sizes"""
+    import torch
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    rev = torch.from_numpy(_bitrev_perm(log_n)).cuda()
+    x = ab.gen_scalars_dev(n, 6000 + log_n, 0, True)
+    for direction, kind in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        ref = dom._run_dev(x.clone(), direction, kind)                                   # II, checked against the oracle above
+        io = dom._run_dev_ordered(x.clone(), direction, kind, 1)
+        assert torch.equal(io, ref[rev]), ("IO", direction, kind)
+        oi = dom._run_dev_ordered(x[rev].contiguous(), direction, kind, 2)
+        assert torch.equal(oi, ref), ("OI", direction, kind)
+    assert torch.equal(dom.out_order_fft_in_place_with_pc_dev(x.clone(), pc=object()), dom.fft_in_place_dev(x.clone())[rev])
+    if log_n <= 12:
+        two = torch.cat([x, x.flip(0)]).contiguous()
+        want = torch.cat([dom.fft_in_place_dev(x.clone())[rev], dom.fft_in_place_dev(x.flip(0).contiguous())[rev]])
+        assert torch.equal(dom._run_dev_ordered(two, 0, 0, 1, batch=2), want)
+    assert ab.get_lib().ntt_fr_ordered_dev(x.data_ptr(), log_n, 1, 0, 0, 7, None) == -1
