@@ -1,0 +1,72 @@
+"""Parity of the polynomial helpers (distribute_powers, evaluate, KZG witness polynomial, kzg_open) with the oracle:
+bit-exact at sizes the oracle reaches, algebraic identities at 2^20."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import aleo_b200 as ab
+from aleo_b200 import poly
+from oracle import bls12_377 as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(vals):
+    return torch.from_numpy(np.frombuffer(o.fr_vec_to_bytes(vals), dtype=np.int64).reshape(-1, 4).copy()).cuda()
+
+
+def _host(t):
+    return o.fr_vec_from_bytes(t.cpu().numpy().tobytes())
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 256, 2047, 2049, 8192, 8193, 70000])
+def test_helpers_match_oracle(n):
+    c = o.random_fr_vec(n, 1700 + n)
+    g, k, z = o.random_fr_vec(3, 1800 + n)
+    assert _host(poly.distribute_powers_dev(_dev(c), g, k)) == o.distribute_powers(c, g, k)
+    assert _host(poly.distribute_powers_dev(_dev(c), g)) == o.distribute_powers(c, g)
+    assert _host(poly.distribute_powers_dev(_dev(c), 22)) == o.distribute_powers(c, 22)
+    assert poly.evaluate_dev(_dev(c), z) == o.poly_eval(c, z)
+    assert poly.evaluate_dev(_dev(c), 0) == c[0]
+    for zz in (z, 0, 1, o.R_MOD - 1):
+        assert _host(poly.divide_by_linear_dev(_dev(c), zz)) == o.divide_by_linear(c, zz), zz
+
+
+def test_coset_fft_is_distribute_powers_then_fft():
+    """EvaluationDomain::coset_fft = distribute_powers(g = 22) followed by fft"""
+    n = 1 << 14
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 321, 0, True)
+    a = dom.coset_fft_in_place_dev(x.clone())
+    b = dom.fft_in_place_dev(poly.distribute_powers_dev(x.clone(), 22))
+    assert torch.equal(a, b)
+
+
+def test_witness_polynomial_identity_at_scale():
+    """p(x) - p(z) == q(x) (x - z) at a random x, 2^20 + 5 coefficients"""
+    n = (1 << 20) + 5
+    p = ab.gen_scalars_dev(n, 99, 0, True)
+    z, x = o.random_fr_vec(2, 4455)
+    q = poly.divide_by_linear_dev(p, z)
+    assert _host(q[-1:]) == [0]
+    lhs = (poly.evaluate_dev(p, x) - poly.evaluate_dev(p, z)) % o.R_MOD
+    assert lhs == poly.evaluate_dev(q, x) * (x - z) % o.R_MOD
+
+
+def test_kzg_open_matches_oracle():
+    n = 500
+    B = o.synthetic_bases(n, 191)
+    srs = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(B, 104), 104)
+    try:
+        c = o.random_fr_vec(n, 192)
+        z = o.random_fr_vec(1, 193)[0]
+        out = torch.empty(48, dtype=torch.uint8, device="cuda")
+        lib = ab.get_lib()
+        lib.check(lib.kzg_open_dev(srs._h, out.data_ptr(), _dev(c).data_ptr(), n, o.int_to_le_bytes(o.fr_to_mont(z), 32), None), "open")
+        torch.cuda.synchronize()
+        q = o.divide_by_linear(c, z)
+        assert out.cpu().numpy().tobytes() == o.g1_compress(o.msm_pippenger(B[:n - 1], q[:n - 1]))
+    finally:
+        srs.close()
