@@ -305,13 +305,19 @@ struct Session {
     st.mark("plan", s);
     st.report(s);
     if (phase_ev) cudaEventRecord(phase_ev[1], s);
-    static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
-    if (acc_inline)
-      LAUNCH_NOSYNC(accumulate_kernel<false>, dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
+    // ALEO_B200_MSM_ACC: i = inlined field products, f = fill step (A/B switches for tuning); default: calls, no fill
+    // (measured on B200, accumulate ms at 2^24 c=20 / 2^24 c=16 / 2^22 c=17: fill 72.9 / 89.8 / 21.3, no fill 72.9 / 88.9 / 21.0)
+    static const char acc_mode = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e ? e[0] : 'n'; }();
+#define ACC_LAUNCH(CALLV, FILLV)                                                                                              \
+  LAUNCH_NOSYNC((accumulate_kernel<CALLV, FILLV>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted, \
+                (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into)
+    if (acc_mode == 'i')
+      ACC_LAUNCH(false, false);
+    else if (acc_mode == 'f')
+      ACC_LAUNCH(true, true);
     else
-      LAUNCH_NOSYNC(accumulate_kernel<true>, dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
+      ACC_LAUNCH(true, false);
+#undef ACC_LAUNCH
     if (phase_ev) cudaEventRecord(phase_ev[2], s);
     TailTrace tr;
     tr.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;

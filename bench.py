@@ -149,6 +149,87 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def proof_shaped_throughput(ab, o, torch, dev, world, dist, args):
+    """SYNTHETIC stand-in for BASELINE.json configs 3 / 5 (end-to-end Varuna proofs need snarkVM's Rust, absent here;
+    SURVEY.md 8d).  One "proof-shaped unit" = the MSM / NTT schedule of a 1-circuit proof as decoded from the
+    reference's fixture (13 large MSMs) at proof-realistic sizes, all operands device resident:
+    13 KZG commitments against a resident 2^18-point SRS (3 x 2^18, 4 x 2^17, 6 x 2^16 coefficients), 8 ifft 2^17,
+    8 coset_fft 2^18, 8 pointwise products 2^18, 4 coset_ifft 2^18.  `threads` host threads with one CUDA stream
+    each submit units concurrently (snarkVM commits on a rayon ExecutionPool; the library is re-entrant), every GPU
+    runs its own replica stream (no collective).  Not a proof: no witness synthesis, no transcript."""
+    import threading
+
+    n_srs = 1 << 18
+    s0, d = o.base_dlogs(n_srs, 777)
+    srs_bases = ab.gen_bases_dev(n_srs, s0, d, 0, 104, device=dev)
+    srs = ab.ResidentSRS.from_device(srs_bases, n_srs, 104)
+    del srs_bases
+    threads = max(1, args.proof_threads)
+    units_per_thread = 2
+    commit_sizes = [18] * 3 + [17] * 4 + [16] * 6
+    d17, d18 = ab.EvaluationDomain.new(1 << 17), ab.EvaluationDomain.new(1 << 18)
+
+    class Work:
+        def __init__(self, seed):
+            self.stream = torch.cuda.Stream(device=dev)
+            self.polys = {ln: ab.gen_scalars_dev(1 << ln, seed + ln, 0, True, device=dev) for ln in (16, 17, 18)}
+            self.b17 = ab.gen_scalars_dev(8 << 17, seed + 1, 0, True, device=dev)
+            self.b18 = ab.gen_scalars_dev(8 << 18, seed + 2, 0, True, device=dev)
+            self.c18 = ab.gen_scalars_dev(8 << 18, seed + 3, 0, True, device=dev)
+            self.out = torch.empty((13, 48), dtype=torch.uint8, device=dev)
+
+        def unit(self):
+            with torch.cuda.stream(self.stream):
+                d17.ifft_in_place_dev(self.b17, batch=8)
+                d18.coset_fft_in_place_dev(self.b18, batch=8)
+                ab.Evaluations.mul(self.b18, self.c18, out=self.b18)
+                d18.coset_ifft_in_place_dev(self.b18[: 4 << 18], batch=4)
+                for k, ln in enumerate(commit_sizes):
+                    ab.KZG10.commit_dev(srs, self.polys[ln], 1 << ln, out=self.out[k])
+
+    works = [Work(1000 * (t + 1)) for t in range(threads)]
+    # one commitment checked against the oracle through known discrete logs: sum_i c_i (s0 + i d) G, compressed
+    w0 = works[0]
+    canon = o.fr_vec_from_bytes(w0.polys[16][:256].cpu().numpy().tobytes())
+    small = ab.KZG10.commit_dev(srs, w0.polys[16], 256).cpu().numpy().tobytes()
+    ok = small == o.g1_compress(o.g1_mul(o.G1_GEN, sum(c * (s0 + i * d) for i, c in enumerate(canon)) % o.R_MOD))
+
+    def run(nunits):
+        def body(w):
+            torch.cuda.set_device(dev)
+            for _ in range(nunits):
+                w.unit()
+            w.stream.synchronize()
+        ts = [threading.Thread(target=body, args=(w,)) for w in works]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    run(1)                                   # warm-up: plans, pool growth
+    secs = run(units_per_thread)
+    serial = None
+    if world == 1:
+        t0 = time.perf_counter()
+        for _ in range(2):
+            works[0].unit()
+        works[0].stream.synchronize()
+        serial = (time.perf_counter() - t0) / 2
+    secs_t = torch.tensor([secs], device=dev)
+    if dist is not None:
+        dist.all_reduce(secs_t, op=dist.ReduceOp.MAX)
+    units = world * threads * units_per_thread
+    srs.close()
+    return {"label": "SYNTHETIC proof-shaped units (13 resident-SRS KZG commits 2^16..2^18 + 20 NTTs 2^17..2^18 + 8 pointwise "
+                     "products); NOT Varuna proofs -- BASELINE configs 3 / 5 need snarkVM's Rust toolchain",
+            "value": units / secs_t.item(), "unit": "units/s", "units": units, "host_threads_per_gpu": threads,
+            "ms_per_unit_one_stream": None if serial is None else serial * 1e3,
+            "commit_checked_against_oracle": bool(ok), "replicas": world}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -453,6 +534,11 @@ def run_ours(args):
                           "msm_checked_against_oracle": bool(ok_s), "ntt_ms": ntt_ms_s, "ntt_melem_per_s": m / ntt_ms_s / 1e3})
             del sb, ss, sx
 
+    # ---- synthetic proof-shaped stream (stand-in for BASELINE configs 3 / 5, which need snarkVM's Rust) ----------
+    proof_shaped = None
+    if not args.no_proof_shape:
+        proof_shaped = proof_shaped_throughput(ab, o, torch, dev, world, dist if world > 1 else None, args)
+
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -475,7 +561,7 @@ def run_ours(args):
                     "window_bits": host_plan["window_bits"],
                     "note": "the call copies and accumulates point range by point range: H2D of range k+1 overlaps range k"},
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
-            "roofline": roofline, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "sweep": sweep, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "sweep": sweep, "proof_shaped": proof_shaped, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -493,6 +579,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-srs", action="store_true", help="skip the resident-SRS (KZG commit) measurement")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^22 size sweep")
+    ap.add_argument("--no-proof-shape", action="store_true", help="skip the synthetic proof-shaped stream")
+    ap.add_argument("--proof-threads", type=int, default=4, help="host threads (one CUDA stream each) submitting proof-shaped work")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
