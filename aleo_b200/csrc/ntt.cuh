@@ -147,6 +147,8 @@ struct PassArgs {
   u32 log_r3;       // LAST only: log2 of the third pass's radix when P == 4, else 0
   const Fr* inner;  // w_R^j, j < R, R = this pass's radix
   PowTable tw;      // powers of w_N (inverse: hi table carries n^-1 when fold_scale)
+  const Fr* tw_direct;  // passes after the first: w_N^(x << (log_n - log_cur)), x < 2^log_cur, one lookup and no product
+                        // (2^16 entries = 2 MB at L = 24, L2 resident); nullptr = use the two-level table
   PowTable pre;     // PRE : coset powers c^i applied to inputs of the first pass
   PowTable post;    // POST: powers applied to outputs of the last pass (coset inverse, carries n^-1)
   u32 use_pre, use_post;
@@ -280,10 +282,13 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
     SYNC_THREADS();
   }
   // ---- store: thread takes outputs kappa = j*RT + sr for its column sg (lanes along g) ------------
+  // Rolled on purpose (2 iterations per trip): nothing here indexes the register array, and 8 inlined copies of
+  // the two products below were a third of the kernel's code (ncu: 1.0-1.2 issue slots per instruction lost to
+  // instruction fetch).
   {
     const u32 sr = tid >> LG, sg = tid & (G - 1);
     constexpr u32 C1 = R >> S1, C2 = C1 >> S2;
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < 8; j++) {
       const u32 kap = j * RT + sr;
       // position of output kappa after the in-place decimation-in-frequency steps
@@ -292,8 +297,11 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       Fr v = smem_get(plane0, plane1, tile_phys<K, LAST>(pos, sg));
       const u64 go = out_base + kap * ostride_r + sg;
       if (!LAST) {
-        const u32 e = ((i2_base + sg) * kap) << (a.log_n - a.log_cur);
-        v = fr_mul_v(v, pow_lookup(a.tw, e));
+        const u32 x = (i2_base + sg) * kap;
+        if (a.tw_direct)
+          v = fr_mul_v(v, a.tw_direct[x]);
+        else
+          v = fr_mul_v(v, pow_lookup(a.tw, x << (a.log_n - a.log_cur)));
       }
       if (LAST && a.use_post) v = fr_mul_v(v, pow_lookup(a.post, (u32)go));
       dst[go] = v;

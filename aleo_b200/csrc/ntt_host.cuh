@@ -23,6 +23,8 @@ static inline int split_passes(int L, int* K) {
   return P;
 }
 
+constexpr u32 DIRECT_TW_MAX_LOG = 18;
+
 struct Plan {
   int device = -1;
   u32 log_n = 0;
@@ -33,6 +35,7 @@ struct Plan {
   Fr* inner[4] = {nullptr, nullptr, nullptr, nullptr};
   Fr* small_inner = nullptr;     // n <= 2^11: w^j, j < n
   Fr *tw_lo = nullptr, *tw_hi = nullptr, *tw_hi_scaled = nullptr;
+  Fr* tw_direct[4] = {nullptr, nullptr, nullptr, nullptr};  // per pass i >= 1 (not the last): w^(x << (L - log_cur_i)), x < 2^log_cur_i
   Fr *cs_lo = nullptr, *cs_hi = nullptr;  // coset powers (inverse: hi carries n^-1)
   u32 lo_bits = 0;
   Fr scale_host;                 // n^-1 (Montgomery) for the small kernel
@@ -86,9 +89,16 @@ static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool invers
       NTT_CK(plan_alloc(p, &p.tw_hi_scaled, (size_t)1 << hi_bits));
       NTT_CK(fill_pow_table(p.tw_hi_scaled, w, ninv, 1u << hi_bits, p.lo_bits, s));
     }
+    u32 log_cur = log_n;
     for (int i = 0; i < p.npass; i++) {
       NTT_CK(plan_alloc(p, &p.inner[i], (size_t)1 << p.K[i]));
       NTT_CK(fill_pow_table(p.inner[i], w, one, 1u << p.K[i], log_n - p.K[i], s));
+      // direct inter-pass twiddles for the middle passes while the table stays L2 sized (<= 2^18 entries = 8 MB)
+      if (i >= 1 && i + 1 < p.npass && log_cur <= DIRECT_TW_MAX_LOG) {
+        NTT_CK(plan_alloc(p, &p.tw_direct[i], (size_t)1 << log_cur));
+        NTT_CK(fill_pow_table(p.tw_direct[i], w, one, 1u << log_cur, log_n - log_cur, s));
+      }
+      log_cur -= (u32)p.K[i];
     }
   }
   return cudaStreamSynchronize(s);
@@ -188,6 +198,7 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
       a.log_r3 = p.npass >= 4 ? (u32)p.K[2] : 0;
       a.inner = p.inner[i];
       a.tw = PowTable{p.tw_lo, (i == 0 && p.tw_hi_scaled) ? p.tw_hi_scaled : p.tw_hi, p.lo_bits};
+      a.tw_direct = p.tw_direct[i];
       a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
       a.post = a.pre;
       const u32 grid = (u32)(n >> TILE_LOG);
