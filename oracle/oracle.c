@@ -334,8 +334,22 @@ int oracle_msm_g1(uint8_t* out144, const uint8_t* bases, size_t n, const u64* sc
   xyzz total;
   xyzz_set_identity(&total);
   if (n > 0) {
-    const uint32_t c = (uint32_t)oracle_msm_window_bits(n), nwin = (253 + c - 1) / c;
     if (nthreads < 1) nthreads = 1;
+    /* windows are the unit of parallelism: pick the window size whose ceil(windows / threads) rounds of
+       (n mixed additions + 2 * 2^c full additions) are cheapest (c0 = the classic ln(n) + 2 for one thread) */
+    uint32_t c = (uint32_t)oracle_msm_window_bits(n);
+    {
+      double best = 0;
+      uint32_t best_c = c;
+      for (uint32_t cc = (c > 4 ? c - 3 : 2); cc <= c + 4 && cc <= 20; cc++) {
+        const uint32_t nw = (253 + cc - 1) / cc;
+        const double rounds = (double)((nw + (uint32_t)nthreads - 1) / (uint32_t)nthreads);
+        const double cost = rounds * ((double)n * 10.0 + 2.0 * 14.0 * (double)((size_t)1 << cc));
+        if (best == 0 || cost < best) { best = cost; best_c = cc; }
+      }
+      c = best_c;
+    }
+    const uint32_t nwin = (253 + c - 1) / c;
     if ((uint32_t)nthreads > nwin) nthreads = (int)nwin;
     xyzz* sums = (xyzz*)calloc(nwin, sizeof(xyzz));
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
