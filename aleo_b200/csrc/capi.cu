@@ -200,6 +200,56 @@ int aleo_b200_ntt_twiddle_dev(void* data_dev, uint32_t log_n_global, int directi
   return ALEO_B200_OK;
 }
 
+int aleo_b200_ntt_dist_layout(uint32_t log_n, int world, uint32_t* log_r_first_out, uint32_t* log_r_last_out, int* passes_out) {
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  return aleo::ntt_dist_layout(log_n, world, log_r_first_out, log_r_last_out, passes_out) == 0 ? ALEO_B200_OK : ALEO_B200_EINVAL;
+}
+
+int aleo_b200_ntt_dist_create(void** ctx_out, uint32_t log_n, int rank, int world) {
+  if (ctx_out == nullptr) return ALEO_B200_EINVAL;
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (aleo::ntt_dist_layout(log_n, world, nullptr, nullptr, nullptr) != 0 || rank < 0 || rank >= world) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::ntt_dist_create(log_n, rank, world, ctx_out));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_dist_handles(void* ctx, void* handles128_out) {
+  if (ctx == nullptr || handles128_out == nullptr) return ALEO_B200_EINVAL;
+  API_CK(aleo::ntt_dist_handles(ctx, handles128_out));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_dist_open(void* ctx, const void* all_handles) {
+  if (ctx == nullptr || all_handles == nullptr) return ALEO_B200_EINVAL;
+  API_CK(aleo::ntt_dist_open(ctx, all_handles));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_dist_stage1(void* ctx, const void* local_in_dev, int direction, void* stream) {
+  if (ctx == nullptr || local_in_dev == nullptr) return ALEO_B200_EINVAL;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::ntt_dist_stage1(ctx, local_in_dev, direction == ALEO_B200_NTT_INVERSE, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, void* stream) {
+  if (ctx == nullptr || local_out_dev == nullptr) return ALEO_B200_EINVAL;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::ntt_dist_stage2(ctx, local_out_dev, direction == ALEO_B200_NTT_INVERSE, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_ntt_dist_destroy(void* ctx) {
+  aleo::ntt_dist_destroy(ctx);
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) {
   if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
   if (inout_host == nullptr) return ALEO_B200_EINVAL;

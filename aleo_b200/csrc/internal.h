@@ -13,6 +13,13 @@ cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void*
                                cudaStream_t s);
 cudaError_t ntt_bitrev(u32 log_n, size_t batch, void* data_dev, cudaStream_t s);
 int ntt_launches(u32 log_n);
+int ntt_dist_layout(u32 log_n, int world, u32* log_r_first, u32* log_r_last, int* npass);
+cudaError_t ntt_dist_create(u32 log_n, int rank, int world, void** ctx_out);
+cudaError_t ntt_dist_handles(void* ctx, void* handles_out /* 128 bytes */);
+cudaError_t ntt_dist_open(void* ctx, const void* all_handles /* world x 128 bytes */);
+cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, cudaStream_t s);
+cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, cudaStream_t s);
+void ntt_dist_destroy(void* ctx);
 int ntt_max_log_n();
 void ntt_clear_plans();
 // msm_lib.cu

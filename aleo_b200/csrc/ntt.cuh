@@ -152,7 +152,23 @@ struct PassArgs {
   PowTable pre;     // PRE : coset powers c^i applied to inputs of the first pass
   PowTable post;    // POST: powers applied to outputs of the last pass (coset inverse, carries n^-1)
   u32 use_pre, use_post;
+  // ---- one transform spread over 2^lg GPUs (ntt_dist_*; all zero / neutral on a single GPU) -------------------------
+  // The local array holds N / 2^lg elements whose last digit is shortened to `d_k2l` = K_last - lg bits: geometry
+  // (log_n, log_cur, log_r1) is LOCAL, twiddles use the GLOBAL index (the rank's bits spliced in above d_k2l).
+  u32 d_k2l;         // bits of the last digit held locally (>= 31: single GPU, every mask below is the identity)
+  u32 d_klast;       // K_last
+  u32 d_rank_bits;   // rank << d_k2l
+  u32 d_log_chunk;   // log2(N / 4^lg): elements one rank sends to one peer
+  u32 d_exchange;    // this (last-but-one) pass stores straight into the peers' receive buffers (NVLink P2P)
+  u32 d_rank;
+  Fr* peer[8];       // receive buffer of every rank (own included), device pointers valid on this GPU
 };
+
+// global index of the local index i2l of a strided pass: the rank's bits go in above the shortened last digit
+DEV u32 dist_expand(const PassArgs& a, u32 i2l) {
+  if (a.d_k2l >= 31u) return i2l;
+  return ((i2l >> a.d_k2l) << a.d_klast) | a.d_rank_bits | (i2l & ((1u << a.d_k2l) - 1u));
+}
 
 // One pass.  K = bits handled, LAST = writes the natural-order result.  Coset scaling (use_pre on
 // the first pass, use_post on the last) is a CTA-uniform runtime branch.
@@ -215,7 +231,10 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const u32 p = j * C1 + tr;
-      const u64 gi = in_base + p * stride_r + tg * stride_g;
+      u64 gi = in_base + p * stride_r + tg * stride_g;
+      if (LAST && a.d_k2l < 31u)  // a row's R elements arrived as 2^lg pieces of 2^d_k2l, one per source rank
+        gi = ((u64)(p >> a.d_k2l) << a.d_log_chunk) + (((in_base >> K) + ((u64)tg * (stride_g >> K))) << a.d_k2l) +
+             (p & ((1u << a.d_k2l) - 1u));
       x[j] = src[gi];
       if (!LAST && a.use_pre) x[j] = fr_mul_v(x[j], pow_lookup(a.pre, (u32)gi));
     }
@@ -297,14 +316,17 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       Fr v = smem_get(plane0, plane1, tile_phys<K, LAST>(pos, sg));
       const u64 go = out_base + kap * ostride_r + sg;
       if (!LAST) {
-        const u32 x = (i2_base + sg) * kap;
+        const u32 x = dist_expand(a, i2_base + sg) * kap;
         if (a.tw_direct)
           v = fr_mul_v(v, a.tw_direct[x]);
         else
           v = fr_mul_v(v, pow_lookup(a.tw, x << (a.log_n - a.log_cur)));
       }
       if (LAST && a.use_post) v = fr_mul_v(v, pow_lookup(a.post, (u32)go));
-      dst[go] = v;
+      if (!LAST && a.d_exchange)  // flat all-to-all: chunk t of the local result goes to rank t, slot = my rank
+        a.peer[go >> a.d_log_chunk][((u64)a.d_rank << a.d_log_chunk) + (go & (((u64)1 << a.d_log_chunk) - 1u))] = v;
+      else
+        dst[go] = v;
     }
   }
 }

@@ -25,6 +25,59 @@ static inline int split_passes(int L, int* K) {
 
 constexpr u32 DIRECT_TW_MAX_LOG = 18;
 
+static inline void set_single_gpu(PassArgs& a) {
+  a.d_k2l = 31;
+  a.d_klast = 0;
+  a.d_rank_bits = 0;
+  a.d_log_chunk = 0;
+  a.d_exchange = 0;
+  a.d_rank = 0;
+  for (int i = 0; i < 8; i++) a.peer[i] = nullptr;
+}
+
+// Pass split of a transform spread over 2^lg GPUs (ntt_dist_*): every radix 2^5..2^8, and
+//   K_p + (bits below digit p) - lg >= 11 for every strided pass (its tile is 2^(11 - K_p) local columns wide),
+//   K_0 + K_last - lg >= 11 for the last pass (its tile takes 2^(11 - K_last) local values of the first digit),
+//   K_last >= lg (every rank holds at least one value of the last digit).
+// Returns the number of passes (2..4) or 0 when the size cannot be spread that far.
+static inline int split_passes_dist(int L, int lg, int* K) {
+  for (int P = (L + MAX_PASS_BITS - 1) / MAX_PASS_BITS; P <= 4; P++) {
+    if (P < 2) continue;
+    int best[4] = {0, 0, 0, 0}, best_spread = 99, k[4];
+    const int lim = 4 * 4 * 4 * 4;
+    for (int code = 0; code < lim; code++) {
+      int sum = 0, c = code;
+      for (int i = 0; i < 4; i++) {
+        k[i] = 5 + (c & 3);
+        c >>= 2;
+      }
+      for (int i = 0; i < P; i++) sum += k[i];
+      if (sum != L) continue;
+      bool ok = k[P - 1] >= lg && k[0] + k[P - 1] - lg >= TILE_LOG;
+      int below = 0;
+      for (int i = P - 1; i >= 1 && ok; i--) {
+        below += k[i];
+        ok = k[i - 1] + below - lg >= TILE_LOG;
+      }
+      if (!ok) continue;
+      int mx = 0, mn = 99;
+      for (int i = 0; i < P; i++) {
+        mx = k[i] > mx ? k[i] : mx;
+        mn = k[i] < mn ? k[i] : mn;
+      }
+      if (mx - mn < best_spread) {
+        best_spread = mx - mn;
+        for (int i = 0; i < P; i++) best[i] = k[i];
+      }
+    }
+    if (best_spread != 99) {
+      for (int i = 0; i < P; i++) K[i] = best[i];
+      return P;
+    }
+  }
+  return 0;
+}
+
 struct Plan {
   int device = -1;
   u32 log_n = 0;
@@ -55,7 +108,8 @@ static inline cudaError_t fill_pow_table(Fr* out, const Fr* base, const Fr* scal
   return cudaGetLastError();
 }
 
-static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool inverse, bool coset, cudaStream_t s) {
+// dist_lg > 0: the plan of a transform spread over 2^dist_lg GPUs (same tables, the pass split of split_passes_dist)
+static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool inverse, bool coset, cudaStream_t s, int dist_lg = 0) {
   p.device = device;
   p.log_n = log_n;
   p.inverse = inverse;
@@ -75,12 +129,13 @@ static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool invers
     NTT_CK(fill_pow_table(p.cs_lo, cg, one, 1u << p.lo_bits, 0, s));
     NTT_CK(fill_pow_table(p.cs_hi, cg, inverse ? ninv : one, 1u << hi_bits, p.lo_bits, s));
   }
-  if (log_n <= (u32)SMALL_MAX_LOG) {
+  if (log_n <= (u32)SMALL_MAX_LOG && dist_lg == 0) {
     NTT_CK(plan_alloc(p, &p.small_inner, (size_t)1 << log_n));
     NTT_CK(fill_pow_table(p.small_inner, w, one, 1u << log_n, 0, s));
     NTT_CK(cudaMemcpyAsync(&p.scale_host, ninv, sizeof(Fr), cudaMemcpyDeviceToHost, s));
   } else {
-    p.npass = split_passes((int)log_n, p.K);
+    p.npass = dist_lg ? split_passes_dist((int)log_n, dist_lg, p.K) : split_passes((int)log_n, p.K);
+    if (p.npass == 0) return cudaErrorInvalidValue;
     NTT_CK(plan_alloc(p, &p.tw_lo, (size_t)1 << p.lo_bits));
     NTT_CK(plan_alloc(p, &p.tw_hi, (size_t)1 << hi_bits));
     NTT_CK(fill_pow_table(p.tw_lo, w, one, 1u << p.lo_bits, 0, s));
@@ -189,6 +244,7 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
     for (int i = 0; i < p.npass; i++) {
       const bool last = (i == p.npass - 1);
       PassArgs a;
+      set_single_gpu(a);
       a.src = (i == 0) ? x : scratch;
       a.dst = last ? x : scratch;
       a.log_n = p.log_n;
@@ -213,16 +269,81 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
   return cudaSuccess;
 }
 
+// ---- one transform over 2^lg GPUs ---------------------------------------------------------------------------------
+// Rank j holds the column block of the (N / R_last) x R_last row-major matrix (local[a * R_last / g + b] =
+// x[a * R_last + j * R_last / g + b]).  Stage 1 = passes 0 .. P-2 on the local N / g elements (twiddles by global
+// index); the last of them stores chunk t of its result straight into rank t's receive buffer.  After a cross-rank
+// barrier stage 2 = the last pass from the receive buffer; rank t ends with X[k], k mod R_0 in its range, as the column
+// block of the (N / R_0) x R_0 matrix.
+static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const Fr* in, Fr* scratch, Fr* const* peers,
+                                          cudaStream_t s) {
+  const u32 L = p.log_n, Ll = L - (u32)lg;
+  const u32 klast = (u32)p.K[p.npass - 1];
+  u32 log_cur = L;
+  for (int i = 0; i + 1 < p.npass; i++) {
+    const bool exchange = (i + 2 == p.npass);
+    PassArgs a;
+    a.src = (i == 0) ? in : scratch;
+    a.dst = scratch;
+    a.log_n = Ll;
+    a.log_cur = log_cur - (u32)lg;
+    a.log_r1 = a.log_r2 = a.log_r3 = 0;
+    a.inner = p.inner[i];
+    a.tw = PowTable{p.tw_lo, (i == 0 && p.tw_hi_scaled) ? p.tw_hi_scaled : p.tw_hi, p.lo_bits};
+    a.tw_direct = p.tw_direct[i];
+    a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
+    a.post = a.pre;
+    a.use_pre = a.use_post = 0;
+    a.d_k2l = klast - (u32)lg;
+    a.d_klast = klast;
+    a.d_rank_bits = (u32)rank << a.d_k2l;
+    a.d_log_chunk = L - 2 * (u32)lg;
+    a.d_exchange = exchange ? 1 : 0;
+    a.d_rank = (u32)rank;
+    for (int r = 0; r < 8; r++) a.peer[r] = (r < (1 << lg)) ? peers[r] : nullptr;
+    NTT_CK(launch_pass_k<false>(p.K[i], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s));
+    log_cur -= (u32)p.K[i];
+  }
+  return cudaSuccess;
+}
+
+static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const Fr* recv, Fr* out, cudaStream_t s) {
+  const u32 L = p.log_n, Ll = L - (u32)lg;
+  const int last = p.npass - 1;
+  PassArgs a;
+  a.src = recv;
+  a.dst = out;
+  a.log_n = Ll;
+  a.log_cur = (u32)p.K[last];
+  a.log_r1 = (u32)p.K[0] - (u32)lg;
+  a.log_r2 = p.npass >= 3 ? (u32)p.K[1] : 0;
+  a.log_r3 = p.npass >= 4 ? (u32)p.K[2] : 0;
+  a.inner = p.inner[last];
+  a.tw = PowTable{p.tw_lo, p.tw_hi, p.lo_bits};
+  a.tw_direct = nullptr;
+  a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
+  a.post = a.pre;
+  a.use_pre = a.use_post = 0;
+  a.d_k2l = (u32)p.K[last] - (u32)lg;
+  a.d_klast = (u32)p.K[last];
+  a.d_rank_bits = (u32)rank << a.d_k2l;
+  a.d_log_chunk = L - 2 * (u32)lg;
+  a.d_exchange = 0;
+  a.d_rank = (u32)rank;
+  for (int r = 0; r < 8; r++) a.peer[r] = nullptr;
+  return launch_pass_k<true>(p.K[last], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s);
+}
+
 // ---- plan cache (immutable after construction; guarded by one mutex) -----------------------------
 class PlanCache {
  public:
-  cudaError_t get(int device, u32 log_n, bool inverse, bool coset, cudaStream_t s, const Plan** out) {
+  cudaError_t get(int device, u32 log_n, bool inverse, bool coset, cudaStream_t s, const Plan** out, int dist_lg = 0) {
     std::lock_guard<std::mutex> lk(mu_);
-    auto key = std::make_tuple(device, log_n, inverse, coset);
+    auto key = std::make_tuple(device, log_n, inverse, coset, dist_lg);
     auto it = plans_.find(key);
     if (it == plans_.end()) {
       Plan p;
-      cudaError_t e = build_plan(p, device, log_n, inverse, coset, s);
+      cudaError_t e = build_plan(p, device, log_n, inverse, coset, s, dist_lg);
       if (e != cudaSuccess) {
         destroy_plan(p);
         return e;
@@ -240,7 +361,7 @@ class PlanCache {
 
  private:
   std::mutex mu_;
-  std::map<std::tuple<int, u32, bool, bool>, Plan> plans_;
+  std::map<std::tuple<int, u32, bool, bool, int>, Plan> plans_;
 };
 
 }  // namespace ntt

@@ -56,6 +56,138 @@ cudaError_t ntt_bitrev(u32 log_n, size_t batch, void* data_dev, cudaStream_t s) 
   return cudaGetLastError();
 }
 
+// ---- one transform over the GPUs of a node, exchange by stores into peer memory (NVLink) -------------------------------
+struct NttDist {
+  int device = 0, rank = 0, world = 1, lg = 0;
+  u32 log_n = 0;
+  Fr* recv[2] = {nullptr, nullptr};          // double-buffered receive buffers (N / world elements each), cudaMalloc'ed
+  Fr* peers[2][8] = {{nullptr}, {nullptr}};  // recv[b] of every rank, mapped into this process
+  bool opened[2][8] = {{false}, {false}};
+  bool have_peers = false;
+  unsigned long long calls = 0;              // parity selects the buffer; every rank issues the same sequence of calls
+};
+
+int ntt_dist_layout(u32 log_n, int world, u32* log_r_first, u32* log_r_last, int* npass) {
+  int lg = 0;
+  while ((1 << lg) < world) lg++;
+  if ((1 << lg) != world || world > 8 || world < 1) return -1;
+  int K[4];
+  const int P = ntt::split_passes_dist((int)log_n, lg, K);
+  if (P == 0 || (int)log_n - 2 * lg < 0) return -1;
+  if (log_r_first) *log_r_first = (u32)K[0];
+  if (log_r_last) *log_r_last = (u32)K[P - 1];
+  if (npass) *npass = P;
+  return 0;
+}
+
+cudaError_t ntt_dist_create(u32 log_n, int rank, int world, void** ctx_out) {
+  if (ntt_dist_layout(log_n, world, nullptr, nullptr, nullptr) != 0 || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+  NttDist* c = new NttDist();
+  cudaGetDevice(&c->device);
+  c->rank = rank;
+  c->world = world;
+  while ((1 << c->lg) < world) c->lg++;
+  c->log_n = log_n;
+  const size_t bytes = (sizeof(Fr) << log_n) / (size_t)world;
+  for (int b = 0; b < 2; b++) {
+    cudaError_t e = cudaMalloc((void**)&c->recv[b], bytes);
+    if (e != cudaSuccess) {
+      if (b == 1) cudaFree(c->recv[0]);
+      delete c;
+      return e;
+    }
+  }
+  *ctx_out = c;
+  return cudaSuccess;
+}
+
+// handles_out: 2 x 64 bytes describing this rank's two receive buffers for the other processes
+cudaError_t ntt_dist_handles(void* ctx, void* handles_out) {
+  NttDist* c = (NttDist*)ctx;
+  std::memset(handles_out, 0, 128);
+  for (int b = 0; b < 2; b++) {
+#ifndef ALEO_EMU
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, c->recv[b]);
+    if (e != cudaSuccess) return e;
+    std::memcpy((unsigned char*)handles_out + 64 * b, &h, 64);
+#else
+    std::memcpy((unsigned char*)handles_out + 64 * b, &c->recv[b], sizeof(Fr*));  // emulator: ranks share one address space
+#endif
+  }
+  return cudaSuccess;
+}
+
+// all_handles: world x (2 x 64 bytes), rank-major, as gathered from every rank's ntt_dist_handles
+cudaError_t ntt_dist_open(void* ctx, const void* all_handles) {
+  NttDist* c = (NttDist*)ctx;
+  for (int r = 0; r < c->world; r++)
+    for (int b = 0; b < 2; b++) {
+      const unsigned char* h = (const unsigned char*)all_handles + ((size_t)r * 2 + b) * 64;
+      if (r == c->rank) {
+        c->peers[b][r] = c->recv[b];
+        continue;
+      }
+#ifndef ALEO_EMU
+      cudaIpcMemHandle_t ih;
+      std::memcpy(&ih, h, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return e;
+      c->peers[b][r] = (Fr*)ptr;
+      c->opened[b][r] = true;
+#else
+      Fr* ptr = nullptr;
+      std::memcpy(&ptr, h, sizeof(Fr*));
+      c->peers[b][r] = ptr;
+#endif
+    }
+  c->have_peers = true;
+  return cudaSuccess;
+}
+
+// passes 0 .. P-2 of the local part; the last of them writes into the peers' receive buffers
+cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, cudaStream_t s) {
+  NttDist* c = (NttDist*)ctx;
+  if (!c->have_peers) return cudaErrorInvalidValue;
+  const ntt::Plan* plan = nullptr;
+  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, false, s, &plan, c->lg);
+  if (e != cudaSuccess) return e;
+  Fr* scratch = nullptr;
+  if (plan->npass > 2) {
+    e = cudaMallocAsync((void**)&scratch, (sizeof(Fr) << c->log_n) / (size_t)c->world, s);
+    if (e != cudaSuccess) return e;
+  }
+  e = ntt::run_dist_stage1(*plan, c->lg, c->rank, (const Fr*)local_in_dev, scratch, c->peers[c->calls & 1], s);
+  if (scratch) cudaFreeAsync(scratch, s);
+  return e;
+}
+
+// the last pass from this rank's receive buffer (call after a cross-rank barrier ordered on the same stream)
+cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, cudaStream_t s) {
+  NttDist* c = (NttDist*)ctx;
+  const ntt::Plan* plan = nullptr;
+  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, false, s, &plan, c->lg);
+  if (e != cudaSuccess) return e;
+  e = ntt::run_dist_stage2(*plan, c->lg, c->rank, c->recv[c->calls & 1], (Fr*)local_out_dev, s);
+  c->calls++;
+  return e;
+}
+
+void ntt_dist_destroy(void* ctx) {
+  NttDist* c = (NttDist*)ctx;
+  if (!c) return;
+#ifndef ALEO_EMU
+  for (int b = 0; b < 2; b++)
+    for (int r = 0; r < 8; r++)
+      if (c->opened[b][r]) cudaIpcCloseMemHandle(c->peers[b][r]);
+#endif
+  cudaFree(c->recv[0]);
+  cudaFree(c->recv[1]);
+  delete c;
+}
+
 // data[r][c] *= w_N^(+-(r + row0)(c + col0)), N = 2^log_n_global (multi-GPU four-step twiddle step)
 cudaError_t ntt_twiddle_matrix(int device, u32 log_n_global, bool inverse, void* data_dev, u32 rows, u32 cols, u32 row0, u32 col0,
                                cudaStream_t s) {

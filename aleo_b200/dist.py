@@ -137,3 +137,85 @@ def ntt_four_step(block, log_n: int, inverse: bool = False, group=None, backend=
     rows = rows.transpose(0, 1).contiguous()                                     # (n1/g, n2, 4)
     backend.ntt_batch(rows, l2, wr, inverse)                                     # step 4
     return rows
+
+
+# ---- NTT with the exchange fused into the transform (peer-memory stores over NVLink) ---------------------------------
+class PeerNTT:
+    """One Fr NTT of size 2^log_n spread over the GPUs of a node, one process per GPU (include/aleo_b200.h
+    ``aleo_b200_ntt_dist_*``).  The pass split is the single-GPU one; the last-but-one pass stores every result
+    element straight into the receive buffer of the rank that needs it (CUDA IPC mapped peer memory), a
+    1-element all-reduce on the same stream is the cross-rank barrier, and the last pass runs from the receive
+    buffer.  Input: this rank's column block of the (N / R_last) x R_last matrix of x; output: its column block
+    of the (N / R_first) x R_first matrix of X (natural order) -- see ``layout``."""
+
+    def __init__(self, log_n: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+
+        self._lib = _lib.get_lib()
+        self.log_n = log_n
+        self.group = group
+        self.rank, self.world = _world(group)
+        kf, kl, npass = C.c_uint32(), C.c_uint32(), C.c_int()
+        self._lib.check(self._lib.ntt_dist_layout(log_n, self.world, C.byref(kf), C.byref(kl), C.byref(npass)),
+                        "aleo_b200_ntt_dist_layout")
+        self.log_r_first, self.log_r_last, self.passes = kf.value, kl.value, npass.value
+        self._h = C.c_void_p()
+        self._lib.check(self._lib.ntt_dist_create(C.byref(self._h), log_n, self.rank, self.world), "aleo_b200_ntt_dist_create")
+        mine = C.create_string_buffer(128)
+        self._lib.check(self._lib.ntt_dist_handles(self._h, C.cast(mine, C.c_void_p)), "aleo_b200_ntt_dist_handles")
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(dev)
+            allh = torch.empty(128 * self.world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t, group=group)
+            raw = allh.cpu().numpy().tobytes()
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            raw = mine.raw
+            self._flag = None
+        buf = C.create_string_buffer(raw, len(raw))
+        self._lib.check(self._lib.ntt_dist_open(self._h, C.cast(buf, C.c_void_p)), "aleo_b200_ntt_dist_open")
+
+    def layout(self):
+        """(rows_in, cols_in, rows_out, cols_out) of this rank's input / output column blocks"""
+        n = 1 << self.log_n
+        rl, rf = 1 << self.log_r_last, 1 << self.log_r_first
+        return n // rl, rl // self.world, n // rf, rf // self.world
+
+    def input_block(self, x_full):
+        """helper: natural-order (N, 4) tensor -> this rank's input block"""
+        rows, cols, _, _ = self.layout()
+        return x_full.reshape(rows, cols * self.world, 4)[:, self.rank * cols:(self.rank + 1) * cols, :].contiguous()
+
+    def output_block_of(self, X_full):
+        """helper: natural-order (N, 4) result -> the block this rank ends up with"""
+        _, _, rows, cols = self.layout()
+        return X_full.reshape(rows, cols * self.world, 4)[:, self.rank * cols:(self.rank + 1) * cols, :].contiguous()
+
+    def transform(self, block, out=None, inverse: bool = False):
+        import torch
+        import torch.distributed as dist
+
+        if out is None:
+            out = torch.empty_like(block).reshape(-1, 4)
+        direction = _lib.NTT_INVERSE if inverse else _lib.NTT_FORWARD
+        with torch.cuda.device(block.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._lib.check(self._lib.ntt_dist_stage1(self._h, block.data_ptr(), direction, stream), "aleo_b200_ntt_dist_stage1")
+            if self.world > 1:
+                dist.all_reduce(self._flag, group=self.group)      # barrier ordered on the stream: peers' stores are complete
+            self._lib.check(self._lib.ntt_dist_stage2(self._h, out.data_ptr(), direction, stream), "aleo_b200_ntt_dist_stage2")
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.ntt_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -467,44 +467,79 @@ def run_ours(args):
                         "note": "the 253-bit NTT is integer-pipe bound (about %.1f Fr products of 120 IMAD.WIDE per element); int_frac is "
                                 "measured against the same live IMAD.WIDE peak as the MSM" % mults_per_elem}}
 
-    # ---- N > 1: one NTT of 2^(log_n + log2 N) sharded four-step with a single NCCL all-to-all ---------
+    # ---- N > 1: ONE NTT of 2^(log_n + log2 N) over the N GPUs: exchange fused into the transform (peer-memory stores),
+    #      with the NCCL all-to-all schedule timed beside it -----------------------------------------------------------
     ntt_dist = None
-    if world > 1 and (world & (world - 1)) == 0:
+    if world > 1 and (world & (world - 1)) == 0 and world <= 8:
         from aleo_b200 import dist as adist
 
         glog = log_n + world.bit_length() - 1
-        l1, l2 = adist.four_step_shape(glog)
-        g1, g2 = 1 << l1, 1 << l2
-        wc, wr = g2 // world, g1 // world
-        # order / twiddle / transpose check: a delta at index 1 must transform to the powers of omega
-        blk = torch.zeros((g1, wc, 4), dtype=torch.int64, device=dev)
-        if rank == 1 // wc:
-            one = np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64)
-            blk[0, 1 % wc] = torch.from_numpy(one.copy()).to(dev)
-        outb = adist.ntt_four_step(blk, glog).cpu().numpy()
         w = o.fr_root_of_unity(glog)
-        dist_ok = all(outb[k, k2].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, rank * wr + k + g1 * k2, o.R_MOD)), 32)
-                      for k, k2 in ((0, 0), (1, 0), (wr - 1, 1), (wr // 2, g2 - 1), (3, g2 // 2)))
-        flags = [None] * world
-        dist.all_gather_object(flags, bool(dist_ok))
-        del blk, outb
-        xb = x.reshape(g1, wc, 4) if x.numel() == g1 * wc * 4 else ab.gen_scalars_dev(g1 * wc, 78, first, True, device=dev).reshape(g1, wc, 4)
+        one = np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64)
+        peer = adist.PeerNTT(glog)
+        rows_in, cols_in, rows_out, cols_out = peer.layout()
+        # order / twiddle / exchange check: a delta at index 1 must transform to the powers of omega
+        blk = torch.zeros((rows_in * cols_in, 4), dtype=torch.int64, device=dev)
+        if rank == 1 // cols_in:
+            blk[1 % cols_in] = torch.from_numpy(one.copy()).to(dev)
+        outp = peer.transform(blk).cpu().numpy()
+        r0 = cols_out * world
+        picks = ((0, 0), (1, 0), (rows_out - 1, 1 % cols_out), (rows_out // 2, cols_out - 1), (3, cols_out // 2))
+        peer_ok = all(outp[a * cols_out + b].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, a * r0 + rank * cols_out + b, o.R_MOD)), 32)
+                      for a, b in picks)
+        xb = ab.gen_scalars_dev(rows_in * cols_in, 78, first, True, device=dev)
+        xo = torch.empty_like(xb)
         for _ in range(args.warmup):
-            adist.ntt_four_step(xb, glog)
+            peer.transform(xb, out=xo)
         barrier()
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d0.record()
         for _ in range(args.steps):
-            adist.ntt_four_step(xb, glog)
+            peer.transform(xb, out=xo)
         d1.record()
         barrier()
         dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
         dist.all_reduce(dms, op=dist.ReduceOp.MAX)
         dstep = dms.item() / args.steps
+        peer_passes, peer_rf, peer_rl = peer.passes, peer.log_r_first, peer.log_r_last
+        peer.close()
+        del blk, xo
+        # the same transform with the exchange as a separate NCCL all-to-all (aleo_b200/dist.py ntt_four_step)
+        l1, l2 = adist.four_step_shape(glog)
+        g1, g2 = 1 << l1, 1 << l2
+        wc, wr = g2 // world, g1 // world
+        blk = torch.zeros((g1, wc, 4), dtype=torch.int64, device=dev)
+        if rank == 1 // wc:
+            blk[0, 1 % wc] = torch.from_numpy(one.copy()).to(dev)
+        outb = adist.ntt_four_step(blk, glog).cpu().numpy()
+        nccl_ok = all(outb[k, k2].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, rank * wr + k + g1 * k2, o.R_MOD)), 32)
+                      for k, k2 in ((0, 0), (1, 0), (wr - 1, 1), (wr // 2, g2 - 1), (3, g2 // 2)))
+        flags = [None] * world
+        dist.all_gather_object(flags, (bool(peer_ok), bool(nccl_ok)))
+        del blk, outb
+        xb = xb.reshape(g1, wc, 4)
+        for _ in range(args.warmup):
+            adist.ntt_four_step(xb, glog)
+        barrier()
+        d0.record()
+        for _ in range(args.steps):
+            adist.ntt_four_step(xb, glog)
+        d1.record()
+        barrier()
+        nms = torch.tensor([d0.elapsed_time(d1)], device=dev)
+        dist.all_reduce(nms, op=dist.ReduceOp.MAX)
+        nstep = nms.item() / args.steps
+        del xb
         ntt_dist = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": (1 << glog) / dstep / 1e3, "unit": "Melem/s", "ms_per_step": dstep,
-                    "log_n_global": glog, "schedule": "four-step %dx%d, column blocks in, transposed row blocks out" % (g1, g2),
-                    "collective": "one all_to_all_single (NCCL) of %d bytes per rank" % (g1 * wc * 32 * (world - 1) // world),
-                    "scaling": "weak", "delta_impulse_check": all(flags)}
+                    "log_n_global": glog, "passes": peer_passes,
+                    "schedule": "single-GPU pass split %d passes (R_first 2^%d, R_last 2^%d); the last-but-one pass stores into the peers' "
+                                "receive buffers (CUDA IPC peer memory over NVLink), 1-element all-reduce as barrier, last pass from "
+                                "the receive buffer" % (peer_passes, peer_rf, peer_rl),
+                    "exchange_bytes_per_rank": (1 << glog) // world * 32 * (world - 1) // world,
+                    "scaling": "weak", "delta_impulse_check": all(f[0] for f in flags),
+                    "nccl_all_to_all_schedule": {"value": (1 << glog) / nstep / 1e3, "unit": "Melem/s", "ms_per_step": nstep,
+                                                 "what": "four-step %dx%d with torch transposes around one all_to_all_single (NCCL)" % (g1, g2),
+                                                 "delta_impulse_check": all(f[1] for f in flags)}}
 
     # ---- size sweep 2^16 .. 2^22 (BASELINE.json metric range / config 2), single-GPU run only -----------------
     sweep = None

@@ -80,6 +80,26 @@ int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction,
  * domain of size 2^log_n_global (its inverse for ALEO_B200_NTT_INVERSE).  12 <= log_n_global <= 32. */
 int aleo_b200_ntt_twiddle_dev(void* data_dev, uint32_t log_n_global, int direction, uint32_t rows, uint32_t cols,
                               uint32_t row0, uint32_t col0, void* stream);
+/* ---- one Fr NTT spread over the GPUs of a node (one process per GPU), exchange fused into the transform ---------
+ * BASELINE config 4 / SURVEY.md 8e: the four-step decomposition with ONE exchange.  The pass split is the single-GPU
+ * one (radices 2^K_0 .. 2^K_last); the transposing exchange is not a separate collective: the last-but-one pass
+ * stores every result element straight into the receive buffer of the rank that needs it (peer memory over
+ * NVLink, CUDA IPC between the processes), so the transfer overlaps the butterflies tile by tile.
+ *   input  (rank j): column block of the (N / R_last) x R_last row-major matrix of x:
+ *                    local[a * R_last / g + b] = x[a * R_last + j * R_last / g + b]
+ *   output (rank t): column block of the (N / R_0) x R_0 row-major matrix of X (natural order):
+ *                    local[a * R_0 / g + b] = X[a * R_0 + t * R_0 / g + b]
+ * Usage, every rank, same call sequence:  ctx = create;  gather every rank's 128-byte `handles` (e.g. an
+ * all_gather);  open(all handles);  then per transform: stage1(in) -> a cross-rank barrier ordered on the same
+ * stream (e.g. a 1-element NCCL all-reduce) -> stage2(out).  Two receive buffers alternate, so the next
+ * transform's stage1 may be enqueued at once.  world = 1, 2, 4, 8; standard (non-coset) transforms. */
+int aleo_b200_ntt_dist_layout(uint32_t log_n, int world, uint32_t* log_r_first_out, uint32_t* log_r_last_out, int* passes_out);
+int aleo_b200_ntt_dist_create(void** ctx_out, uint32_t log_n, int rank, int world);
+int aleo_b200_ntt_dist_handles(void* ctx, void* handles128_out);
+int aleo_b200_ntt_dist_open(void* ctx, const void* all_handles /* world x 128 bytes, rank-major */);
+int aleo_b200_ntt_dist_stage1(void* ctx, const void* local_in_dev, int direction, void* stream);
+int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, void* stream);
+int aleo_b200_ntt_dist_destroy(void* ctx);
 /* kernel launches one transform of this size issues (for launch accounting) */
 int aleo_b200_ntt_launches(uint32_t log_n);
 

@@ -303,3 +303,56 @@ def test_emu_kzg_open(emu_lib):
     emu_lib.check(emu_lib.kzg_open_dev(h, C.cast(out48, C.c_void_p), C.cast(src, C.c_void_p), 1, o.int_to_le_bytes(o.fr_to_mont(z), 32), None), "open1")
     assert out48.raw == o.g1_compress(None)          # a constant polynomial has the zero witness
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+def _dist_ntt_emulated(lib, x, log_n, world, direction):
+    """all ranks of aleo_b200_ntt_dist_* in ONE process (the emulator's 'peer memory' is the shared address space):
+    returns the natural-order result assembled from the ranks' output blocks"""
+    n = 1 << log_n
+    kf, kl, npass = C.c_uint32(), C.c_uint32(), C.c_int()
+    lib.check(lib.ntt_dist_layout(log_n, world, C.byref(kf), C.byref(kl), C.byref(npass)), "layout")
+    r0, rl = 1 << kf.value, 1 << kl.value
+    ctxs, handles = [], b""
+    for r in range(world):
+        h = C.c_void_p()
+        lib.check(lib.ntt_dist_create(C.byref(h), log_n, r, world), "create")
+        hb = C.create_string_buffer(128)
+        lib.check(lib.ntt_dist_handles(h, C.cast(hb, C.c_void_p)), "handles")
+        ctxs.append(h)
+        handles += hb.raw
+    allh = C.create_string_buffer(handles, len(handles))
+    for h in ctxs:
+        lib.check(lib.ntt_dist_open(h, C.cast(allh, C.c_void_p)), "open")
+    wl = rl // world
+    ins = []
+    for r in range(world):   # column block of the (n / rl) x rl matrix
+        loc = [x[a * rl + r * wl + b] for a in range(n // rl) for b in range(wl)]
+        ins.append(C.create_string_buffer(o.fr_vec_to_bytes(loc), len(loc) * 32))
+    for twice in range(2):   # second round exercises the other receive buffer
+        for r in range(world):
+            lib.check(lib.ntt_dist_stage1(ctxs[r], C.cast(ins[r], C.c_void_p), direction, None), "stage1")
+        outs = []
+        for r in range(world):   # (the barrier between the stages is implicit: stage 1 of every rank has returned)
+            ob = C.create_string_buffer(n // world * 32)
+            lib.check(lib.ntt_dist_stage2(ctxs[r], C.cast(ob, C.c_void_p), direction, None), "stage2")
+            outs.append(o.fr_vec_from_bytes(ob.raw))
+    for h in ctxs:
+        lib.check(lib.ntt_dist_destroy(h), "destroy")
+    w0 = r0 // world
+    X = [0] * n
+    for t in range(world):   # column block of the (n / r0) x r0 matrix
+        for a in range(n // r0):
+            for b in range(w0):
+                X[a * r0 + t * w0 + b] = outs[t][a * w0 + b]
+    return X, npass.value
+
+
+@pytest.mark.parametrize("log_n,world", [(13, 2), (14, 4), (16, 2), (15, 8), (17, 2), (18, 4)])
+def test_emu_distributed_ntt_peer_exchange(emu_lib, log_n, world):
+    """one NTT over `world` ranks, exchange by stores into the peers' receive buffers: bit-exact with the oracle,
+    forward and inverse, 2 / 3 passes, both receive buffers"""
+    v = o.random_fr_vec(1 << log_n, 4000 + log_n)
+    got, npass = _dist_ntt_emulated(emu_lib, v, log_n, world, 0)
+    assert got == o.fft(v), (log_n, world, npass)
+    got, _ = _dist_ntt_emulated(emu_lib, v, log_n, world, 1)
+    assert got == o.ifft(v)

@@ -184,3 +184,26 @@ def test_fft_order_variants(log_n):
         want = torch.cat([dom.fft_in_place_dev(x.clone())[rev], dom.fft_in_place_dev(x.flip(0).contiguous())[rev]])
         assert torch.equal(dom._run_dev_ordered(two, 0, 0, 1, batch=2), want)
     assert ab.get_lib().ntt_fr_ordered_dev(x.data_ptr(), log_n, 1, 0, 0, 7, None) == -1
+
+
+@pytest.mark.parametrize("log_n", [12, 16, 20, 24])
+def test_peer_ntt_single_rank_equals_plain_transform(log_n):
+    """aleo_b200_ntt_dist_* with world = 1: the same passes, the 'exchange' pass stores into this rank's own receive
+    buffer -- must equal the in-place transform (the multi-rank schedule is checked on the emulator and, under
+    torchrun, by tools/dist_ntt_check.py and bench.py)"""
+    import torch
+    from aleo_b200.dist import PeerNTT
+
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 8100 + log_n, 0, True)
+    p = PeerNTT(log_n)
+    try:
+        assert p.layout() == (n >> p.log_r_last, 1 << p.log_r_last, n >> p.log_r_first, 1 << p.log_r_first)
+        for inverse in (False, True):
+            want = dom._run_dev(x.clone(), 1 if inverse else 0, 0)
+            for _ in range(2):                     # both receive buffers
+                got = p.transform(x, inverse=inverse)
+                assert torch.equal(got.reshape(-1, 4), want)
+    finally:
+        p.close()
