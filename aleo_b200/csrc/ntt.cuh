@@ -7,7 +7,7 @@
 // coset variants shift by g = 22 (forward: c_i *= g^i before; inverse: c_i *= g^-i after).
 //
 // Design (B200 first, not a translation of any CPU loop nest):
-//   * N = 2^L is split into P = ceil(L/8) passes of K_p <= 8 bits.  One pass = one HBM round trip
+//   * N = 2^L is split into P = ceil(L/9) passes of K_p <= 9 bits (a 9-bit pass = three radix-8 steps).  One pass = one HBM round trip
 //     (64 B per element), so the algorithmic traffic is 64*P bytes per element.
 //   * A pass handles a 2048-element tile per 256-thread CTA: every thread owns 8 elements in
 //     registers, does radix-8 / radix-4 / radix-2 butterflies on them, and trades elements with
@@ -30,7 +30,7 @@ constexpr int TILE_LOG = 11;            // elements per CTA tile
 constexpr int TILE = 1 << TILE_LOG;     // 2048 elements = 64 KB
 constexpr int TPB = TILE / 8;           // 256 threads, 8 elements each
 constexpr int SMALL_MAX_LOG = 11;       // single-CTA kernel handles n <= 2^11
-constexpr int MAX_PASS_BITS = 8;
+constexpr int MAX_PASS_BITS = 9;
 constexpr int MAX_LOG_N = 32;           // memory bound, far below the field's two-adicity (47)
 
 // Fr product used by the transform kernels.  Inlined by default: the out-of-line variant (by-value
@@ -181,7 +181,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
   constexpr int S1 = 3;
   constexpr int S2 = (K - 3 >= 3) ? 3 : (K - 3);
   constexpr int S3 = K - S1 - S2;
-  static_assert(K >= 5 && K <= 8, "pass radix");
+  static_assert(K >= 5 && K <= 9, "pass radix");
   DYN_SMEM(uint4, plane0);
   uint4* plane1 = plane0 + tile_plane_elems<K, LAST>();
 
@@ -287,12 +287,19 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
     constexpr int PTS = 1 << S3;
     Fr w4;
     if (S3 == 2) w4 = a.inner[R / 4];
+    Fr w8[4];
+    if (S3 == 3) {  // 9-bit pass: a third radix-8 step
+      w8[1] = a.inner[R / 8];
+      w8[2] = a.inner[R / 4];
+      w8[3] = a.inner[3 * (R / 8)];
+    }
 #pragma unroll
     for (int h = 0; h < GROUPS; h++) {
       const u32 gam = tr + h * RT;
       const u32 bp = gam * CP;
 #pragma unroll
       for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j, tg));
+      if (S3 == 3) ntt8(x + h * PTS, w8);
       if (S3 == 2) ntt4(x + h * PTS, w4);
       if (S3 == 1) ntt2(x + h * PTS);
 #pragma unroll

@@ -1,5 +1,6 @@
 // ntt_host.cuh -- host-side plan (pass split, twiddle tables) and launcher for ntt.cuh.
 #pragma once
+#include <cstdlib>
 #include <mutex>
 #include <map>
 #include <tuple>
@@ -40,32 +41,38 @@ static inline void set_single_gpu(PassArgs& a) {
 //   K_0 + K_last - lg >= 11 for the last pass (its tile takes 2^(11 - K_last) local values of the first digit),
 //   K_last >= lg (every rank holds at least one value of the last digit).
 // Returns the number of passes (2..4) or 0 when the size cannot be spread that far.
+static inline bool split_ok(const int* k, int P, int lg) {
+  bool ok = k[P - 1] >= lg && k[0] + k[P - 1] - lg >= TILE_LOG;
+  int below = 0;
+  for (int i = P - 1; i >= 1 && ok; i--) {
+    below += k[i];
+    ok = k[i - 1] + below - lg >= TILE_LOG;
+  }
+  return ok;
+}
+
 static inline int split_passes_dist(int L, int lg, int* K) {
   for (int P = (L + MAX_PASS_BITS - 1) / MAX_PASS_BITS; P <= 4; P++) {
     if (P < 2) continue;
-    int best[4] = {0, 0, 0, 0}, best_spread = 99, k[4];
-    const int lim = 4 * 4 * 4 * 4;
+    int best[4] = {0, 0, 0, 0}, best_spread = 99, k[4] = {0, 0, 0, 0};
+    const int nk = MAX_PASS_BITS - 5 + 1;
+    int lim = 1;
+    for (int i = 0; i < P; i++) lim *= nk;
     for (int code = 0; code < lim; code++) {
       int sum = 0, c = code;
-      for (int i = 0; i < 4; i++) {
-        k[i] = 5 + (c & 3);
-        c >>= 2;
+      for (int i = 0; i < P; i++) {
+        k[i] = 5 + c % nk;
+        c /= nk;
+        sum += k[i];
       }
-      for (int i = 0; i < P; i++) sum += k[i];
-      if (sum != L) continue;
-      bool ok = k[P - 1] >= lg && k[0] + k[P - 1] - lg >= TILE_LOG;
-      int below = 0;
-      for (int i = P - 1; i >= 1 && ok; i--) {
-        below += k[i];
-        ok = k[i - 1] + below - lg >= TILE_LOG;
-      }
-      if (!ok) continue;
+      if (sum != L || !split_ok(k, P, lg)) continue;
       int mx = 0, mn = 99;
       for (int i = 0; i < P; i++) {
         mx = k[i] > mx ? k[i] : mx;
         mn = k[i] < mn ? k[i] : mn;
       }
-      if (mx - mn < best_spread) {
+      // most balanced split; among equals the one with the larger first radix (code order visits small k[0] first)
+      if (mx - mn <= best_spread) {
         best_spread = mx - mn;
         for (int i = 0; i < P; i++) best[i] = k[i];
       }
@@ -76,6 +83,26 @@ static inline int split_passes_dist(int L, int lg, int* K) {
     }
   }
   return 0;
+}
+
+// ALEO_B200_NTT_SPLIT="7,9,5": forces the pass split of sizes with that digit sum (tests: a 9-bit middle pass at 2^21)
+static inline int forced_split(int L, int* K) {
+  const char* e = getenv("ALEO_B200_NTT_SPLIT");
+  if (!e) return 0;
+  int k[4] = {0, 0, 0, 0}, n = 0, sum = 0;
+  for (const char* p = e; *p && n < 4;) {
+    k[n] = atoi(p);
+    sum += k[n];
+    n++;
+    while (*p && *p != ',') p++;
+    if (*p == ',') p++;
+  }
+  if (n < 2 || sum != L) return 0;
+  for (int i = 0; i < n; i++) {
+    if (k[i] < 5 || k[i] > MAX_PASS_BITS) return 0;
+    K[i] = k[i];
+  }
+  return split_ok(k, n, 0) ? n : 0;
 }
 
 struct Plan {
@@ -134,7 +161,8 @@ static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool invers
     NTT_CK(fill_pow_table(p.small_inner, w, one, 1u << log_n, 0, s));
     NTT_CK(cudaMemcpyAsync(&p.scale_host, ninv, sizeof(Fr), cudaMemcpyDeviceToHost, s));
   } else {
-    p.npass = dist_lg ? split_passes_dist((int)log_n, dist_lg, p.K) : split_passes((int)log_n, p.K);
+    p.npass = dist_lg ? split_passes_dist((int)log_n, dist_lg, p.K) : forced_split((int)log_n, p.K);
+    if (p.npass == 0 && !dist_lg) p.npass = split_passes((int)log_n, p.K);
     if (p.npass == 0) return cudaErrorInvalidValue;
     NTT_CK(plan_alloc(p, &p.tw_lo, (size_t)1 << p.lo_bits));
     NTT_CK(plan_alloc(p, &p.tw_hi, (size_t)1 << hi_bits));
@@ -187,6 +215,7 @@ static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, u32 
     case 6: return launch_pass<6, LAST>(a, grid, batch, s);
     case 7: return launch_pass<7, LAST>(a, grid, batch, s);
     case 8: return launch_pass<8, LAST>(a, grid, batch, s);
+    case 9: return launch_pass<9, LAST>(a, grid, batch, s);
   }
   return cudaErrorInvalidValue;
 }

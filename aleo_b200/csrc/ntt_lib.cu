@@ -15,7 +15,8 @@ int ntt_launches(u32 log_n) {
   if (log_n == 0) return 0;
   if (log_n <= (u32)ntt::SMALL_MAX_LOG) return 1;
   int K[4];
-  return ntt::split_passes((int)log_n, K);
+  const int forced = ntt::forced_split((int)log_n, K);
+  return forced ? forced : ntt::split_passes((int)log_n, K);
 }
 
 cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s,

@@ -356,3 +356,21 @@ def test_emu_distributed_ntt_peer_exchange(emu_lib, log_n, world):
     assert got == o.fft(v), (log_n, world, npass)
     got, _ = _dist_ntt_emulated(emu_lib, v, log_n, world, 1)
     assert got == o.ifft(v)
+
+
+def test_emu_ntt_nine_bit_middle_pass(emu_lib, c_oracle, monkeypatch):
+    """forced split 7 + 9 + 5 at 2^21: a 9-bit pass (three radix-8 steps) in the middle position, checked against
+    the C oracle (2^17 = 9 + 8 and 2^18 = 9 + 9 cover the first / last positions in test_emu_ntt_*)"""
+    import numpy as np
+    monkeypatch.setenv("ALEO_B200_NTT_SPLIT", "7,9,5")
+    log_n = 21
+    n = 1 << log_n
+    assert emu_lib.ntt_launches(log_n) == 3
+    rng = np.random.default_rng(21)
+    x = rng.integers(0, 2**62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    x[:, 3] &= np.uint64((1 << 60) - 1)                      # any value < 2^252 is a valid (Montgomery) residue
+    want = x.copy()
+    assert c_oracle.oracle_ntt_fr(want.ctypes.data, log_n, 0, 0, os.cpu_count() or 1) == 0
+    got = x.copy()
+    emu_lib.check(emu_lib.ntt_fr_dev(got.ctypes.data, log_n, 1, 0, 0, None), "ntt")
+    assert np.array_equal(got, want)
