@@ -36,8 +36,8 @@ SYMBOLS = [
     ("aleo_b200_ntt_dist_create", _int, [C.POINTER(_vp), _u32, _int, _int]),
     ("aleo_b200_ntt_dist_handles", _int, [_vp, _vp]),
     ("aleo_b200_ntt_dist_open", _int, [_vp, _vp]),
-    ("aleo_b200_ntt_dist_stage1", _int, [_vp, _vp, _int, _vp]),
-    ("aleo_b200_ntt_dist_stage2", _int, [_vp, _vp, _int, _vp]),
+    ("aleo_b200_ntt_dist_stage1", _int, [_vp, _vp, _int, _int, _vp]),
+    ("aleo_b200_ntt_dist_stage2", _int, [_vp, _vp, _int, _int, _vp]),
     ("aleo_b200_ntt_dist_destroy", _int, [_vp]),
     ("aleo_b200_msm_g1", _int, [_vp, _vp, _sz, _vp, _sz]),
     ("aleo_b200_msm_g1_dev", _int, [_vp, _vp, _sz, _vp, _sz, _vp]),

@@ -227,21 +227,23 @@ int aleo_b200_ntt_dist_open(void* ctx, const void* all_handles) {
   return ALEO_B200_OK;
 }
 
-int aleo_b200_ntt_dist_stage1(void* ctx, const void* local_in_dev, int direction, void* stream) {
+int aleo_b200_ntt_dist_stage1(void* ctx, const void* local_in_dev, int direction, int kind, void* stream) {
   if (ctx == nullptr || local_in_dev == nullptr) return ALEO_B200_EINVAL;
   if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
-  API_CK(aleo::ntt_dist_stage1(ctx, local_in_dev, direction == ALEO_B200_NTT_INVERSE, (cudaStream_t)stream));
+  API_CK(aleo::ntt_dist_stage1(ctx, local_in_dev, direction == ALEO_B200_NTT_INVERSE, kind == ALEO_B200_NTT_COSET, (cudaStream_t)stream));
   return ALEO_B200_OK;
 }
 
-int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, void* stream) {
+int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, int kind, void* stream) {
   if (ctx == nullptr || local_out_dev == nullptr) return ALEO_B200_EINVAL;
   if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
-  API_CK(aleo::ntt_dist_stage2(ctx, local_out_dev, direction == ALEO_B200_NTT_INVERSE, (cudaStream_t)stream));
+  API_CK(aleo::ntt_dist_stage2(ctx, local_out_dev, direction == ALEO_B200_NTT_INVERSE, kind == ALEO_B200_NTT_COSET, (cudaStream_t)stream));
   return ALEO_B200_OK;
 }
 

@@ -17,8 +17,8 @@ int ntt_dist_layout(u32 log_n, int world, u32* log_r_first, u32* log_r_last, int
 cudaError_t ntt_dist_create(u32 log_n, int rank, int world, void** ctx_out);
 cudaError_t ntt_dist_handles(void* ctx, void* handles_out /* 128 bytes */);
 cudaError_t ntt_dist_open(void* ctx, const void* all_handles /* world x 128 bytes */);
-cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, cudaStream_t s);
-cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, cudaStream_t s);
+cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, bool coset, cudaStream_t s);
+cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, bool coset, cudaStream_t s);
 void ntt_dist_destroy(void* ctx);
 int ntt_max_log_n();
 void ntt_clear_plans();

@@ -307,8 +307,8 @@ KERNEL void plan_pieces_kernel(const u32* starts, const u32* ends, u32 nb, u32 n
 // FILL: a lane whose accumulator is empty (first entry of a bucket) copies the point and moves straight on to its
 // next entry before the warp's common addition, instead of idling through one addition slot per bucket
 // (1 / 32 of all slots at n = 2^24, c = 20).
-template <bool CALL, bool FILL>
-KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
+template <bool CALL, bool FILL, int MINB = 3>
+KERNEL void __launch_bounds__(128, MINB) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
                                                       u32* piece_bucket, u32 into) {

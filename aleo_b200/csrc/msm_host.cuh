@@ -315,6 +315,9 @@ struct Session {
       ACC_LAUNCH(false, false);
     else if (acc_mode == 'f')
       ACC_LAUNCH(true, true);
+    else if (acc_mode == '4')  // 4 CTAs per SM (128 registers, spills): experiment
+      LAUNCH_NOSYNC((accumulate_kernel<true, false, 4>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
     else
       ACC_LAUNCH(true, false);
 #undef ACC_LAUNCH

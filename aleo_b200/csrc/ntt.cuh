@@ -161,6 +161,7 @@ struct PassArgs {
   u32 d_log_chunk;   // log2(N / 4^lg): elements one rank sends to one peer
   u32 d_exchange;    // this (last-but-one) pass stores straight into the peers' receive buffers (NVLink P2P)
   u32 d_rank;
+  u32 d_lg;          // log2 of the number of GPUs
   Fr* peer[8];       // receive buffer of every rank (own included), device pointers valid on this GPU
 };
 
@@ -236,7 +237,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
         gi = ((u64)(p >> a.d_k2l) << a.d_log_chunk) + (((in_base >> K) + ((u64)tg * (stride_g >> K))) << a.d_k2l) +
              (p & ((1u << a.d_k2l) - 1u));
       x[j] = src[gi];
-      if (!LAST && a.use_pre) x[j] = fr_mul_v(x[j], pow_lookup(a.pre, (u32)gi));
+      if (!LAST && a.use_pre) x[j] = fr_mul_v(x[j], pow_lookup(a.pre, dist_expand(a, (u32)gi)));  // coset: g^(global index)
     }
     Fr w8[4];
     w8[1] = a.inner[R / 8];
@@ -329,7 +330,11 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
         else
           v = fr_mul_v(v, pow_lookup(a.tw, x << (a.log_n - a.log_cur)));
       }
-      if (LAST && a.use_post) v = fr_mul_v(v, pow_lookup(a.post, (u32)go));
+      if (LAST && a.use_post) {
+        u32 gk = (u32)go;  // global output index: the rank's bits sit above the local part of the first digit
+        if (a.d_k2l < 31u) gk = (((u32)go >> a.log_r1) << (a.log_r1 + a.d_lg)) | (a.d_rank << a.log_r1) | ((u32)go & ((1u << a.log_r1) - 1u));
+        v = fr_mul_v(v, pow_lookup(a.post, gk));
+      }
       if (!LAST && a.d_exchange)  // flat all-to-all: chunk t of the local result goes to rank t, slot = my rank
         a.peer[go >> a.d_log_chunk][((u64)a.d_rank << a.d_log_chunk) + (go & (((u64)1 << a.d_log_chunk) - 1u))] = v;
       else

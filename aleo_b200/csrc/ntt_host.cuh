@@ -33,6 +33,7 @@ static inline void set_single_gpu(PassArgs& a) {
   a.d_log_chunk = 0;
   a.d_exchange = 0;
   a.d_rank = 0;
+  a.d_lg = 0;
   for (int i = 0; i < 8; i++) a.peer[i] = nullptr;
 }
 
@@ -322,7 +323,9 @@ static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const
     a.tw_direct = p.tw_direct[i];
     a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
     a.post = a.pre;
-    a.use_pre = a.use_post = 0;
+    a.use_pre = (i == 0 && p.coset && !p.inverse) ? 1 : 0;
+    a.use_post = 0;
+    a.d_lg = (u32)lg;
     a.d_k2l = klast - (u32)lg;
     a.d_klast = klast;
     a.d_rank_bits = (u32)rank << a.d_k2l;
@@ -352,7 +355,9 @@ static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const
   a.tw_direct = nullptr;
   a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
   a.post = a.pre;
-  a.use_pre = a.use_post = 0;
+  a.use_pre = 0;
+  a.use_post = (p.coset && p.inverse) ? 1 : 0;
+  a.d_lg = (u32)lg;
   a.d_k2l = (u32)p.K[last] - (u32)lg;
   a.d_klast = (u32)p.K[last];
   a.d_rank_bits = (u32)rank << a.d_k2l;

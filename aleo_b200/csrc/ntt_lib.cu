@@ -149,11 +149,11 @@ cudaError_t ntt_dist_open(void* ctx, const void* all_handles) {
 }
 
 // passes 0 .. P-2 of the local part; the last of them writes into the peers' receive buffers
-cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, cudaStream_t s) {
+cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, bool coset, cudaStream_t s) {
   NttDist* c = (NttDist*)ctx;
   if (!c->have_peers) return cudaErrorInvalidValue;
   const ntt::Plan* plan = nullptr;
-  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, false, s, &plan, c->lg);
+  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, coset, s, &plan, c->lg);
   if (e != cudaSuccess) return e;
   Fr* scratch = nullptr;
   if (plan->npass > 2) {
@@ -166,10 +166,10 @@ cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, c
 }
 
 // the last pass from this rank's receive buffer (call after a cross-rank barrier ordered on the same stream)
-cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, cudaStream_t s) {
+cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, bool coset, cudaStream_t s) {
   NttDist* c = (NttDist*)ctx;
   const ntt::Plan* plan = nullptr;
-  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, false, s, &plan, c->lg);
+  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, coset, s, &plan, c->lg);
   if (e != cudaSuccess) return e;
   e = ntt::run_dist_stage2(*plan, c->lg, c->rank, c->recv[c->calls & 1], (Fr*)local_out_dev, s);
   c->calls++;

@@ -194,19 +194,20 @@ class PeerNTT:
         _, _, rows, cols = self.layout()
         return X_full.reshape(rows, cols * self.world, 4)[:, self.rank * cols:(self.rank + 1) * cols, :].contiguous()
 
-    def transform(self, block, out=None, inverse: bool = False):
+    def transform(self, block, out=None, inverse: bool = False, coset: bool = False):
         import torch
         import torch.distributed as dist
 
         if out is None:
             out = torch.empty_like(block).reshape(-1, 4)
         direction = _lib.NTT_INVERSE if inverse else _lib.NTT_FORWARD
+        kind = _lib.NTT_COSET if coset else _lib.NTT_STANDARD
         with torch.cuda.device(block.device):
             stream = torch.cuda.current_stream().cuda_stream
-            self._lib.check(self._lib.ntt_dist_stage1(self._h, block.data_ptr(), direction, stream), "aleo_b200_ntt_dist_stage1")
+            self._lib.check(self._lib.ntt_dist_stage1(self._h, block.data_ptr(), direction, kind, stream), "aleo_b200_ntt_dist_stage1")
             if self.world > 1:
                 dist.all_reduce(self._flag, group=self.group)      # barrier ordered on the stream: peers' stores are complete
-            self._lib.check(self._lib.ntt_dist_stage2(self._h, out.data_ptr(), direction, stream), "aleo_b200_ntt_dist_stage2")
+            self._lib.check(self._lib.ntt_dist_stage2(self._h, out.data_ptr(), direction, kind, stream), "aleo_b200_ntt_dist_stage2")
         return out
 
     def close(self):

@@ -305,7 +305,7 @@ def test_emu_kzg_open(emu_lib):
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
 
 
-def _dist_ntt_emulated(lib, x, log_n, world, direction):
+def _dist_ntt_emulated(lib, x, log_n, world, direction, kind=0):
     """all ranks of aleo_b200_ntt_dist_* in ONE process (the emulator's 'peer memory' is the shared address space):
     returns the natural-order result assembled from the ranks' output blocks"""
     n = 1 << log_n
@@ -330,11 +330,11 @@ def _dist_ntt_emulated(lib, x, log_n, world, direction):
         ins.append(C.create_string_buffer(o.fr_vec_to_bytes(loc), len(loc) * 32))
     for twice in range(2):   # second round exercises the other receive buffer
         for r in range(world):
-            lib.check(lib.ntt_dist_stage1(ctxs[r], C.cast(ins[r], C.c_void_p), direction, None), "stage1")
+            lib.check(lib.ntt_dist_stage1(ctxs[r], C.cast(ins[r], C.c_void_p), direction, kind, None), "stage1")
         outs = []
         for r in range(world):   # (the barrier between the stages is implicit: stage 1 of every rank has returned)
             ob = C.create_string_buffer(n // world * 32)
-            lib.check(lib.ntt_dist_stage2(ctxs[r], C.cast(ob, C.c_void_p), direction, None), "stage2")
+            lib.check(lib.ntt_dist_stage2(ctxs[r], C.cast(ob, C.c_void_p), direction, kind, None), "stage2")
             outs.append(o.fr_vec_from_bytes(ob.raw))
     for h in ctxs:
         lib.check(lib.ntt_dist_destroy(h), "destroy")
@@ -356,6 +356,11 @@ def test_emu_distributed_ntt_peer_exchange(emu_lib, log_n, world):
     assert got == o.fft(v), (log_n, world, npass)
     got, _ = _dist_ntt_emulated(emu_lib, v, log_n, world, 1)
     assert got == o.ifft(v)
+    if log_n <= 16:
+        got, _ = _dist_ntt_emulated(emu_lib, v, log_n, world, 0, 1)
+        assert got == o.coset_fft(v)
+        got, _ = _dist_ntt_emulated(emu_lib, v, log_n, world, 1, 1)
+        assert got == o.coset_ifft(v)
 
 
 def test_emu_ntt_nine_bit_middle_pass(emu_lib, c_oracle, monkeypatch):

@@ -201,9 +201,10 @@ def test_peer_ntt_single_rank_equals_plain_transform(log_n):
     try:
         assert p.layout() == (n >> p.log_r_last, 1 << p.log_r_last, n >> p.log_r_first, 1 << p.log_r_first)
         for inverse in (False, True):
-            want = dom._run_dev(x.clone(), 1 if inverse else 0, 0)
-            for _ in range(2):                     # both receive buffers
-                got = p.transform(x, inverse=inverse)
-                assert torch.equal(got.reshape(-1, 4), want)
+            for coset in (False, True):
+                want = dom._run_dev(x.clone(), 1 if inverse else 0, 1 if coset else 0)
+                for _ in range(2):                     # both receive buffers
+                    got = p.transform(x, inverse=inverse, coset=coset)
+                    assert torch.equal(got.reshape(-1, 4), want)
     finally:
         p.close()

@@ -25,11 +25,11 @@ for log_n in [int(a) for a in sys.argv[1:]] or [16, 20, 24]:
     dom = ab.EvaluationDomain.new(n)
     p = PeerNTT(log_n)
     oks = []
-    for inverse in (False, True):
-        want = dom._run_dev(x.clone(), 1 if inverse else 0, 0)
+    for inverse, coset in ((False, False), (True, False), (False, True), (True, True)):
+        want = dom._run_dev(x.clone(), 1 if inverse else 0, 1 if coset else 0)
         blk = p.input_block(x)
         for _ in range(3):
-            got = p.transform(blk, inverse=inverse)
+            got = p.transform(blk, inverse=inverse, coset=coset)
         oks.append(bool(torch.equal(got.reshape(-1), p.output_block_of(want).reshape(-1))))
     blk = p.input_block(x)
     out = torch.empty_like(blk).reshape(-1, 4)
@@ -51,7 +51,7 @@ for log_n in [int(a) for a in sys.argv[1:]] or [16, 20, 24]:
     good = all(all(f) for f in flags)
     ok_all = ok_all and good
     if rank == 0:
-        print("log_n=%d world=%d passes=%d R_first=2^%d R_last=2^%d parity(fwd,inv) per rank=%s  %.3f ms -> %.0f Melem/s" %
+        print("log_n=%d world=%d passes=%d R_first=2^%d R_last=2^%d parity(fwd,inv,coset fwd,coset inv) per rank=%s  %.3f ms -> %.0f Melem/s" %
               (log_n, world, p.passes, p.log_r_first, p.log_r_last, flags, ms.item(), n / ms.item() / 1e3), flush=True)
     p.close()
 dist.destroy_process_group()
