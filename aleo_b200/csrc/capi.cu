@@ -264,13 +264,17 @@ int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) 
   const size_t bytes = (size_t)32 << log_n;
   void* d = nullptr;
   API_CK(cudaMallocAsync(&d, bytes, s));
-  cudaError_t e = cudaMemcpyAsync(d, inout_host, bytes, cudaMemcpyHostToDevice, s);
+  cudaEvent_t ready = nullptr;
+  cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ready, s);
+  if (e == cudaSuccess) e = aleo::feed_h2d(d, inout_host, bytes, s, ready);  // pageable callers (a Rust Vec) are staged
   if (e == cudaSuccess) {
     rc = aleo_b200_ntt_fr_dev(d, log_n, 1, direction, kind, (void*)s);
-    if (rc == ALEO_B200_OK) e = cudaMemcpyAsync(inout_host, d, bytes, cudaMemcpyDeviceToHost, s);
+    if (rc == ALEO_B200_OK) e = aleo::feed_d2h_sync(inout_host, d, bytes, s);
   }
   cudaFreeAsync(d, s);
   cudaError_t e2 = cudaStreamSynchronize(s);
+  if (ready) cudaEventDestroy(ready);
   if (rc) return rc;
   if (e != cudaSuccess) return fail_cuda(e);
   if (e2 != cudaSuccess) return fail_cuda(e2);

@@ -32,6 +32,9 @@ int msm_host_chunks(size_t n);
 int msm_host_window_bits(size_t n);
 cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool montgomery_in, void* out_host, size_t out_bytes,
                          cudaStream_t s);
+// host <-> device copies of caller memory that may be pageable (staged through pinned double buffers by helper threads)
+cudaError_t feed_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t cs, cudaEvent_t ready);
+cudaError_t feed_d2h_sync(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
 bool msm_size_supported(size_t n);
 int msm_window_bits(size_t n);
 cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);

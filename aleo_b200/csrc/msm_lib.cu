@@ -1,6 +1,9 @@
 // msm_lib.cu -- translation unit holding the G1 MSM kernels.
 #include "internal.h"
 #include "msm_host.cuh"
+#ifndef ALEO_EMU
+#include <thread>
+#endif
 
 namespace aleo {
 cudaError_t msm_upload_constants() { return aleo_upload_field_constants(); }
@@ -60,7 +63,157 @@ struct EventSet {
       if (e) cudaEventDestroy(e);
   }
 };
+// ---- host -> device copies of caller memory that may be PAGEABLE (a Rust Vec is) ---------------------------------------
+// Pinned / registered memory goes out as one cudaMemcpyAsync.  A large pageable block would be staged by the driver
+// through one bounce buffer at a few GB/s -- slower than the MSM itself -- so it is staged here instead: FEED_THREADS
+// helper threads memcpy 4 MB slices into their own pinned double buffers and enqueue the DMA from there (the CPU copy
+// of slice i + T overlaps the DMA of slice i).  The call returns when everything is enqueued; `cs` then waits on the
+// helpers' streams.  Staging buffers and streams live per calling thread (32 MB pinned).
+#ifndef ALEO_EMU
+constexpr int FEED_THREADS = 4;
+constexpr size_t FEED_SLICE = (size_t)4 << 20;
+constexpr size_t FEED_MIN_BYTES = (size_t)8 << 20;  // below this the plain pageable copy is fine
+
+struct FeedState {
+  int dev = -1;
+  unsigned char* buf[FEED_THREADS][2] = {};
+  cudaEvent_t ev[FEED_THREADS][2] = {};
+  cudaStream_t st[FEED_THREADS] = {};
+  cudaError_t init(int device) {
+    if (dev == device) return cudaSuccess;
+    for (int t = 0; t < FEED_THREADS; t++) {
+      cudaError_t e = cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking);
+      for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+        e = cudaMallocHost((void**)&buf[t][b], FEED_SLICE);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming);
+      }
+      if (e != cudaSuccess) return e;
+    }
+    dev = device;
+    return cudaSuccess;
+  }
+};
+thread_local FeedState t_feed;
+
+bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // older drivers report unregistered memory as an error: clear it
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+#endif
+
 }  // namespace
+
+// dst_dev <- src_host on `cs` (after `ready`, the event that orders dst's allocation); may block the caller while it
+// stages pageable memory, never waits for the GPU beyond its own double buffers
+cudaError_t feed_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t cs, cudaEvent_t ready) {
+  if (bytes == 0) return cudaSuccess;
+#ifndef ALEO_EMU
+  static const bool force_plain = getenv("ALEO_B200_NO_STAGING") != nullptr;
+  if (bytes >= FEED_MIN_BYTES && !force_plain && !host_pointer_is_pinned(src_host)) {
+    int dev = 0;
+    MSM_CK(cudaGetDevice(&dev));
+    MSM_CK(t_feed.init(dev));
+    FeedState* fs = &t_feed;
+    const size_t nslices = (bytes + FEED_SLICE - 1) / FEED_SLICE;
+    cudaError_t errs[FEED_THREADS];
+    std::thread workers[FEED_THREADS];
+    for (int t = 0; t < FEED_THREADS; t++) {
+      errs[t] = cudaSuccess;
+      workers[t] = std::thread([=, &errs]() {
+        cudaError_t e = cudaSetDevice(dev);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(fs->st[t], ready, 0);
+        for (size_t i = (size_t)t, round = 0; i < nslices && e == cudaSuccess; i += FEED_THREADS, round++) {
+          const int b = (int)(round & 1);
+          const size_t off = i * FEED_SLICE, len = (bytes - off < FEED_SLICE) ? bytes - off : FEED_SLICE;
+          e = cudaEventSynchronize(fs->ev[t][b]);  // the DMA that last read this buffer is done
+          if (e != cudaSuccess) break;
+          std::memcpy(fs->buf[t][b], (const unsigned char*)src_host + off, len);
+          e = cudaMemcpyAsync((unsigned char*)dst_dev + off, fs->buf[t][b], len, cudaMemcpyHostToDevice, fs->st[t]);
+          if (e == cudaSuccess) e = cudaEventRecord(fs->ev[t][b], fs->st[t]);
+        }
+        errs[t] = e;
+      });
+    }
+    cudaError_t e = cudaSuccess;
+    for (int t = 0; t < FEED_THREADS; t++) {
+      workers[t].join();
+      if (errs[t] != cudaSuccess) e = errs[t];
+    }
+    // cs continues after every helper stream's last copy (events of both buffers cover the tail of each stream)
+    for (int t = 0; t < FEED_THREADS && e == cudaSuccess; t++)
+      for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaStreamWaitEvent(cs, fs->ev[t][b], 0);
+    return e;
+  }
+#endif
+  (void)ready;
+  return cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, cs);
+}
+
+// dst_host <- src_dev, everything enqueued on `s` before the call is complete when the data is read.  Pageable
+// destinations are staged like feed_h2d (DMA into pinned double buffers, helper threads copy out).  Blocks until done.
+cudaError_t feed_d2h_sync(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return cudaStreamSynchronize(s);
+#ifndef ALEO_EMU
+  static const bool force_plain = getenv("ALEO_B200_NO_STAGING") != nullptr;
+  if (bytes >= FEED_MIN_BYTES && !force_plain && !host_pointer_is_pinned(dst_host)) {
+    int dev = 0;
+    MSM_CK(cudaGetDevice(&dev));
+    MSM_CK(t_feed.init(dev));
+    FeedState* fs = &t_feed;
+    cudaEvent_t done;
+    MSM_CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    MSM_CK(cudaEventRecord(done, s));
+    const size_t nslices = (bytes + FEED_SLICE - 1) / FEED_SLICE;
+    cudaError_t errs[FEED_THREADS];
+    std::thread workers[FEED_THREADS];
+    for (int t = 0; t < FEED_THREADS; t++) {
+      errs[t] = cudaSuccess;
+      workers[t] = std::thread([=, &errs]() {
+        cudaError_t e = cudaSetDevice(dev);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(fs->st[t], done, 0);
+        for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaEventSynchronize(fs->ev[t][b]);  // buffers idle
+        size_t prev_off = 0, prev_len = 0;
+        int prev_b = -1;
+        for (size_t i = (size_t)t, round = 0; e == cudaSuccess; i += FEED_THREADS, round++) {
+          const int b = (int)(round & 1);
+          const bool more = i < nslices;
+          size_t off = 0, len = 0;
+          if (more) {
+            off = i * FEED_SLICE;
+            len = (bytes - off < FEED_SLICE) ? bytes - off : FEED_SLICE;
+            e = cudaMemcpyAsync(fs->buf[t][b], (const unsigned char*)src_dev + off, len, cudaMemcpyDeviceToHost, fs->st[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(fs->ev[t][b], fs->st[t]);
+          }
+          if (prev_b >= 0 && e == cudaSuccess) {  // copy the previous slice out while this one is in flight
+            e = cudaEventSynchronize(fs->ev[t][prev_b]);
+            if (e == cudaSuccess) std::memcpy((unsigned char*)dst_host + prev_off, fs->buf[t][prev_b], prev_len);
+          }
+          if (!more) break;
+          prev_off = off;
+          prev_len = len;
+          prev_b = b;
+        }
+        errs[t] = e;
+      });
+    }
+    cudaError_t e = cudaSuccess;
+    for (int t = 0; t < FEED_THREADS; t++) {
+      workers[t].join();
+      if (errs[t] != cudaSuccess) e = errs[t];
+    }
+    cudaEventDestroy(done);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    return e != cudaSuccess ? e : e2;
+  }
+#endif
+  cudaError_t e = cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  return e != cudaSuccess ? e : e2;
+}
 
 int msm_host_chunks(size_t n) {
   size_t sizes[4];
@@ -88,25 +241,21 @@ cudaError_t msm_run_host(const void* bases_host, u32 stride, const void* scalars
     msm::Session ss;
     if (e == cudaSuccess) e = cudaEventRecord(evs.ev[4], s);          // the allocation is ordered on s
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, evs.ev[4], 0);
-    size_t first = 0;
-    for (int i = 0; i < k && e == cudaSuccess; i++) {
-      const size_t m = sizes[i];
-      e = cudaMemcpyAsync(d + o_s + first * 32, (const unsigned char*)scalars_host + first * 32, m * 32, cudaMemcpyHostToDevice, cs);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d + first * stride, (const unsigned char*)bases_host + first * stride, m * stride,
-                            cudaMemcpyHostToDevice, cs);
-      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
-      first += m;
-    }
     size_t max_chunk = 0;
     for (int i = 0; i < k; i++) max_chunk = sizes[i] > max_chunk ? sizes[i] : max_chunk;
     if (e == cudaSuccess) e = ss.begin(n, max_chunk, (u32)k, nullptr, s, false);
-    first = 0;
+    // range by range: copy (asynchronous for pinned memory, staged for pageable memory -- then this thread is busy
+    // feeding range i + 1 while the GPU accumulates range i), then enqueue the range's sort + accumulation
+    size_t first = 0;
     for (int i = 0; i < k && e == cudaSuccess; i++) {
-      e = cudaStreamWaitEvent(s, evs.ev[i], 0);
+      const size_t m = sizes[i];
+      e = feed_h2d(d + o_s + first * 32, (const unsigned char*)scalars_host + first * 32, m * 32, cs, evs.ev[4]);
       if (e == cudaSuccess)
-        e = ss.add_chunk(d + first * stride, stride, (const u32*)(d + o_s + first * 32), sizes[i], first, s);
-      first += sizes[i];
+        e = feed_h2d(d + first * stride, (const unsigned char*)bases_host + first * stride, m * stride, cs, evs.ev[4]);
+      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i], 0);
+      if (e == cudaSuccess) e = ss.add_chunk(d + first * stride, stride, (const u32*)(d + o_s + first * 32), m, first, s);
+      first += m;
     }
     if (e == cudaSuccess) e = ss.finish(d + o_out, s);
     else ss.release(s);
@@ -232,16 +381,12 @@ cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool
     if (e == cudaSuccess) e = cudaEventRecord(evs.ev[4], s);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, evs.ev[4], 0);
     size_t first = 0, max_chunk = 0;
-    for (int i = 0; i < k && e == cudaSuccess; i++) {
-      e = cudaMemcpyAsync(d + first * 32, (const unsigned char*)in_host + first * 32, sizes[i] * 32, cudaMemcpyHostToDevice, cs);
-      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
-      first += sizes[i];
-      max_chunk = sizes[i] > max_chunk ? sizes[i] : max_chunk;
-    }
+    for (int i = 0; i < k; i++) max_chunk = sizes[i] > max_chunk ? sizes[i] : max_chunk;
     if (e == cudaSuccess) e = ss.begin(n, max_chunk, (u32)k, &v, s, false);
-    first = 0;
     for (int i = 0; i < k && e == cudaSuccess; i++) {
-      e = cudaStreamWaitEvent(s, evs.ev[i], 0);
+      e = feed_h2d(d + first * 32, (const unsigned char*)in_host + first * 32, sizes[i] * 32, cs, evs.ev[4]);
+      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i], 0);
       if (e == cudaSuccess && montgomery_in) e = fr_to_bigint(d + first * 32, d + first * 32, sizes[i], s);
       if (e == cudaSuccess) e = ss.add_chunk(nullptr, 96, (const u32*)(d + first * 32), sizes[i], first, s);
       first += sizes[i];

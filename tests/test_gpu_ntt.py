@@ -208,3 +208,18 @@ def test_peer_ntt_single_rank_equals_plain_transform(log_n):
                     assert torch.equal(got.reshape(-1, 4), want)
     finally:
         p.close()
+
+
+def test_host_call_on_pageable_memory_is_staged():
+    """aleo_b200_ntt_fr on a 64 MB pageable numpy buffer (what a Rust Vec is): both directions of the copy go through
+    the pinned staging buffers of the helper threads; result equals the device-resident transform"""
+    log_n = 21
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 9100, 0, True)
+    host = x.cpu().numpy().copy()                       # pageable
+    want = dom.coset_fft_in_place_dev(x.clone()).cpu().numpy()
+    dom.ntt_host_buffer(host, 0, 1)
+    assert np.array_equal(host, want)
+    dom.ntt_host_buffer(host, 1, 1)                     # and back
+    assert np.array_equal(host, x.cpu().numpy())
