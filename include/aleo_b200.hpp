@@ -81,4 +81,47 @@ class EvaluationDomain {
   }
 };
 
+// Commitment as it appears in a proof: compressed G1 (x little-endian | bit 383: larger y | bit 382: infinity)
+struct KZGCommitment { uint8_t bytes[48]; };
+static_assert(sizeof(KZGCommitment) == 48, "compressed G1");
+
+// `Powers` whose powers_of_beta_g (or lagrange_basis_at_beta_g) stay resident on the device (aleo_b200_srs_*):
+// uploaded and expanded once, then every commitment only moves its coefficients.  Move-only.
+class ResidentPowers {
+ public:
+  explicit ResidentPowers(const std::vector<G1Affine>& powers_of_beta_g) {
+    check(aleo_b200_srs_create(&h_, powers_of_beta_g.data(), powers_of_beta_g.size(), sizeof(G1Affine)), "srs_create");
+  }
+  ResidentPowers(const ResidentPowers&) = delete;
+  ResidentPowers& operator=(const ResidentPowers&) = delete;
+  ResidentPowers(ResidentPowers&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  ~ResidentPowers() {
+    if (h_) aleo_b200_srs_destroy(h_);
+  }
+  const void* handle() const { return h_; }
+  size_t size() const {
+    size_t n = 0;
+    check(aleo_b200_srs_info(h_, &n, nullptr, nullptr, nullptr), "srs_info");
+    return n;
+  }
+  // VariableBase::msm over a prefix of the resident bases
+  G1Projective msm(const std::vector<BigInteger256>& scalars) const {
+    G1Projective out;
+    check(aleo_b200_srs_msm(h_, &out, scalars.data(), scalars.size()), "srs_msm");
+    return out;
+  }
+
+ private:
+  void* h_ = nullptr;
+};
+
+struct KZG10 {
+  // KZG10::commit(powers, polynomial, hiding_bound = None): coefficients as the polynomial holds them (Montgomery Fr)
+  static KZGCommitment commit(const ResidentPowers& powers, const std::vector<Fr>& coeffs) {
+    KZGCommitment c;
+    check(aleo_b200_kzg_commit(powers.handle(), c.bytes, coeffs.data(), coeffs.size()), "KZG10::commit");
+    return c;
+  }
+};
+
 }  // namespace aleo_b200

@@ -55,6 +55,23 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 4; k++) REQUIRE(w[i].v[k] == (i < 5 ? v[i].v[k] : 0));
   std::vector<Fr> c = dom.coset_ifft(dom.coset_fft(v));
   for (size_t i = 0; i < 5; i++) REQUIRE(c[i].v[0] == v[i].v[0]);
+  // KZG10::commit against resident powers: all-identity powers commit to the identity (flag bit 382 set, x = 0),
+  // and a handle serves any prefix length
+  {
+    std::vector<G1Affine> powers(300);
+    std::memset(powers.data(), 0, powers.size() * sizeof(G1Affine));
+    for (auto& b : powers) b.infinity = true;
+    ResidentPowers rp(powers);
+    REQUIRE(rp.size() == 300);
+    std::vector<Fr> poly(123, Fr{{5, 0, 0, 0}});
+    KZGCommitment cm = KZG10::commit(rp, poly);
+    REQUIRE(cm.bytes[47] == 0x40);
+    for (int i = 0; i < 47; i++) REQUIRE(cm.bytes[i] == 0);
+    G1Projective z = rp.msm(std::vector<BigInteger256>(7, BigInteger256{{3, 0, 0, 0}}));
+    uint64_t acc = 0;
+    for (int i = 0; i < 6; i++) acc |= z.z.v[i];
+    REQUIRE(acc == 0);
+  }
   std::printf("gpu mirror ok\n");
   return 0;
 }
