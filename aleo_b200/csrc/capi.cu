@@ -544,6 +544,19 @@ int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const 
   return srs_host_call(handle, out_compressed48_host, 48, coeffs_montgomery_host, n_coeffs, true);
 }
 
+int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_dev, const void* const* coeffs_dev_ptrs_host,
+                                   const size_t* n_coeffs_host, size_t count, void* stream) {
+  if (handle == nullptr) return ALEO_B200_EINVAL;
+  if (count == 0) return ALEO_B200_OK;
+  if (out_compressed48_dev == nullptr || coeffs_dev_ptrs_host == nullptr || n_coeffs_host == nullptr || count > 64) return ALEO_B200_EINVAL;
+  for (size_t m = 0; m < count; m++)
+    if (n_coeffs_host[m] && coeffs_dev_ptrs_host[m] == nullptr) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::srs_msm_batch(handle, coeffs_dev_ptrs_host, n_coeffs_host, count, true, out_compressed48_dev, true, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                              void* stream) {
   if (handle == nullptr || out_compressed48_dev == nullptr || (n_coeffs && coeffs_montgomery_dev == nullptr)) return ALEO_B200_EINVAL;

@@ -43,6 +43,8 @@ void srs_destroy(void* handle);
 void srs_info(const void* handle, size_t* n, int* c, int* W, size_t* bytes);
 cudaError_t srs_msm(const void* handle, const void* scalars_dev, size_t n_used, void* out144_dev, cudaStream_t s, bool dry,
                     int* launches_out, float* phase_ms);
+cudaError_t srs_msm_batch(const void* handle, const void* const* scalars_dev_ptrs, const size_t* n_each, size_t count,
+                          bool montgomery_in, void* out_dev, bool compressed, cudaStream_t s);
 cudaError_t fr_to_bigint(const void* in_dev, void* out_dev, size_t n, cudaStream_t s);
 cudaError_t g1_compress(const void* jac144_dev, void* out48_dev, cudaStream_t s);
 // poly_lib.cu

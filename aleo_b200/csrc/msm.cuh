@@ -43,9 +43,26 @@ struct Params {
   // it also turns the "negative small" scalars of a witness (r - k) into k, whose digits are zero above window 0,
   // instead of one crowded bucket in every window.
   u32 half_range;
+  // Batch of independent MSMs against ONE resident SRS (KZG10 commits the ~13 polynomials of a proof against the
+  // same powers): the scalar vectors lie back to back, batch_off[m] .. batch_off[m + 1] are the scalars of MSM m,
+  // and MSM m owns the bucket set m (a "window" of the reduction kernels).  nbatch = 0: a single MSM.
+  const u32* batch_off;
+  u32 nbatch;
 };
 
-DEV u32 bucket_slot(const Params& prm, u32 w, u32 mag) { return prm.n_stride ? (mag - 1) : (w * prm.B + (mag - 1)); }
+// which MSM of a batch scalar i belongs to (nbatch <= 64: a short walk), and its index inside that MSM
+DEV u32 batch_member(const Params& prm, u32 i, u32& local) {
+  u32 m = 0;
+  while (m + 1 < prm.nbatch && prm.batch_off[m + 1] <= i) m++;
+  local = i - prm.batch_off[m];
+  return m;
+}
+
+// set = bucket set: the window (plain MSM), 0 (resident SRS) or the batch member
+DEV u32 bucket_slot(const Params& prm, u32 w, u32 mag, u32 member = 0) {
+  if (prm.nbatch) return member * prm.B + (mag - 1);
+  return prm.n_stride ? (mag - 1) : (w * prm.B + (mag - 1));
+}
 DEV u32 entry_index(const Params& prm, u32 w, u32 i) { return prm.n_stride ? (w * prm.n_stride + prm.first + i) : i; }
 
 // scalar i -> t (local copy, indexed by window position); returns 1 when half-range recoding replaced it by r - s
@@ -167,10 +184,12 @@ KERNEL void count_kernel_sm(const u32* scalars, u32 n, Params prm, u32* counts) 
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   u32 t[8];
   load_scalar(scalars + (size_t)(i < n ? i : 0) * 8, t, prm.half_range);
+  u32 li = i, member = 0;
+  if (prm.nbatch && i < n) member = batch_member(prm, i, li);
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
     const u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
-    warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
+    warp_aggregated_inc(counts, mag ? bucket_slot(prm, w, mag, member) : 0u, mag != 0);
   }
 }
 
@@ -178,11 +197,13 @@ KERNEL void scatter_kernel_sm(const u32* scalars, u32 n, Params prm, u32* cursor
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   u32 t[8];
   const u32 flip = load_scalar(scalars + (size_t)(i < n ? i : 0) * 8, t, prm.half_range);
+  u32 li = i, member = 0;
+  if (prm.nbatch && i < n) member = batch_member(prm, i, li);
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
     const u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
-    const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag) : 0u, mag != 0);
-    if (mag) sorted[pos] = entry_index(prm, w, i) | ((neg ^ flip) << 31);
+    const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag, member) : 0u, mag != 0);
+    if (mag) sorted[pos] = entry_index(prm, w, li) | ((neg ^ flip) << 31);
   }
 }
 
@@ -641,6 +662,10 @@ KERNEL void __launch_bounds__(TAIL_TPB, 1) weigh_sum_kernel(const G1Xyzz* S, u32
   TAIL_CLOCK(3);
 }
 
+// Batch tail: MSM m's result is S[m] (no window weights against a resident SRS); one CTA per member normalises it
+// (one inversion each, in parallel) and writes the 48-byte compressed point or the 144-byte Jacobian image.
+KERNEL void batch_finalize_kernel(const G1Xyzz* S, u32 count, unsigned char* out, u32 compressed);
+
 // sum of `count` Jacobian points -> normalised Jacobian (multi-GPU combine; count is tiny)
 KERNEL void g1_sum_kernel(const unsigned char* pts144, u32 count, unsigned char* out144) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -703,8 +728,9 @@ KERNEL void fr_to_bigint_kernel(const Fr* in, Fr* out, u32 n) {
 
 // normalised Jacobian (144 B, Montgomery) -> 48-byte compressed G1 (snarkVM wire format, pinned by the
 // reference's proof fixture: x little-endian canonical, bit 383 = y is the larger root, bit 382 = infinity)
-KERNEL void g1_compress_kernel(const unsigned char* jac144, unsigned char* out48) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+KERNEL void g1_compress_kernel(const unsigned char* jac144, unsigned char* out48);
+
+DEV void g1_compress_to(const unsigned char* jac144, unsigned char* out48) {
   const Fq z = fq_load8(jac144 + 96);
   Fq x = fp_zero<FqParams>();
   u32 flags = 0;
@@ -725,6 +751,23 @@ KERNEL void g1_compress_kernel(const unsigned char* jac144, unsigned char* out48
   }
   x.l[FqParams::N - 1] |= flags;
   fq_store8(out48, x);
+}
+
+KERNEL void batch_finalize_kernel(const G1Xyzz* S, u32 count, unsigned char* out, u32 compressed) {
+  SHARED unsigned char jac[144];
+  const u32 m = blockIdx.x;
+  if (m >= count || threadIdx.x != 0) return;
+  if (compressed) {
+    jacobian_store_normalised(jac, S[m]);
+    g1_compress_to(jac, out + (size_t)m * 48);
+  } else {
+    jacobian_store_normalised(out + (size_t)m * 144, S[m]);
+  }
+}
+
+KERNEL void g1_compress_kernel(const unsigned char* jac144, unsigned char* out48) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  g1_compress_to(jac144, out48);
 }
 
 KERNEL void write_identity_kernel(unsigned char* out144) {

@@ -87,6 +87,8 @@ static inline Params make_params(size_t n, const SrsView* srs = nullptr, u32 chu
   p.c = srs ? srs->c : choose_window(n, chunks);
   p.W = srs ? srs->W : windows_for(p.c);
   p.half_range = 1u;
+  p.batch_off = nullptr;
+  p.nbatch = 0;
   p.B = 1u << (p.c - 1);
   p.n_stride = srs ? srs->n_total : 0;
   p.first = 0;
@@ -179,12 +181,17 @@ struct Session {
   T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
 
   // n_total: points of the whole MSM; max_chunk: largest point range add_chunk() will see; chunks: how many
-  cudaError_t begin(size_t n_total, size_t max_chunk_, u32 chunks, const SrsView* srs_, cudaStream_t s, bool dry_) {
+  // batch (resident SRS only): nbatch independent MSMs whose scalar vectors lie back to back, batch_off = nbatch + 1
+  // prefix offsets on the device; every member gets its own bucket set and finish_batch() returns nbatch results
+  cudaError_t begin(size_t n_total, size_t max_chunk_, u32 chunks, const SrsView* srs_, cudaStream_t s, bool dry_,
+                    u32 nbatch = 0, const u32* batch_off = nullptr) {
     srs = srs_;
     dry = dry_;
     max_chunk = max_chunk_;
     prm = make_params(n_total, srs, chunks);
-    nwin = srs ? 1u : prm.W;  // bucket sets (the resident SRS shares one across all windows)
+    prm.nbatch = nbatch;
+    prm.batch_off = batch_off;
+    nwin = nbatch ? nbatch : (srs ? 1u : prm.W);  // bucket sets (the resident SRS shares one across all windows)
     NB = nwin * prm.B;
     max_lanes = lanes_for(max_chunk, prm.W);
     cap_small = max_lanes + 1;  // every run boundary cuts at most one bucket
@@ -341,8 +348,9 @@ struct Session {
     return cudaGetLastError();
   }
 
-  // bucket reduction + window combination + normalisation -> 144-byte Jacobian; frees the workspace
-  cudaError_t finish(unsigned char* out144, cudaStream_t s, cudaEvent_t* done_ev = nullptr) {
+  // bucket reduction + window combination + normalisation -> 144-byte Jacobian; frees the workspace.
+  // Batch sessions: `out144` receives nbatch results, 48-byte compressed points when batch_compressed, else 144 bytes each.
+  cudaError_t finish(unsigned char* out144, cudaStream_t s, cudaEvent_t* done_ev = nullptr, bool batch_compressed = true) {
     launches += (int)lv.size() + 2;
     if (dry) return cudaSuccess;
     G1Xyzz* buckets = at<G1Xyzz>(o_buckets);
@@ -383,6 +391,15 @@ struct Session {
       const u32 span = scan_span;
       LAUNCH(reduce_scan_kernel, dim3(nwin), dim3(span), span * sizeof(G1Xyzz), s, sa);
       tr.mark("scan", s);
+    }
+    if (prm.nbatch) {
+      LAUNCH(batch_finalize_kernel, dim3(nwin), dim3(32), 0, s, (const G1Xyzz*)S, nwin, out144, (u32)(batch_compressed ? 1 : 0));
+      tr.mark("batch finalize", s);
+      tr.report(s);
+      if (done_ev) cudaEventRecord(*done_ev, s);
+      cudaError_t eb = cudaGetLastError();
+      release(s);
+      return eb;
     }
     // per-window weights 2^(c w) (none for a resident SRS: they are baked into the expanded bases), sum, normalise
     unsigned long long* dbg = nullptr;

@@ -406,6 +406,48 @@ cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool
   return e != cudaSuccess ? e : e2;
 }
 
+// `count` independent commitments against one resident SRS in ONE launch sequence (KZG10 commits the polynomials of a
+// proof against the same powers): the coefficient vectors (device, Montgomery when montgomery_in)
+// are converted into one back-to-back scalar buffer, sorted together, accumulated by one kernel (MSM m owns bucket set
+// m), reduced with the members as "windows", and normalised / compressed by one CTA per member.
+// out_dev: count x 48 bytes (compressed) or count x 144 bytes.  count <= 64.
+cudaError_t srs_msm_batch(const void* handle, const void* const* scalars_dev_ptrs, const size_t* n_each, size_t count,
+                          bool montgomery_in, void* out_dev, bool compressed, cudaStream_t s) {
+  const Srs* h = (const Srs*)handle;
+  if (count == 0) return cudaSuccess;
+  if (count > 64) return cudaErrorInvalidValue;
+  std::vector<u32> off(count + 1, 0);
+  size_t total = 0;
+  for (size_t m = 0; m < count; m++) {
+    if (n_each[m] > h->n) return cudaErrorInvalidValue;
+    off[m] = (u32)total;
+    total += n_each[m];
+  }
+  off[count] = (u32)total;
+  if (total * h->W >= ((size_t)1 << 32) || total >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
+  msm::SrsView v{h->pre, (u32)h->n, h->c, h->W};
+  unsigned char* d = nullptr;
+  const size_t sb = ((total ? total : 1) * 32 + 255) & ~(size_t)255, ob = ((count + 1) * 4 + 255) & ~(size_t)255;
+  MSM_CK(cudaMallocAsync((void**)&d, sb + ob, s));
+  u32* off_dev = (u32*)(d + sb);
+  cudaError_t e = cudaMemcpyAsync(off_dev, off.data(), (count + 1) * 4, cudaMemcpyHostToDevice, s);
+  for (size_t m = 0; m < count && e == cudaSuccess; m++) {
+    if (n_each[m] == 0) continue;
+    if (montgomery_in)
+      e = fr_to_bigint(scalars_dev_ptrs[m], d + (size_t)off[m] * 32, n_each[m], s);
+    else
+      e = cudaMemcpyAsync(d + (size_t)off[m] * 32, scalars_dev_ptrs[m], n_each[m] * 32, cudaMemcpyDeviceToDevice, s);
+  }
+  // (`off` is pageable host memory: cudaMemcpyAsync has staged it by the time it returns, the vector may go away)
+  msm::Session ss;
+  if (e == cudaSuccess) e = ss.begin(total ? total : 1, total ? total : 1, 1, &v, s, false, (u32)count, off_dev);
+  if (e == cudaSuccess) e = ss.add_chunk(nullptr, 96, (const u32*)d, total, 0, s);
+  if (e == cudaSuccess) e = ss.finish((unsigned char*)out_dev, s, nullptr, compressed);
+  else ss.release(s);
+  cudaFreeAsync(d, s);
+  return e;
+}
+
 cudaError_t fr_to_bigint(const void* in_dev, void* out_dev, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   LAUNCH_NOSYNC(msm::fr_to_bigint_kernel, dim3((u32)((n + 255) / 256)), dim3(256), 0, s, (const Fr*)in_dev, (Fr*)out_dev, (u32)n);

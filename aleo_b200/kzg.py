@@ -96,3 +96,20 @@ class KZG10:
             srs._lib.check(srs._lib.kzg_commit_dev(srs._h, out.data_ptr(), coeffs_t.data_ptr(), n_coeffs,
                                                    torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_dev")
         return out
+
+    @staticmethod
+    def commit_batch_dev(srs: ResidentSRS, coeff_tensors, out=None):
+        """`count` (<= 64) non-hiding commitments against the same resident powers in ONE launch sequence
+        (aleo_b200_kzg_commit_batch_dev): list of CUDA tensors of Montgomery Fr -> (count, 48) uint8 CUDA tensor"""
+        import torch
+
+        count = len(coeff_tensors)
+        dev = coeff_tensors[0].device if count else torch.device("cuda", torch.cuda.current_device())
+        if out is None:
+            out = torch.empty((max(count, 1), 48), dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * max(count, 1))(*[t.data_ptr() for t in coeff_tensors])
+        lens = (C.c_size_t * max(count, 1))(*[t.numel() * t.element_size() // 32 for t in coeff_tensors])
+        with torch.cuda.device(dev):
+            srs._lib.check(srs._lib.kzg_commit_batch_dev(srs._h, out.data_ptr(), ptrs, lens, count,
+                                                         torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_batch_dev")
+        return out[:count]

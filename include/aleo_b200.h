@@ -147,6 +147,15 @@ int aleo_b200_srs_msm_launches(const void* handle, size_t n_used);
 int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs);
 int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                              void* stream);
+/* `count` (<= 64) commitments against the same resident SRS in ONE launch sequence: snarkVM commits the ~13 polynomials
+ * of a proof against the same powers (SonicKZG10::commit over an ExecutionPool, src/polycommit/sonic_pc/mod.rs;
+ * SURVEY.md 8f rank 1).  The coefficient vectors are sorted together, accumulated by one kernel (every polynomial
+ * owns a bucket set), and each result is normalised and compressed by its own CTA, so the latency-bound tails of
+ * proof-sized MSMs (2^15 .. 2^18) run side by side instead of one after the other.
+ * coeffs_dev_ptrs_host / n_coeffs_host: HOST arrays of `count` device pointers / lengths (Montgomery Fr);
+ * out_compressed48_dev: count x 48 bytes. */
+int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_dev, const void* const* coeffs_dev_ptrs_host,
+                                   const size_t* n_coeffs_host, size_t count, void* stream);
 /* window size c (bits) the MSM uses for n device-resident points, and the kernel launches one MSM issues */
 int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);

@@ -379,3 +379,25 @@ def test_emu_ntt_nine_bit_middle_pass(emu_lib, c_oracle, monkeypatch):
     got = x.copy()
     emu_lib.check(emu_lib.ntt_fr_dev(got.ctypes.data, log_n, 1, 0, 0, None), "ntt")
     assert np.array_equal(got, want)
+
+
+def test_emu_kzg_commit_batch(emu_lib):
+    """several commitments against one resident SRS in one launch sequence: each equals the single commitment"""
+    n = 400
+    B = o.synthetic_bases(n, 131)
+    B[9] = None
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    h = C.c_void_p()
+    emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, 104, None), "srs_create")
+    sizes = [400, 1, 0, 257, 33, 400]
+    polys = [o.random_fr_vec(m, 140 + k) for k, m in enumerate(sizes)]
+    polys[0][0], polys[0][1], polys[3][5] = 0, o.R_MOD - 1, 1
+    bufs = [C.create_string_buffer(o.fr_vec_to_bytes(p), max(1, len(p)) * 32) for p in polys]
+    ptrs = (C.c_void_p * len(sizes))(*[C.cast(b, C.c_void_p) for b in bufs])
+    lens = (C.c_size_t * len(sizes))(*sizes)
+    out = C.create_string_buffer(48 * len(sizes))
+    emu_lib.check(emu_lib.kzg_commit_batch_dev(h, C.cast(out, C.c_void_p), ptrs, lens, len(sizes), None), "batch")
+    for k, p in enumerate(polys):
+        want = o.g1_compress(o.msm_pippenger(B[:len(p)], p) if p else None)
+        assert out.raw[48 * k:48 * (k + 1)] == want, k
+    emu_lib.check(emu_lib.srs_destroy(h), "destroy")

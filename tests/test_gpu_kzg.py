@@ -55,3 +55,29 @@ def test_srs_matches_plain_msm_and_known_dlogs(log_n):
     want = o.g1_mul(o.G1_GEN, ab.dlog_dot_dev(cc, m, s0, d))
     assert got48 == o.g1_compress(want)
     srs.close()
+
+
+def test_commit_batch_equals_single_commits():
+    """aleo_b200_kzg_commit_batch_dev: 13 polynomials of proof-like sizes in one launch sequence, byte-equal to 13
+    single commitments (which test_kzg_commit_* pins against the oracle); empty and length-1 members included"""
+    import torch
+
+    n = 1 << 16
+    s0, d = o.base_dlogs(n, 2024)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    srs = ab.ResidentSRS.from_device(bases, n, 104)
+    try:
+        sizes = [n, n, n // 2, n // 2, n // 4, 12345, 1, 0, 777, n, 3, n // 8, 4097]
+        polys = [ab.gen_scalars_dev(max(m, 1), 300 + k, 0, True)[:m] for k, m in enumerate(sizes)]
+        polys[4][::2] = 0                                  # witness-like: zeros ...
+        one_mont = torch.from_numpy(np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64).copy()).cuda()
+        polys[4][1::4] = one_mont                          # ... and ones
+        got = ab.KZG10.commit_batch_dev(srs, polys)
+        want = torch.stack([ab.KZG10.commit_dev(srs, p, p.shape[0]) for p in polys])
+        assert torch.equal(got, want)
+        # a small member checked directly against the oracle through known discrete logs
+        c = o.fr_vec_from_bytes(polys[10].cpu().numpy().tobytes())
+        assert got[10].cpu().numpy().tobytes() == o.g1_compress(o.g1_mul(o.G1_GEN, sum(ci * (s0 + i * d) for i, ci in enumerate(c)) % o.R_MOD))
+        assert got[7].cpu().numpy().tobytes() == o.g1_compress(None)
+    finally:
+        srs.close()
