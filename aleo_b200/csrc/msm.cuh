@@ -208,6 +208,131 @@ KERNEL void scatter_kernel_sm(const u32* scalars, u32 n, Params prm, u32* cursor
 }
 
 // ---------------------------------------------------------------------------------------------
+// Partitioned sort (plain MSM, large sizes).  The count + scatter pair above pays one global atomic WITH return per
+// entry (ATOM: ~45 G/s on B200 against ~140 G/s for the fire-and-forget RED of the count kernel) and 4-byte stores
+// at random heads.  Here the sort is two levels and every atomic is a shared-memory one:
+//   part_count   CTA x walks ITS scalars (all windows), histogram over coarse BINS (bin = bucket id >> fb, 2^fb fine
+//                buckets per bin) in shared memory, one plain store per (bin, CTA) of the count -- layout
+//                cnt[bin][cta], so that ONE flat exclusive scan yields the exact output offset of every (bin, CTA)
+//   part_scatter grid (cta, window group): the same walk, shared-memory cursors initialised from the scan, 8-byte
+//                records {entry, fine bucket} appended to the bin's region.  A group holds few enough bins
+//                (<= PART_GROUP_BINS) that the partially written sectors of all CTAs stay L2 resident.
+//   part_finish  one CTA per bin: shared-memory histogram of the fine buckets, block scan -> the bin's bucket
+//                starts / ends, then the final 4-byte entries in bucket order (the bin's output region is a few
+//                hundred KB: L2 resident, written back as whole sectors).
+// ---------------------------------------------------------------------------------------------
+constexpr u32 PART_TPB = 256;
+constexpr u32 PART_GROUP_BINS = 2048;
+
+struct PartArgs {
+  const u32* scalars;
+  u32 n;
+  Params prm;
+  u32 fb;          // fine bits: 2^fb buckets per bin
+  u32 bps;         // bins per bucket set (window) = B >> fb
+  u32 nbin;        // W * bps
+  u32 ncta;        // CTAs that split the scalars (gridDim.x of part_count / part_scatter)
+  u32 wpg;         // windows per scatter group
+};
+
+struct PartRecord {
+  u32 entry;  // point index | sign << 31
+  u32 fine;   // bucket id inside the bin
+};
+
+// cnt[bin * ncta + cta] = entries of bin produced by CTA cta
+KERNEL void __launch_bounds__(PART_TPB) part_count_kernel(PartArgs a, u32* cnt) {
+  DYN_SMEM(u32, hist);
+  for (u32 b = threadIdx.x; b < a.nbin; b += PART_TPB) hist[b] = 0;
+  SYNC_THREADS();
+  for (u32 base = blockIdx.x * PART_TPB; base < a.n; base += a.ncta * PART_TPB) {
+    const u32 i = base + threadIdx.x;
+    if (i >= a.n) continue;
+    u32 t[8];
+    load_scalar(a.scalars + (size_t)i * 8, t, a.prm.half_range);
+    u32 carry = 0, neg = 0;
+    for (u32 w = 0; w < a.prm.W; w++) {
+      const u32 mag = recode_digit(t, w, a.prm.c, carry, neg);
+      if (mag) atomic_add_shared_u32(&hist[w * a.bps + ((mag - 1) >> a.fb)], 1u);
+    }
+  }
+  SYNC_THREADS();
+  for (u32 b = threadIdx.x; b < a.nbin; b += PART_TPB) cnt[(size_t)b * a.ncta + blockIdx.x] = hist[b];
+}
+
+// offs = exclusive scan of cnt (same layout); part[pos] = record
+KERNEL void __launch_bounds__(PART_TPB) part_scatter_kernel(PartArgs a, const u32* offs, PartRecord* part) {
+  DYN_SMEM(u32, cur);
+  const u32 w0 = blockIdx.y * a.wpg;
+  const u32 w1 = (w0 + a.wpg < a.prm.W) ? w0 + a.wpg : a.prm.W;
+  const u32 bin0 = w0 * a.bps, nb = (w1 - w0) * a.bps;
+  for (u32 b = threadIdx.x; b < nb; b += PART_TPB) cur[b] = offs[(size_t)(bin0 + b) * a.ncta + blockIdx.x];
+  SYNC_THREADS();
+  for (u32 base = blockIdx.x * PART_TPB; base < a.n; base += a.ncta * PART_TPB) {
+    const u32 i = base + threadIdx.x;
+    if (i >= a.n) continue;
+    u32 t[8];
+    const u32 flip = load_scalar(a.scalars + (size_t)i * 8, t, a.prm.half_range);
+    u32 carry = 0, neg = 0;
+    for (u32 w = 0; w < w1; w++) {  // the carry walks up from window 0; only the group's windows are emitted
+      const u32 mag = recode_digit(t, w, a.prm.c, carry, neg);
+      if (w < w0 || !mag) continue;
+      const u32 pos = atomic_add_shared_u32(&cur[(w - w0) * a.bps + ((mag - 1) >> a.fb)], 1u);
+      PartRecord r;
+      r.entry = i | ((neg ^ flip) << 31);
+      r.fine = (mag - 1) & ((1u << a.fb) - 1u);
+      part[pos] = r;
+    }
+  }
+}
+
+// one CTA per bin: starts / ends of its 2^fb buckets, and the bin's entries in bucket order
+KERNEL void __launch_bounds__(PART_TPB) part_finish_kernel(PartArgs a, const u32* offs, const u32* total, const PartRecord* part,
+                                                          u32* starts, u32* ends, u32* sorted) {
+  DYN_SMEM(u32, sm);  // [0, nf): histogram, then cursors; [nf, nf + PART_TPB): scan scratch
+  const u32 nf = 1u << a.fb;
+  u32* hist = sm;
+  u32* scratch = sm + nf;
+  const u32 bin = blockIdx.x;
+  const u32 lo = offs[(size_t)bin * a.ncta];
+  const u32 hi = (bin + 1 < a.nbin) ? offs[(size_t)(bin + 1) * a.ncta] : *total;
+  for (u32 f = threadIdx.x; f < nf; f += PART_TPB) hist[f] = 0;
+  SYNC_THREADS();
+  for (u32 p = lo + threadIdx.x; p < hi; p += PART_TPB) atomic_add_shared_u32(&hist[part[p].fine], 1u);
+  SYNC_THREADS();
+  // exclusive scan of hist (nf values, nf / PART_TPB consecutive values per thread)
+  const u32 per = (nf + PART_TPB - 1) / PART_TPB;
+  const u32 f0 = threadIdx.x * per;
+  u32 sum = 0;
+  for (u32 k = 0; k < per; k++)
+    if (f0 + k < nf) sum += hist[f0 + k];
+  scratch[threadIdx.x] = sum;
+  SYNC_THREADS();
+  for (u32 off = 1; off < PART_TPB; off <<= 1) {
+    const u32 add = (threadIdx.x >= off) ? scratch[threadIdx.x - off] : 0u;
+    SYNC_THREADS();
+    scratch[threadIdx.x] += add;
+    SYNC_THREADS();
+  }
+  u32 run = lo + scratch[threadIdx.x] - sum;
+  const u32 g0 = bin << a.fb;  // first global bucket of the bin
+  for (u32 k = 0; k < per; k++) {
+    if (f0 + k < nf) {
+      const u32 c = hist[f0 + k];
+      starts[g0 + f0 + k] = run;
+      ends[g0 + f0 + k] = run + c;
+      hist[f0 + k] = run;  // becomes the bucket's cursor
+      run += c;
+    }
+  }
+  SYNC_THREADS();
+  for (u32 p = lo + threadIdx.x; p < hi; p += PART_TPB) {
+    const PartRecord r = part[p];
+    sorted[atomic_add_shared_u32(&hist[r.fine], 1u)] = r.entry;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // exclusive scan of u32 (three launches; 2048 items per CTA)
 // ---------------------------------------------------------------------------------------------
 constexpr u32 SCAN_TPB = 256;

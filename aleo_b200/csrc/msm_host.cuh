@@ -35,8 +35,9 @@ static inline u32 choose_window(size_t n, u32 chunks = 1) {
   for (u32 c = 4; c <= 22; c++) {
     const double W = (double)windows_for(c);
     // an MSM that arrives in `chunks` point ranges re-opens every bucket once per extra range: one more
-    // mixed addition per bucket and range (the first addition into an empty bucket is a copy)
-    const double cost = (double)n * W * 10.0 + W * (double)(1u << (c - 1)) * (2.0 * 14.0 * 1.5 + 10.0 * (chunks - 1));
+    // mixed addition per bucket and range (the first addition into an empty bucket is a copy); weighted 5 rather
+    // than 10: measured on B200 at 2^24 in 3 ranges, c = 20 runs 102.3 ms against 105.5 ms for c = 19
+    const double cost = (double)n * W * 10.0 + W * (double)(1u << (c - 1)) * (2.0 * 14.0 * 1.5 + 5.0 * (chunks - 1));
     if (c == 4 || cost < best) {
       best = cost;
       best_c = c;
@@ -169,6 +170,10 @@ struct Session {
   size_t max_chunk = 0;
   std::vector<RedLevel> lv;
   u32 scan_m = 0, scan_t_in = 0, scan_scale_log = 0, scan_span = 32;  // last reduction stage (one CTA per window)
+  // partitioned sort (plain MSM, large ranges): see part_count_kernel
+  bool part = false;
+  u32 part_fb = 0, part_bps = 0, part_nbin = 0, part_ncta_max = 0, part_wpg = 1;
+  size_t o_pcnt = 0, o_poffs = 0, o_part = 0;
   size_t o_counts = 0, o_starts = 0, o_ends = 0, o_piece_bucket = 0, o_bsums = 0, o_meta = 0, o_sorted = 0, o_small = 0,
          o_large = 0, o_buckets = 0, o_pieces = 0, o_D = 0, bytes = 0;
   std::vector<size_t> o_R, o_P;
@@ -241,6 +246,32 @@ struct Session {
       o_P[l] = cv.take((size_t)nwin * lv[l].T * sizeof(G1Xyzz));
     }
     o_D = cv.take((size_t)nwin * sizeof(G1Xyzz));  // S_w: one sum per window
+    {
+      // ALEO_B200_MSM_SORT = p selects the partitioned sort.  NOT the default: measured on B200 it loses to the atomic
+      // sort -- 2^22 (c = 17): 2.6 against 1.6 ms; 2^24 (c = 20): 29.7 against 6.9 ms, because the top window of c = 20
+      // holds 13 bits, so 4 of its 512 bins receive all 2^24 of its entries and 4 CTAs of part_finish walk 4 M
+      // records each.  Kept (and tested) as the starting point for a version that slices heavy bins.
+      const char* sort_env = getenv("ALEO_B200_MSM_SORT");
+      const bool forced = sort_env && sort_env[0] == 'p';
+      part = !srs && !nbatch && forced;
+      if (part) {
+        part_fb = prm.c - 1 > 9 ? prm.c - 1 - 9 : 0;
+        if (const char* fbe = getenv("ALEO_B200_MSM_PART_FB")) part_fb = (u32)atoi(fbe) < prm.c ? (u32)atoi(fbe) : part_fb;  // tests
+        part_bps = prm.B >> part_fb;
+        part_nbin = prm.W * part_bps;
+        part_wpg = PART_GROUP_BINS / part_bps ? PART_GROUP_BINS / part_bps : 1;
+        const size_t ctas = (max_chunk + PART_TPB - 1) / PART_TPB;
+        part_ncta_max = (u32)(ctas < 592 ? ctas : 592);
+        if ((size_t)part_nbin * 4 > (size_t)160 * 1024) part = false;  // histogram of part_count must fit shared memory
+      }
+      if (part) {
+        o_pcnt = cv.take((size_t)part_nbin * part_ncta_max * 4);
+        o_poffs = cv.take((size_t)part_nbin * part_ncta_max * 4);
+        o_part = cv.take((size_t)max_chunk * prm.W * sizeof(PartRecord));
+        const size_t sb = ((size_t)part_nbin * part_ncta_max + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
+        if (sb > scan_blocks + 1) o_bsums = cv.take(sb * 4);  // the scan of cnt needs more block sums than the bucket scan
+      }
+    }
     bytes = cv.off;
     if (dry) return cudaSuccess;
     MSM_CK(cudaMallocAsync((void**)&ws, bytes, s));
@@ -266,7 +297,7 @@ struct Session {
     }
     const u32 into = chunks_done > 0 ? 1u : 0u;  // later chunks start every bucket from its stored sum
     chunks_done++;
-    launches += 9;
+    launches += part ? 10 : 9;
     if (dry) return cudaSuccess;
     u32* counts = at<u32>(o_counts);
     u32* starts = at<u32>(o_starts);
@@ -283,6 +314,43 @@ struct Session {
     MSM_CK(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
     MSM_CK(cudaMemsetAsync(meta, 0, 64, s));
     const u32 g_all = (n + 255) / 256, g_n = g_all < 1184 ? g_all : 1184;  // <= 8 CTAs of 256 per SM and window
+    TailTrace st;
+    st.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
+    st.mark("start", s);
+    if (part) {
+      PartArgs pa;
+      pa.scalars = scalars;
+      pa.n = n;
+      pa.prm = p;
+      pa.fb = part_fb;
+      pa.bps = part_bps;
+      pa.nbin = part_nbin;
+      pa.ncta = g_all < 592 ? g_all : 592;
+      pa.wpg = part_wpg;
+      u32* pcnt = at<u32>(o_pcnt);
+      u32* poffs = at<u32>(o_poffs);
+      PartRecord* precs = at<PartRecord>(o_part);
+      const u32 ngroups = (p.W + pa.wpg - 1) / pa.wpg;
+      const u32 nfine = 1u << pa.fb;
+#ifndef ALEO_EMU
+      static thread_local int attr_dev = -1;
+      int devnow = 0;
+      MSM_CK(cudaGetDevice(&devnow));
+      if (attr_dev != devnow) {
+        MSM_CK(cudaFuncSetAttribute(part_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_dev = devnow;
+      }
+#endif
+      LAUNCH(part_count_kernel, dim3(pa.ncta), dim3(PART_TPB), (size_t)pa.nbin * 4, s, pa, pcnt);
+      st.mark("part count", s);
+      int scan_launches = 0;
+      MSM_CK(exclusive_scan(pcnt, pa.nbin * pa.ncta, at<u32>(o_bsums), poffs, nullptr, meta + 0, s, scan_launches));
+      st.mark("part scan", s);
+      LAUNCH(part_scatter_kernel, dim3(pa.ncta, ngroups), dim3(PART_TPB), (size_t)pa.wpg * pa.bps * 4, s, pa, (const u32*)poffs, precs);
+      st.mark("part scatter", s);
+      LAUNCH(part_finish_kernel, dim3(pa.nbin), dim3(PART_TPB), (size_t)(nfine + PART_TPB) * 4, s, pa, (const u32*)poffs,
+             (const u32*)(meta + 0), (const PartRecord*)precs, starts, ends, sorted);
+    } else {
     // count: scalar-major (every warp iteration spreads its 32 atomics over one window's counters and moves on);
     // scatter: window-major once the bucket heads of all windows (W * 2^(c-1) sectors of 32 B) outgrow L2 --
     // measured on B200 at n = 2^24, c = 20: count 3.3 (scalar) / 4.5 (window) ms, scatter 9.2 / 5.3 ms;
@@ -291,9 +359,6 @@ struct Session {
     const bool heads_fit_l2 = (size_t)NB * 32 <= ((size_t)48 << 20);
     const bool count_wm = sort_env && sort_env[0] == 'w';
     const bool scatter_wm = sort_env ? sort_env[0] == 'w' : (!heads_fit_l2 && !srs);  // a resident SRS shares one bucket set: nothing to gain
-    TailTrace st;
-    st.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
-    st.mark("start", s);
     if (count_wm)
       LAUNCH_NOSYNC(count_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, counts);
     else
@@ -306,6 +371,7 @@ struct Session {
       LAUNCH_NOSYNC(scatter_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, ends, sorted);
     else
       LAUNCH_NOSYNC(scatter_kernel_sm, dim3(g_all), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    }
     st.mark("scatter", s);
     LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB, p.nlanes,
                   small_list, large_list, cap_small, cap_large, meta);

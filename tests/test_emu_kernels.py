@@ -401,3 +401,30 @@ def test_emu_kzg_commit_batch(emu_lib):
         want = o.g1_compress(o.msm_pippenger(B[:len(p)], p) if p else None)
         assert out.raw[48 * k:48 * (k + 1)] == want, k
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+@pytest.mark.parametrize("c,fb", [(5, 0), (7, 3), (8, 2)])
+def test_emu_msm_partitioned_sort(emu_lib, c, fb, monkeypatch):
+    """the two-level shared-memory sort (part_count / part_scatter / part_finish) forced on small inputs, with and
+    without fine bits and with several window groups; witness-like scalars, infinity bases, and the host path in
+    3 point ranges (kept small: the emulator runs every CTA of a synchronising kernel on 256 OS threads)"""
+    monkeypatch.setenv("ALEO_B200_MSM_SORT", "p")
+    monkeypatch.setenv("ALEO_B200_MSM_C", str(c))
+    monkeypatch.setenv("ALEO_B200_MSM_PART_FB", str(fb))
+    n = 300
+    B = o.synthetic_bases(n, 151)
+    B[11] = None
+    s = o.random_fr_vec(n, 152)
+    for i in range(0, n, 5):
+        s[i] = 0
+    for i in range(1, n, 7):
+        s[i] = 1
+    s[3], s[4] = o.R_MOD - 1, o.R_MOD - 2
+    want = o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+    assert _msm(emu_lib, B, s, 104) == want
+    monkeypatch.setenv("ALEO_B200_MSM_CHUNKS", "3")
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 96), n * 96)
+    sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), n * 32)
+    out = C.create_string_buffer(144)
+    emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), 96), "msm_g1")
+    assert out.raw == want
