@@ -57,7 +57,7 @@ def test_argument_validation_precedes_device_use(product_lib_path):
     assert lib.msm_g1(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1, C.cast(buf, C.c_void_p), 100) == _lib.EINVAL
     assert lib.msm_g1(None, C.cast(buf, C.c_void_p), 1, C.cast(buf, C.c_void_p), 104) == _lib.EINVAL
     assert lib.msm_window_bits(1 << 24) == 20 and lib.msm_window_bits(1 << 16) == 12 and lib.msm_window_bits(1) == 4
-    assert lib.ntt_launches(24) == 3 and lib.ntt_launches(16) == 2 and lib.ntt_launches(8) == 1 and lib.ntt_launches(26) == 4
+    assert lib.ntt_launches(24) == 3 and lib.ntt_launches(16) == 2 and lib.ntt_launches(8) == 1 and lib.ntt_launches(26) == 3 and lib.ntt_launches(28) == 4
 
 
 def test_product_package_never_touches_oracle_or_emulator():

@@ -403,7 +403,7 @@ def test_emu_kzg_commit_batch(emu_lib):
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
 
 
-@pytest.mark.parametrize("c,fb", [(5, 0), (7, 3), (8, 2)])
+@pytest.mark.parametrize("c,fb", [(7, 3)])
 def test_emu_msm_partitioned_sort(emu_lib, c, fb, monkeypatch):
     """the two-level shared-memory sort (part_count / part_scatter / part_finish) forced on small inputs, with and
     without fine bits and with several window groups; witness-like scalars, infinity bases, and the host path in
