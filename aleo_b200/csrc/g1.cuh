@@ -177,31 +177,6 @@ DEV void xyzz_add_affine_t(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
   acc.y = y3;
 }
 
-// acc += (x2, y2) for an accumulator that is NOT the identity (the accumulation loop fills empty accumulators itself)
-template <bool CALL>
-DEV void xyzz_add_affine_nz(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
-  Fq u2 = fq_mul_sel<CALL>(x2, acc.zz);
-  Fq s2 = fq_mul_sel<CALL>(y2, acc.zzz);
-  Fq p = fp_sub(u2, acc.x);
-  Fq r = fp_sub(s2, acc.y);
-  if (fp_is_zero(p)) {  // same x: doubling or cancellation (rare; the reference's edge-case tests hit it)
-    if (fp_is_zero(r))
-      acc = xyzz_double_affine(x2, y2);
-    else
-      acc = xyzz_identity();
-    return;
-  }
-  Fq pp = fq_sqr_sel<CALL>(p);
-  Fq ppp = fq_mul_sel<CALL>(p, pp);
-  Fq q = fq_mul_sel<CALL>(acc.x, pp);
-  Fq x3 = fp_sub(fp_sub(fq_sqr_sel<CALL>(r), ppp), fp_dbl(q));
-  Fq y3 = fp_sub(fq_mul_sel<CALL>(r, fp_sub(q, x3)), fq_mul_sel<CALL>(acc.y, ppp));
-  acc.zz = fq_mul_sel<CALL>(acc.zz, pp);
-  acc.zzz = fq_mul_sel<CALL>(acc.zzz, ppp);
-  acc.x = x3;
-  acc.y = y3;
-}
-
 // acc += b   (add-2008-s).  All products go through the out-of-line multiplier: the tail kernels run a handful of
 // warps, and 14 inlined products (~80 KB of SASS per addition) made them instruction-fetch bound.
 DEV void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {

@@ -450,11 +450,12 @@ KERNEL void plan_pieces_kernel(const u32* starts, const u32* ends, u32 nb, u32 n
 
 // into != 0: the buckets already hold the sums of earlier point ranges of the same MSM (Session::add_chunk);
 // a bucket that lies inside the run then starts from its stored sum instead of the identity.
-// FILL: a lane whose accumulator is empty (first entry of a bucket) copies the point and moves straight on to its
-// next entry before the warp's common addition, instead of idling through one addition slot per bucket
-// (1 / 32 of all slots at n = 2^24, c = 20).
-template <bool CALL, bool FILL, int MINB = 3>
-KERNEL void __launch_bounds__(128, MINB) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
+// The gather / bucket-boundary bookkeeping of a lane (cheap, divergent) is separated from the warp's common addition
+// (expensive, convergent).  Variants that were measured and dropped: letting a lane with an empty accumulator copy its
+// point and move straight on to its next entry (no gain: 72.9 ms either way at 2^24, 1 % slower at c = 16), and 4 CTAs
+// per SM at 128 registers (75.3 ms).
+template <bool CALL>
+KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
                                                       u32* piece_bucket, u32 into) {
@@ -500,23 +501,13 @@ KERNEL void __launch_bounds__(128, MINB) accumulate_kernel(const unsigned char* 
       G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
       if (p.inf) continue;
       if (e >> 31) p.y = fp_neg(p.y);
-      if (FILL && xyzz_is_identity(acc)) {
-        acc.x = p.x;
-        acc.y = p.y;
-        acc.zz = fp_one<FqParams>();
-        acc.zzz = acc.zz;
-        continue;
-      }
       px = p.x;
       py = p.y;
       have = true;
       break;
     }
     if (!have) break;
-    if (FILL)
-      xyzz_add_affine_nz<CALL>(acc, px, py);
-    else
-      xyzz_add_affine_t<CALL>(acc, px, py);
+    xyzz_add_affine_t<CALL>(acc, px, py);
   }
   if (cur_end == end && !cut_at_start) {
     buckets[wb] = acc;  // the bucket ends exactly with the run and began inside it

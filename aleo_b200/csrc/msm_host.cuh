@@ -378,21 +378,16 @@ struct Session {
     st.mark("plan", s);
     st.report(s);
     if (phase_ev) cudaEventRecord(phase_ev[1], s);
-    // ALEO_B200_MSM_ACC: i = inlined field products, f = fill step (A/B switches for tuning); default: calls, no fill
-    // (measured on B200, accumulate ms at 2^24 c=20 / 2^24 c=16 / 2^22 c=17: fill 72.9 / 89.8 / 21.3, no fill 72.9 / 88.9 / 21.0)
-    static const char acc_mode = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e ? e[0] : 'n'; }();
-#define ACC_LAUNCH(CALLV, FILLV)                                                                                              \
-  LAUNCH_NOSYNC((accumulate_kernel<CALLV, FILLV>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted, \
+    // ALEO_B200_MSM_ACC=i: inlined field products instead of the two out-of-line functions (A/B switch behind the
+    // I-cache finding of DESIGN.md: 85.0 against 72.9 ms at 2^24)
+    static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
+#define ACC_LAUNCH(CALLV)                                                                                              \
+  LAUNCH_NOSYNC((accumulate_kernel<CALLV>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted, \
                 (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into)
-    if (acc_mode == 'i')
-      ACC_LAUNCH(false, false);
-    else if (acc_mode == 'f')
-      ACC_LAUNCH(true, true);
-    else if (acc_mode == '4')  // 4 CTAs per SM (128 registers, spills): experiment
-      LAUNCH_NOSYNC((accumulate_kernel<true, false, 4>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
+    if (acc_inline)
+      ACC_LAUNCH(false);
     else
-      ACC_LAUNCH(true, false);
+      ACC_LAUNCH(true);
 #undef ACC_LAUNCH
     if (phase_ev) cudaEventRecord(phase_ev[2], s);
     TailTrace tr;
