@@ -193,15 +193,20 @@ KERNEL void count_kernel_sm(const u32* scalars, u32 n, Params prm, u32* counts) 
   }
 }
 
+// gridDim.y > 1: bucket-range passes.  A resident SRS shares one bucket set, so window-major order cannot shrink
+// the set of live bucket heads; instead pass blockIdx.y only emits the entries whose bucket lies in its
+// 1 / gridDim.y slice of the set (2^22 buckets x 32-byte sectors = 134 MB of heads at c = 23: four passes of 32 MB).
 KERNEL void scatter_kernel_sm(const u32* scalars, u32 n, Params prm, u32* cursor, u32* sorted) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 slice_shift = (gridDim.y > 1) ? (prm.c - 1 - (31 - __clz((int)gridDim.y))) : 31;
   u32 t[8];
   const u32 flip = load_scalar(scalars + (size_t)(i < n ? i : 0) * 8, t, prm.half_range);
   u32 li = i, member = 0;
   if (prm.nbatch && i < n) member = batch_member(prm, i, li);
   u32 carry = 0, neg = 0;
   for (u32 w = 0; w < prm.W; w++) {
-    const u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
+    u32 mag = (i < n) ? recode_digit(t, w, prm.c, carry, neg) : 0u;
+    if (mag && gridDim.y > 1 && ((mag - 1) >> slice_shift) != blockIdx.y) mag = 0;  // another pass owns this bucket
     const u32 pos = warp_aggregated_inc(cursor, mag ? bucket_slot(prm, w, mag, member) : 0u, mag != 0);
     if (mag) sorted[pos] = entry_index(prm, w, li) | ((neg ^ flip) << 31);
   }

@@ -369,8 +369,15 @@ struct Session {
     st.mark("scan", s);
     if (scatter_wm)
       LAUNCH_NOSYNC(scatter_kernel, dim3(g_n, p.W), dim3(256), 0, s, scalars, n, p, ends, sorted);
-    else
-      LAUNCH_NOSYNC(scatter_kernel_sm, dim3(g_all), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    else {
+      // single bucket set (resident SRS) whose heads outgrow L2: bucket-range passes (power of two, <= 8)
+      u32 passes = 1;
+      if (srs && !prm.nbatch && !sort_env)
+        while (passes < 8 && ((size_t)p.B * 32) / passes > ((size_t)48 << 20) && (p.B / passes) > 1) passes <<= 1;
+      if (const char* pe = getenv("ALEO_B200_MSM_SRS_PASSES"))  // tests: force the number of bucket-range passes
+        if (srs && !prm.nbatch && (atoi(pe) == 2 || atoi(pe) == 4 || atoi(pe) == 8) && p.B >= 8) passes = (u32)atoi(pe);
+      LAUNCH_NOSYNC(scatter_kernel_sm, dim3(g_all, passes), dim3(256), 0, s, scalars, n, p, ends, sorted);
+    }
     }
     st.mark("scatter", s);
     LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB, p.nlanes,

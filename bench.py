@@ -125,6 +125,15 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(log_n, world):
+    """the `config` object shared by both arms (BASELINE.json configs[1]: the sweep's largest single-GPU size)"""
+    return {"workload": "BLS12-377 G1 MSM n=2^%d points per GPU (point range of an %d*2^%d-point MSM; bases (s0+i*d)G 104-byte "
+                        "stride, uniform 252-bit scalars), bases+scalars resident in HBM; N>1 adds the single final combine"
+                        % (log_n, world, log_n),
+            "log_n": log_n, "cache": "inputs (%.1f GB per GPU) larger than L2" % ((1 << log_n) * 136 / 1e9),
+            "parallelism": "point-range shard x%d" % world}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,8 +146,9 @@ def run_reference(args):
         "impl": "reference", "metric": "bls12_377_g1_msm_mpts_per_s", "value": val, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_run"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (384-bit Montgomery Fq)", "data": "synthetic",
-        "config": {"workload": "G1 MSM, CPU arm: bounded sample n=2^%d of the n=2^%d-per-GPU workload" % (sample, args.log_n),
-                   "log_n": args.log_n, "sample_log_n": sample},
+        "config": dict(workload_config(args.log_n, max(1, args.gpus)),
+                       reference_sample="CPU arm: each step is a bounded sample n=2^%d of the n=2^%d-per-GPU workload" % (sample, args.log_n),
+                       sample_log_n=sample),
         "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                          "note": "C restatement of the Pippenger algorithm class (oracle/oracle.c); the snarkVM Rust binary "
                                  "cannot be built here (no Rust toolchain)"},
@@ -621,11 +631,7 @@ def run_ours(args):
             "metric": "bls12_377_g1_msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (384-bit Montgomery Fq, 256-bit Fr)", "data": "synthetic",
-            "config": {"workload": "BLS12-377 G1 MSM n=2^%d points per GPU (point range of an %d*2^%d-point MSM; bases (s0+i*d)G 104-byte "
-                                   "stride, uniform 252-bit scalars), bases+scalars resident in HBM; N>1 adds the single final combine"
-                                   % (log_n, world, log_n),
-                       "log_n": log_n, "window_bits": c_bits, "cache": "inputs (%.1f GB per GPU) larger than L2" % (n * 136 / 1e9),
-                       "parallelism": "point-range shard x%d" % world},
+            "config": dict(workload_config(log_n, world), window_bits=c_bits),
             "checked_against_oracle": checked and e2e_ok,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
                     "api": "aleo_b200_msm_g1 (host pointers, pinned)", "point_ranges": host_plan["ranges"],

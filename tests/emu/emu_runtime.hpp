@@ -101,6 +101,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool needs_sync, F body) {
 inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomic_add_shared_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 
 // ---- the handful of runtime calls the host drivers use ----------------------------------------
 typedef int cudaError_t;

@@ -287,6 +287,23 @@ def test_emu_poly_helpers(emu_lib, n):
         assert o.fr_vec_from_bytes(q.raw) == o.divide_by_linear(c, zz), zz
 
 
+def test_emu_srs_bucket_range_passes(emu_lib, monkeypatch):
+    """resident SRS scatter in 4 bucket-range passes (what 2^24-point handles do so that the live bucket heads fit L2)"""
+    monkeypatch.setenv("ALEO_B200_MSM_SRS_PASSES", "4")
+    n = 500
+    B = o.synthetic_bases(n, 171)
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    h = C.c_void_p()
+    emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, 104, None), "srs_create")
+    s = o.random_fr_vec(n, 172)
+    s[0], s[1], s[2] = 0, 1, o.R_MOD - 1
+    sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), n * 32)
+    out = C.create_string_buffer(144)
+    emu_lib.check(emu_lib.srs_msm_dev(h, C.cast(out, C.c_void_p), C.cast(sb, C.c_void_p), n, None), "srs_msm")
+    assert out.raw == o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+    emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
 def test_emu_kzg_open(emu_lib):
     n = 300
     B = o.synthetic_bases(n, 91)
