@@ -53,12 +53,15 @@ SYMBOLS = [
     ("aleo_b200_srs_msm_launches", _int, [_vp, _sz]),
     ("aleo_b200_kzg_commit", _int, [_vp, _vp, _vp, _sz]),
     ("aleo_b200_kzg_commit_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
+    ("aleo_b200_kzg_commit_hiding_dev", _int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_kzg_commit_batch_dev", _int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp]),
     ("aleo_b200_field_op_dev", _int, [_int, _int, _vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_fr_distribute_powers_dev", _int, [_vp, _sz, _vp, _vp, _vp]),
     ("aleo_b200_fr_poly_eval_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_fr_divide_by_linear_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_kzg_open_dev", _int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    ("aleo_b200_g1_decompress_dev", _int, [_vp, _sz, _vp, _sz, _vp]),
+    ("aleo_b200_g1_compress_dev", _int, [_vp, _vp, _sz, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
     ("aleo_b200_msm_host_plan", _int, [_sz, C.POINTER(_int), C.POINTER(_int)]),

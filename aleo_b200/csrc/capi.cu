@@ -446,6 +446,27 @@ int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const
   return rc2;
 }
 
+int aleo_b200_g1_decompress_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream) {
+  if (!stride_ok(affine_stride)) return ALEO_B200_EINVAL;
+  if (n == 0) return 0;
+  if (out_affine_dev == nullptr || in48_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  u32 bad = 0;
+  API_CK(aleo::g1_decompress(in48_dev, n, out_affine_dev, (u32)affine_stride, (cudaStream_t)stream, &bad));
+  return bad > 0x7fffffffu ? 0x7fffffff : (int)bad;
+}
+
+int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t affine_stride, size_t n, void* stream) {
+  if (!stride_ok(affine_stride)) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  if (out48_dev == nullptr || affine_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::g1_compress_affine(affine_dev, (u32)affine_stride, n, out48_dev, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   if (kind < 0 || kind > 3 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
@@ -542,6 +563,29 @@ int aleo_b200_srs_msm(const void* handle, void* out_projective_host, const void*
 
 int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs) {
   return srs_host_call(handle, out_compressed48_host, 48, coeffs_montgomery_host, n_coeffs, true);
+}
+
+int aleo_b200_kzg_commit_hiding_dev(const void* handle_beta, const void* handle_beta_gamma, void* out_compressed48_dev,
+                                    const void* coeffs_montgomery_dev, size_t n_coeffs, const void* random_coeffs_montgomery_dev,
+                                    size_t n_random, void* stream) {
+  if (handle_beta == nullptr || handle_beta_gamma == nullptr || out_compressed48_dev == nullptr) return ALEO_B200_EINVAL;
+  if ((n_coeffs && coeffs_montgomery_dev == nullptr) || (n_random && random_coeffs_montgomery_dev == nullptr)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* d = nullptr;
+  const size_t sb = ((n_coeffs > n_random ? n_coeffs : n_random) * 32 + 255) & ~(size_t)255;
+  API_CK(cudaMallocAsync((void**)&d, sb + 512, s));
+  unsigned char* parts = d + sb;  // two 144-byte partial results, then the sum
+  cudaError_t e = aleo::fr_to_bigint(coeffs_montgomery_dev, d, n_coeffs, s);
+  if (e == cudaSuccess) e = aleo::srs_msm(handle_beta, d, n_coeffs, parts, s, false, nullptr, nullptr);
+  if (e == cudaSuccess) e = aleo::fr_to_bigint(random_coeffs_montgomery_dev, d, n_random, s);
+  if (e == cudaSuccess) e = aleo::srs_msm(handle_beta_gamma, d, n_random, parts + 144, s, false, nullptr, nullptr);
+  if (e == cudaSuccess) e = aleo::g1_sum(parts, 2, parts + 288, s);
+  if (e == cudaSuccess) e = aleo::g1_compress(parts + 288, out_compressed48_dev, s);
+  cudaFreeAsync(d, s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return ALEO_B200_OK;
 }
 
 int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_dev, const void* const* coeffs_dev_ptrs_host,

@@ -53,6 +53,8 @@ cudaError_t field_op(int field, int op, void* out_dev, const void* a_dev, const 
 cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s);
 cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
 cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
+cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out);
+cudaError_t g1_compress_affine(const void* affine_dev, u32 stride, size_t n, void* out48_dev, cudaStream_t s);
 // util_lib.cu
 cudaError_t util_upload_constants();
 cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);

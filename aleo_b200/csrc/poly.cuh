@@ -241,3 +241,136 @@ KERNEL void shift_down_kernel(const Fr* p, u64 n, Fr* q) {
 }
 
 }  // namespace poly
+
+// =============================================================================================
+// Compressed G1 wire format (snarkVM CanonicalSerialize / CanonicalDeserialize of G1Affine, the format of every
+// commitment inside a proof and of the points in key files; pinned by the reference's own proof string
+// wasm/src/programs/transaction.rs:100): 48 bytes, x canonical little-endian, bit 383 = y is the
+// larger root, bit 382 = infinity.  SURVEY.md 8f rank 3.
+// =============================================================================================
+namespace wire {
+
+// square root in Fq by Tonelli-Shanks (p - 1 = 2^46 t; z = 15^t); returns false when a is not a square
+DEV bool fq_sqrt(const Fq& a, Fq& root) {
+  if (fp_is_zero(a)) {
+    root = a;
+    return true;
+  }
+  u32 e[FqParams::N];
+#pragma unroll
+  for (int i = 0; i < FqParams::N; i++) e[i] = FqParams::TS_T_MINUS_1_DIV_2(i);
+  const Fq w0 = fp_pow(a, e, FqParams::N);  // a^((t-1)/2)
+  Fq x = fp_mul(a, w0);                     // a^((t+1)/2)
+  Fq b = fp_mul(x, w0);                     // a^t
+  Fq z = fp_const<FqParams, FqParams::TS_ROOT_M>();
+  const Fq one = fp_one<FqParams>();
+  u32 v = FQ_TWO_ADICITY;
+  while (!fp_eq(b, one)) {
+    u32 k = 0;
+    Fq b2 = b;
+    while (!fp_eq(b2, one)) {  // least k with b^(2^k) = 1
+      b2 = fp_sqr(b2);
+      k++;
+      if (k == v) return false;  // a is not a square
+    }
+    Fq w = z;
+    for (u32 i = 0; i + k + 1 < v; i++) w = fp_sqr(w);  // z^(2^(v-k-1))
+    z = fp_sqr(w);
+    b = fp_mul(b, z);
+    x = fp_mul(x, w);
+    v = k;
+  }
+  root = x;
+  return true;
+}
+
+// y > (p - 1) / 2 for a canonical (non-Montgomery) y
+DEV bool is_larger_root(const Fq& y_canon) {
+  for (int k = FqParams::N - 1; k >= 0; k--) {
+    const u32 h = FqParams::HALF_P_MINUS_1(k);
+    if (y_canon.l[k] != h) return y_canon.l[k] > h;
+  }
+  return false;
+}
+
+DEV void store_affine(unsigned char* out, u32 stride, size_t i, const Fq& x, const Fq& y, bool inf) {
+  uint2* q = reinterpret_cast<uint2*>(out + i * stride);
+  const Fq zero = fp_zero<FqParams>();
+  const Fq ox = inf ? zero : x;
+  const Fq oy = inf ? (stride >= 97 ? fp_one<FqParams>() : zero) : y;  // Rust: Affine::zero() = (0, 1, infinity)
+#pragma unroll
+  for (int k = 0; k < 6; k++) q[k] = make_uint2(ox.l[2 * k], ox.l[2 * k + 1]);
+#pragma unroll
+  for (int k = 0; k < 6; k++) q[6 + k] = make_uint2(oy.l[2 * k], oy.l[2 * k + 1]);
+  if (stride >= 97) q[12] = make_uint2(inf ? 1u : 0u, 0u);
+}
+
+// out[i] = affine point of in48[i]; invalid encodings (x >= p, x^3 + 1 not a square, stray bits with the infinity
+// flag are ignored as upstream does) are stored as the identity and counted in *bad
+KERNEL void __launch_bounds__(128) g1_decompress_kernel(const unsigned char* in48, u32 n, unsigned char* out, u32 stride, u32* bad) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2* q = reinterpret_cast<const uint2*>(in48 + (size_t)i * 48);
+  Fq xc;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const uint2 t = q[k];
+    xc.l[2 * k] = t.x;
+    xc.l[2 * k + 1] = t.y;
+  }
+  const u32 top = xc.l[FqParams::N - 1];
+  const bool y_flag = (top >> 31) & 1u, inf_flag = (top >> 30) & 1u;
+  xc.l[FqParams::N - 1] = top & 0x3fffffffu;
+  if (inf_flag) {
+    store_affine(out, stride, i, xc, xc, true);
+    return;
+  }
+  // x < p ?
+  bool lt = false;
+  for (int k = FqParams::N - 1; k >= 0; k--) {
+    if (xc.l[k] != FqParams::MOD(k)) {
+      lt = xc.l[k] < FqParams::MOD(k);
+      break;
+    }
+  }
+  Fq x = fp_to_mont(xc), y;
+  const Fq rhs = fp_add(fp_mul(fp_sqr(x), x), fp_one<FqParams>());
+  if (!lt || !fq_sqrt(rhs, y)) {
+    atomic_add_u32(bad, 1u);
+    store_affine(out, stride, i, x, x, true);
+    return;
+  }
+  if (is_larger_root(fp_from_mont(y)) != y_flag) y = fp_neg(y);
+  store_affine(out, stride, i, x, y, false);
+}
+
+KERNEL void __launch_bounds__(128) g1_compress_affine_kernel(const unsigned char* in, u32 stride, u32 n, unsigned char* out48) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = in + (size_t)i * stride;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+  Fq x, y;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const uint2 a = q[k], b = q[6 + k];
+    x.l[2 * k] = a.x;
+    x.l[2 * k + 1] = a.y;
+    y.l[2 * k] = b.x;
+    y.l[2 * k + 1] = b.y;
+  }
+  const bool inf = (stride >= 97) ? (p[96] != 0) : (fp_is_zero(x) && fp_is_zero(y));
+  Fq xc = fp_zero<FqParams>();
+  u32 flags = 0;
+  if (inf) {
+    flags = 1u << 30;
+  } else {
+    xc = fp_from_mont(x);
+    if (is_larger_root(fp_from_mont(y))) flags = 1u << 31;
+  }
+  xc.l[FqParams::N - 1] |= flags;
+  uint2* o = reinterpret_cast<uint2*>(out48 + (size_t)i * 48);
+#pragma unroll
+  for (int k = 0; k < 6; k++) o[k] = make_uint2(xc.l[2 * k], xc.l[2 * k + 1]);
+}
+
+}  // namespace wire

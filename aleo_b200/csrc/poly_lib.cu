@@ -109,6 +109,29 @@ cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size
   return e;
 }
 
+// 48-byte compressed G1 -> affine (stride 104 / 96); *bad_out = number of invalid encodings.  Synchronises s.
+cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out) {
+  *bad_out = 0;
+  if (n == 0) return cudaSuccess;
+  u32* bad = nullptr;
+  PL_CK(cudaMallocAsync((void**)&bad, 4, s));
+  cudaMemsetAsync(bad, 0, 4, s);
+  LAUNCH_NOSYNC(wire::g1_decompress_kernel, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)in48_dev, (u32)n,
+                (unsigned char*)out_affine_dev, stride, bad);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bad_out, bad, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(bad, s);
+  return e;
+}
+
+cudaError_t g1_compress_affine(const void* affine_dev, u32 stride, size_t n, void* out48_dev, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  LAUNCH_NOSYNC(wire::g1_compress_affine_kernel, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)affine_dev,
+                stride, (u32)n, (unsigned char*)out48_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t field_op(int field, int op, void* out, const void* a, const void* b, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   return field == 0 ? field_op_t<FrParams>(op, out, a, b, n, s) : field_op_t<FqParams>(op, out, a, b, n, s);

@@ -113,3 +113,17 @@ class KZG10:
             srs._lib.check(srs._lib.kzg_commit_batch_dev(srs._h, out.data_ptr(), ptrs, lens, count,
                                                          torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_batch_dev")
         return out[:count]
+
+    @staticmethod
+    def commit_hiding_dev(srs_beta: ResidentSRS, srs_beta_gamma: ResidentSRS, coeffs_t, random_coeffs_t, out=None):
+        """KZG10::commit with a hiding bound: msm(powers_of_beta_g, coeffs) + msm(powers_of_beta_times_gamma_g, random)"""
+        import torch
+
+        if out is None:
+            out = torch.empty(48, dtype=torch.uint8, device=coeffs_t.device)
+        with torch.cuda.device(coeffs_t.device):
+            srs_beta._lib.check(srs_beta._lib.kzg_commit_hiding_dev(
+                srs_beta._h, srs_beta_gamma._h, out.data_ptr(), coeffs_t.data_ptr(), coeffs_t.numel() * coeffs_t.element_size() // 32,
+                random_coeffs_t.data_ptr(), random_coeffs_t.numel() * random_coeffs_t.element_size() // 32,
+                torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_hiding_dev")
+        return out

@@ -147,6 +147,13 @@ int aleo_b200_srs_msm_launches(const void* handle, size_t n_used);
 int aleo_b200_kzg_commit(const void* handle, void* out_compressed48_host, const void* coeffs_montgomery_host, size_t n_coeffs);
 int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                              void* stream);
+/* KZG10::commit with a hiding bound: commitment = msm(powers_of_beta_g, coeffs) + msm(powers_of_beta_times_gamma_g,
+ * random_coeffs), the second polynomial being the blinding polynomial the caller drew (src/polycommit/kzg10/mod.rs
+ * `commit`: `random_ints` against `powers_of_beta_times_gamma_g`).  Two resident handles, both
+ * vectors Montgomery Fr on the device, result 48-byte compressed. */
+int aleo_b200_kzg_commit_hiding_dev(const void* handle_beta, const void* handle_beta_gamma, void* out_compressed48_dev,
+                                    const void* coeffs_montgomery_dev, size_t n_coeffs, const void* random_coeffs_montgomery_dev,
+                                    size_t n_random, void* stream);
 /* `count` (<= 64) commitments against the same resident SRS in ONE launch sequence: snarkVM commits the ~13 polynomials
  * of a proof against the same powers (SonicKZG10::commit over an ExecutionPool, src/polycommit/sonic_pc/mod.rs;
  * SURVEY.md 8f rank 1).  The coefficient vectors are sorted together, accumulated by one kernel (every polynomial
@@ -191,6 +198,16 @@ int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, 
 int aleo_b200_fr_divide_by_linear_dev(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);
 int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                            const void* z_host, void* stream);
+
+/* ---- compressed G1 wire format ---------------------------------------------------------
+ * snarkVM's CanonicalSerialize / CanonicalDeserialize of G1Affine -- every commitment inside a proof and the points of
+ * key / SRS files: 48 bytes, x canonical little-endian, bit 383 = y is the larger root, bit 382 = infinity.  Pinned by
+ * the reference's own proof string (wasm/src/programs/transaction.rs:100; tests/golden/proof_fixture.json).
+ * decompress: n x 48 bytes -> n affine points (stride 104 / 96, Montgomery); returns the number of invalid encodings
+ * (x >= p or x^3 + 1 not a square; stored as the identity), < 0 on error; synchronises the stream.
+ * compress: the inverse, asynchronous. */
+int aleo_b200_g1_decompress_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream);
+int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t affine_stride, size_t n, void* stream);
 
 /* ---- synthetic workload generation and on-device checks (bench / tests) --------------------
  * bases[i] = (s0 + (first_index + i) * d) * G, G the G1 generator; s0, d canonical 32-byte scalars.

@@ -445,3 +445,50 @@ def test_emu_msm_partitioned_sort(emu_lib, c, fb, monkeypatch):
     out = C.create_string_buffer(144)
     emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), 96), "msm_g1")
     assert out.raw == want
+
+
+def test_emu_g1_wire_format_on_reference_fixture(emu_lib, golden_dir):
+    """compressed G1 <-> affine on the device kernels, pinned by the REFERENCE's own proof string
+    (wasm/src/programs/transaction.rs:100): its 12 commitments decompress to the points the oracle finds (all in
+    the r-torsion, tests/test_oracle.py) and compress back to the fixture bytes; plus identity / invalid encodings"""
+    fx = json.load(open(os.path.join(golden_dir, "proof_fixture.json")))
+    _, payload = o.bech32m_decode(fx["proof"])
+    chunks = [bytes(payload[off:off + 48]) for off in fx["g1_offsets"]]
+    pts = [o.g1_decompress(c) for c in chunks]
+    extra = [o.g1_mul(o.G1_GEN, k) for k in (1, 2, 12345)] + [None]
+    blob = b"".join(chunks) + b"".join(o.g1_compress(p) for p in extra)
+    bad_x = next(x for x in range(2, 50) if o.fq_sqrt((x ** 3 + 1) % o.P_MOD) is None)
+    blob += o.int_to_le_bytes(bad_x, 48) + o.int_to_le_bytes(o.P_MOD + 1, 48)          # not on the curve; x >= p
+    n = len(blob) // 48
+    for stride in (104, 96):
+        src = C.create_string_buffer(blob, len(blob))
+        out = C.create_string_buffer(n * stride)
+        nbad = emu_lib.g1_decompress_dev(C.cast(out, C.c_void_p), stride, C.cast(src, C.c_void_p), n, None)
+        assert nbad == 2
+        want = o.g1_affine_vec_to_bytes(pts + extra + [None, None], stride)
+        assert out.raw == want
+        back = C.create_string_buffer(n * 48)
+        emu_lib.check(emu_lib.g1_compress_dev(C.cast(back, C.c_void_p), C.cast(out, C.c_void_p), stride, n, None), "compress")
+        assert back.raw[:48 * (n - 2)] == blob[:48 * (n - 2)]
+        assert back.raw[48 * (n - 2):] == o.g1_compress(None) * 2
+
+
+def test_emu_kzg_commit_hiding(emu_lib):
+    """commitment + blinding commitment against a second SRS (powers_of_beta_times_gamma_g)"""
+    n, m = 120, 5
+    B1, B2 = o.synthetic_bases(n, 181), o.synthetic_bases(m, 182)
+    hs = []
+    for B in (B1, B2):
+        bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), len(B) * 104)
+        h = C.c_void_p()
+        emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), len(B), 104, None), "srs_create")
+        hs.append(h)
+    p, r = o.random_fr_vec(n, 183), o.random_fr_vec(m, 184)
+    pb = C.create_string_buffer(o.fr_vec_to_bytes(p), n * 32)
+    rb = C.create_string_buffer(o.fr_vec_to_bytes(r), m * 32)
+    out = C.create_string_buffer(48)
+    emu_lib.check(emu_lib.kzg_commit_hiding_dev(hs[0], hs[1], C.cast(out, C.c_void_p), C.cast(pb, C.c_void_p), n,
+                                                C.cast(rb, C.c_void_p), m, None), "hiding")
+    assert out.raw == o.g1_compress(o.g1_add(o.msm_pippenger(B1, p), o.msm_pippenger(B2, r)))
+    for h in hs:
+        emu_lib.check(emu_lib.srs_destroy(h), "destroy")

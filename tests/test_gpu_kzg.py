@@ -81,3 +81,24 @@ def test_commit_batch_equals_single_commits():
         assert got[7].cpu().numpy().tobytes() == o.g1_compress(None)
     finally:
         srs.close()
+
+
+def test_commit_hiding_is_commit_plus_blinding_commit():
+    import torch
+
+    n, m = 5000, 4
+    s0, d = o.base_dlogs(n, 31)
+    t0, e = o.base_dlogs(m, 32)
+    srs1 = ab.ResidentSRS.from_device(ab.gen_bases_dev(n, s0, d, 0, 104), n, 104)
+    srs2 = ab.ResidentSRS.from_device(ab.gen_bases_dev(m, t0, e, 0, 104), m, 104)
+    try:
+        p = ab.gen_scalars_dev(n, 33, 0, True)
+        r = ab.gen_scalars_dev(m, 34, 0, True)
+        got = ab.KZG10.commit_hiding_dev(srs1, srs2, p, r).cpu().numpy().tobytes()
+        pc = o.fr_vec_from_bytes(p.cpu().numpy().tobytes())
+        rc = o.fr_vec_from_bytes(r.cpu().numpy().tobytes())
+        k = (sum(c * (s0 + i * d) for i, c in enumerate(pc)) + sum(c * (t0 + i * e) for i, c in enumerate(rc))) % o.R_MOD
+        assert got == o.g1_compress(o.g1_mul(o.G1_GEN, k))
+    finally:
+        srs1.close()
+        srs2.close()
