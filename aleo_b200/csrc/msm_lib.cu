@@ -35,9 +35,14 @@ int chunk_schedule(size_t n, size_t* sizes) {
   const char* env = getenv("ALEO_B200_MSM_CHUNKS");  // read per call: tests and sweeps switch it
   const long k_env = env ? atol(env) : 0L;
   int k = n < ((size_t)1 << 19) ? 1 : (n < ((size_t)1 << 22) ? 2 : 3);
-  if (k_env >= 1 && k_env <= 3 && n >= 8) k = (int)k_env;
+  if (k_env >= 1 && k_env <= 4 && n >= 16) k = (int)k_env;
   if (k == 1) {
     sizes[0] = n;
+  } else if (k == 4) {
+    sizes[0] = n / 16;
+    sizes[1] = (n * 3) / 16;
+    sizes[2] = n / 4;
+    sizes[3] = n - sizes[0] - sizes[1] - sizes[2];
   } else if (k == 2) {
     sizes[0] = n / 4;
     sizes[1] = n - sizes[0];
@@ -50,7 +55,7 @@ int chunk_schedule(size_t n, size_t* sizes) {
 }
 
 struct EventSet {
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // ev[4]: allocation ordered; 0..3, 5: ranges
   cudaError_t init() {
     for (auto& e : ev) {
       cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -252,8 +257,8 @@ cudaError_t msm_run_host(const void* bases_host, u32 stride, const void* scalars
       e = feed_h2d(d + o_s + first * 32, (const unsigned char*)scalars_host + first * 32, m * 32, cs, evs.ev[4]);
       if (e == cudaSuccess)
         e = feed_h2d(d + first * stride, (const unsigned char*)bases_host + first * stride, m * stride, cs, evs.ev[4]);
-      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i], 0);
+      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i < 4 ? i : 5], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i < 4 ? i : 5], 0);
       if (e == cudaSuccess) e = ss.add_chunk(d + first * stride, stride, (const u32*)(d + o_s + first * 32), m, first, s);
       first += m;
     }
@@ -385,8 +390,8 @@ cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool
     if (e == cudaSuccess) e = ss.begin(n, max_chunk, (u32)k, &v, s, false);
     for (int i = 0; i < k && e == cudaSuccess; i++) {
       e = feed_h2d(d + first * 32, (const unsigned char*)in_host + first * 32, sizes[i] * 32, cs, evs.ev[4]);
-      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i], cs);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i], 0);
+      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[i < 4 ? i : 5], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[i < 4 ? i : 5], 0);
       if (e == cudaSuccess && montgomery_in) e = fr_to_bigint(d + first * 32, d + first * 32, sizes[i], s);
       if (e == cudaSuccess) e = ss.add_chunk(nullptr, 96, (const u32*)(d + first * 32), sizes[i], first, s);
       first += sizes[i];
