@@ -33,7 +33,7 @@ build/libaleo_b200_emu.so: $(EMUOBJ)
 oracle: oracle/_build/liboracle.so
 oracle/_build/liboracle.so: oracle/oracle.c
 	@mkdir -p oracle/_build
-	$(CC) -O3 -march=native -fPIC -shared -pthread -o $@ $<
+	$(CC) -O3 -march=x86-64-v3 -fPIC -shared -pthread -o $@ $<
 
 clean:
 	rm -rf build aleo_b200/libaleo_b200.so oracle/_build
