@@ -459,7 +459,18 @@ KERNEL void plan_pieces_kernel(const u32* starts, const u32* ends, u32 nb, u32 n
 // (expensive, convergent).  Variants that were measured and dropped: letting a lane with an empty accumulator copy its
 // point and move straight on to its next entry (no gain: 72.9 ms either way at 2^24, 1 % slower at c = 16), and 4 CTAs
 // per SM at 128 registers (75.3 ms).
-template <bool CALL>
+// pulls the two cache lines of base `idx` towards L1 (no registers held, unlike loading it early)
+DEV void prefetch_base(const unsigned char* bases, size_t stride, u32 idx) {
+#ifndef ALEO_EMU
+  const unsigned char* p = bases + (size_t)idx * stride;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 88));
+#else
+  (void)bases; (void)stride; (void)idx;
+#endif
+}
+
+template <bool CALL, bool PREFETCH = false>
 KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
@@ -504,6 +515,7 @@ KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bas
       const u32 e = sorted[pos];
       pos++;
       G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
+      if (PREFETCH && pos < end) prefetch_base(bases, stride, sorted[pos] & 0x7fffffffu);  // the next gather, while this addition runs
       if (p.inf) continue;
       if (e >> 31) p.y = fp_neg(p.y);
       px = p.x;

@@ -391,8 +391,13 @@ struct Session {
 #define ACC_LAUNCH(CALLV)                                                                                              \
   LAUNCH_NOSYNC((accumulate_kernel<CALLV>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted, \
                 (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into)
+    // next base prefetched into L1 while the current addition runs: 73.00 -> 72.71 ms at 2^24 (n = no prefetch)
+    static const bool acc_prefetch = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return !(e && e[0] == 'n'); }();
     if (acc_inline)
       ACC_LAUNCH(false);
+    else if (acc_prefetch)
+      LAUNCH_NOSYNC((accumulate_kernel<true, true>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
+                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
     else
       ACC_LAUNCH(true);
 #undef ACC_LAUNCH
