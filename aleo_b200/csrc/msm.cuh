@@ -5,26 +5,32 @@
 // commit_lagrange / open and reached from the reference at rust/src/program/execute.rs:74,177.
 //
 // Pipeline (all on device, nothing returns to the host until the 144-byte result):
-//   1 count     signed-window recoding of every scalar (digits in [-2^(c-1), 2^(c-1)]), histogram
-//               of (window, |digit|-1) with L2 atomics                                  [HBM/atomic]
-//   2 scan      exclusive scan of the histogram -> bucket start offsets                 [tiny]
+//   1 count     half-range scalars (s > (r-1)/2 -> r - s on the negated point), signed-window recoding (digits in
+//               [-2^(c-1), 2^(c-1)]), histogram of (window, |digit|-1) with L2 atomics, one atomic per distinct
+//               slot of a warp when the warp has duplicates                               [atomic]
+//   2 scan      exclusive scan of the histogram -> bucket start offsets                   [tiny]
 //   3 scatter   recode again, claim a slot per (window, bucket) with an atomic cursor, write
-//               point index | sign<<31   (order inside a bucket is irrelevant: + commutes) [HBM]
+//               point index | sign<<31 (order inside a bucket is irrelevant: + commutes); window-major, or in
+//               bucket-range passes for a resident SRS, once the bucket heads outgrow L2   [atomic / HBM]
 //   4 plan      the sorted entry list is cut into equal runs, one per thread; buckets cut by a run
 //               boundary are listed for the combine step (skew-proof: KZG witnesses are full of 0 / 1)
-//   5 accumulate one thread per run: XYZZ mixed additions of gathered affine bases       [IMAD]
-//               -- this is >95 % of the work: n * W additions of 8M + 2S in Fq
+//   5 accumulate one thread per run: XYZZ mixed additions (8 products + 2 dedicated squares, two out-of-line field
+//               functions) of gathered affine bases                                        [IMAD.WIDE]
+//               -- ~80 % of the time: n * W additions
 //   6 combine   the pieces of cut buckets are added (thread per bucket, or CTA per bucket)
-//   7 reduce    per window sum_b (b+1) * bucket[b] by chunked running sums, one launch per level
-//   8 final     per window 2^(c w) * S_w (windows in parallel), sum, one inversion -> normalised Jacobian
+//   7 reduce    per window sum_b (b+1) * bucket[b]: chunk levels (running sums) down to <= 256 elements per
+//               window, then one CTA per window (log-depth suffix scan + tree)
+//   8 tail      one CTA: a quad of lanes per window doubles 2^(c w) S_w cooperatively, tree over the windows,
+//               one binary-GCD inversion -> normalised Jacobian
+// A resident SRS (bases expanded to 2^(c w) P_i) shares one bucket set across windows and has no step-8 doublings;
+// a batch of MSMs against one SRS gives every member its own bucket set.  Host-pointer calls run steps 1-6 once
+// per point range while the next range is copied, the buckets accumulating across ranges.
 #pragma once
 #include "g1.cuh"
 
 namespace msm {
 
 constexpr u32 SCALAR_BITS = 253;
-constexpr u32 RED_LOG_KC = 4;            // bucket-reduction chunk: 16 buckets per thread
-constexpr u32 RED_KC = 1u << RED_LOG_KC;
 constexpr u32 SMALL_SPLIT_MAX = 64;      // split buckets with <= 64 tasks are combined by one thread
 constexpr u32 COMBINE_TPB = 128;
 

@@ -7,8 +7,8 @@
 // coset variants shift by g = 22 (forward: c_i *= g^i before; inverse: c_i *= g^-i after).
 //
 // Design (B200 first, not a translation of any CPU loop nest):
-//   * N = 2^L is split into P = ceil(L/9) passes of K_p <= 9 bits (a 9-bit pass = three radix-8 steps).  One pass = one HBM round trip
-//     (64 B per element), so the algorithmic traffic is 64*P bytes per element.
+//   * N = 2^L is split into P = ceil(L/9) passes of K_p <= 9 bits (a 9-bit pass = three radix-8 steps).
+//     One pass = one HBM round trip (64 B per element), so the algorithmic traffic is 64*P bytes per element.
 //   * A pass handles a 2048-element tile per 256-thread CTA: every thread owns 8 elements in
 //     registers, does radix-8 / radix-4 / radix-2 butterflies on them, and trades elements with
 //     the other threads of the CTA through a 64 KB shared-memory tile (two uint4 planes, so all
@@ -16,10 +16,13 @@
 //   * Global accesses are 256-bit (LDG.E.256 / STG.E.256), each warp touching runs of >= 256
 //     contiguous bytes.  The last pass writes the digit-reversed (natural-order) positions
 //     directly, so no separate permutation pass exists.
-//   * Twiddles: the inter-pass factor w^(i2*k1) is rebuilt from two L2-resident power tables
-//     (w^lo * w^(hi<<lo_bits)); the in-tile factors come from an 8 KB table of the tile's own root.
-//     The inverse transform's n^-1 and the coset powers ride on the same two-table scheme.
-//   The transform is integer-pipe bound (about 14 Fr products per element at L = 24, 120
+//   * Twiddles: the first inter-pass factor w^(i2*k1) is rebuilt from two L2-resident power tables
+//     (w^lo * w^(hi<<lo_bits)), the later ones are read from a direct table; the in-tile factors come from
+//     an 8-16 KB table of the tile's own root.  The inverse transform's n^-1 and the coset powers ride on
+//     the two-table scheme.
+//   * The same pass kernels run one transform over 2 / 4 / 8 GPUs: local geometry, twiddles at the global
+//     index, and the last-but-one pass stores straight into the peers' receive buffers (PassArgs d_*).
+//   The transform is integer-pipe bound (12.75 Fr products per element at L = 24, 120
 //   IMAD.WIDE each), not HBM bound -- see DESIGN.md for the two rooflines.
 #pragma once
 #include "mont.cuh"
