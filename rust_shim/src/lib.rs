@@ -69,3 +69,51 @@ pub unsafe fn ntt_fr<T>(x_s: &mut [T], log_size_of_group: u32, direction: c_int,
         die("EvaluationDomain::fft", rc);
     }
 }
+
+// ---- resident SRS / KZG10 (src/polycommit/kzg10/mod.rs) -------------------------------------------------------------
+extern "C" {
+    pub fn aleo_b200_srs_create(handle_out: *mut *mut c_void, bases_host: *const c_void, n: usize, affine_stride: usize) -> c_int;
+    pub fn aleo_b200_srs_destroy(handle: *mut c_void) -> c_int;
+    pub fn aleo_b200_srs_msm(handle: *const c_void, out_projective_host: *mut c_void, scalars_host: *const c_void, n_used: usize) -> c_int;
+    pub fn aleo_b200_kzg_commit(handle: *const c_void, out_compressed48_host: *mut c_void, coeffs_montgomery_host: *const c_void, n_coeffs: usize) -> c_int;
+}
+
+/// `Powers::powers_of_beta_g` (or `lagrange_basis_at_beta_g`) kept on the device: uploaded and expanded once, then every
+/// `KZG10::commit` against it only moves the polynomial's coefficients.
+pub struct SrsHandle(*mut c_void);
+unsafe impl Send for SrsHandle {}
+unsafe impl Sync for SrsHandle {} // the library is re-entrant; a handle is immutable after creation
+
+impl SrsHandle {
+    /// # Safety
+    /// `A` must be the 104-byte `G1Affine`.
+    pub unsafe fn new<A>(powers: &[A]) -> Self {
+        assert_eq!(std::mem::size_of::<A>(), 104);
+        let mut h: *mut c_void = std::ptr::null_mut();
+        let rc = aleo_b200_srs_create(&mut h, powers.as_ptr() as *const c_void, powers.len(), 104);
+        if rc != 0 {
+            die("aleo_b200_srs_create", rc);
+        }
+        SrsHandle(h)
+    }
+
+    /// Non-hiding `KZG10::commit`: the polynomial's coefficients as it holds them (`Fp256`, Montgomery) -> the 48-byte
+    /// compressed commitment (`G1Affine::deserialize_compressed` reads it back).
+    /// # Safety
+    /// `T` must be `Fp256<FrParameters>`.
+    pub unsafe fn commit<T>(&self, coeffs: &[T]) -> [u8; 48] {
+        assert_eq!(std::mem::size_of::<T>(), 32);
+        let mut out = [0u8; 48];
+        let rc = aleo_b200_kzg_commit(self.0, out.as_mut_ptr() as *mut c_void, coeffs.as_ptr() as *const c_void, coeffs.len());
+        if rc != 0 {
+            die("KZG10::commit", rc);
+        }
+        out
+    }
+}
+
+impl Drop for SrsHandle {
+    fn drop(&mut self) {
+        unsafe { aleo_b200_srs_destroy(self.0) };
+    }
+}
