@@ -40,6 +40,7 @@ SYMBOLS = [
     ("aleo_b200_ntt_dist_stage2", _int, [_vp, _vp, _int, _int, _vp]),
     ("aleo_b200_ntt_dist_destroy", _int, [_vp]),
     ("aleo_b200_msm_g1", _int, [_vp, _vp, _sz, _vp, _sz]),
+    ("aleo_b200_msm_g1_multi", _int, [_vp, _vp, _sz, _vp, _sz, _int]),
     ("aleo_b200_msm_g1_dev", _int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_msm_g1_dev_profile", _int, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(C.c_float)]),
     ("aleo_b200_g1_sum_dev", _int, [_vp, _vp, _sz, _vp]),

@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#ifndef ALEO_EMU
+#include <thread>
+#endif
+#include <vector>
 #include "internal.h"
 
 namespace {
@@ -322,6 +326,58 @@ int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n
   if (rc) return rc;
   API_CK(aleo::msm_run_host(bases_host, (u32)affine_stride, scalars_host, n, out_projective_host, s));
   return ALEO_B200_OK;
+}
+
+int aleo_b200_msm_g1_multi(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
+                           size_t affine_stride, int n_devices) {
+  if (n_devices < 1 || n_devices > 64) return ALEO_B200_EINVAL;
+  if (n_devices == 1 || n < (size_t)n_devices * 1024) return aleo_b200_msm_g1(out_projective_host, bases_host, n, scalars_host, affine_stride);
+  if (!stride_ok(affine_stride) || out_projective_host == nullptr || bases_host == nullptr || scalars_host == nullptr) return ALEO_B200_EINVAL;
+  if (n_devices > aleo_b200_device_count()) return ALEO_B200_ENODEVICE;
+#ifdef ALEO_EMU
+  return ALEO_B200_ENODEVICE;
+#else
+  int home = 0;
+  cudaGetDevice(&home);
+  std::vector<unsigned char> partials((size_t)n_devices * 144);
+  std::vector<int> rcs(n_devices, ALEO_B200_OK);
+  std::vector<std::thread> workers;
+  const size_t base = n / n_devices, rem = n % n_devices;
+  size_t first = 0;
+  for (int d = 0; d < n_devices; d++) {
+    const size_t cnt = base + ((size_t)d < rem ? 1 : 0);
+    const unsigned char* b = (const unsigned char*)bases_host + first * affine_stride;
+    const unsigned char* sc = (const unsigned char*)scalars_host + first * 32;
+    unsigned char* out = partials.data() + (size_t)d * 144;
+    workers.emplace_back([=, &rcs]() {
+      int rc = aleo_b200_init(d);  // selects device d for this thread and prepares it
+      if (rc == ALEO_B200_OK) rc = aleo_b200_msm_g1(out, b, cnt, sc, affine_stride);
+      rcs[d] = rc;
+    });
+    first += cnt;
+  }
+  for (auto& w : workers) w.join();
+  cudaSetDevice(home);
+  for (int rc : rcs)
+    if (rc) return rc;
+  // single final combine on the calling thread's device
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  unsigned char* dbuf = nullptr;
+  API_CK(cudaMallocAsync((void**)&dbuf, partials.size() + 256, s));
+  cudaError_t e = cudaMemcpyAsync(dbuf, partials.data(), partials.size(), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = aleo::g1_sum(dbuf, (u32)n_devices, dbuf + partials.size(), s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_projective_host, dbuf + partials.size(), 144, cudaMemcpyDeviceToHost, s);
+  cudaFreeAsync(dbuf, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+#endif
 }
 
 int aleo_b200_msm_g1_dev_profile(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,

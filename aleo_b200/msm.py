@@ -47,6 +47,17 @@ class VariableBase:
         return out.raw
 
     @staticmethod
+    def msm_multi(bases, scalars, n_devices: int, affine_stride: int = AFFINE_STRIDE_RUST) -> bytes:
+        """the same MSM spread over the first n_devices GPUs from this one process (aleo_b200_msm_g1_multi)"""
+        lib = _lib.get_lib()
+        bp, bbytes, _keep_b = _host_ptr(bases)
+        sp, sbytes, _keep_s = _host_ptr(scalars)
+        n = min(bbytes // affine_stride, sbytes // 32)
+        out = C.create_string_buffer(PROJECTIVE_BYTES)
+        lib.check(lib.msm_g1_multi(C.cast(out, C.c_void_p), bp, n, sp, affine_stride, n_devices), "aleo_b200_msm_g1_multi")
+        return out.raw
+
+    @staticmethod
     def msm_dev(bases_t, scalars_t, n: int, affine_stride: int = AFFINE_STRIDE_RUST, out=None):
         """device-resident operands (torch CUDA tensors); asynchronous on torch's current stream.
         Returns a uint8 CUDA tensor of 144 bytes."""

@@ -111,6 +111,12 @@ int aleo_b200_ntt_launches(uint32_t log_n);
  * Like upstream the two slices are zipped: n is the shorter length.  n = 0 gives the identity. */
 int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
                      size_t affine_stride);
+/* The same MSM spread over the first `n_devices` GPUs of the node from ONE process (how a single prover process uses
+ * the box; BASELINE config 4 / SURVEY.md 8e): contiguous point ranges, one host thread and stream per device, each
+ * range copied and accumulated as in aleo_b200_msm_g1, and a single final combine of the 144-byte partial sums on
+ * device 0.  n_devices <= aleo_b200_device_count(); 1 is aleo_b200_msm_g1. */
+int aleo_b200_msm_g1_multi(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
+                           size_t affine_stride, int n_devices);
 /* Device-resident operands (bases typically stay resident: the SRS is reused by every commitment).
  * out_projective_dev: 144 B of device memory.  Asynchronous on `stream`. */
 int aleo_b200_msm_g1_dev(void* out_projective_dev, const void* bases_dev, size_t n, const void* scalars_dev,

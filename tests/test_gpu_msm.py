@@ -182,3 +182,21 @@ def test_host_call_streams_point_ranges(chunks, monkeypatch):
         assert srs.msm(sc.cpu().numpy()) == want
     finally:
         srs.close()
+
+
+def test_single_process_multi_gpu_msm():
+    """aleo_b200_msm_g1_multi: one process, one host thread per GPU, point ranges, single final combine.  Uses every
+    visible GPU (1 on the default box: then it must equal the plain call)."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    n = (1 << 18) + 77
+    s0, d = o.base_dlogs(n, 8181)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, 8182)
+    want = o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, ab.dlog_dot_dev(sc, n, s0, d, 0)))
+    hb, hs = bases.cpu().numpy(), sc.cpu().numpy()
+    for k in sorted({1, ndev, min(2, ndev)}):
+        assert ab.VariableBase.msm_multi(hb, hs, k, 104) == want, k
+    assert ab.get_lib().msm_g1_multi(None, None, 10, None, 104, 0) == -1
+    assert ab.get_lib().msm_g1_multi(hb.ctypes.data, hb.ctypes.data, n, hs.ctypes.data, 104, ndev + 1) == -3
