@@ -71,12 +71,20 @@ static inline u32 choose_window_srs(size_t n) {
   return best_c;
 }
 
-// accumulation threads for `n_chunk` points: 16 waves of (148 SMs x 3 CTAs x 128 threads) -- measured best on
-// B200: 4 waves 96.1 ms, 16 waves 93.4 ms at n = 2^24 -- but at least ~32 entries per run
+// Accumulation threads (= equal runs of the sorted entry list) for `n_chunk` points.  At most 16 waves of
+// (148 SMs x 3 CTAs x 128 threads) -- measured best on B200 at n = 2^24: 4 waves 96.1 ms, 16 waves 93.4 ms.  Below
+// that, runs of 64 entries (every run boundary cuts a bucket whose pieces cost two more additions on the latency
+// path: 2^20 runs 3 % faster with 64 than with 32), but never fewer than 4 waves while runs of 32 can fill them.
 static inline u32 lanes_for(size_t n_chunk, u32 W) {
-  size_t lanes = ((size_t)n_chunk * W + 31) / 32;
+  const size_t entries = (size_t)n_chunk * W;
   static const long waves_env = []() { const char* e = getenv("ALEO_B200_MSM_WAVES"); return e ? atol(e) : 0L; }();
-  const size_t full = (size_t)148 * 384 * (waves_env > 0 ? (size_t)waves_env : 16);
+  const size_t wave = (size_t)148 * 384;
+  const size_t full = wave * (waves_env > 0 ? (size_t)waves_env : 16);
+  size_t lanes = (entries + 63) / 64;
+  if (lanes < 4 * wave) {
+    const size_t by32 = (entries + 31) / 32;
+    lanes = by32 < 4 * wave ? by32 : 4 * wave;
+  }
   if (lanes > full) lanes = full;
   if (lanes < 128) lanes = 128;
   return (u32)((lanes + 127) / 128 * 128);
