@@ -456,6 +456,16 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
   return ALEO_B200_OK;
 }
 
+int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_host, size_t n, void* stream) {
+  if (a_host == nullptr) return ALEO_B200_EINVAL;
+  if (n == 0) return ALEO_B200_OK;
+  if (y_inout_dev == nullptr || x_dev == nullptr) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_axpy(y_inout_dev, x_dev, a_host, n, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream) {
   if (g_host == nullptr) return ALEO_B200_EINVAL;
   if (n == 0) return ALEO_B200_OK;

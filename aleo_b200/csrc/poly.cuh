@@ -107,6 +107,11 @@ KERNEL void __launch_bounds__(PW_TPB) distribute_powers_kernel(Fr* a, u64 n, con
   }
 }
 
+// y[i] <- y[i] + a * x[i]: the linear-combination step of SonicKZG10::open_combinations / batch_open (sum_i xi^i p_i)
+KERNEL void __launch_bounds__(256) axpy_kernel(Fr* y, const Fr* x, Fr a, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) y[i] = fp_add(y[i], fp_mul(a, x[i]));
+}
+
 // block-wide sum of one Fr per thread (blockDim.x = PW_TPB), result valid in thread 0
 DEV Fr block_sum(Fr v, Fr* sh) {
   sh[threadIdx.x] = v;

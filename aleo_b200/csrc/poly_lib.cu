@@ -47,6 +47,14 @@ static cudaError_t make_setup(Fr** s_out, const void* g32, const void* k32, cuda
 
 static inline u32 pw_grid(size_t n) { return (u32)((n + (size_t)poly::PW_TPB * poly::PW_RUN - 1) / ((size_t)poly::PW_TPB * poly::PW_RUN)); }
 
+cudaError_t fr_axpy(void* y_dev, const void* x_dev, const void* a32, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  LAUNCH_NOSYNC(poly::axpy_kernel, dim3((u32)blocks), dim3(256), 0, s, (Fr*)y_dev, (const Fr*)x_dev, host_fr(a32), (u64)n);
+  return cudaGetLastError();
+}
+
 cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   Fr* sc = nullptr;

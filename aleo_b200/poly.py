@@ -104,3 +104,15 @@ def divide_by_linear_dev(coeffs_t, z, out=None):
         lib.check(lib.fr_divide_by_linear_dev(out.data_ptr(), coeffs_t.data_ptr(), n, _fr_host(z),
                                               torch.cuda.current_stream().cuda_stream), "aleo_b200_fr_divide_by_linear_dev")
     return out
+
+
+def axpy_dev(y_t, x_t, a):
+    """y += a * x in place (the linear-combination step of SonicKZG10::open_combinations); a canonical int"""
+    import torch
+
+    lib = _lib.get_lib()
+    n = y_t.numel() * y_t.element_size() // 32
+    with torch.cuda.device(y_t.device):
+        lib.check(lib.fr_axpy_dev(y_t.data_ptr(), x_t.data_ptr(), _fr_host(a), n, torch.cuda.current_stream().cuda_stream),
+                  "aleo_b200_fr_axpy_dev")
+    return y_t

@@ -199,6 +199,9 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
  *                       elements, q[n-1] = 0; must not alias coeffs_dev
  *   kzg_open          : commitment (48-byte compressed G1) to that witness polynomial against the resident SRS =
  *                       the non-hiding part of KZG10::open */
+/*   axpy              : y[i] += a * x[i]: the linear combination sum_i xi^i p_i of SonicKZG10::open_combinations /
+ *                       batch_open (src/polycommit/sonic_pc/mod.rs); a: 32-byte Montgomery Fr on the host */
+int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_host, size_t n, void* stream);
 int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream);
 int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);
 int aleo_b200_fr_divide_by_linear_dev(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);

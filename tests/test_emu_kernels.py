@@ -277,6 +277,11 @@ def test_emu_poly_helpers(emu_lib, n):
     buf = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
     emu_lib.check(emu_lib.fr_distribute_powers_dev(C.cast(buf, C.c_void_p), n, mont(g), None, None), "distribute k=1")
     assert o.fr_vec_from_bytes(buf.raw) == o.distribute_powers(c, g)
+    ybuf = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
+    xs = o.random_fr_vec(n, 900 + n)
+    xbuf = C.create_string_buffer(o.fr_vec_to_bytes(xs), n * 32)
+    emu_lib.check(emu_lib.fr_axpy_dev(C.cast(ybuf, C.c_void_p), C.cast(xbuf, C.c_void_p), mont(k), n, None), "axpy")
+    assert o.fr_vec_from_bytes(ybuf.raw) == [(y + k * x) % o.R_MOD for y, x in zip(c, xs)]
     src = C.create_string_buffer(o.fr_vec_to_bytes(c), n * 32)
     out = C.create_string_buffer(32)
     emu_lib.check(emu_lib.fr_poly_eval_dev(C.cast(out, C.c_void_p), C.cast(src, C.c_void_p), n, mont(z), None), "eval")

@@ -28,6 +28,8 @@ def test_helpers_match_oracle(n):
     assert _host(poly.distribute_powers_dev(_dev(c), g, k)) == o.distribute_powers(c, g, k)
     assert _host(poly.distribute_powers_dev(_dev(c), g)) == o.distribute_powers(c, g)
     assert _host(poly.distribute_powers_dev(_dev(c), 22)) == o.distribute_powers(c, 22)
+    xs = o.random_fr_vec(n, 1900 + n)
+    assert _host(poly.axpy_dev(_dev(c), _dev(xs), k)) == [(y + k * x) % o.R_MOD for y, x in zip(c, xs)]
     assert poly.evaluate_dev(_dev(c), z) == o.poly_eval(c, z)
     assert poly.evaluate_dev(_dev(c), 0) == c[0]
     for zz in (z, 0, 1, o.R_MOD - 1):
