@@ -57,6 +57,7 @@ SYMBOLS = [
     ("aleo_b200_kzg_commit_hiding_dev", _int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_kzg_commit_batch_dev", _int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp]),
     ("aleo_b200_field_op_dev", _int, [_int, _int, _vp, _vp, _vp, _sz, _vp]),
+    ("aleo_b200_fr_lagrange_coeffs_dev", _int, [_vp, _u32, _vp, _vp]),
     ("aleo_b200_fr_axpy_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_fr_distribute_powers_dev", _int, [_vp, _sz, _vp, _vp, _vp]),
     ("aleo_b200_fr_poly_eval_dev", _int, [_vp, _vp, _sz, _vp, _vp]),

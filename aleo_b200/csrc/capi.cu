@@ -456,6 +456,15 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
   return ALEO_B200_OK;
 }
 
+int aleo_b200_fr_lagrange_coeffs_dev(void* out_dev, uint32_t log_n, const void* tau_host, void* stream) {
+  if (out_dev == nullptr || tau_host == nullptr) return ALEO_B200_EINVAL;
+  if (log_n > 31) return ALEO_B200_ETOOLARGE;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_lagrange_coeffs(out_dev, log_n, tau_host, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_host, size_t n, void* stream) {
   if (a_host == nullptr) return ALEO_B200_EINVAL;
   if (n == 0) return ALEO_B200_OK;

@@ -50,6 +50,7 @@ cudaError_t g1_compress(const void* jac144_dev, void* out48_dev, cudaStream_t s)
 // poly_lib.cu
 cudaError_t poly_upload_constants();
 cudaError_t field_op(int field, int op, void* out_dev, const void* a_dev, const void* b_dev, size_t n, cudaStream_t s);
+cudaError_t fr_lagrange_coeffs(void* out_dev, u32 log_n, const void* tau32, cudaStream_t s);
 cudaError_t fr_axpy(void* y_dev, const void* x_dev, const void* a32, size_t n, cudaStream_t s);
 cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s);
 cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);

@@ -240,6 +240,51 @@ KERNEL void __launch_bounds__(PW_TPB) witness_fix_kernel(const Fr* S, const Fr* 
   }
 }
 
+// EvaluationDomain::evaluate_all_lagrange_coefficients(tau): L_i(tau) = (tau^n - 1) / n * w^i / (tau - w^i), i < n.
+// s[0] = (tau^n - 1) / n, s[1] = w, s[2] = w^256 (setup as for distribute_powers with g = w, k = that constant).
+// When tau lies in the domain (some tau - w^i = 0) upstream returns the indicator vector: *hit records that index + 1.
+KERNEL void __launch_bounds__(PW_TPB) lagrange_kernel(Fr* out, u64 n, const Fr* s, Fr tau, u32* hit) {
+  const u64 first = (u64)blockIdx.x * PW_TPB * PW_RUN + threadIdx.x;
+  if (first >= n) return;
+  Fr w = thread_power(s[1], fp_one<FrParams>(), first, 0);
+  const Fr step = s[2], c = s[0];
+  for (u32 j = 0; j < PW_RUN; j++) {
+    const u64 i = first + (u64)j * PW_TPB;
+    if (i >= n) break;
+    const Fr d = fp_sub(tau, w);
+    if (fp_is_zero(d)) *hit = (u32)i + 1u;
+    out[i] = fp_mul(fp_mul(c, w), inv_elem<FrParams>(d));
+    w = fp_mul(w, step);
+  }
+}
+
+// tau = w^(idx): out = indicator of idx
+KERNEL void lagrange_indicator_kernel(Fr* out, u64 n, const u32* hit) {
+  const u32 h = *hit;
+  if (h == 0) return;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    out[i] = (i + 1 == h) ? fp_one<FrParams>() : fp_zero<FrParams>();
+}
+
+// s[0] <- (tau^n - 1) * n^-1 for n = 2^log_n (single thread; n^-1 = (1/2)^log_n)
+KERNEL void lagrange_const_kernel(Fr* s, Fr tau, u32 log_n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fr t = tau;
+  for (u32 i = 0; i < log_n; i++) t = fp_sqr(t);
+  Fr ninv = fp_one<FrParams>();
+  const Fr half = fp_const<FrParams, FrParams::TWO_INV_M>();
+  for (u32 i = 0; i < log_n; i++) ninv = fp_mul(ninv, half);
+  s[0] = fp_mul(fp_sub(t, fp_one<FrParams>()), ninv);
+}
+
+// domain generator w = TWO_ADIC_ROOT^(2^(47 - log_n)) (Montgomery), for the host wrapper
+KERNEL void domain_root_kernel(Fr* out, u32 log_n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fr w = fp_const<FrParams, FrParams::TWO_ADIC_ROOT_M>();
+  for (u32 i = log_n; i < (u32)FR_TWO_ADICITY; i++) w = fp_sqr(w);
+  *out = w;
+}
+
 // z = 0: q_j = p_(j+1)
 KERNEL void shift_down_kernel(const Fr* p, u64 n, Fr* q) {
   for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j + 1 < n; j += (u64)gridDim.x * blockDim.x) q[j] = p[j + 1];

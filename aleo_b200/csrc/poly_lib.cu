@@ -47,6 +47,31 @@ static cudaError_t make_setup(Fr** s_out, const void* g32, const void* k32, cuda
 
 static inline u32 pw_grid(size_t n) { return (u32)((n + (size_t)poly::PW_TPB * poly::PW_RUN - 1) / ((size_t)poly::PW_TPB * poly::PW_RUN)); }
 
+// out[i] = L_i(tau) over the domain of size 2^log_n (EvaluationDomain::evaluate_all_lagrange_coefficients)
+cudaError_t fr_lagrange_coeffs(void* out_dev, u32 log_n, const void* tau32, cudaStream_t s) {
+  const size_t n = (size_t)1 << log_n;
+  Fr* sc = nullptr;
+  PL_CK(cudaMallocAsync((void**)&sc, 10 * sizeof(Fr), s));
+  u32* hit = reinterpret_cast<u32*>(sc + 8);
+  cudaError_t e = cudaMemsetAsync(hit, 0, 4, s);
+  const Fr tau = host_fr(tau32);
+  // s[1] = w, s[2] = w^256 through the common setup (g = w read back from the device scalar), s[0] = (tau^n - 1) / n
+  LAUNCH_NOSYNC(poly::domain_root_kernel, dim3(1), dim3(1), 0, s, sc + 7, log_n);
+  Fr w_host;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&w_host, sc + 7, sizeof(Fr), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) {
+    LAUNCH_NOSYNC(poly::setup_kernel, dim3(1), dim3(1), 0, s, sc, w_host, w_host, (u32)0);
+    LAUNCH_NOSYNC(poly::lagrange_const_kernel, dim3(1), dim3(1), 0, s, sc, tau, log_n);
+    LAUNCH_NOSYNC(poly::lagrange_kernel, dim3(pw_grid(n)), dim3(poly::PW_TPB), 0, s, (Fr*)out_dev, (u64)n, (const Fr*)sc, tau, hit);
+    u32 blocks = (u32)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    LAUNCH_NOSYNC(poly::lagrange_indicator_kernel, dim3(blocks), dim3(256), 0, s, (Fr*)out_dev, (u64)n, (const u32*)hit);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(sc, s);
+  return e;
+}
+
 cudaError_t fr_axpy(void* y_dev, const void* x_dev, const void* a32, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   size_t blocks = (n + 255) / 256;

@@ -116,3 +116,16 @@ def axpy_dev(y_t, x_t, a):
         lib.check(lib.fr_axpy_dev(y_t.data_ptr(), x_t.data_ptr(), _fr_host(a), n, torch.cuda.current_stream().cuda_stream),
                   "aleo_b200_fr_axpy_dev")
     return y_t
+
+
+def lagrange_coeffs_dev(log_n: int, tau, device=None):
+    """EvaluationDomain::evaluate_all_lagrange_coefficients(tau) over the domain of size 2^log_n: (n, 4) int64 CUDA tensor"""
+    import torch
+
+    lib = _lib.get_lib()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((1 << log_n, 4), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        lib.check(lib.fr_lagrange_coeffs_dev(out.data_ptr(), log_n, _fr_host(tau), torch.cuda.current_stream().cuda_stream),
+                  "aleo_b200_fr_lagrange_coeffs_dev")
+    return out

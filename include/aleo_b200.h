@@ -201,6 +201,10 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
  *                       the non-hiding part of KZG10::open */
 /*   axpy              : y[i] += a * x[i]: the linear combination sum_i xi^i p_i of SonicKZG10::open_combinations /
  *                       batch_open (src/polycommit/sonic_pc/mod.rs); a: 32-byte Montgomery Fr on the host */
+/*   lagrange_coeffs   : out[i] = L_i(tau) over the domain of size 2^log_n (EvaluationDomain::
+ *                       evaluate_all_lagrange_coefficients, src/fft/domain.rs: (tau^n - 1) / n * w^i / (tau - w^i), the
+ *                       indicator vector when tau lies in the domain); synchronises the stream once */
+int aleo_b200_fr_lagrange_coeffs_dev(void* out_dev, uint32_t log_n, const void* tau_host, void* stream);
 int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_host, size_t n, void* stream);
 int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream);
 int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);

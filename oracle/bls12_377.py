@@ -233,6 +233,19 @@ def distribute_powers(coeffs, g: int, k: int = 1):
     return out
 
 
+def lagrange_coefficients(log_n: int, tau: int):
+    """EvaluationDomain::evaluate_all_lagrange_coefficients (snarkvm-algorithms 0.14.5 src/fft/domain.rs [U]):
+    L_i(tau) = (tau^n - 1) / n * w^i / (tau - w^i); the indicator vector when tau is in the domain."""
+    n = 1 << log_n
+    w = fr_root_of_unity(log_n)
+    tn = pow(tau, n, R_MOD)
+    pw = [pow(w, i, R_MOD) for i in range(n)]
+    if tn == 1:
+        return [1 if p == tau % R_MOD else 0 for p in pw]
+    c = (tn - 1) * pow(n, -1, R_MOD) % R_MOD
+    return [c * p % R_MOD * pow((tau - p) % R_MOD, -1, R_MOD) % R_MOD for p in pw]
+
+
 def divide_by_linear(coeffs, z: int):
     """witness polynomial of KZG10::open: q(x) = (p(x) - p(z)) / (x - z) by synthetic division, returned with
     len(coeffs) entries (the last one 0) (KZG10::compute_witness_polynomial, src/polycommit/kzg10/mod.rs [U];

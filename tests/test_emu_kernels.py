@@ -497,3 +497,16 @@ def test_emu_kzg_commit_hiding(emu_lib):
     assert out.raw == o.g1_compress(o.g1_add(o.msm_pippenger(B1, p), o.msm_pippenger(B2, r)))
     for h in hs:
         emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+@pytest.mark.parametrize("log_n", [0, 3, 9, 13])
+def test_emu_lagrange_coefficients(emu_lib, log_n):
+    n = 1 << log_n
+    tau = o.random_fr_vec(1, 7700 + log_n)[0]
+    w = o.fr_root_of_unity(log_n)
+    for t in (tau, pow(w, 5 % n, o.R_MOD)):                       # generic point; a point of the domain (indicator vector)
+        out = C.create_string_buffer(n * 32)
+        emu_lib.check(emu_lib.fr_lagrange_coeffs_dev(C.cast(out, C.c_void_p), log_n, o.int_to_le_bytes(o.fr_to_mont(t), 32), None), "lagrange")
+        got = o.fr_vec_from_bytes(out.raw)
+        assert got == o.lagrange_coefficients(log_n, t)
+        assert sum(got) % o.R_MOD == 1                             # the Lagrange basis sums to one

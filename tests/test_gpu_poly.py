@@ -72,3 +72,23 @@ def test_kzg_open_matches_oracle():
         assert out.cpu().numpy().tobytes() == o.g1_compress(o.msm_pippenger(B[:n - 1], q[:n - 1]))
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("log_n", [0, 4, 13, 18])
+def test_lagrange_coefficients(log_n):
+    """EvaluationDomain::evaluate_all_lagrange_coefficients: against the oracle at small sizes, by identities at 2^18
+    (sum_i L_i(tau) = 1 and sum_i L_i(tau) p(w^i) = p(tau) for a polynomial of degree < n)"""
+    n = 1 << log_n
+    tau = o.random_fr_vec(1, 8800 + log_n)[0]
+    L = poly.lagrange_coeffs_dev(log_n, tau)
+    if log_n <= 13:
+        assert _host(L) == o.lagrange_coefficients(log_n, tau)
+        w = o.fr_root_of_unity(log_n)
+        assert _host(poly.lagrange_coeffs_dev(log_n, pow(w, 3 % n, o.R_MOD))) == o.lagrange_coefficients(log_n, pow(w, 3 % n, o.R_MOD))
+    else:
+        ones = _dev([1])          # <L, 1> via evaluate at z = 1
+        assert poly.evaluate_dev(L, 1) == 1
+        p = ab.gen_scalars_dev(n, 8900, 0, True)
+        evals = ab.EvaluationDomain.new(n).fft_in_place_dev(p.clone())
+        prod = ab.Evaluations.mul(L, evals)
+        assert poly.evaluate_dev(prod, 1) == poly.evaluate_dev(p, tau)
