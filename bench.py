@@ -512,13 +512,14 @@ def run_ours(args):
         peaks = json.load(open(mp))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ntt_bytes = NTT_BYTES_PER_ELEM_PER_PASS * n
-    # DESIGN.md "NTT arithmetic": 3.25 products per element and pass inside the tile; the first pass boundary costs 2
-    # (two-level table product + apply), later boundaries 1 while their direct table has <= 2^18 entries
+    # DESIGN.md "NTT arithmetic": 3.25 products per element and pass inside the tile; a pass boundary costs 1 (apply) when
+    # its twiddles come from a direct table, 2 (two-level table product + apply) otherwise
     npass = dom.launches()
     k_bits = [log_n // npass + (1 if i < log_n % npass else 0) for i in range(npass)]
     mults_per_elem, log_cur = 3.25 * npass, log_n
     for i in range(npass - 1):
-        mults_per_elem += 2 if (i == 0 or log_cur > 18) else 1
+        direct = (21 <= log_n <= 24) if i == 0 else (log_cur <= 18)      # ntt_host.cuh: DIRECT0_* / DIRECT_TW_MAX_LOG
+        mults_per_elem += 1 if direct else 2
         log_cur -= k_bits[i]
     ntt = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": world * n / ntt_step / 1e3, "unit": "Melem/s", "ms_per_step": ntt_step,
            "log_n": log_n, "passes": dom.launches(), "round_trip_ok": ntt_ok,
