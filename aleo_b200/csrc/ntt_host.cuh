@@ -187,7 +187,7 @@ static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool invers
       // (n x 32 B in HBM per plan, read once per transform: +32 B per element on a pass that uses 13 % of the HBM
       // roof) instead of one table product per element: 2^24 3.80 -> 3.59 ms, 2^22 0.956 -> 0.902 ms on B200; no gain
       // at 2^20; above 2^24 (9-bit first pass, 4-element runs) the scattered table reads LOSE: 2^25 3.26 -> 3.97 ms.  ALEO_B200_NTT_DIRECT0=0 switches it off (memory).
-      if (i == 0 && p.npass >= 2 && log_n >= DIRECT0_MIN_LOG && log_n <= DIRECT0_MAX_LOG && dist_lg == 0) {
+      if (i == 0 && p.npass >= 2 && log_n >= DIRECT0_MIN_LOG && log_n <= DIRECT0_MAX_LOG) {
         const char* e0 = getenv("ALEO_B200_NTT_DIRECT0");
         if (!(e0 && e0[0] == '0')) {
           NTT_CK(plan_alloc(p, &p.tw_direct[0], (size_t)1 << log_n));
