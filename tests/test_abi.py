@@ -56,6 +56,12 @@ def test_argument_validation_precedes_device_use(product_lib_path):
     assert lib.ntt_fr_dev(C.cast(buf, C.c_void_p), 3, 1, 5, 0, None) == _lib.EINVAL
     assert lib.msm_g1(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1, C.cast(buf, C.c_void_p), 100) == _lib.EINVAL
     assert lib.msm_g1(None, C.cast(buf, C.c_void_p), 1, C.cast(buf, C.c_void_p), 104) == _lib.EINVAL
+    # maximum sizes: sorted positions are 32-bit, the field's two-adicity (47) is far above what memory allows
+    assert lib.msm_g1(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1 << 31, C.cast(buf, C.c_void_p), 104) == _lib.ETOOLARGE
+    assert lib.ntt_fr(C.cast(buf, C.c_void_p), 33, 0, 0) == _lib.ETOOLARGE
+    assert lib.kzg_commit_batch_dev(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), None, None, 65, None) == _lib.EINVAL
+    assert lib.ntt_dist_layout(12, 8, None, None, None) == _lib.EINVAL          # 2^12 cannot be spread over 8 GPUs
+    assert lib.ntt_dist_layout(27, 8, None, None, None) == 0 and lib.ntt_dist_layout(24, 3, None, None, None) == _lib.EINVAL
     assert lib.msm_window_bits(1 << 24) == 20 and lib.msm_window_bits(1 << 16) == 12 and lib.msm_window_bits(1) == 4
     assert lib.ntt_launches(24) == 3 and lib.ntt_launches(16) == 2 and lib.ntt_launches(8) == 1 and lib.ntt_launches(26) == 3 and lib.ntt_launches(28) == 4
 
