@@ -60,6 +60,7 @@ SYMBOLS = [
     ("aleo_b200_fr_lagrange_coeffs_dev", _int, [_vp, _u32, _vp, _vp]),
     ("aleo_b200_fr_axpy_dev", _int, [_vp, _vp, _vp, _sz, _vp]),
     ("aleo_b200_fr_distribute_powers_dev", _int, [_vp, _sz, _vp, _vp, _vp]),
+    ("aleo_b200_fr_divide_by_vanishing_on_coset_dev", _int, [_vp, _u32, _u32, _vp, _vp]),
     ("aleo_b200_fr_poly_eval_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_fr_divide_by_linear_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_kzg_open_dev", _int, [_vp, _vp, _vp, _sz, _vp, _vp]),

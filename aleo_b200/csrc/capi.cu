@@ -475,6 +475,17 @@ int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_ho
   return ALEO_B200_OK;
 }
 
+int aleo_b200_fr_divide_by_vanishing_on_coset_dev(void* evals_inout_dev, uint32_t log_m, uint32_t log_n, const void* g_host,
+                                                  void* stream) {
+  if (evals_inout_dev == nullptr || g_host == nullptr) return ALEO_B200_EINVAL;
+  if (log_n > log_m) return ALEO_B200_EINVAL;
+  if (log_m > 31) return ALEO_B200_ETOOLARGE;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fr_divide_by_vanishing_on_coset(evals_inout_dev, log_m, log_n, g_host, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream) {
   if (g_host == nullptr) return ALEO_B200_EINVAL;
   if (n == 0) return ALEO_B200_OK;

@@ -53,6 +53,7 @@ cudaError_t field_op(int field, int op, void* out_dev, const void* a_dev, const 
 cudaError_t fr_lagrange_coeffs(void* out_dev, u32 log_n, const void* tau32, cudaStream_t s);
 cudaError_t fr_axpy(void* y_dev, const void* x_dev, const void* a32, size_t n, cudaStream_t s);
 cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s);
+cudaError_t fr_divide_by_vanishing_on_coset(void* inout_dev, u32 log_m, u32 log_n, const void* g32, cudaStream_t s);
 cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
 cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
 cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out);

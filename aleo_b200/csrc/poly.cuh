@@ -285,6 +285,32 @@ KERNEL void domain_root_kernel(Fr* out, u32 log_n) {
   *out = w;
 }
 
+// Division by the vanishing polynomial Z_n(x) = x^n - 1 of the domain of size n = 2^log_n on the coset g H_m of a
+// domain of size m = 2^log_m >= n (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place, src/fft/domain.rs, and
+// the mul-domain quotients of the prover rounds): x_i^n = g^n * w_k^i with k = m / n and w_k the generator of the
+// domain of size k, so the divisor has period k.  table[j] = (g^n * w_k^j - 1)^-1 (a zero divisor stays 0, as
+// batch_inversion leaves zeros untouched).
+KERNEL void __launch_bounds__(256) vanishing_table_kernel(Fr* table, u32 log_k, u32 log_n, Fr g) {
+  const u32 k = 1u << log_k;
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+    Fr gn = g;
+    for (u32 i = 0; i < log_n; i++) gn = fp_sqr(gn);
+    Fr w = fp_const<FrParams, FrParams::TWO_ADIC_ROOT_M>();
+    for (u32 i = log_k; i < (u32)FR_TWO_ADICITY; i++) w = fp_sqr(w);
+    Fr acc = gn;                                  // g^n * w^j by square-and-multiply over the bits of j
+    for (u32 b = 0; b < log_k; b++) {
+      if ((j >> b) & 1) acc = fp_mul(acc, w);
+      w = fp_sqr(w);
+    }
+    table[j] = inv_elem<FrParams>(fp_sub(acc, fp_one<FrParams>()));
+  }
+}
+
+KERNEL void __launch_bounds__(256) mul_periodic_kernel(Fr* e, u64 n, const Fr* table, u32 mask) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    e[i] = fp_mul(e[i], table[(u32)i & mask]);
+}
+
 // z = 0: q_j = p_(j+1)
 KERNEL void shift_down_kernel(const Fr* p, u64 n, Fr* q) {
   for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j + 1 < n; j += (u64)gridDim.x * blockDim.x) q[j] = p[j + 1];

@@ -80,6 +80,23 @@ cudaError_t fr_axpy(void* y_dev, const void* x_dev, const void* a32, size_t n, c
   return cudaGetLastError();
 }
 
+// evals (on the coset g H_m, m = 2^log_m) /= Z_n(x) = x^n - 1, n = 2^log_n <= m
+cudaError_t fr_divide_by_vanishing_on_coset(void* inout_dev, u32 log_m, u32 log_n, const void* g32, cudaStream_t s) {
+  const u32 log_k = log_m - log_n;
+  const size_t m = (size_t)1 << log_m, k = (size_t)1 << log_k;
+  Fr* table = nullptr;
+  PL_CK(cudaMallocAsync((void**)&table, k * sizeof(Fr), s));
+  size_t tb = (k + 255) / 256;
+  if (tb > 148 * 8) tb = 148 * 8;
+  LAUNCH_NOSYNC(poly::vanishing_table_kernel, dim3((u32)tb), dim3(256), 0, s, table, log_k, log_n, host_fr(g32));
+  size_t blocks = (m + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  LAUNCH_NOSYNC(poly::mul_periodic_kernel, dim3((u32)blocks), dim3(256), 0, s, (Fr*)inout_dev, (u64)m, (const Fr*)table, (u32)(k - 1));
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(table, s);
+  return e;
+}
+
 cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, const void* k32, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   Fr* sc = nullptr;

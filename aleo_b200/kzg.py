@@ -127,3 +127,24 @@ class KZG10:
                 random_coeffs_t.data_ptr(), random_coeffs_t.numel() * random_coeffs_t.element_size() // 32,
                 torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_commit_hiding_dev")
         return out
+
+    @staticmethod
+    def commit_lagrange_dev(srs_lagrange: ResidentSRS, evaluations_t, n_evals: int, out=None):
+        """KZG10::commit_lagrange: the same msm over a handle built from lagrange_basis_at_beta_g, fed with the
+        evaluations over the domain instead of coefficients (lets the prover skip an ifft)"""
+        return KZG10.commit_dev(srs_lagrange, evaluations_t, n_evals, out)
+
+    @staticmethod
+    def open_dev(srs: ResidentSRS, coeffs_t, point, out=None):
+        """non-hiding KZG10::open at `point` (canonical int): witness polynomial (p(x) - p(z)) / (x - z) built on the
+        device, then its commitment against the resident powers -> 48-byte compressed G1 (CUDA tensor)"""
+        import torch
+
+        from .poly import _fr_host
+        if out is None:
+            out = torch.empty(48, dtype=torch.uint8, device=coeffs_t.device)
+        n = coeffs_t.numel() * coeffs_t.element_size() // 32
+        with torch.cuda.device(coeffs_t.device):
+            srs._lib.check(srs._lib.kzg_open_dev(srs._h, out.data_ptr(), coeffs_t.data_ptr(), n, _fr_host(point),
+                                                 torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_open_dev")
+        return out

@@ -106,6 +106,22 @@ def divide_by_linear_dev(coeffs_t, z, out=None):
     return out
 
 
+def divide_by_vanishing_on_coset_dev(evals_t, log_n: int, g=22):
+    """evals of a polynomial on the coset g * H_m (m = len(evals)) divided in place by Z_n(x) = x^n - 1, n = 2^log_n
+    (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place when m == n); g canonical int, 22 = the coset_fft shift"""
+    import torch
+
+    lib = _lib.get_lib()
+    m = evals_t.numel() * evals_t.element_size() // 32
+    if m == 0 or m & (m - 1):
+        raise ValueError("the evaluation vector must have a power-of-two length")
+    with torch.cuda.device(evals_t.device):
+        lib.check(lib.fr_divide_by_vanishing_on_coset_dev(evals_t.data_ptr(), m.bit_length() - 1, log_n, _fr_host(g),
+                                                          torch.cuda.current_stream().cuda_stream),
+                  "aleo_b200_fr_divide_by_vanishing_on_coset_dev")
+    return evals_t
+
+
 def axpy_dev(y_t, x_t, a):
     """y += a * x in place (the linear-combination step of SonicKZG10::open_combinations); a canonical int"""
     import torch

@@ -204,6 +204,13 @@ int aleo_b200_field_op_dev(int field, int op, void* out_dev, const void* a_dev, 
 /*   lagrange_coeffs   : out[i] = L_i(tau) over the domain of size 2^log_n (EvaluationDomain::
  *                       evaluate_all_lagrange_coefficients, src/fft/domain.rs: (tau^n - 1) / n * w^i / (tau - w^i), the
  *                       indicator vector when tau lies in the domain); synchronises the stream once */
+/*   divide_by_vanishing_on_coset : evals[i] /= Z_n(g w_m^i), Z_n(x) = x^n - 1, for the evaluations of a polynomial on the
+ *                       coset g H_m (m = 2^log_m >= n = 2^log_n; g = 22 for coset_fft): EvaluationDomain::
+ *                       divide_by_vanishing_poly_on_coset_in_place (src/fft/domain.rs) when m = n, and the quotient by the
+ *                       constraint-domain vanishing polynomial over a larger multiplication domain in the prover rounds;
+ *                       the divisor has period m / n, so the kernel inverts m / n values and multiplies */
+int aleo_b200_fr_divide_by_vanishing_on_coset_dev(void* evals_inout_dev, uint32_t log_m, uint32_t log_n, const void* g_host,
+                                                  void* stream);
 int aleo_b200_fr_lagrange_coeffs_dev(void* out_dev, uint32_t log_n, const void* tau_host, void* stream);
 int aleo_b200_fr_axpy_dev(void* y_inout_dev, const void* x_dev, const void* a_host, size_t n, void* stream);
 int aleo_b200_fr_distribute_powers_dev(void* inout_dev, size_t n, const void* g_host, const void* k_host, void* stream);

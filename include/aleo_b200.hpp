@@ -122,6 +122,10 @@ struct KZG10 {
     check(aleo_b200_kzg_commit(powers.handle(), c.bytes, coeffs.data(), coeffs.size()), "KZG10::commit");
     return c;
   }
+  // KZG10::commit_lagrange(lagrange_basis, evaluations): `lagrange_basis` = a handle built from lagrange_basis_at_beta_g
+  static KZGCommitment commit_lagrange(const ResidentPowers& lagrange_basis, const std::vector<Fr>& evaluations) {
+    return commit(lagrange_basis, evaluations);
+  }
 };
 
 }  // namespace aleo_b200

@@ -246,6 +246,21 @@ def lagrange_coefficients(log_n: int, tau: int):
     return [c * p % R_MOD * pow((tau - p) % R_MOD, -1, R_MOD) % R_MOD for p in pw]
 
 
+def divide_by_vanishing_on_coset(evals, log_n: int, g: int = None):
+    """evals[i] = p(g w_m^i) over the coset of the domain of size m = len(evals), divided by Z_n(x) = x^n - 1,
+    n = 2^log_n <= m (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place for m == n, snarkvm-algorithms
+    0.14.5 src/fft/domain.rs [U]).  Every divisor is evaluated directly, no period shortcut."""
+    g = FR_GENERATOR if g is None else g
+    m = len(evals)
+    w = fr_root_of_unity(m.bit_length() - 1)
+    out, x = [], g % R_MOD
+    for v in evals:
+        d = (pow(x, 1 << log_n, R_MOD) - 1) % R_MOD
+        out.append(v * pow(d, -1, R_MOD) % R_MOD if d else 0)
+        x = x * w % R_MOD
+    return out
+
+
 def divide_by_linear(coeffs, z: int):
     """witness polynomial of KZG10::open: q(x) = (p(x) - p(z)) / (x - z) by synthetic division, returned with
     len(coeffs) entries (the last one 0) (KZG10::compute_witness_polynomial, src/polycommit/kzg10/mod.rs [U];

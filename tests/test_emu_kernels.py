@@ -510,3 +510,22 @@ def test_emu_lagrange_coefficients(emu_lib, log_n):
         got = o.fr_vec_from_bytes(out.raw)
         assert got == o.lagrange_coefficients(log_n, t)
         assert sum(got) % o.R_MOD == 1                             # the Lagrange basis sums to one
+
+
+@pytest.mark.parametrize("log_m,log_n", [(0, 0), (4, 4), (6, 2), (9, 0), (10, 7)])
+def test_emu_divide_by_vanishing_on_coset(emu_lib, log_m, log_n):
+    e = o.random_fr_vec(1 << log_m, 7800 + 16 * log_m + log_n)
+    for g in (22, o.random_fr_vec(1, 7900 + log_m)[0]):
+        buf = C.create_string_buffer(o.fr_vec_to_bytes(e), (1 << log_m) * 32)
+        emu_lib.check(emu_lib.fr_divide_by_vanishing_on_coset_dev(C.cast(buf, C.c_void_p), log_m, log_n,
+                                                                   o.int_to_le_bytes(o.fr_to_mont(g), 32), None), "vanishing")
+        assert o.fr_vec_from_bytes(buf.raw) == o.divide_by_vanishing_on_coset(e, log_n, g)
+    # the quotient identity: p = q (x^n - 1)  =>  coset_fft(p) / Z_n = coset_fft(q)
+    if log_m > log_n:
+        m, n = 1 << log_m, 1 << log_n
+        q = o.random_fr_vec(m - n, 7950 + log_m)
+        p = [0] * m
+        for i, v in enumerate(q):
+            p[i + n] = (p[i + n] + v) % o.R_MOD
+            p[i] = (p[i] - v) % o.R_MOD
+        assert o.divide_by_vanishing_on_coset(o.coset_fft(p, m), log_n) == o.coset_fft(q, m)

@@ -92,3 +92,54 @@ def test_lagrange_coefficients(log_n):
         evals = ab.EvaluationDomain.new(n).fft_in_place_dev(p.clone())
         prod = ab.Evaluations.mul(L, evals)
         assert poly.evaluate_dev(prod, 1) == poly.evaluate_dev(p, tau)
+
+
+@pytest.mark.parametrize("log_m,log_n", [(0, 0), (5, 5), (6, 2), (10, 7), (12, 0), (13, 12)])
+def test_divide_by_vanishing_on_coset_matches_oracle(log_m, log_n):
+    e = o.random_fr_vec(1 << log_m, 9100 + 16 * log_m + log_n)
+    assert _host(poly.divide_by_vanishing_on_coset_dev(_dev(e), log_n)) == o.divide_by_vanishing_on_coset(e, log_n)
+    g = o.random_fr_vec(1, 9200 + log_m)[0]
+    assert _host(poly.divide_by_vanishing_on_coset_dev(_dev(e), log_n, g)) == o.divide_by_vanishing_on_coset(e, log_n, g)
+
+
+def test_quotient_by_vanishing_polynomial_round_trip_at_scale():
+    """p = q * (x^n - 1) with deg q < m - n: coset_fft(p) / Z_n on the coset, coset_ifft -> q (the shape of the prover's
+    quotient polynomials: constraint domain n = 2^18 inside a multiplication domain m = 2^20)"""
+    log_m, log_n = 20, 18
+    m, n = 1 << log_m, 1 << log_n
+    q = ab.gen_scalars_dev(m - n, 9300, 0, True)
+    p = torch.zeros((m, 4), dtype=torch.int64, device="cuda")
+    p[n:] = q                                                    # q * x^n ...
+    p[:m - n] = ab.Evaluations.sub(p[:m - n].contiguous(), q)    # ... - q
+    dom = ab.EvaluationDomain.new(m)
+    e = dom.coset_fft_in_place_dev(p)
+    poly.divide_by_vanishing_on_coset_dev(e, log_n)
+    back = dom.coset_ifft_in_place_dev(e)
+    assert torch.equal(back[:m - n], q)
+    assert not back[m - n:].any()
+
+
+def test_kzg_open_and_commit_lagrange_wrappers():
+    """KZG10.open_dev is the C call of test_kzg_open_matches_oracle; commit_lagrange over a handle built from the
+    Lagrange basis commits the evaluations to the same point as commit over the monomial basis commits the coefficients
+    (here with bases whose discrete logs are powers of a known tau, so that both bases can be built)"""
+    log_n = 6
+    n = 1 << log_n
+    tau = o.random_fr_vec(1, 9400)[0]
+    G = o.G1_GEN
+    powers = [o.g1_mul(G, pow(tau, i, o.R_MOD)) for i in range(n)]
+    lag = [o.g1_mul(G, v) for v in o.lagrange_coefficients(log_n, tau)]
+    srs = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(powers, 104), 104)
+    srs_l = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(lag, 104), 104)
+    try:
+        c = o.random_fr_vec(n, 9401)
+        evals = o.fft(c, n)
+        a = ab.KZG10.commit_dev(srs, _dev(c), n).cpu().numpy().tobytes()
+        b = ab.KZG10.commit_lagrange_dev(srs_l, _dev(evals), n).cpu().numpy().tobytes()
+        assert a == b == o.g1_compress(o.g1_mul(G, o.poly_eval(c, tau)))
+        z = o.random_fr_vec(1, 9402)[0]
+        w = ab.KZG10.open_dev(srs, _dev(c), z).cpu().numpy().tobytes()
+        assert w == o.g1_compress(o.g1_mul(G, o.poly_eval(o.divide_by_linear(c, z), tau)))
+    finally:
+        srs.close()
+        srs_l.close()
