@@ -131,11 +131,16 @@ namespace montdetail {
 // CARRY_IN: first instruction consumes CF.  TOP: add the chain's carry-out into acc[pos+N'].
 // X_IS_MOD: the row operand is the modulus, read from the constant bank (uniform registers; an
 // immediate would stop ptxas from fusing the pair into IMAD.WIDE) instead of x[].
-template <class P, int POS, int J0, bool CARRY_IN, bool X_IS_MOD, int LEN>
+// UNIT0 (modulus rows of the leading accumulator): limb 0 of both moduli is 1 and y = -acc[POS], so the first
+// pair adds nothing but the carry of acc[POS] + y = (acc[POS] != 0), which the caller left in CF (neg_cc): one
+// addc instead of a product (ptxas otherwise keeps an IMAD.HI.U32 on the heavy pipe for it).
+template <class P, int POS, int J0, bool CARRY_IN, bool X_IS_MOD, int LEN, bool UNIT0 = false>
 DEV void row_chain(u32 (&acc)[LEN], const u32* x, u32 y) {
   constexpr int N = P::N;
+  static_assert(!UNIT0 || (X_IS_MOD && J0 == 0 && CARRY_IN && P::MOD(0) == 1u), "UNIT0: leading modulus row only");
+  if (UNIT0) acc[POS + 1] = ptx::addc_cc(acc[POS + 1], 0);
 #pragma unroll
-  for (int j = J0; j < N; j += 2) {
+  for (int j = UNIT0 ? 2 : J0; j < N; j += 2) {
     const u32 xj = X_IS_MOD ? P::MODC()[j] : x[j];
     if (j == J0 && !CARRY_IN)
       acc[POS + j] = ptx::mad_lo_cc(xj, y, acc[POS + j]);
@@ -160,8 +165,8 @@ DEV void iter(u32 (&E)[LEN], u32 (&O)[LEN], const u32* a, u32 bi) {
     row_chain<P, I, 1, false, false>(T, a, bi);
   }
   row_chain<P, I, 0, false, false>(L, a, bi);
-  u32 m = ptx::neg_opaque(L[I]);  // Montgomery factor: INV == -1 mod 2^32 for both BLS12-377 moduli
-  row_chain<P, I, 0, false, true>(L, a, m);
+  u32 m = ptx::neg_cc(L[I]);  // Montgomery factor: INV == -1 mod 2^32 for both BLS12-377 moduli; CF = (L[I] != 0)
+  row_chain<P, I, 0, true, true, LEN, true>(L, a, m);
   row_chain<P, I, 1, false, true>(T, a, m);
 }
 
@@ -249,12 +254,13 @@ DEV void red_iter(u32 (&E)[LEN], u32 (&O)[LEN]) {
   u32(&L)[LEN] = (I & 1) ? O : E;
   u32(&T)[LEN] = (I & 1) ? E : O;
   if (I > 0) L[I] = ptx::add_cc(L[I], T[I]);  // carry-out belongs to position I+1 = first trailing pair
-  const u32 m = ptx::neg_opaque(L[I]);
+  // the fold's carry-out (position I+1) must be consumed by the trailing chain before neg_cc overwrites CF
   if (I > 0)
-    row_chain<P, I, 1, true, true>(T, (const u32*)nullptr, m);
+    row_chain<P, I, 1, true, true>(T, (const u32*)nullptr, ptx::neg_opaque(L[I]));
   else
-    row_chain<P, I, 1, false, true>(T, (const u32*)nullptr, m);
-  row_chain<P, I, 0, false, true>(L, (const u32*)nullptr, m);
+    row_chain<P, I, 1, false, true>(T, (const u32*)nullptr, ptx::neg_opaque(L[I]));
+  const u32 m = ptx::neg_cc(L[I]);
+  row_chain<P, I, 0, true, true, LEN, true>(L, (const u32*)nullptr, m);
 }
 template <class P, int I, int LEN>
 struct RedRows {

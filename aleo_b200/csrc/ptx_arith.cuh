@@ -25,6 +25,15 @@ DEV u32 mul_lo(u32 a, u32 b) { return a * b; }
 // rewrites the following mad pairs and ptxas no longer fuses them into IMAD.WIDE (measured: 2x the
 // fma-pipe instructions on the modulus rows).
 DEV u32 neg_opaque(u32 a) { u32 r; asm volatile("sub.u32 %0, 0, %1;" : "=r"(r) : "r"(a)); return r; }
+// 0 - a, and CF = (a != 0) = the carry of a + (0 - a), i.e. of the limb that a modulus row with unit low limb clears.
+// CF comes from an addition (a + 0xffffffff carries iff a != 0): a borrow left by sub.cc is NOT what a following
+// addc consumes on sm_100a (measured: wrong products), whatever the PTX manual says about CC.CF.
+DEV u32 neg_cc(u32 a) {
+  u32 r, t;
+  asm volatile("sub.u32 %0, 0, %1;" : "=r"(r) : "r"(a));
+  asm volatile("add.cc.u32 %0, %1, 0xffffffff;" : "=r"(t) : "r"(a));
+  return r;
+}
 #else
 #define CF (emu::t_cf)
 DEV u32 add_cc(u32 a, u32 b) { u64 t = (u64)a + b; CF = (u32)(t >> 32); return (u32)t; }
@@ -40,6 +49,7 @@ DEV u32 madc_hi_cc(u32 a, u32 b, u32 c) { u64 t = (((u64)a * b) >> 32) + c + CF;
 DEV u32 madc_hi(u32 a, u32 b, u32 c) { return (u32)((((u64)a * b) >> 32) + c + CF); }
 DEV u32 mul_lo(u32 a, u32 b) { return a * b; }
 DEV u32 neg_opaque(u32 a) { return 0u - a; }
+DEV u32 neg_cc(u32 a) { CF = (a != 0u); return 0u - a; }
 #undef CF
 #endif
 }  // namespace ptx
