@@ -183,8 +183,9 @@ struct Unroll<P, -1, LEN> {
 };
 }  // namespace montdetail
 
+// (a * b + q * m) / R without the final conditional subtraction: < a*b/R + m.
 template <class P>
-DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+DEV Fp<P> fp_mul_raw(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   static_assert(P::INV == 0xffffffffu, "multiplier assumes modulus == 1 mod 2^32");
   constexpr int LEN = 2 * N + 1;
@@ -197,7 +198,90 @@ DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #pragma unroll
   for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(E[N + k], O[N + k]);
   r.l[N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 1]);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r = fp_mul_raw(a, b);
   fp_reduce_once(r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lazy ("semi-reduced") arithmetic for kernels that chain butterflies and products (the NTT passes): values live
+// in [0, 2m) and only the final result is brought back to [0, m).  The modulus must leave spare bits: with
+// rho = m / R, a raw Montgomery product of a < A*m and b < B*m is < (A*B*rho + 1) * m.  For Fr rho = 0.0729
+// (R / m = 13.7): A*B <= 8 gives < 1.59 m, so
+//   lz_mul  (a < 4m, b < 2m)  -> < 2m   no conditional subtraction at all
+//   lz_add  (a, b < 2m)       -> < 2m   a + b, minus 2m when that is not negative
+//   lz_sub  (a, b < 2m)       -> < 2m   a - b, plus 2m when that borrowed
+//   lz_add_wide / lz_sub_wide -> < 4m   a + b / a - b + 2m with no test: only as the operand of the next lz_mul
+// ---------------------------------------------------------------------------------------------
+template <class P>
+CONSTFN u32 fp_mod2_limb(int i) {  // limb i of 2m
+  return (P::MOD(i) << 1) | (i > 0 ? (P::MOD(i > 0 ? i - 1 : 0) >> 31) : 0u);
+}
+
+template <class P>
+DEV Fp<P> lz_mul(const Fp<P>& a, const Fp<P>& b) {
+  static_assert(32 * P::N - P::BITS >= 3, "lazy products need three spare bits");
+  return fp_mul_raw(a, b);
+}
+
+template <class P>
+DEV Fp<P> lz_add_wide(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+  r.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> lz_sub_wide(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  // (a + 2m) - b, in this order: the intermediate never goes negative
+  r.l[0] = ptx::add_cc(a.l[0], fp_mod2_limb<P>(0));
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], fp_mod2_limb<P>(i));
+  r.l[N - 1] = ptx::addc(a.l[N - 1], fp_mod2_limb<P>(N - 1));
+  r.l[0] = ptx::sub_cc(r.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::subc_cc(r.l[i], b.l[i]);
+  r.l[N - 1] = ptx::subc(r.l[N - 1], b.l[N - 1]);
+  return r;
+}
+
+template <class P>
+DEV Fp<P> lz_add(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r = lz_add_wide(a, b);
+  u32 s[N];
+  s[0] = ptx::sub_cc(r.l[0], fp_mod2_limb<P>(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) s[i] = ptx::subc_cc(r.l[i], fp_mod2_limb<P>(i));
+  u32 borrow = ptx::subc(0, 0);  // 0xffffffff when a + b < 2m
+#pragma unroll
+  for (int i = 0; i < N; i++) r.l[i] = borrow ? r.l[i] : s[i];
+  return r;
+}
+
+template <class P>
+DEV Fp<P> lz_sub(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+  u32 mask = ptx::subc(0, 0);  // all ones when a < b
+  r.l[0] = ptx::add_cc(r.l[0], fp_mod2_limb<P>(0) & mask);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], fp_mod2_limb<P>(i) & mask);
+  r.l[N - 1] = ptx::addc(r.l[N - 1], fp_mod2_limb<P>(N - 1) & mask);
   return r;
 }
 

@@ -114,6 +114,82 @@ DEV void ntt8(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same transforms on semi-reduced values (mont.cuh "Lazy arithmetic"): inputs and outputs in [0, 2r), products
+// without a final subtraction, and a difference (or, at the last level, a sum) that is about to be multiplied is
+// left in [0, 4r) with no test at all.  POSTMUL: the caller multiplies every output except x[0] by a twiddle next,
+// so the last level leaves those wide.  The pass kernels use only these; the canonical ones above serve the
+// single-CTA kernel.  ALU-pipe instructions per element drop by about a fifth (the passes are co-limited by the
+// ALU and the heavy FMA pipe).
+// ---------------------------------------------------------------------------------------------
+DEV Fr lzm(const Fr& a, const Fr& b) { return lz_mul(a, b); }
+
+DEV Fr pow_lookup_lz(const PowTable& t, u32 e) {  // < 2r
+  Fr a = t.lo[e & ((1u << t.lo_bits) - 1u)];
+  Fr b = t.hi[e >> t.lo_bits];
+  return lzm(a, b);
+}
+
+DEV void bfly_lz(Fr& a, Fr& b) {  // (a + b, a - b), both < 2r
+  Fr s = lz_add(a, b);
+  b = lz_sub(a, b);
+  a = s;
+}
+DEV void bfly_lz_mul(Fr& a, Fr& b, const Fr& w) {  // (a + b, (a - b) * w)
+  Fr s = lz_add(a, b);
+  b = lzm(lz_sub_wide(a, b), w);
+  a = s;
+}
+template <bool WIDE>
+DEV void bfly_lz_out(Fr& a, Fr& b) {  // last level: both outputs wide when the caller multiplies them next
+  Fr s = WIDE ? lz_add_wide(a, b) : lz_add(a, b);
+  b = WIDE ? lz_sub_wide(a, b) : lz_sub(a, b);
+  a = s;
+}
+template <bool WIDE>
+DEV void bfly_lz_out0(Fr& a, Fr& b) {  // ... except x[0], which is never multiplied
+  Fr s = lz_add(a, b);
+  b = WIDE ? lz_sub_wide(a, b) : lz_sub(a, b);
+  a = s;
+}
+
+template <bool POSTMUL>
+DEV void ntt2_lz(Fr* x) { bfly_lz_out0<POSTMUL>(x[0], x[1]); }
+
+template <bool POSTMUL>
+DEV void ntt4_lz(Fr* x, const Fr& w4) {
+  bfly_lz(x[0], x[2]);
+  bfly_lz_mul(x[1], x[3], w4);
+  bfly_lz_out0<POSTMUL>(x[0], x[1]);
+  bfly_lz_out<POSTMUL>(x[2], x[3]);
+  Fr t = x[1];  // bit-reversed -> natural
+  x[1] = x[2];
+  x[2] = t;
+}
+
+template <bool POSTMUL>
+DEV void ntt8_lz(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
+  bfly_lz(x[0], x[4]);
+  bfly_lz_mul(x[1], x[5], w8[1]);
+  bfly_lz_mul(x[2], x[6], w8[2]);
+  bfly_lz_mul(x[3], x[7], w8[3]);
+  bfly_lz(x[0], x[2]);
+  bfly_lz_mul(x[1], x[3], w8[2]);
+  bfly_lz(x[4], x[6]);
+  bfly_lz_mul(x[5], x[7], w8[2]);
+  bfly_lz_out0<POSTMUL>(x[0], x[1]);
+  bfly_lz_out<POSTMUL>(x[2], x[3]);
+  bfly_lz_out<POSTMUL>(x[4], x[5]);
+  bfly_lz_out<POSTMUL>(x[6], x[7]);
+  // positions hold X[bitrev3(pos)]: swap 1<->4, 3<->6
+  Fr t = x[1];
+  x[1] = x[4];
+  x[4] = t;
+  t = x[3];
+  x[3] = x[6];
+  x[6] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Shared-memory tile: two planes of uint4 (low / high half of an element).
 // ---------------------------------------------------------------------------------------------
 template <int K, bool LAST>
@@ -240,15 +316,15 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
         gi = ((u64)(p >> a.d_k2l) << a.d_log_chunk) + (((in_base >> K) + ((u64)tg * (stride_g >> K))) << a.d_k2l) +
              (p & ((1u << a.d_k2l) - 1u));
       x[j] = src[gi];
-      if (!LAST && a.use_pre) x[j] = fr_mul_v(x[j], pow_lookup(a.pre, dist_expand(a, (u32)gi)));  // coset: g^(global index)
+      if (!LAST && a.use_pre) x[j] = lzm(x[j], pow_lookup_lz(a.pre, dist_expand(a, (u32)gi)));  // coset: g^(global index)
     }
     Fr w8[4];
     w8[1] = a.inner[R / 8];
     w8[2] = a.inner[R / 4];
     w8[3] = a.inner[3 * (R / 8)];
-    ntt8(x, w8);
+    ntt8_lz<true>(x, w8);
 #pragma unroll
-    for (int k = 1; k < 8; k++) x[k] = fr_mul_v(x[k], a.inner[tr * k]);
+    for (int k = 1; k < 8; k++) x[k] = lzm(x[k], a.inner[tr * k]);
 #pragma unroll
     for (int k = 0; k < 8; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(k * C1 + tr, tg), x[k]);
   }
@@ -272,12 +348,12 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u32 bp = blk * CP + t;
 #pragma unroll
       for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j * C, tg));
-      if (S2 == 3) ntt8(x + h * PTS, w8);
-      if (S2 == 2) ntt4(x + h * PTS, w8[2]);
-      if (S2 == 1) ntt2(x + h * PTS);
+      if (S2 == 3) ntt8_lz<(C > 1)>(x + h * PTS, w8);
+      if (S2 == 2) ntt4_lz<(C > 1)>(x + h * PTS, w8[2]);
+      if (S2 == 1) ntt2_lz<(C > 1)>(x + h * PTS);
       if (C > 1) {
 #pragma unroll
-        for (int k = 1; k < PTS; k++) x[h * PTS + k] = fr_mul_v(x[h * PTS + k], a.inner[(R / CP) * t * k]);
+        for (int k = 1; k < PTS; k++) x[h * PTS + k] = lzm(x[h * PTS + k], a.inner[(R / CP) * t * k]);
       }
 #pragma unroll
       for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k * C, tg), x[h * PTS + k]);
@@ -303,9 +379,9 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u32 bp = gam * CP;
 #pragma unroll
       for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j, tg));
-      if (S3 == 3) ntt8(x + h * PTS, w8);
-      if (S3 == 2) ntt4(x + h * PTS, w4);
-      if (S3 == 1) ntt2(x + h * PTS);
+      if (S3 == 3) ntt8_lz<false>(x + h * PTS, w8);
+      if (S3 == 2) ntt4_lz<false>(x + h * PTS, w4);
+      if (S3 == 1) ntt2_lz<false>(x + h * PTS);
 #pragma unroll
       for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k, tg), x[h * PTS + k]);
     }
@@ -328,15 +404,17 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u64 go = out_base + kap * ostride_r + sg;
       if (!LAST) {
         const u32 x = dist_expand(a, i2_base + sg) * kap;
-        if (a.tw_direct)
-          v = fr_mul_v(v, a.tw_direct[x]);
+        if (a.tw_direct)  // the passes in between exchange semi-reduced values (< 2r)
+          v = lzm(v, a.tw_direct[x]);
         else
-          v = fr_mul_v(v, pow_lookup(a.tw, x << (a.log_n - a.log_cur)));
+          v = lzm(v, pow_lookup_lz(a.tw, x << (a.log_n - a.log_cur)));
       }
       if (LAST && a.use_post) {
         u32 gk = (u32)go;  // global output index: the rank's bits sit above the local part of the first digit
         if (a.d_k2l < 31u) gk = (((u32)go >> a.log_r1) << (a.log_r1 + a.d_lg)) | (a.d_rank << a.log_r1) | ((u32)go & ((1u << a.log_r1) - 1u));
-        v = fr_mul_v(v, pow_lookup(a.post, gk));
+        v = fp_mul(v, pow_lookup_lz(a.post, gk));  // full reduction: this is the result
+      } else if (LAST) {
+        fp_reduce_once(v);  // [0, 2r) -> canonical
       }
       if (!LAST && a.d_exchange)  // flat all-to-all: chunk t of the local result goes to rank t, slot = my rank
         a.peer[go >> a.d_log_chunk][((u64)a.d_rank << a.d_log_chunk) + (go & (((u64)1 << a.d_log_chunk) - 1u))] = v;
