@@ -4,6 +4,7 @@
   python tools/msm_sweep.py phases LOG_N [C ...]     resident MSM phases (sort / accumulate / tail) per window size c
   python tools/msm_sweep.py host LOG_N [K ...]       host-pointer aleo_b200_msm_g1 wall time per chunk count K (1..3)
   python tools/msm_sweep.py sizes LOG_A LOG_B        resident MSM total time per size with the default window choice
+  python tools/msm_sweep.py split LOG_N W,W,.. [...]  host-pointer call per explicit point-range weights (ALEO_B200_MSM_SPLIT)
 """
 import ctypes as C
 import os
@@ -63,6 +64,40 @@ elif mode == "host":
         ref = ref or raw
         print("log_n=%d chunks=%d host-call ms: %s  -> %.1f Mpts/s same_result=%s" %
               (log_n, k, " ".join("%.2f" % t for t in ts), n / min(ts[1:]) / 1e3, raw == ref), flush=True)
+elif mode == "split":
+    log_n = int(sys.argv[2])
+    n, bases, sc = setup(log_n)
+    hb = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
+    hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    hb.copy_(bases)
+    hs.copy_(sc)
+    torch.cuda.synchronize()
+    ref = None
+    for w in sys.argv[3:]:
+        if w == "default":
+            os.environ.pop("ALEO_B200_MSM_SPLIT", None)
+        else:
+            os.environ["ALEO_B200_MSM_SPLIT"] = w
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            raw = ab.VariableBase.msm(hb, hs, 104)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ref = ref or raw
+        print("log_n=%d split=%s host-call ms: %s  -> %.1f Mpts/s same_result=%s" %
+              (log_n, w, " ".join("%.2f" % t for t in ts), n / min(ts[1:]) / 1e3, raw == ref), flush=True)
+elif mode == "pageable":  # one process per ALEO_B200_FEED_THREADS value (read once per process)
+    log_n = int(sys.argv[2])
+    n, bases, sc = setup(log_n)
+    hb = bases.cpu().numpy().copy()   # plain (pageable) numpy memory, like a Rust Vec
+    hs = sc.cpu().numpy().copy()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        raw = ab.VariableBase.msm(hb, hs, 104)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print("log_n=%d feed_threads=%s pageable host-call ms: %s  -> %.1f Mpts/s" %
+          (log_n, os.environ.get("ALEO_B200_FEED_THREADS", "default"), " ".join("%.2f" % t for t in ts), n / min(ts[1:]) / 1e3), flush=True)
 elif mode == "sizes":
     for log_n in range(int(sys.argv[2]), int(sys.argv[3]) + 1):
         n, bases, sc = setup(log_n)
