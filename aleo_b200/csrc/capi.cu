@@ -554,7 +554,7 @@ int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t af
 }
 
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
-  if (kind < 0 || kind > 3 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
+  if (kind < 0 || kind > 5 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
   API_CK(aleo::bench_imad(kind, iters, ms_out, ops_out));

@@ -226,6 +226,36 @@ KERNEL void __launch_bounds__(256) imad_bench_kernel(u32* sink, u32 iters, u32 s
 #pragma unroll
       for (int k = 0; k < 9; k++) s ^= acc[r][k];
     if (s == 0x12345678u) sink[0] = s;
+  } else if (KIND == 4 || KIND == 5) {
+    // KIND 4: independent DFMA chains (the FP64 pipe: candidate carrier of 52-bit-limb products);
+    // KIND 5: the same DFMAs interleaved one to one with 32 x 32 + 64 IMAD.WIDE chains -- do the two pipes overlap?
+    double d[16];
+    u64 a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      d[k] = (double)(seed + tid * 16 + k) * 1e-9;
+      a[k] = seed + tid * 16 + k;
+    }
+    const double x = 1.0 + (double)(seed & 7u) * 1e-12, y = (double)tid * 1e-15;
+    const u32 xi = seed | 1u;
+    for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          d[k] = d[k] * x + y;  // contracted into one DFMA
+          if (KIND == 5) a[k] = (u64)(u32)a[k] * xi + a[k];
+        }
+      }
+    }
+    double sd = 0.0;
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      sd += d[k];
+      s ^= a[k];
+    }
+    if (sd == 0.12345678 || s == 0x12345678u) sink[0] = (u32)s;
   } else {
     Fq a = fp_zero<FqParams>(), b = fp_zero<FqParams>();
 #pragma unroll

@@ -88,13 +88,15 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const u32 grid = 148 * 8, block = 256;
-  const double per_thread[4] = {64.0, 64.0, 64.0, 2.0 * 276.0};
+  const double per_thread[6] = {64.0, 64.0, 64.0, 2.0 * 276.0, 64.0, 64.0};  // kind 5: 64 DFMA + 64 IMAD.WIDE, counted as 64 pairs
   for (int rep = 0; rep < 2; rep++) {  // first launch warms up
     cudaEventRecord(e0, 0);
     switch (kind) {
       case 0: util::imad_bench_kernel<0><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       case 1: util::imad_bench_kernel<1><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       case 2: util::imad_bench_kernel<2><<<grid, block>>>(sink, (u32)iters, 12345u); break;
+      case 4: util::imad_bench_kernel<4><<<grid, block>>>(sink, (u32)iters, 12345u); break;
+      case 5: util::imad_bench_kernel<5><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       default: util::imad_bench_kernel<3><<<grid, block>>>(sink, (u32)iters, 12345u); break;
     }
     cudaEventRecord(e1, 0);
@@ -107,7 +109,7 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   cudaEventDestroy(e1);
   cudaFree(sink);
   *ms_out = ms;
-  *ops_out = per_thread[kind] * (double)iters * (double)grid * (double)block;
+  *ops_out = per_thread[(kind >= 0 && kind < 6) ? kind : 3] * (double)iters * (double)grid * (double)block;
   return e;
 #endif
 }

@@ -244,7 +244,9 @@ int aleo_b200_dlog_dot_dev(void* out_scalar_dev, const void* scalars_dev, size_t
 int aleo_b200_check_on_curve_dev(const void* bases_dev, size_t n, size_t affine_stride, void* stream);
 /* dependent-free IMAD / IMAD.WIDE issue-rate microbenchmark: returns elapsed ms for
  * `iters` x 64 chains per thread on a full-chip grid, and the op count through *ops_out.
- * kind 0 = mad.lo (IMAD), 1 = mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.U32.X). */
+ * kind 0 = mad.lo (IMAD), 1 = 32x32+64 (IMAD.WIDE), 2 = mad.lo.cc/madc.hi.cc carry chains (IMAD.WIDE.U32.X),
+ * 3 = dependent Fq products, 4 = DFMA chains (FP64 pipe), 5 = DFMA and IMAD.WIDE interleaved one to one
+ * (ops = pairs): do the two pipes overlap? */
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out);
 
 #ifdef __cplusplus
