@@ -221,7 +221,11 @@ struct Session {
         RedLevel l;
         l.m = m;
         l.log_kc = ceil_log2((need + SCAN_MAX - 1) / SCAN_MAX);
-        if (l.log_kc > 4) l.log_kc = 4;
+        // a chunk is serial inside its thread (2 * Kc additions): chunks of 16 while they still fill the chip, chunks of
+        // 4 once a level would run on a few warps per SM and its time is the chain, not the work (ncu at 2^22: the second
+        // level of 16 ran 3840 threads for 0.82 ms at 26 % of the pipe -- as long as the first with 1/16 of its work)
+        const u32 cap = ((u64)nwin * ((need + 15) >> 4) < 32768u) ? 2u : 4u;
+        if (l.log_kc > cap) l.log_kc = cap;
         l.scale_log = scale_log;
         l.T = (need + (1u << l.log_kc) - 1) >> l.log_kc;
         lv.push_back(l);
