@@ -32,6 +32,11 @@ namespace ntt {
 constexpr int TILE_LOG = 11;            // elements per CTA tile
 constexpr int TILE = 1 << TILE_LOG;     // 2048 elements = 64 KB
 constexpr int TPB = TILE / 8;           // 256 threads, 8 elements each
+// Transforms of <= 2^SMALL_TILE_MAX_LOG elements use 1024-element tiles (128 threads, 4 CTAs per SM): twice the CTAs
+// for the same data, which is what a grid of 32 .. 512 CTAs on 148 SMs needs (B200: 2^16 0.061 -> 0.054 ms, 2^20
+// 0.238 -> 0.214 ms; above 2^24 the 9-bit passes would fall to 64-byte global runs and lose 2 %).
+constexpr int SMALL_TILE_LOG = 10;
+constexpr int SMALL_TILE_MAX_LOG = 20;
 constexpr int SMALL_MAX_LOG = 11;       // single-CTA kernel handles n <= 2^11
 constexpr int MAX_PASS_BITS = 9;
 constexpr int MAX_LOG_N = 32;           // memory bound, far below the field's two-adicity (47)
@@ -192,16 +197,16 @@ DEV void ntt8_lz(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
 // ---------------------------------------------------------------------------------------------
 // Shared-memory tile: two planes of uint4 (low / high half of an element).
 // ---------------------------------------------------------------------------------------------
-template <int K, bool LAST>
+template <int K, bool LAST, int TL>
 DEV u32 tile_phys(u32 p, u32 g) {
   constexpr u32 R = 1u << K;
-  constexpr u32 G = TILE >> K;
+  constexpr u32 G = (1u << TL) >> K;
   if (LAST) return g * (R + 1) + (p ^ ((p >> 3) & 7u));  // lanes run along p (loads) or g (stores)
   return p * G + g;                                      // lanes always run along g
 }
-template <int K, bool LAST>
+template <int K, bool LAST, int TL>
 CONSTFN u32 tile_plane_elems() {
-  return LAST ? (TILE >> K) * ((1u << K) + 1u) : (u32)TILE;
+  return LAST ? ((1u << TL) >> K) * ((1u << K) + 1u) : (1u << TL);
 }
 
 DEV void smem_put(uint4* plane0, uint4* plane1, u32 idx, const Fr& v) {
@@ -252,10 +257,10 @@ DEV u32 dist_expand(const PassArgs& a, u32 i2l) {
 
 // One pass.  K = bits handled, LAST = writes the natural-order result.  Coset scaling (use_pre on
 // the first pass, use_post on the last) is a CTA-uniform runtime branch.
-template <int K, bool LAST>
-KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
+template <int K, bool LAST, int TL>
+KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(PassArgs a) {
   constexpr u32 R = 1u << K;
-  constexpr u32 LG = TILE_LOG - K;
+  constexpr u32 LG = TL - K;
   constexpr u32 G = 1u << LG;
   constexpr u32 RT = R / 8;  // threads along r
   constexpr int S1 = 3;
@@ -263,7 +268,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
   constexpr int S3 = K - S1 - S2;
   static_assert(K >= 5 && K <= 9, "pass radix");
   DYN_SMEM(uint4, plane0);
-  uint4* plane1 = plane0 + tile_plane_elems<K, LAST>();
+  uint4* plane1 = plane0 + tile_plane_elems<K, LAST, TL>();
 
   const u32 tid = threadIdx.x;
   // gridDim.y = batch of independent transforms laid out back to back
@@ -326,7 +331,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
 #pragma unroll
     for (int k = 1; k < 8; k++) x[k] = lzm(x[k], a.inner[tr * k]);
 #pragma unroll
-    for (int k = 0; k < 8; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(k * C1 + tr, tg), x[k]);
+    for (int k = 0; k < 8; k++) smem_put(plane0, plane1, tile_phys<K, LAST, TL>(k * C1 + tr, tg), x[k]);
   }
   SYNC_THREADS();
   // ---- step 2 ------------------------------------------------------------------------------------
@@ -347,7 +352,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u32 blk = gam / C, t = gam % C;
       const u32 bp = blk * CP + t;
 #pragma unroll
-      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j * C, tg));
+      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST, TL>(bp + j * C, tg));
       if (S2 == 3) ntt8_lz<(C > 1)>(x + h * PTS, w8);
       if (S2 == 2) ntt4_lz<(C > 1)>(x + h * PTS, w8[2]);
       if (S2 == 1) ntt2_lz<(C > 1)>(x + h * PTS);
@@ -356,7 +361,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
         for (int k = 1; k < PTS; k++) x[h * PTS + k] = lzm(x[h * PTS + k], a.inner[(R / CP) * t * k]);
       }
 #pragma unroll
-      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k * C, tg), x[h * PTS + k]);
+      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST, TL>(bp + k * C, tg), x[h * PTS + k]);
     }
   }
   SYNC_THREADS();
@@ -378,12 +383,12 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       const u32 gam = tr + h * RT;
       const u32 bp = gam * CP;
 #pragma unroll
-      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST>(bp + j, tg));
+      for (int j = 0; j < PTS; j++) x[h * PTS + j] = smem_get(plane0, plane1, tile_phys<K, LAST, TL>(bp + j, tg));
       if (S3 == 3) ntt8_lz<false>(x + h * PTS, w8);
       if (S3 == 2) ntt4_lz<false>(x + h * PTS, w4);
       if (S3 == 1) ntt2_lz<false>(x + h * PTS);
 #pragma unroll
-      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST>(bp + k, tg), x[h * PTS + k]);
+      for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST, TL>(bp + k, tg), x[h * PTS + k]);
     }
     SYNC_THREADS();
   }
@@ -400,7 +405,7 @@ KERNEL void __launch_bounds__(TPB, 2) pass_kernel(PassArgs a) {
       // position of output kappa after the in-place decimation-in-frequency steps
       const u32 d1 = kap & 7u, d2 = (kap >> S1) & ((1u << S2) - 1u), d3 = kap >> (S1 + S2);
       const u32 pos = d1 * C1 + d2 * C2 + d3;
-      Fr v = smem_get(plane0, plane1, tile_phys<K, LAST>(pos, sg));
+      Fr v = smem_get(plane0, plane1, tile_phys<K, LAST, TL>(pos, sg));
       const u64 go = out_base + kap * ostride_r + sg;
       if (!LAST) {
         const u32 x = dist_expand(a, i2_base + sg) * kap;

@@ -205,32 +205,52 @@ static inline void destroy_plan(Plan& p) {
   p.owned.clear();
 }
 
-template <int K, bool LAST>
+template <int K, bool LAST, int TL>
 static inline cudaError_t launch_pass(const PassArgs& a, u32 grid, u32 batch, cudaStream_t s) {
-  const size_t smem = 2 * sizeof(uint4) * tile_plane_elems<K, LAST>();
+  const size_t smem = 2 * sizeof(uint4) * tile_plane_elems<K, LAST, TL>();
 #ifndef ALEO_EMU
   static thread_local int attr_done_dev = -1;  // per instantiation, per thread: cheap and race free
   int dev = 0;
   NTT_CK(cudaGetDevice(&dev));
   if (attr_done_dev != dev) {
-    NTT_CK(cudaFuncSetAttribute(pass_kernel<K, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NTT_CK(cudaFuncSetAttribute(pass_kernel<K, LAST, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done_dev = dev;
   }
 #endif
-  LAUNCH((pass_kernel<K, LAST>), dim3(grid, batch), dim3(TPB), smem, s, a);
+  LAUNCH((pass_kernel<K, LAST, TL>), dim3(grid, batch), dim3((1u << TL) / 8), smem, s, a);
   return cudaGetLastError();
 }
 
+// tile_log: TILE_LOG (2048-element tiles) or SMALL_TILE_LOG; grid = local elements >> tile_log
 template <bool LAST>
-static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, u32 batch, cudaStream_t s) {
+static inline cudaError_t launch_pass_k(int K, const PassArgs& a, u32 grid, u32 batch, cudaStream_t s, int tile_log = TILE_LOG) {
+  if (tile_log == SMALL_TILE_LOG) {
+    switch (K) {
+      case 5: return launch_pass<5, LAST, SMALL_TILE_LOG>(a, grid, batch, s);
+      case 6: return launch_pass<6, LAST, SMALL_TILE_LOG>(a, grid, batch, s);
+      case 7: return launch_pass<7, LAST, SMALL_TILE_LOG>(a, grid, batch, s);
+      case 8: return launch_pass<8, LAST, SMALL_TILE_LOG>(a, grid, batch, s);
+      case 9: return launch_pass<9, LAST, SMALL_TILE_LOG>(a, grid, batch, s);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (K) {
-    case 5: return launch_pass<5, LAST>(a, grid, batch, s);
-    case 6: return launch_pass<6, LAST>(a, grid, batch, s);
-    case 7: return launch_pass<7, LAST>(a, grid, batch, s);
-    case 8: return launch_pass<8, LAST>(a, grid, batch, s);
-    case 9: return launch_pass<9, LAST>(a, grid, batch, s);
+    case 5: return launch_pass<5, LAST, TILE_LOG>(a, grid, batch, s);
+    case 6: return launch_pass<6, LAST, TILE_LOG>(a, grid, batch, s);
+    case 7: return launch_pass<7, LAST, TILE_LOG>(a, grid, batch, s);
+    case 8: return launch_pass<8, LAST, TILE_LOG>(a, grid, batch, s);
+    case 9: return launch_pass<9, LAST, TILE_LOG>(a, grid, batch, s);
   }
   return cudaErrorInvalidValue;
+}
+
+// tile size of a single-GPU transform (ALEO_B200_NTT_TILE=10|11 forces one: A/B sweeps and tests)
+static inline int tile_log_for(u32 log_n) {
+  if (const char* e = getenv("ALEO_B200_NTT_TILE")) {
+    const int v = atoi(e);
+    if (v == SMALL_TILE_LOG || v == TILE_LOG) return v;
+  }
+  return log_n <= (u32)SMALL_TILE_MAX_LOG ? SMALL_TILE_LOG : TILE_LOG;
 }
 
 // number of kernel launches one transform of this plan issues (bench.py's gpu_launches)
@@ -299,11 +319,12 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
       a.tw_direct = p.tw_direct[i];
       a.pre = PowTable{p.cs_lo, p.cs_hi, p.lo_bits};
       a.post = a.pre;
-      const u32 grid = (u32)(n >> TILE_LOG);
+      const int tl = tile_log_for(p.log_n);
+      const u32 grid = (u32)(n >> tl);
       a.use_pre = ((i == 0) && p.coset && !p.inverse) ? 1 : 0;
       a.use_post = (last && p.coset && p.inverse) ? 1 : 0;
       if (pass_ev && i == 0) cudaEventRecord(pass_ev[0], s);
-      NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, nb, s) : launch_pass_k<false>(p.K[i], a, grid, nb, s));
+      NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, nb, s, tl) : launch_pass_k<false>(p.K[i], a, grid, nb, s, tl));
       if (pass_ev) cudaEventRecord(pass_ev[i + 1], s);
       log_cur -= (u32)p.K[i];
     }

@@ -30,6 +30,8 @@ ISSUED_MACS_PER_MIXED_ADD = 8 * 276 + 2 * 210   # IMAD.WIDE actually issued: 8 p
 NTT_BYTES_PER_ELEM_PER_PASS = 64   # 32 B read + 32 B write
 
 
+_JSON_OUT = None  # the process's original stdout (main() points file descriptor 1 at stderr)
+
 def load_c_oracle():
     path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
     if not os.path.exists(path):
@@ -156,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def proof_shaped_throughput(ab, o, torch, dev, world, dist, args):
@@ -666,7 +668,7 @@ def run_ours(args):
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
             "roofline": roofline, "witness_like_scalars": witness, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "sweep": sweep, "proof_shaped": proof_shaped, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -685,6 +687,13 @@ def main():
     ap.add_argument("--no-proof-shape", action="store_true", help="skip the synthetic proof-shaped stream")
     ap.add_argument("--proof-threads", type=int, default=4, help="host threads (one CUDA stream each) submitting proof-shaped work")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints to file descriptor 1 on the way (NCCL's version
+    # banner under NCCL_DEBUG=VERSION / INFO does) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
