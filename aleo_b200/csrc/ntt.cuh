@@ -126,7 +126,11 @@ DEV void ntt8(Fr* x, const Fr* w8 /* w8[1..3] valid */) {
 // single-CTA kernel.  ALU-pipe instructions per element drop by about a fifth (the passes are co-limited by the
 // ALU and the heavy FMA pipe).
 // ---------------------------------------------------------------------------------------------
+#ifdef ALEO_NTT_LZM_CALL
+DEV_NOINLINE Fr lzm(Fr a, Fr b) { return lz_mul(a, b); }
+#else
 DEV Fr lzm(const Fr& a, const Fr& b) { return lz_mul(a, b); }
+#endif
 
 DEV Fr pow_lookup_lz(const PowTable& t, u32 e) {  // < 2r
   Fr a = t.lo[e & ((1u << t.lo_bits) - 1u)];

@@ -25,7 +25,7 @@ static inline int split_passes(int L, int* K) {
 }
 
 constexpr u32 DIRECT_TW_MAX_LOG = 18;
-constexpr u32 DIRECT0_MIN_LOG = 21, DIRECT0_MAX_LOG = 24;
+constexpr u32 DIRECT0_MIN_LOG = 12, DIRECT0_MAX_LOG = 24;
 
 static inline void set_single_gpu(PassArgs& a) {
   a.d_k2l = 31;
@@ -183,11 +183,14 @@ static inline cudaError_t build_plan(Plan& p, int device, u32 log_n, bool invers
         NTT_CK(plan_alloc(p, &p.tw_direct[i], (size_t)1 << log_cur));
         NTT_CK(fill_pow_table(p.tw_direct[i], w, one, 1u << log_cur, log_n - log_cur, s));
       }
-      // The FIRST boundary has n distinct twiddles.  For 2^21 <= n <= 2^24 they are streamed from a direct table too
+      // The FIRST boundary has n distinct twiddles.  Up to 2^24 they come from a direct table too (L2 resident up to
+      // 2^20: 2^16 0.054 -> 0.051 ms, 2^20 0.213 -> 0.202 ms).  For 2^21 <= n <= 2^24 they are streamed
       // (n x 32 B in HBM per plan, read once per transform: +32 B per element on a pass that uses 13 % of the HBM
       // roof) instead of one table product per element: 2^24 3.80 -> 3.59 ms, 2^22 0.956 -> 0.902 ms on B200; no gain
       // at 2^20; above 2^24 (9-bit first pass, 4-element runs) the scattered table reads LOSE: 2^25 3.26 -> 3.97 ms.  ALEO_B200_NTT_DIRECT0=0 switches it off (memory).
-      if (i == 0 && p.npass >= 2 && log_n >= DIRECT0_MIN_LOG && log_n <= DIRECT0_MAX_LOG) {
+      u32 direct0_min = DIRECT0_MIN_LOG;
+      if (const char* em = getenv("ALEO_B200_NTT_DIRECT0_MIN")) direct0_min = (u32)atoi(em);  // sweeps
+      if (i == 0 && p.npass >= 2 && log_n >= direct0_min && log_n <= DIRECT0_MAX_LOG) {
         const char* e0 = getenv("ALEO_B200_NTT_DIRECT0");
         if (!(e0 && e0[0] == '0')) {
           NTT_CK(plan_alloc(p, &p.tw_direct[0], (size_t)1 << log_n));

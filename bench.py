@@ -520,7 +520,7 @@ def run_ours(args):
     k_bits = [log_n // npass + (1 if i < log_n % npass else 0) for i in range(npass)]
     mults_per_elem, log_cur = 3.25 * npass, log_n
     for i in range(npass - 1):
-        direct = (21 <= log_n <= 24) if i == 0 else (log_cur <= 18)      # ntt_host.cuh: DIRECT0_* / DIRECT_TW_MAX_LOG
+        direct = (12 <= log_n <= 24) if i == 0 else (log_cur <= 18)      # ntt_host.cuh: DIRECT0_* / DIRECT_TW_MAX_LOG
         mults_per_elem += 1 if direct else 2
         log_cur -= k_bits[i]
     ntt = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": world * n / ntt_step / 1e3, "unit": "Melem/s", "ms_per_step": ntt_step,

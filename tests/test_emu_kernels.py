@@ -38,6 +38,16 @@ def test_emu_ntt_all_variants(emu_lib, log_n):
     assert _ntt(emu_lib, v, log_n, 1, 1) == o.coset_ifft(v)
 
 
+@pytest.mark.parametrize("tile", [10, 11])
+def test_emu_ntt_both_tile_sizes(emu_lib, monkeypatch, tile):
+    """1024- and 2048-element tiles on the same sizes (the default picks 1024 up to 2^20)"""
+    monkeypatch.setenv("ALEO_B200_NTT_TILE", str(tile))
+    for log_n in (12, 15):
+        v = o.random_fr_vec(1 << log_n, 500 + log_n)
+        assert _ntt(emu_lib, v, log_n, 0, 0) == o.fft(v)
+        assert _ntt(emu_lib, v, log_n, 1, 1) == o.coset_ifft(v)
+
+
 def test_emu_ntt_three_passes(emu_lib):
     log_n = 17                      # 6 + 6 + 5 bits: exercises the middle-digit reversal
     v = o.random_fr_vec(1 << log_n, 17)

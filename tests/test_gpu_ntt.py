@@ -66,6 +66,22 @@ def test_parity_with_c_oracle_large(c_oracle, log_n):
         assert np.array_equal(y.cpu().numpy(), ref), name
 
 
+@pytest.mark.parametrize("tile,log_n", [(11, 13), (11, 18), (10, 21), (10, 25)])
+def test_both_tile_sizes_at_sizes_that_default_to_the_other(c_oracle, monkeypatch, tile, log_n):
+    """pass kernels come in two tile sizes (1024 elements up to 2^20, 2048 above): force the one a size would not pick"""
+    monkeypatch.setenv("ALEO_B200_NTT_TILE", str(tile))
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    x = ab.gen_scalars_dev(n, 777 + log_n, 0, True)
+    host = x.cpu().numpy()
+    for name, inv, coset, _ in VARIANTS:
+        y = x.clone()
+        getattr(dom, name + "_in_place_dev")(y)
+        ref = host.copy()
+        assert c_oracle.oracle_ntt_fr(ref.ctypes.data, log_n, inv, coset, os.cpu_count() or 1) == 0
+        assert np.array_equal(y.cpu().numpy(), ref), name
+
+
 @pytest.mark.parametrize("log_n", [22, 24, 26])
 def test_round_trip_and_linearity_at_full_size(log_n):
     import torch
