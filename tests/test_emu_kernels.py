@@ -48,6 +48,19 @@ def test_emu_ntt_both_tile_sizes(emu_lib, monkeypatch, tile):
         assert _ntt(emu_lib, v, log_n, 1, 1) == o.coset_ifft(v)
 
 
+def test_emu_ntt_extreme_values(emu_lib):
+    """the passes keep semi-reduced values (< 2r) and feed untested sums / differences (< 4r) into raw products:
+    vectors made of r - 1, r - 2, 0 and 1 push every intermediate towards those bounds"""
+    import random
+    log_n = 12
+    n = 1 << log_n
+    rnd = random.Random(12)
+    top = o.R_MOD - 1
+    for v in ([top] * n, [top if i & 1 else 0 for i in range(n)], [rnd.choice((0, 1, top, top - 1)) for _ in range(n)]):
+        assert _ntt(emu_lib, v, log_n, 0, 0) == o.fft(v)
+        assert _ntt(emu_lib, v, log_n, 1, 1) == o.coset_ifft(v)
+
+
 def test_emu_ntt_three_passes(emu_lib):
     log_n = 17                      # 6 + 6 + 5 bits: exercises the middle-digit reversal
     v = o.random_fr_vec(1 << log_n, 17)

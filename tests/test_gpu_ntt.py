@@ -38,6 +38,21 @@ def test_parity_with_python_oracle(log_n):
         assert t.cpu().numpy().tobytes() == want, (name, "device")        # device-resident entry point
 
 
+@pytest.mark.parametrize("log_n", [12, 15, 17])
+def test_extreme_values(log_n):
+    """the passes keep semi-reduced values (< 2r) and feed untested sums / differences (< 4r) into raw products:
+    vectors made of r - 1, r - 2, 0 and 1 push every intermediate towards those bounds (2 and 3 passes, both tiles)"""
+    import random
+    n = 1 << log_n
+    rnd = random.Random(log_n)
+    top = o.R_MOD - 1
+    dom = ab.EvaluationDomain.new(n)
+    for v in ([top] * n, [top if i & 1 else 0 for i in range(n)], [rnd.choice((0, 1, top, top - 1)) for _ in range(n)]):
+        raw = o.fr_vec_to_bytes(v)
+        for name, _, _, ref in VARIANTS:
+            assert getattr(dom, name)(raw) == o.fr_vec_to_bytes(ref(v)), name
+
+
 def test_golden_vectors(golden_dir):
     g = json.load(open(os.path.join(golden_dir, "ntt_golden.json")))
     for key in ("0", "1", "3", "6", "10"):
