@@ -533,6 +533,24 @@ def run_ours(args):
                         "note": "the 253-bit NTT is integer-pipe bound (about %.1f Fr products of 120 IMAD.WIDE per element); int_frac is "
                                 "measured against the same live IMAD.WIDE peak as the MSM" % mults_per_elem}}
 
+    # the same transform through the host-pointer entry point (aleo_b200_ntt_fr on a pinned host buffer: H2D + 3 passes +
+    # D2H inside the timed region) -- PCIe bound, which is why the prover-side helpers keep polynomials resident
+    if world == 1:
+        hx = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+        hx.copy_(x)
+        torch.cuda.synchronize()
+        want_h = x.clone()
+        dom.fft_in_place_dev(want_h)
+        dom.ntt_host_buffer(hx, 0, 0)                      # warm-up + check
+        h_ok = bool(torch.equal(hx, want_h.cpu()))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dom.ntt_host_buffer(hx, 0, 0)
+        h_s = (time.perf_counter() - t0) / args.steps
+        ntt["e2e"] = {"value": n / h_s / 1e6, "unit": "Melem/s", "ms_per_step": h_s * 1e3, "h2d_bytes_per_step": n * 32,
+                      "d2h_bytes_per_step": n * 32, "api": "aleo_b200_ntt_fr (host pointer, pinned)", "matches_resident_path": h_ok}
+        del hx, want_h
+
     # ---- N > 1: ONE NTT of 2^(log_n + log2 N) over the N GPUs: exchange fused into the transform (peer-memory stores),
     #      with the NCCL all-to-all schedule timed beside it -----------------------------------------------------------
     ntt_dist = None
