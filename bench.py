@@ -43,8 +43,10 @@ def load_c_oracle():
     return lib
 
 
-def cpu_msm_baseline(log_n_sample, steps, seed=0xA1E0B200 + 2):
-    """C oracle port (Pippenger, pthreads over windows) on all host cores; returns (Mpts/s, info)"""
+def cpu_msm_baseline(log_n_sample, steps, warmup=0, seed=0xA1E0B200 + 2, budget_s=None):
+    """C oracle port (Pippenger, pthreads over windows) on all host cores; returns (Mpts/s, info).
+    `steps` timed runs after `warmup` untimed ones; with budget_s the timed runs stop early (never below 3) once the
+    budget is spent, and info says how many were timed."""
     import numpy as np
 
     from oracle import bls12_377 as o
@@ -60,32 +62,45 @@ def cpu_msm_baseline(log_n_sample, steps, seed=0xA1E0B200 + 2):
     scalars |= rng.integers(0, 2, size=(n, 4), dtype=np.uint64) << np.uint64(63)
     scalars[:, 3] &= np.uint64((1 << 60) - 1)          # 252 bits < r
     out = C.create_string_buffer(144)
+    t_begin = time.perf_counter()
+    for _ in range(max(0, warmup)):
+        lib.oracle_msm_g1(out, bases.ctypes.data, n, scalars.ctypes.data, 104, cores)
     times = []
     for _ in range(max(1, steps)):
         t = time.perf_counter()
         lib.oracle_msm_g1(out, bases.ctypes.data, n, scalars.ctypes.data, 104, cores)
         times.append(time.perf_counter() - t)
-    # correctness of the timed run itself (known discrete logs)
+        if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_begin + times[-1] > budget_s:
+            break
+    # correctness of the timed code itself (known discrete logs) on a prefix the big-integer oracle finishes quickly
     sc = [int.from_bytes(scalars[i].tobytes(), "little") for i in range(min(n, 1 << 12))]
     chk = C.create_string_buffer(144)
     lib.oracle_msm_g1(chk, bases.ctypes.data, len(sc), scalars.ctypes.data, 104, cores)
     assert chk.raw == o.g1_projective_to_bytes(o.msm_expected_from_dlogs(len(sc), seed, sc)), "CPU baseline produced a wrong result"
-    best = sorted(times)[len(times) // 2]
-    return n / best / 1e6, {"cores": cores, "sample": "G1 MSM n=2^%d, uniform 252-bit scalars, %d timed run(s), median" % (log_n_sample, len(times)),
-                            "seconds_per_run": best}
+    med = sorted(times)[len(times) // 2]
+    return n / med / 1e6, {"cores": cores, "sample": "G1 MSM n=2^%d, uniform 252-bit scalars, median of %d timed run(s) after %d warm-up"
+                                                     % (log_n_sample, len(times), max(0, warmup)),
+                           "seconds_per_run": med, "timed_runs": len(times), "log_n": log_n_sample}
 
 
-def cpu_ntt_baseline(log_n_sample):
+def cpu_ntt_baseline(log_n_sample, runs=3):
+    """forward Fr NTT of the C oracle port on all host cores: one untimed call builds (and caches) the root table --
+    snarkVM's prover hands its cached FFTPrecomputation to the transform as well --, then the median of `runs`"""
     import numpy as np
 
     lib = load_c_oracle()
     cores = os.cpu_count() or 1
     n = 1 << log_n_sample
     data = np.random.default_rng(5).integers(0, 2**60, size=(n, 4), dtype=np.int64).astype(np.uint64)
-    t = time.perf_counter()
     lib.oracle_ntt_fr(data.ctypes.data, log_n_sample, 0, 0, cores)
-    dt = time.perf_counter() - t
-    return n / dt / 1e6, {"cores": cores, "sample": "Fr NTT n=2^%d forward, 1 run (includes root-table build)" % log_n_sample}
+    times = []
+    for _ in range(max(1, runs)):
+        t = time.perf_counter()
+        lib.oracle_ntt_fr(data.ctypes.data, log_n_sample, 0, 0, cores)
+        times.append(time.perf_counter() - t)
+    med = sorted(times)[len(times) // 2]
+    return n / med / 1e6, {"cores": cores, "sample": "Fr NTT n=2^%d forward, root table cached, median of %d runs" % (log_n_sample, len(times)),
+                           "seconds_per_run": med}
 
 
 class ClockSampler:
@@ -137,23 +152,28 @@ def workload_config(log_n, world):
 
 
 def run_reference(args):
+    """CPU arm: the C restatement (oracle/oracle.c) on all host cores at the SAME workload as the GPU arm (one step = one
+    G1 MSM over the 2^log_n points of a GPU's point range).  A step takes ~10-20 s at 2^24, so the timed steps stop once
+    --cpu-budget-s is spent (never fewer than 3); `steps` reports how many were timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(args.log_n, args.cpu_log_n)
     t0 = time.perf_counter()
-    val, info = cpu_msm_baseline(sample, args.steps + args.warmup)
-    ntt_val, ntt_info = cpu_ntt_baseline(min(args.log_n, 22))
+    log_n = args.log_n if args.cpu_log_n <= 0 else min(args.log_n, args.cpu_log_n)
+    val, info = cpu_msm_baseline(log_n, args.steps, warmup=min(args.warmup, 1), budget_s=args.cpu_budget_s)
+    ntt_val, ntt_info = cpu_ntt_baseline(min(log_n, 24))
+    world = max(1, args.gpus)
+    sample = info["sample"] + (" (the full per-GPU workload)" if log_n == args.log_n else " (BOUNDED SAMPLE of the 2^%d workload)" % args.log_n)
+    if world > 1:
+        sample += "; N > 1: the CPU runs ONE rank's point range, Mpts/s is per whole host"
     line = {
         "impl": "reference", "metric": "bls12_377_g1_msm_mpts_per_s", "value": val, "unit": "Mpts/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_run"] * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (384-bit Montgomery Fq)", "data": "synthetic",
-        "config": dict(workload_config(args.log_n, max(1, args.gpus)),
-                       reference_sample="CPU arm: each step is a bounded sample n=2^%d of the n=2^%d-per-GPU workload" % (sample, args.log_n),
-                       sample_log_n=sample),
-        "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
-                         "note": "C restatement of the Pippenger algorithm class (oracle/oracle.c); the snarkVM Rust binary "
-                                 "cannot be built here (no Rust toolchain)"},
+        "steps": info["timed_runs"], "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": info["seconds_per_run"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (384-bit Montgomery Fq)",
+        "data": "synthetic", "config": workload_config(args.log_n, world),
+        "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": sample,
+                         "note": "C restatement of the Pippenger algorithm class (oracle/oracle.c, windows in parallel like "
+                                 "snarkVM's standard::msm); the snarkVM Rust binary cannot be built here (no Rust toolchain)"},
         "ntt": {"value": ntt_val, "unit": "Melem/s", **ntt_info},
         "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -258,6 +278,174 @@ def proof_shaped_throughput(ab, o, torch, dev, world, dist, args):
             "commits": "aleo_b200_kzg_commit_batch_dev: the 13 commitments of a unit in one launch sequence",
             "units_per_s_with_13_separate_commit_calls": one_by_one,
             "commit_checked_against_oracle": bool(ok), "replicas": world}
+
+
+def ntt_spot_check(ab, o, torch, x_in, X_out, log_n, picks=(1, 0x2F3A7, -5)):
+    """size-independent parity of a forward transform: X[k] must equal the polynomial x evaluated at w^k
+    (aleo_b200_fr_poly_eval_dev, an independent kernel that tests/test_gpu_poly.py pins against the oracle)"""
+    n = 1 << log_n
+    w = o.fr_root_of_unity(log_n)
+    ok = True
+    for k in picks:
+        k %= n
+        got = int.from_bytes(X_out[k].cpu().numpy().tobytes(), "little")
+        ok = ok and got == o.fr_to_mont(ab.poly.evaluate_dev(x_in, pow(w, k, o.R_MOD)))
+    return bool(ok)
+
+
+def dist_ntt_block(ab, o, torch, dist, dev, rank, world, glog, args, barrier, scaling):
+    """ONE Fr NTT of 2^glog over `world` GPUs (aleo_b200_ntt_dist_*: the exchange is fused into the last-but-one pass).
+    Parity: every rank builds the same seeded 2^glog vector, runs the single-GPU transform on it (itself spot-checked
+    against polynomial evaluation) and compares ITS WHOLE output block of the distributed transform with it, for the
+    forward and the coset-inverse kind; asserted."""
+    from aleo_b200 import dist as adist
+
+    n_g = 1 << glog
+    x_full = ab.gen_scalars_dev(n_g, 78, 0, True, device=dev)          # same vector on every rank
+    dom = ab.EvaluationDomain.new(n_g)
+    peer = adist.PeerNTT(glog)
+    blk = peer.input_block(x_full)
+    oks = {}
+    for name, inverse, coset in (("forward", False, False), ("coset_inverse", True, True)):
+        want = dom._run_dev(x_full.clone(), 1 if inverse else 0, 1 if coset else 0)
+        if name == "forward":
+            oks["single_gpu_vs_poly_eval"] = ntt_spot_check(ab, o, torch, x_full, want, glog)
+        got = peer.transform(blk, inverse=inverse, coset=coset)
+        oks[name] = bool(torch.equal(got.reshape(-1), peer.output_block_of(want).reshape(-1)))
+        del want, got
+    del x_full
+    flags = [None] * world
+    dist.all_gather_object(flags, oks)
+    parity = all(all(f.values()) for f in flags)
+    assert parity, "distributed NTT: a rank's block differs from the single-GPU transform: %r" % (flags,)
+    xo = torch.empty_like(blk).reshape(-1, 4)
+    for _ in range(args.warmup):
+        peer.transform(blk, out=xo)
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.steps):
+        peer.transform(blk, out=xo)
+    d1.record()
+    barrier()
+    dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
+    dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+    dstep = dms.item() / args.steps
+    stage_ms = peer.stage_times(blk, xo) if hasattr(peer, "stage_times") else None
+    peer_passes, peer_rf, peer_rl = peer.passes, peer.log_r_first, peer.log_r_last
+    peer.close()
+    del xo
+    # the same transform with the exchange as a separate NCCL all-to-all (aleo_b200/dist.py ntt_four_step)
+    l1, l2 = adist.four_step_shape(glog)
+    g1, g2 = 1 << l1, 1 << l2
+    xb = blk.reshape(-1)[: (g1 * (g2 // world)) * 4].reshape(g1, g2 // world, 4).contiguous()
+    del blk
+    for _ in range(args.warmup):
+        adist.ntt_four_step(xb, glog)
+    barrier()
+    d0.record()
+    for _ in range(args.steps):
+        adist.ntt_four_step(xb, glog)
+    d1.record()
+    barrier()
+    nms = torch.tensor([d0.elapsed_time(d1)], device=dev)
+    dist.all_reduce(nms, op=dist.ReduceOp.MAX)
+    nstep = nms.item() / args.steps
+    del xb
+    torch.cuda.empty_cache()
+    return {"metric": "bls12_377_fr_ntt_melem_per_s", "value": n_g / dstep / 1e3, "unit": "Melem/s", "ms_per_step": dstep,
+            "log_n_global": glog, "passes": peer_passes, "scaling": scaling,
+            "schedule": "single-GPU pass split %d passes (R_first 2^%d, R_last 2^%d); the last-but-one pass stores into the peers' "
+                        "receive buffers (CUDA IPC peer memory over NVLink); the last pass runs from the receive buffer"
+                        % (peer_passes, peer_rf, peer_rl),
+            "exchange_bytes_per_rank": n_g // world * 32 * (world - 1) // world,
+            "parity": parity, "parity_what": "every rank's whole output block == single-GPU transform (forward and coset inverse); "
+                                             "single-GPU transform spot-checked against polynomial evaluation",
+            "stage_ms": stage_ms,
+            "nccl_all_to_all_schedule": {"value": n_g / nstep / 1e3, "unit": "Melem/s", "ms_per_step": nstep,
+                                         "what": "four-step %dx%d with torch transposes around one all_to_all_single (NCCL)" % (g1, g2)}}
+
+
+def config4_fixed_size(ab, o, torch, dist, dev, rank, world, args, barrier):
+    """BASELINE.json configs[3] as written (strong scaling): ONE G1 MSM of 2^26 points sharded by contiguous point range
+    (2^26 / N per GPU, single final combine) and ONE Fr NTT of 2^26 elements over the N GPUs (N = 1: the single-GPU
+    kernels).  Both checked: the MSM through known discrete logs, the NTT block by block against the single-GPU
+    transform, which is spot-checked against polynomial evaluation."""
+    lt = args.config4_log_n
+    n_tot = 1 << lt
+    n = n_tot // world
+    first = rank * n
+    seed = 0xA1E0B200 + 4
+    steps = max(1, min(args.steps, 5))
+    s0, d = o.base_dlogs(n_tot, seed)
+    bases = ab.gen_bases_dev(n, s0, d, first, 104, device=dev)
+    scalars = ab.gen_scalars_dev(n, seed, first, False, device=dev)
+    partial = torch.empty(144, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(144 * world, dtype=torch.uint8, device=dev)
+    result = torch.empty(144, dtype=torch.uint8, device=dev)
+
+    def step():
+        ab.VariableBase.msm_dev(bases, scalars, n, 104, out=partial)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, partial)
+            ab.VariableBase.sum_partials_dev(gathered, world, out=result)
+            return result
+        return partial
+
+    ks = [ab.dlog_dot_dev(scalars, n, s0, d, first)]
+    if world > 1:
+        mine = ks[0]
+        ks = [None] * world
+        dist.all_gather_object(ks, mine)
+    msm_ok = step().cpu().numpy().tobytes() == o.g1_projective_to_bytes(o.g1_mul(o.G1_GEN, sum(ks) % o.R_MOD))
+    assert msm_ok, "config 4: sharded MSM result does not match the oracle"
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    msm_ms = ms.item() / steps
+    c_bits = ab.VariableBase.window_bits(n)
+    del bases, scalars
+    torch.cuda.empty_cache()
+    out = {"what": "BASELINE.json configs[3]: fixed-size 2^%d MSM by point range + 2^%d NTT over N GPUs (strong scaling)" % (lt, lt),
+           "n_gpus": world, "scaling": "strong",
+           "msm": {"log_n_total": lt, "points_per_gpu": n, "window_bits": c_bits, "ms_per_step": msm_ms, "value": n_tot / msm_ms / 1e3,
+                   "unit": "Mpts/s", "checked_against_oracle": bool(msm_ok)}}
+    if world == 1:
+        dom = ab.EvaluationDomain.new(n_tot)
+        x = ab.gen_scalars_dev(n_tot, 78, 0, True, device=dev)
+        X = x.clone()
+        dom.fft_in_place_dev(X)
+        ntt_ok = ntt_spot_check(ab, o, torch, x, X, lt)
+        dom.ifft_in_place_dev(X)
+        ntt_ok = ntt_ok and bool(torch.equal(X, x))
+        assert ntt_ok, "config 4: 2^%d NTT failed its polynomial-evaluation / round-trip check" % lt
+        del X
+        dom.fft_in_place_dev(x)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            dom.fft_in_place_dev(x)
+        e1.record()
+        barrier()
+        ntt_ms = e0.elapsed_time(e1) / steps
+        del x
+        out["ntt"] = {"log_n_total": lt, "ms_per_step": ntt_ms, "value": n_tot / ntt_ms / 1e3, "unit": "Melem/s", "passes": dom.launches(),
+                      "parity": bool(ntt_ok), "parity_what": "3 outputs == polynomial evaluation at w^k, and ifft(fft(x)) == x"}
+    elif (world & (world - 1)) == 0 and world <= 8:
+        nd = dist_ntt_block(ab, o, torch, dist, dev, rank, world, lt, args, barrier, scaling="strong")
+        out["ntt"] = {"log_n_total": lt, "ms_per_step": nd["ms_per_step"], "value": nd["value"], "unit": "Melem/s", "passes": nd["passes"],
+                      "parity": nd["parity"], "parity_what": nd["parity_what"], "stage_ms": nd["stage_ms"],
+                      "nccl_all_to_all_ms": nd["nccl_all_to_all_schedule"]["ms_per_step"]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -440,7 +628,9 @@ def run_ours(args):
         del srs, hs_pin
         torch.cuda.empty_cache()
 
-    # ---- e2e through the host-pointer C-ABI call, pinned host buffers ------------------------------
+    # ---- e2e through the host-pointer C-ABI call (H2D of bases + scalars and D2H of the result inside the timed region).
+    #      Headline = PAGEABLE caller memory (what a Rust Vec is: the library stages it through pinned buffers with helper
+    #      threads); the same call on pinned buffers is reported beside it ------------------------------------------------
     hb = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
     hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
     hb.copy_(bases)
@@ -448,37 +638,33 @@ def run_ours(args):
     torch.cuda.synchronize()
     host_parts = torch.empty(144 * world, dtype=torch.uint8, device=dev)
 
-    def e2e_step():
-        raw = ab.VariableBase.msm(hb, hs, 104)              # H2D + MSM + D2H inside
+    def e2e_step(b, sc):
+        raw = ab.VariableBase.msm(b, sc, 104)              # H2D + MSM + D2H inside
         if world > 1:
             mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
             dist.all_gather_into_tensor(host_parts, mine)
             return ab.VariableBase.sum_partials_dev(host_parts, world).cpu().numpy().tobytes()
         return raw
 
-    e2e_ok = e2e_step() == want
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = world * n * args.steps / e2e_s.item() / 1e6
-    host_plan = ab.VariableBase.host_plan(n)
-    # the same call on PAGEABLE host memory (what a Rust Vec is): staged through pinned buffers by helper threads
-    e2e_pageable = None
-    if world == 1:
-        pb, ps = hb.numpy().copy(), hs.numpy().copy()
-        pg_ok = ab.VariableBase.msm(pb, ps, 104) == want
+    def e2e_time(b, sc):
+        ok = e2e_step(b, sc) == want                       # warm-up + check
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ab.VariableBase.msm(pb, ps, 104)
-        e2e_pageable = {"value": n * args.steps / (time.perf_counter() - t0) / 1e6, "unit": "Mpts/s", "checked_against_oracle": bool(pg_ok),
-                        "what": "aleo_b200_msm_g1 on pageable host buffers: 4 helper threads stage 4 MB slices through pinned double buffers"}
-        del pb, ps
+            e2e_step(b, sc)
+        barrier()
+        secs = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        return world * n * args.steps / secs.item() / 1e6, bool(ok)
+
+    e2e_pinned, pin_ok = e2e_time(hb, hs)
+    pb, ps = hb.numpy().copy(), hs.numpy().copy()          # plain malloc'ed (pageable) numpy buffers
     del hb, hs
+    e2e_val, pg_ok = e2e_time(pb, ps)
+    e2e_ok = pin_ok and pg_ok
+    del pb, ps
+    host_plan = ab.VariableBase.host_plan(n)
 
     # ---- secondary: Fr NTT of the same size, resident ---------------------------------------------
     del bases
@@ -552,84 +738,21 @@ def run_ours(args):
         del hx, want_h
 
     # ---- N > 1: ONE NTT of 2^(log_n + log2 N) over the N GPUs: exchange fused into the transform (peer-memory stores),
-    #      with the NCCL all-to-all schedule timed beside it -----------------------------------------------------------
+    #      with the NCCL all-to-all schedule timed beside it; every rank's block is compared with the single-GPU transform ----
     ntt_dist = None
+    del x, x0
+    torch.cuda.empty_cache()
     if world > 1 and (world & (world - 1)) == 0 and world <= 8:
-        from aleo_b200 import dist as adist
+        ntt_dist = dist_ntt_block(ab, o, torch, dist, dev, rank, world, log_n + world.bit_length() - 1, args, barrier, scaling="weak")
 
-        glog = log_n + world.bit_length() - 1
-        w = o.fr_root_of_unity(glog)
-        one = np.frombuffer(o.int_to_le_bytes(o.fr_to_mont(1), 32), dtype=np.int64)
-        peer = adist.PeerNTT(glog)
-        rows_in, cols_in, rows_out, cols_out = peer.layout()
-        # order / twiddle / exchange check: a delta at index 1 must transform to the powers of omega
-        blk = torch.zeros((rows_in * cols_in, 4), dtype=torch.int64, device=dev)
-        if rank == 1 // cols_in:
-            blk[1 % cols_in] = torch.from_numpy(one.copy()).to(dev)
-        outp = peer.transform(blk).cpu().numpy()
-        r0 = cols_out * world
-        picks = ((0, 0), (1, 0), (rows_out - 1, 1 % cols_out), (rows_out // 2, cols_out - 1), (3, cols_out // 2))
-        peer_ok = all(outp[a * cols_out + b].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, a * r0 + rank * cols_out + b, o.R_MOD)), 32)
-                      for a, b in picks)
-        xb = ab.gen_scalars_dev(rows_in * cols_in, 78, first, True, device=dev)
-        xo = torch.empty_like(xb)
-        for _ in range(args.warmup):
-            peer.transform(xb, out=xo)
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record()
-        for _ in range(args.steps):
-            peer.transform(xb, out=xo)
-        d1.record()
-        barrier()
-        dms = torch.tensor([d0.elapsed_time(d1)], device=dev)
-        dist.all_reduce(dms, op=dist.ReduceOp.MAX)
-        dstep = dms.item() / args.steps
-        peer_passes, peer_rf, peer_rl = peer.passes, peer.log_r_first, peer.log_r_last
-        peer.close()
-        del blk, xo
-        # the same transform with the exchange as a separate NCCL all-to-all (aleo_b200/dist.py ntt_four_step)
-        l1, l2 = adist.four_step_shape(glog)
-        g1, g2 = 1 << l1, 1 << l2
-        wc, wr = g2 // world, g1 // world
-        blk = torch.zeros((g1, wc, 4), dtype=torch.int64, device=dev)
-        if rank == 1 // wc:
-            blk[0, 1 % wc] = torch.from_numpy(one.copy()).to(dev)
-        outb = adist.ntt_four_step(blk, glog).cpu().numpy()
-        nccl_ok = all(outb[k, k2].tobytes() == o.int_to_le_bytes(o.fr_to_mont(pow(w, rank * wr + k + g1 * k2, o.R_MOD)), 32)
-                      for k, k2 in ((0, 0), (1, 0), (wr - 1, 1), (wr // 2, g2 - 1), (3, g2 // 2)))
-        flags = [None] * world
-        dist.all_gather_object(flags, (bool(peer_ok), bool(nccl_ok)))
-        del blk, outb
-        xb = xb.reshape(g1, wc, 4)
-        for _ in range(args.warmup):
-            adist.ntt_four_step(xb, glog)
-        barrier()
-        d0.record()
-        for _ in range(args.steps):
-            adist.ntt_four_step(xb, glog)
-        d1.record()
-        barrier()
-        nms = torch.tensor([d0.elapsed_time(d1)], device=dev)
-        dist.all_reduce(nms, op=dist.ReduceOp.MAX)
-        nstep = nms.item() / args.steps
-        del xb
-        ntt_dist = {"metric": "bls12_377_fr_ntt_melem_per_s", "value": (1 << glog) / dstep / 1e3, "unit": "Melem/s", "ms_per_step": dstep,
-                    "log_n_global": glog, "passes": peer_passes,
-                    "schedule": "single-GPU pass split %d passes (R_first 2^%d, R_last 2^%d); the last-but-one pass stores into the peers' "
-                                "receive buffers (CUDA IPC peer memory over NVLink), 1-element all-reduce as barrier, last pass from "
-                                "the receive buffer" % (peer_passes, peer_rf, peer_rl),
-                    "exchange_bytes_per_rank": (1 << glog) // world * 32 * (world - 1) // world,
-                    "scaling": "weak", "delta_impulse_check": all(f[0] for f in flags),
-                    "nccl_all_to_all_schedule": {"value": (1 << glog) / nstep / 1e3, "unit": "Melem/s", "ms_per_step": nstep,
-                                                 "what": "four-step %dx%d with torch transposes around one all_to_all_single (NCCL)" % (g1, g2),
-                                                 "delta_impulse_check": all(f[1] for f in flags)}}
+    # ---- BASELINE.json configs[3] as written: a FIXED 2^26 MSM sharded by point range and a FIXED 2^26 NTT over the N GPUs
+    config4 = None
+    if not args.no_config4:
+        config4 = config4_fixed_size(ab, o, torch, dist, dev, rank, world, args, barrier)
 
     # ---- size sweep 2^16 .. 2^22 (BASELINE.json metric range / config 2), single-GPU run only -----------------
     sweep = None
     if world == 1 and not args.no_sweep:
-        del x, x0
-        torch.cuda.empty_cache()
         sweep = []
         for ln in range(16, min(log_n, 23), 2):
             m = 1 << ln
@@ -668,23 +791,53 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, info = cpu_msm_baseline(min(log_n, args.cpu_log_n), 1)
-        cpu = {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+        val, info = cpu_msm_baseline(min(log_n, args.cpu_sample_log_n), 3, warmup=1)
+        cpu = {"value": val, "unit": "Mpts/s", "cores": info["cores"], "kind": "port",
+               "sample": info["sample"] + " (BOUNDED SAMPLE of the 2^%d workload; `--impl reference` times the full size)" % log_n}
 
     if rank == 0:
+        # the integer roof without trusting the probe: SMs x 32 IMAD.WIDE lanes per clock x the SM clock sampled under load
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        roofline["peak_theoretical"] = sms * 32 * mhz * 1e-3                      # GMAC/s
+        roofline["peak_theoretical_what"] = "%d SMs x 32 IMAD.WIDE/clk/SM (half-rate FMA-heavy pipe) x %.0f MHz (clocks.sm_mhz)" % (sms, mhz)
+        roofline["frac_of_theoretical"] = roofline["achieved"] / roofline["peak_theoretical"]
+        roofline["pipe_frac_of_theoretical"] = roofline["pipe_frac"] * roofline["peak"] / roofline["peak_theoretical"]
+        # compact mirror of the secondary results (the driver's record keeps `roofline` whole)
+        r3 = lambda v: None if v is None else round(v, 4)  # noqa: E731
+        sec = {"ntt_2p%d" % log_n: {"ms": r3(ntt_step), "melem_s": r3(ntt["value"]), "int_frac": r3(ntt["roofline"]["int_frac"]),
+                                     "hbm_frac": r3(ntt["roofline"]["frac"]), "round_trip_ok": ntt_ok}}
+        if ntt_dist:
+            sec["ntt_dist_weak"] = {"log_n": ntt_dist["log_n_global"], "ms": r3(ntt_dist["ms_per_step"]), "melem_s": r3(ntt_dist["value"]),
+                                    "parity": ntt_dist["parity"], "nccl_a2a_ms": r3(ntt_dist["nccl_all_to_all_schedule"]["ms_per_step"]),
+                                    "stage_ms": ntt_dist["stage_ms"]}
+        if config4:
+            sec["config4_msm_2p%d" % args.config4_log_n] = {"ms": r3(config4["msm"]["ms_per_step"]), "mpts_s": r3(config4["msm"]["value"]),
+                                                             "ok": config4["msm"]["checked_against_oracle"], "scaling": "strong"}
+            if "ntt" in config4:
+                sec["config4_ntt_2p%d" % args.config4_log_n] = {"ms": r3(config4["ntt"]["ms_per_step"]), "melem_s": r3(config4["ntt"]["value"]),
+                                                                 "parity": config4["ntt"]["parity"], "scaling": "strong"}
+        if sweep:
+            sec["sweep_ms"] = {"2p%d" % e["log_n"]: [r3(e["msm_ms"]), r3(e["ntt_ms"]), e["msm_checked_against_oracle"]] for e in sweep}
+            sec["sweep_ms_what"] = "[msm ms, ntt ms, msm checked]"
+        sec["e2e_pinned_mpts_s"] = r3(e2e_pinned)
+        if srs_obj:
+            sec["srs_resident_mpts_s"] = r3(srs_obj["value"])
+        roofline["secondary"] = sec
         line = {
             "metric": "bls12_377_g1_msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (384-bit Montgomery Fq, 256-bit Fr)", "data": "synthetic",
-            "config": dict(workload_config(log_n, world), window_bits=c_bits),
+            "config": workload_config(log_n, world),
             "checked_against_oracle": checked and e2e_ok,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": world * n * 136, "d2h_bytes_per_step": world * 144,
-                    "api": "aleo_b200_msm_g1 (host pointers, pinned)", "point_ranges": host_plan["ranges"],
-                    "window_bits": host_plan["window_bits"],
-                    "note": "the call copies and accumulates point range by point range: H2D of range k+1 overlaps range k",
-                    "pageable": e2e_pageable},
+                    "api": "aleo_b200_msm_g1 (host pointers, PAGEABLE caller memory as a Rust Vec is)", "host_memory": "pageable",
+                    "pinned": {"value": e2e_pinned, "unit": "Mpts/s", "what": "the same call on cudaHostAlloc'ed buffers"},
+                    "point_ranges": host_plan["ranges"], "window_bits": host_plan["window_bits"],
+                    "note": "the call stages 4 MB slices through pinned double buffers with helper threads and copies / accumulates "
+                            "point range by point range: H2D of range k+1 overlaps range k"},
             "gpu_launches": (ab.VariableBase.launches(n) + (1 if world > 1 else 0)) * args.steps,
-            "roofline": roofline, "witness_like_scalars": witness, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "sweep": sweep, "proof_shaped": proof_shaped, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "witness_like_scalars": witness, "srs_resident": srs_obj, "ntt": ntt, "ntt_distributed": ntt_dist, "config4": config4, "sweep": sweep, "proof_shaped": proof_shaped, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
@@ -698,10 +851,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
-    ap.add_argument("--cpu-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-log-n", type=int, default=0, help="--impl reference: cap the CPU arm's size (0 = the GPU arm's own --log-n)")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=22, help="GPU arm: size of its bounded cpu_baseline sample")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: stop timing further steps after this many seconds (>= 3 steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-srs", action="store_true", help="skip the resident-SRS (KZG commit) measurement")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^22 size sweep")
+    ap.add_argument("--no-config4", action="store_true", help="skip BASELINE configs[3] (fixed 2^26 MSM + NTT over the N GPUs)")
+    ap.add_argument("--config4-log-n", type=int, default=26)
     ap.add_argument("--no-proof-shape", action="store_true", help="skip the synthetic proof-shaped stream")
     ap.add_argument("--proof-threads", type=int, default=4, help="host threads (one CUDA stream each) submitting proof-shaped work")
     args = ap.parse_args()

@@ -179,9 +179,22 @@ int oracle_ntt_fr(u64* data, uint32_t log_n, int inverse, int coset, int nthread
   const size_t n = (size_t)1 << log_n;
   if (nthreads < 1) nthreads = 1;
   if ((size_t)nthreads > n / 2) nthreads = (int)(n / 2);
-  u64 w[4];
-  fr_root_of_unity(w, log_n, inverse);
-  u64* roots = power_table(w, n / 2, NULL);
+  /* roots table kept across calls for the last (log_n, direction): snarkVM's prover passes a cached FFTPrecomputation
+     too, and bench.py's CPU baseline must not time the table build (a serial chain of n / 2 products) */
+  static pthread_mutex_t roots_mu = PTHREAD_MUTEX_INITIALIZER;
+  static u64* roots_cached = NULL;
+  static uint32_t roots_log_n = 0;
+  static int roots_inverse = -1;
+  pthread_mutex_lock(&roots_mu);
+  if (roots_cached == NULL || roots_log_n != log_n || roots_inverse != inverse) {
+    u64 w[4];
+    fr_root_of_unity(w, log_n, inverse);
+    free(roots_cached);
+    roots_cached = power_table(w, n / 2, NULL);
+    roots_log_n = log_n;
+    roots_inverse = inverse;
+  }
+  const u64* roots = roots_cached;  /* used under the lock: concurrent oracle transforms serialise (test infrastructure) */
   u64 *pre = NULL, *post = NULL, ninv[4], nf[4] = {n, 0, 0, 0}, g[4] = {22, 0, 0, 0}, gm[4];
   fr_to_mont(nf, nf);
   fr_inv(ninv, nf);
@@ -198,7 +211,8 @@ int oracle_ntt_fr(u64* data, uint32_t log_n, int inverse, int coset, int nthread
   }
   for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   pthread_barrier_destroy(&bar);
-  free(th); free(jobs); free(roots); free(pre); free(post);
+  free(th); free(jobs); free(pre); free(post);
+  pthread_mutex_unlock(&roots_mu);
   return 0;
 }
 

@@ -79,7 +79,8 @@ def test_parity_with_c_oracle(c_oracle, log_n):
     assert ab.VariableBase.msm(hb, hs, 104) == out.raw
 
 
-@pytest.mark.parametrize("log_n,dist", [(20, "uniform"), (20, "witness"), (22, "witness-signed"), (22, "uniform"), (24, "uniform")])
+@pytest.mark.parametrize("log_n,dist", [(20, "uniform"), (20, "witness"), (22, "witness-signed"), (22, "uniform"), (24, "uniform"),
+                                          (26, "uniform"), (26, "witness-signed")])   # 2^26: the top of BASELINE.json's metric range
 def test_known_discrete_logs_at_full_size(log_n, dist):
     """bases (s0 + i d) G: the result must be (sum_i s_i (s0 + i d)) G -- checkable at any size"""
     import torch
