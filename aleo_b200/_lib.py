@@ -65,6 +65,7 @@ SYMBOLS = [
     ("aleo_b200_fr_divide_by_linear_dev", _int, [_vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_kzg_open_dev", _int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     ("aleo_b200_g1_decompress_dev", _int, [_vp, _sz, _vp, _sz, _vp]),
+    ("aleo_b200_g1_decompress_unchecked_dev", _int, [_vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_g1_compress_dev", _int, [_vp, _vp, _sz, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),

@@ -532,15 +532,23 @@ int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const
   return rc2;
 }
 
-int aleo_b200_g1_decompress_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream) {
+static int g1_decompress_any(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream, bool unchecked) {
   if (!stride_ok(affine_stride)) return ALEO_B200_EINVAL;
   if (n == 0) return 0;
   if (out_affine_dev == nullptr || in48_dev == nullptr || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
   u32 bad = 0;
-  API_CK(aleo::g1_decompress(in48_dev, n, out_affine_dev, (u32)affine_stride, (cudaStream_t)stream, &bad));
+  API_CK(aleo::g1_decompress(in48_dev, n, out_affine_dev, (u32)affine_stride, (cudaStream_t)stream, &bad, unchecked));
   return bad > 0x7fffffffu ? 0x7fffffff : (int)bad;
+}
+
+int aleo_b200_g1_decompress_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream) {
+  return g1_decompress_any(out_affine_dev, affine_stride, in48_dev, n, stream, false);
+}
+
+int aleo_b200_g1_decompress_unchecked_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream) {
+  return g1_decompress_any(out_affine_dev, affine_stride, in48_dev, n, stream, true);
 }
 
 int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t affine_stride, size_t n, void* stream) {

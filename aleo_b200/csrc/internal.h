@@ -56,7 +56,7 @@ cudaError_t fr_distribute_powers(void* inout_dev, size_t n, const void* g32, con
 cudaError_t fr_divide_by_vanishing_on_coset(void* inout_dev, u32 log_m, u32 log_n, const void* g32, cudaStream_t s);
 cudaError_t fr_poly_eval(void* out_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
 cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z32, cudaStream_t s);
-cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out);
+cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out, bool unchecked);
 cudaError_t g1_compress_affine(const void* affine_dev, u32 stride, size_t n, void* out48_dev, cudaStream_t s);
 // util_lib.cu
 cudaError_t util_upload_constants();

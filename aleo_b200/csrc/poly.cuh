@@ -5,7 +5,7 @@
 // against 120 IMAD.WIDE for a product, so every kernel is one coalesced pass with 256-bit accesses (Fr).
 // Also the entry point the parity tests use to check the field core (mul / sqr / inv) against the oracle.
 #pragma once
-#include "mont.cuh"
+#include "g1.cuh"
 
 namespace poly {
 
@@ -381,8 +381,39 @@ DEV void store_affine(unsigned char* out, u32 stride, size_t i, const Fq& x, con
   if (stride >= 97) q[12] = make_uint2(inf ? 1u : 0u, 0u);
 }
 
-// out[i] = affine point of in48[i]; invalid encodings (x >= p, x^3 + 1 not a square, stray bits with the infinity
-// flag are ignored as upstream does) are stored as the identity and counted in *bad
+// Is the curve point (x, y) in the prime-order subgroup G1?  BLS12-377's G1 cofactor is (u - 1)^2 / 3, so a point
+// that merely satisfies the curve equation can have a component outside the r-torsion; snarkVM's
+// deserialize_compressed (Validate::Yes) calls is_in_correct_subgroup_assuming_on_curve for exactly that.
+// Test: phi(P) == -[u^2] P with phi(x, y) = (beta x, y) (tools/gen_constants.py subgroup_beta: phi^2 + phi + 1 = 0 on
+// the whole curve, so the equation forces [u^4 - u^2 + 1] P = [r] P = O; on G1 phi is multiplication by -u^2).
+// Cost: two multiplications by the 64-bit u = 0x8508c00000000001 (7 bits set): 126 doublings + 12 additions.
+DEV G1Xyzz mul_by_u(const G1Xyzz& p) {
+  constexpr unsigned long long U = 0x8508c00000000001ull;
+  G1Xyzz acc = p;
+  for (int b = 62; b >= 0; b--) {
+    acc = xyzz_double(acc);
+    if ((U >> b) & 1ull) xyzz_add_ni(acc, p);
+  }
+  return acc;
+}
+
+DEV bool g1_in_subgroup(const Fq& x, const Fq& y) {
+  G1Xyzz p;
+  p.x = x;
+  p.y = y;
+  p.zz = fp_one<FqParams>();
+  p.zzz = p.zz;
+  const G1Xyzz q = mul_by_u(mul_by_u(p));  // [u^2] P
+  if (xyzz_is_identity(q)) return false;    // phi(P) is a finite point
+  // -phi(P) = (beta x, -y) == (q.x / q.zz, q.y / q.zzz)
+  const Fq bx = fq_mul_ni(fp_const<FqParams, FqParams::BETA_M>(), x);
+  return fp_eq(fq_mul_ni(bx, q.zz), q.x) && fp_eq(fq_mul_ni(fp_neg(y), q.zzz), q.y);
+}
+
+// out[i] = affine point of in48[i]; invalid encodings (x >= p, x^3 + 1 not a square, and -- unless UNCHECKED -- a curve
+// point outside the prime-order subgroup; stray bits with the infinity flag are ignored as upstream does) are stored as
+// the identity and counted in *bad
+template <bool UNCHECKED>
 KERNEL void __launch_bounds__(128) g1_decompress_kernel(const unsigned char* in48, u32 n, unsigned char* out, u32 stride, u32* bad) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -417,6 +448,11 @@ KERNEL void __launch_bounds__(128) g1_decompress_kernel(const unsigned char* in4
     return;
   }
   if (is_larger_root(fp_from_mont(y)) != y_flag) y = fp_neg(y);
+  if (!UNCHECKED && !g1_in_subgroup(x, y)) {
+    atomic_add_u32(bad, 1u);
+    store_affine(out, stride, i, x, x, true);
+    return;
+  }
   store_affine(out, stride, i, x, y, false);
 }
 

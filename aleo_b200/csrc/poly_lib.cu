@@ -160,14 +160,18 @@ cudaError_t fr_divide_by_linear(void* quotient_dev, const void* coeffs_dev, size
 }
 
 // 48-byte compressed G1 -> affine (stride 104 / 96); *bad_out = number of invalid encodings.  Synchronises s.
-cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out) {
+cudaError_t g1_decompress(const void* in48_dev, size_t n, void* out_affine_dev, u32 stride, cudaStream_t s, u32* bad_out, bool unchecked) {
   *bad_out = 0;
   if (n == 0) return cudaSuccess;
   u32* bad = nullptr;
   PL_CK(cudaMallocAsync((void**)&bad, 4, s));
   cudaMemsetAsync(bad, 0, 4, s);
-  LAUNCH_NOSYNC(wire::g1_decompress_kernel, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)in48_dev, (u32)n,
-                (unsigned char*)out_affine_dev, stride, bad);
+  if (unchecked)
+    LAUNCH_NOSYNC(wire::g1_decompress_kernel<true>, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)in48_dev, (u32)n,
+                  (unsigned char*)out_affine_dev, stride, bad);
+  else
+    LAUNCH_NOSYNC(wire::g1_decompress_kernel<false>, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)in48_dev, (u32)n,
+                  (unsigned char*)out_affine_dev, stride, bad);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(bad_out, bad, 4, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);

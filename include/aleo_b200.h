@@ -224,9 +224,13 @@ int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const
  * key / SRS files: 48 bytes, x canonical little-endian, bit 383 = y is the larger root, bit 382 = infinity.  Pinned by
  * the reference's own proof string (wasm/src/programs/transaction.rs:100; tests/golden/proof_fixture.json).
  * decompress: n x 48 bytes -> n affine points (stride 104 / 96, Montgomery); returns the number of invalid encodings
- * (x >= p or x^3 + 1 not a square; stored as the identity), < 0 on error; synchronises the stream.
+ * (stored as the identity), < 0 on error; synchronises the stream.  Invalid = x >= p, x^3 + 1 not a square, or -- as
+ * deserialize_compressed (Validate::Yes -> is_in_correct_subgroup_assuming_on_curve) rejects it upstream -- a curve
+ * point outside the prime-order subgroup (BLS12-377's G1 cofactor is large); the subgroup test is phi(P) == -[u^2] P.
+ * decompress_unchecked: deserialize_compressed_unchecked (Validate::No): no subgroup test, for trusted SRS / key files.
  * compress: the inverse, asynchronous. */
 int aleo_b200_g1_decompress_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream);
+int aleo_b200_g1_decompress_unchecked_dev(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream);
 int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t affine_stride, size_t n, void* stream);
 
 /* ---- synthetic workload generation and on-device checks (bench / tests) --------------------

@@ -562,6 +562,18 @@ def g1_decompress(buf: bytes):
     return (x, y)
 
 
+def curve_points_outside_subgroup(count: int):
+    """points on y^2 = x^3 + 1 that are NOT in the r-torsion (small x; r * P != O checked) -- negative fixtures for
+    deserialize_compressed's subgroup check"""
+    out, x = [], 2
+    while len(out) < count:
+        y = fq_sqrt((x * x * x + COEFF_B) % P_MOD)
+        if y is not None and g1_mul((x, y), R_MOD) is not None:
+            out.append((x, y))
+        x += 1
+    return out
+
+
 def g1_compress(pt) -> bytes:
     if pt is None:
         return int_to_le_bytes(1 << 382, 48)

@@ -487,18 +487,25 @@ def test_emu_g1_wire_format_on_reference_fixture(emu_lib, golden_dir):
     blob = b"".join(chunks) + b"".join(o.g1_compress(p) for p in extra)
     bad_x = next(x for x in range(2, 50) if o.fq_sqrt((x ** 3 + 1) % o.P_MOD) is None)
     blob += o.int_to_le_bytes(bad_x, 48) + o.int_to_le_bytes(o.P_MOD + 1, 48)          # not on the curve; x >= p
+    # on the curve but OUTSIDE the prime-order subgroup (the G1 cofactor is large): deserialize_compressed rejects these
+    rogue = o.curve_points_outside_subgroup(2)
+    blob += b"".join(o.g1_compress(p) for p in rogue)
     n = len(blob) // 48
     for stride in (104, 96):
         src = C.create_string_buffer(blob, len(blob))
         out = C.create_string_buffer(n * stride)
         nbad = emu_lib.g1_decompress_dev(C.cast(out, C.c_void_p), stride, C.cast(src, C.c_void_p), n, None)
-        assert nbad == 2
-        want = o.g1_affine_vec_to_bytes(pts + extra + [None, None], stride)
+        assert nbad == 4
+        want = o.g1_affine_vec_to_bytes(pts + extra + [None, None, None, None], stride)
         assert out.raw == want
         back = C.create_string_buffer(n * 48)
         emu_lib.check(emu_lib.g1_compress_dev(C.cast(back, C.c_void_p), C.cast(out, C.c_void_p), stride, n, None), "compress")
-        assert back.raw[:48 * (n - 2)] == blob[:48 * (n - 2)]
-        assert back.raw[48 * (n - 2):] == o.g1_compress(None) * 2
+        assert back.raw[:48 * (n - 4)] == blob[:48 * (n - 4)]
+        assert back.raw[48 * (n - 4):] == o.g1_compress(None) * 4
+        # Validate::No: the rogue points come through as they are
+        nbad = emu_lib.g1_decompress_unchecked_dev(C.cast(out, C.c_void_p), stride, C.cast(src, C.c_void_p), n, None)
+        assert nbad == 2
+        assert out.raw == o.g1_affine_vec_to_bytes(pts + extra + [None, None] + rogue, stride)
 
 
 def test_emu_kzg_commit_hiding(emu_lib):
