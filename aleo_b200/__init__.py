@@ -9,6 +9,6 @@ from .msm import (VariableBase, gen_bases_dev, gen_scalars_dev, dlog_dot_dev, ch
                   AFFINE_STRIDE_RUST, AFFINE_STRIDE_PACKED, PROJECTIVE_BYTES)
 
 from .kzg import ResidentSRS, KZG10  # noqa: F401,E402
-from .poly import Evaluations, field_op_dev  # noqa: F401,E402
+from .poly import Evaluations, PolyMultiplier, field_op_dev  # noqa: F401,E402
 
 __version__ = "0.1.0"

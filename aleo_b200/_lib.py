@@ -37,6 +37,10 @@ SYMBOLS = [
     ("aleo_b200_ntt_dist_handles", _int, [_vp, _vp]),
     ("aleo_b200_ntt_dist_open", _int, [_vp, _vp]),
     ("aleo_b200_ntt_dist_stage1", _int, [_vp, _vp, _int, _int, _vp]),
+    ("aleo_b200_ntt_fr_ordered", _int, [_vp, _u32, _int, _int, _int]),
+    ("aleo_b200_polymul", _int, [_vp, _sz, C.POINTER(_vp), C.POINTER(_sz), _sz, C.POINTER(_vp), C.POINTER(_sz), _u32]),
+    ("aleo_b200_polymul_dev", _int, [_vp, _sz, C.POINTER(_vp), C.POINTER(_sz), _sz, C.POINTER(_vp), C.POINTER(_sz), _u32, _vp]),
+    ("aleo_b200_kzg_open_combinations_dev", _int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _vp, _sz, _vp]),
     ("aleo_b200_ntt_dist_stage2", _int, [_vp, _vp, _int, _int, _vp]),
     ("aleo_b200_ntt_dist_destroy", _int, [_vp]),
     ("aleo_b200_msm_g1", _int, [_vp, _vp, _sz, _vp, _sz]),

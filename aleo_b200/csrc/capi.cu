@@ -5,6 +5,7 @@
 // No CPU fallback: if the calling thread's CUDA device is missing or is not sm_100, every entry
 // point returns ALEO_B200_ENODEVICE.
 #include "../../include/aleo_b200.h"
+#include <cstdlib>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -17,12 +18,16 @@
 namespace {
 
 thread_local std::string t_last_cuda_error;
-thread_local cudaStream_t t_stream = nullptr;
-thread_local int t_stream_dev = -1;
+thread_local aleo::ThreadStream t_stream;  // released when the calling thread ends
 
 std::mutex g_dev_mu;
 bool g_dev_ready[64] = {false};
 bool g_dev_bad[64] = {false};
+
+#ifndef ALEO_EMU
+cudaMemPool_t g_pool[64] = {nullptr};
+std::mutex g_pool_mu;
+#endif
 
 int fail_cuda(cudaError_t e) {
   t_last_cuda_error = cudaGetErrorString(e);
@@ -60,16 +65,6 @@ int ensure_ready(int* dev_out) {
           std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", need sm_100 (B200)";
       return ALEO_B200_ENODEVICE;
     }
-    // Workspaces come from the stream-ordered allocator.  Keep freed blocks in the pool: with the
-    // default threshold (0) every synchronisation hands the memory back to the driver and the next
-    // call pays for mapping gigabytes again (measured: ~100 ms per 2^24-point host-pointer MSM).
-    {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-    }
 #endif
     API_CK(aleo::ntt_upload_constants());
     API_CK(aleo::msm_upload_constants());
@@ -82,17 +77,63 @@ int ensure_ready(int* dev_out) {
 }
 
 int thread_stream(int dev, cudaStream_t* out) {
-  if (t_stream == nullptr || t_stream_dev != dev) {
-    API_CK(cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking));
-    t_stream_dev = dev;
-  }
-  *out = t_stream;
+  (void)dev;  // the calling thread's current device (ensure_ready has just read it)
+  API_CK(t_stream.get(out));
   return ALEO_B200_OK;
 }
 
 bool stride_ok(size_t s) { return s == 96 || s == 104; }
 
+// a resident-SRS handle lives on the device it was created on: using it from a thread whose current device differs
+// would fault on the device instead of failing here
+int srs_ready(const void* handle) {
+  if (handle == nullptr) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  if (aleo::srs_device(handle) != dev) {
+    t_last_cuda_error = "SRS handle belongs to device " + std::to_string(aleo::srs_device(handle)) + ", current device is " +
+                        std::to_string(dev);
+    return ALEO_B200_EINVAL;
+  }
+  return ALEO_B200_OK;
+}
+
 }  // namespace
+
+namespace aleo {
+cudaError_t pool_malloc_async(void** p, size_t bytes, cudaStream_t s) {
+#ifdef ALEO_EMU
+  return cudaMalloc(p, bytes);
+#else
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool[dev] == nullptr) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      e = cudaMemPoolCreate(&g_pool[dev], &props);
+      if (e != cudaSuccess) {
+        g_pool[dev] = nullptr;
+        return e;
+      }
+      const char* env = getenv("ALEO_B200_POOL_KEEP_MB");
+      unsigned long long keep = (env && atoll(env) >= 0 ? (unsigned long long)atoll(env) : 16384ull) << 20;
+      cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = g_pool[dev];
+  }
+  return cudaMallocFromPoolAsync(p, bytes, pool, s);
+#endif
+}
+}  // namespace aleo
 
 extern "C" {
 
@@ -133,13 +174,14 @@ int aleo_b200_init(int device) {
 }
 
 int aleo_b200_shutdown(void) {
+  // Must not race with calls in flight on the same device (a transform holds its plan while it enqueues work).
   aleo::ntt_clear_plans();
 #ifndef ALEO_EMU
   int dev = 0;
-  cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
     cudaDeviceSynchronize();
-    cudaMemPoolTrimTo(pool, 0);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool[dev]) cudaMemPoolTrimTo(g_pool[dev], 0);
   }
 #endif
   return ALEO_B200_OK;
@@ -267,7 +309,7 @@ int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) 
   if (rc) return rc;
   const size_t bytes = (size_t)32 << log_n;
   void* d = nullptr;
-  API_CK(cudaMallocAsync(&d, bytes, s));
+  API_CK(aleo::pool_malloc_async(&d, bytes, s));
   cudaEvent_t ready = nullptr;
   cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventRecord(ready, s);
@@ -280,6 +322,147 @@ int aleo_b200_ntt_fr(void* inout_host, uint32_t log_n, int direction, int kind) 
   cudaError_t e2 = cudaStreamSynchronize(s);
   if (ready) cudaEventDestroy(ready);
   if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+// host-pointer transform with upstream's `order` argument (SURVEY.md App. E snarkvm_ntt): one H2D, the transform with
+// its bit-reversal pass, one D2H
+int aleo_b200_ntt_fr_ordered(void* inout_host, uint32_t log_n, int direction, int kind, int order) {
+  if (order != ALEO_B200_NTT_ORDER_II && order != ALEO_B200_NTT_ORDER_IO && order != ALEO_B200_NTT_ORDER_OI) return ALEO_B200_EINVAL;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (inout_host == nullptr) return ALEO_B200_EINVAL;
+  int dev = 0;
+  int rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  const size_t bytes = (size_t)32 << log_n;
+  void* d = nullptr;
+  API_CK(aleo::pool_malloc_async(&d, bytes, s));
+  cudaEvent_t ready = nullptr;
+  cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ready, s);
+  if (e == cudaSuccess) e = aleo::feed_h2d(d, inout_host, bytes, s, ready);
+  if (e == cudaSuccess) {
+    rc = aleo_b200_ntt_fr_ordered_dev(d, log_n, 1, direction, kind, order, (void*)s);
+    if (rc == ALEO_B200_OK) e = aleo::feed_d2h_sync(inout_host, d, bytes, s);
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (ready) cudaEventDestroy(ready);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e);
+  if (e2 != cudaSuccess) return fail_cuda(e2);
+  return ALEO_B200_OK;
+}
+
+// ---- polymul: out = ifft( prod_i fft(p_i) * prod_j e_j ) over the domain of size 2^log_n -----------------------------
+// work: (pcount ? pcount : 1) * n elements of scratch (one batched forward transform for all polynomials)
+static int polymul_check(const void* out, size_t pcount, const void* const* polys, const size_t* plens, size_t ecount,
+                         const void* const* evals, const size_t* elens, uint32_t log_n) {
+  if (log_n > (uint32_t)aleo::ntt_max_log_n()) return ALEO_B200_ETOOLARGE;
+  if (out == nullptr || pcount + ecount == 0 || pcount > 64 || ecount > 64) return ALEO_B200_EINVAL;
+  if ((pcount && (polys == nullptr || plens == nullptr)) || (ecount && (evals == nullptr || elens == nullptr))) return ALEO_B200_EINVAL;
+  const size_t n = (size_t)1 << log_n;
+  for (size_t i = 0; i < pcount; i++)
+    if (plens[i] > n || (plens[i] && polys[i] == nullptr)) return ALEO_B200_EINVAL;
+  for (size_t j = 0; j < ecount; j++)
+    if (elens[j] != n || evals[j] == nullptr) return ALEO_B200_EINVAL;  // evaluations live on the whole domain
+  return ALEO_B200_OK;
+}
+
+// polynomials already staged in `work` (pcount slots of n elements, zero padded); evals on the device
+static cudaError_t polymul_core(int dev, unsigned char* out, unsigned char* work, size_t pcount, size_t ecount,
+                                const void* const* evals_dev, uint32_t log_n, cudaStream_t s) {
+  const size_t n = (size_t)1 << log_n, nb = n * 32;
+  cudaError_t e = cudaSuccess;
+  const unsigned char* acc = nullptr;
+  if (pcount) {
+    e = aleo::ntt_transform(dev, log_n, pcount, false, false, work, s);
+    acc = work;
+    for (size_t i = 1; i < pcount && e == cudaSuccess; i++) {
+      e = aleo::field_op(ALEO_B200_FIELD_FR, ALEO_B200_OP_MUL, i + 1 == pcount && ecount == 0 ? out : work, acc, work + i * nb, n, s);
+      acc = (i + 1 == pcount && ecount == 0) ? out : work;
+    }
+  }
+  for (size_t j = 0; j < ecount && e == cudaSuccess; j++) {
+    if (acc == nullptr) {
+      if (ecount == 1) {
+        e = cudaMemcpyAsync(out, evals_dev[0], nb, cudaMemcpyDeviceToDevice, s);
+      } else {
+        e = aleo::field_op(ALEO_B200_FIELD_FR, ALEO_B200_OP_MUL, out, evals_dev[0], evals_dev[1], n, s);
+        j = 1;
+      }
+      acc = out;
+      continue;
+    }
+    e = aleo::field_op(ALEO_B200_FIELD_FR, ALEO_B200_OP_MUL, out, acc, evals_dev[j], n, s);
+    acc = out;
+  }
+  if (e == cudaSuccess && acc != out) e = cudaMemcpyAsync(out, acc, nb, cudaMemcpyDeviceToDevice, s);  // pcount == 1, ecount == 0
+  if (e == cudaSuccess) e = aleo::ntt_transform(dev, log_n, 1, true, false, out, s);
+  return e;
+}
+
+int aleo_b200_polymul_dev(void* out_dev, size_t pcount, const void* const* polynomials_dev_ptrs_host, const size_t* plens_host,
+                          size_t ecount, const void* const* evaluations_dev_ptrs_host, const size_t* elens_host, uint32_t log_n,
+                          void* stream) {
+  int rc = polymul_check(out_dev, pcount, polynomials_dev_ptrs_host, plens_host, ecount, evaluations_dev_ptrs_host, elens_host, log_n);
+  if (rc) return rc;
+  int dev = 0;
+  rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)1 << log_n, nb = n * 32;
+  unsigned char* work = nullptr;
+  if (pcount) API_CK(aleo::pool_malloc_async((void**)&work, pcount * nb, s));
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < pcount && e == cudaSuccess; i++) {
+    if (plens_host[i]) e = cudaMemcpyAsync(work + i * nb, polynomials_dev_ptrs_host[i], plens_host[i] * 32, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && plens_host[i] < n) e = cudaMemsetAsync(work + i * nb + plens_host[i] * 32, 0, (n - plens_host[i]) * 32, s);
+  }
+  if (e == cudaSuccess) e = polymul_core(dev, (unsigned char*)out_dev, work, pcount, ecount, evaluations_dev_ptrs_host, log_n, s);
+  if (work) cudaFreeAsync(work, s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return ALEO_B200_OK;
+}
+
+int aleo_b200_polymul(void* out_host, size_t pcount, const void* const* polynomials_host, const size_t* plens, size_t ecount,
+                      const void* const* evaluations_host, const size_t* elens, uint32_t log_n) {
+  int rc = polymul_check(out_host, pcount, polynomials_host, plens, ecount, evaluations_host, elens, log_n);
+  if (rc) return rc;
+  int dev = 0;
+  rc = ensure_ready(&dev);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = thread_stream(dev, &s);
+  if (rc) return rc;
+  const size_t n = (size_t)1 << log_n, nb = n * 32;
+  unsigned char* d = nullptr;  // [out][pcount polynomial slots][ecount evaluation vectors]
+  API_CK(aleo::pool_malloc_async((void**)&d, (1 + pcount + ecount) * nb, s));
+  unsigned char *work = d + nb, *ev = d + (1 + pcount) * nb;
+  cudaEvent_t ready = nullptr;
+  cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ready, s);
+  std::vector<const void*> ev_ptrs(ecount);
+  for (size_t i = 0; i < pcount && e == cudaSuccess; i++) {
+    e = aleo::feed_h2d(work + i * nb, polynomials_host[i], plens[i] * 32, s, ready);
+    if (e == cudaSuccess && plens[i] < n) e = cudaMemsetAsync(work + i * nb + plens[i] * 32, 0, (n - plens[i]) * 32, s);
+  }
+  for (size_t j = 0; j < ecount && e == cudaSuccess; j++) {
+    ev_ptrs[j] = ev + j * nb;
+    e = aleo::feed_h2d(ev + j * nb, evaluations_host[j], nb, s, ready);
+  }
+  if (e == cudaSuccess) e = polymul_core(dev, d, work, pcount, ecount, ev_ptrs.data(), log_n, s);
+  if (e == cudaSuccess) e = aleo::feed_d2h_sync(out_host, d, nb, s);
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (ready) cudaEventDestroy(ready);
   if (e != cudaSuccess) return fail_cuda(e);
   if (e2 != cudaSuccess) return fail_cuda(e2);
   return ALEO_B200_OK;
@@ -368,7 +551,7 @@ int aleo_b200_msm_g1_multi(void* out_projective_host, const void* bases_host, si
   rc = thread_stream(dev, &s);
   if (rc) return rc;
   unsigned char* dbuf = nullptr;
-  API_CK(cudaMallocAsync((void**)&dbuf, partials.size() + 256, s));
+  API_CK(aleo::pool_malloc_async((void**)&dbuf, partials.size() + 256, s));
   cudaError_t e = cudaMemcpyAsync(dbuf, partials.data(), partials.size(), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = aleo::g1_sum(dbuf, (u32)n_devices, dbuf + partials.size(), s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_projective_host, dbuf + partials.size(), 144, cudaMemcpyDeviceToHost, s);
@@ -518,18 +701,72 @@ int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const
                            const void* z_host, void* stream) {
   if (handle == nullptr || out_compressed48_dev == nullptr || z_host == nullptr || (n_coeffs && coeffs_montgomery_dev == nullptr))
     return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (n_coeffs <= 1) return aleo_b200_kzg_commit_dev(handle, out_compressed48_dev, coeffs_montgomery_dev, 0, stream);  // q = 0
   unsigned char* q = nullptr;
-  API_CK(cudaMallocAsync((void**)&q, n_coeffs * 32, s));
+  API_CK(aleo::pool_malloc_async((void**)&q, n_coeffs * 32, s));
   cudaError_t e = aleo::fr_divide_by_linear(q, coeffs_montgomery_dev, n_coeffs, z_host, s);
   int rc2 = ALEO_B200_OK;
   if (e == cudaSuccess) rc2 = aleo_b200_kzg_commit_dev(handle, out_compressed48_dev, q, n_coeffs - 1, stream);
   cudaFreeAsync(q, s);
   if (e != cudaSuccess) return fail_cuda(e);
   return rc2;
+}
+
+// SonicKZG10::open_combinations / kzg10 batch_open shape: m openings, opening k of the linear combination
+// p_k = sum_i lc[k][i] * poly_i at the point z_k.  All m witness polynomials are committed in ONE launch sequence.
+int aleo_b200_kzg_open_combinations_dev(const void* handle, void* out_compressed48_dev, const void* const* polys_dev_ptrs_host,
+                                        const size_t* n_coeffs_host, size_t n_polys, const void* lc_coeffs_host,
+                                        const void* points_host, size_t m, void* stream) {
+  if (handle == nullptr) return ALEO_B200_EINVAL;
+  if (m == 0) return ALEO_B200_OK;
+  if (out_compressed48_dev == nullptr || lc_coeffs_host == nullptr || points_host == nullptr || m > 64 || n_polys == 0 || n_polys > 1024)
+    return ALEO_B200_EINVAL;
+  if (polys_dev_ptrs_host == nullptr || n_coeffs_host == nullptr) return ALEO_B200_EINVAL;
+  size_t max_len = 0;
+  for (size_t i = 0; i < n_polys; i++) {
+    if (n_coeffs_host[i] && polys_dev_ptrs_host[i] == nullptr) return ALEO_B200_EINVAL;
+    if (n_coeffs_host[i] > max_len) max_len = n_coeffs_host[i];
+  }
+  int rc = srs_ready(handle);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (max_len <= 1) {  // every combination is a constant: all witness polynomials are zero
+    std::vector<const void*> none(m, nullptr);
+    std::vector<size_t> zero(m, 0);
+    API_CK(aleo::srs_msm_batch(handle, none.data(), zero.data(), m, true, out_compressed48_dev, true, s));
+    return ALEO_B200_OK;
+  }
+  const size_t nb = (max_len * 32 + 255) & ~(size_t)255;
+  unsigned char* d = nullptr;  // [combination][m witness polynomials]
+  API_CK(aleo::pool_malloc_async((void**)&d, (1 + m) * nb, s));
+  const unsigned char* lc = (const unsigned char*)lc_coeffs_host;
+  const unsigned char* zs = (const unsigned char*)points_host;
+  std::vector<const void*> wit(m);
+  std::vector<size_t> wlen(m);
+  cudaError_t e = cudaSuccess;
+  for (size_t k = 0; k < m && e == cudaSuccess; k++) {
+    e = cudaMemsetAsync(d, 0, max_len * 32, s);
+    size_t len = 0;
+    for (size_t i = 0; i < n_polys && e == cudaSuccess; i++) {
+      const unsigned char* a = lc + (k * n_polys + i) * 32;
+      bool is_zero = true;
+      for (int b = 0; b < 32; b++) is_zero = is_zero && a[b] == 0;
+      if (is_zero || n_coeffs_host[i] == 0) continue;
+      e = aleo::fr_axpy(d, polys_dev_ptrs_host[i], a, n_coeffs_host[i], s);
+      if (n_coeffs_host[i] > len) len = n_coeffs_host[i];
+    }
+    unsigned char* q = d + (1 + k) * nb;
+    wit[k] = q;
+    wlen[k] = len > 1 ? len - 1 : 0;
+    if (e == cudaSuccess && len > 1) e = aleo::fr_divide_by_linear(q, d, len, zs + k * 32, s);
+  }
+  if (e == cudaSuccess) e = aleo::srs_msm_batch(handle, wit.data(), wlen.data(), m, true, out_compressed48_dev, true, s);
+  cudaFreeAsync(d, s);
+  if (e != cudaSuccess) return fail_cuda(e);
+  return ALEO_B200_OK;
 }
 
 static int g1_decompress_any(void* out_affine_dev, size_t affine_stride, const void* in48_dev, size_t n, void* stream, bool unchecked) {
@@ -576,7 +813,7 @@ extern "C" {
 
 int aleo_b200_srs_create_dev(void** handle_out, const void* bases_dev, size_t n, size_t affine_stride, void* stream) {
   if (handle_out == nullptr || bases_dev == nullptr || n == 0 || !stride_ok(affine_stride)) return ALEO_B200_EINVAL;
-  if (n >= ((size_t)1 << 28)) return ALEO_B200_ETOOLARGE;
+  if (n >= ((size_t)1 << 28) || !aleo::srs_size_supported(n)) return ALEO_B200_ETOOLARGE;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
   API_CK(aleo::srs_create(bases_dev, (u32)affine_stride, n, (cudaStream_t)stream, handle_out));
@@ -585,7 +822,7 @@ int aleo_b200_srs_create_dev(void** handle_out, const void* bases_dev, size_t n,
 
 int aleo_b200_srs_create(void** handle_out, const void* bases_host, size_t n, size_t affine_stride) {
   if (handle_out == nullptr || bases_host == nullptr || n == 0 || !stride_ok(affine_stride)) return ALEO_B200_EINVAL;
-  if (n >= ((size_t)1 << 28)) return ALEO_B200_ETOOLARGE;
+  if (n >= ((size_t)1 << 28) || !aleo::srs_size_supported(n)) return ALEO_B200_ETOOLARGE;
   int dev = 0;
   int rc = ensure_ready(&dev);
   if (rc) return rc;
@@ -593,7 +830,7 @@ int aleo_b200_srs_create(void** handle_out, const void* bases_host, size_t n, si
   rc = thread_stream(dev, &s);
   if (rc) return rc;
   void* d = nullptr;
-  API_CK(cudaMallocAsync(&d, n * affine_stride, s));
+  API_CK(aleo::pool_malloc_async(&d, n * affine_stride, s));
   cudaError_t e = cudaMemcpyAsync(d, bases_host, n * affine_stride, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = aleo::srs_create(d, (u32)affine_stride, n, s, handle_out);
   cudaFreeAsync(d, s);
@@ -622,7 +859,7 @@ int aleo_b200_srs_msm_launches(const void* handle, size_t n_used) {
 
 int aleo_b200_srs_msm_dev(const void* handle, void* out_projective_dev, const void* scalars_dev, size_t n_used, void* stream) {
   if (handle == nullptr || out_projective_dev == nullptr || (n_used && scalars_dev == nullptr)) return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle);
   if (rc) return rc;
   API_CK(aleo::srs_msm(handle, scalars_dev, n_used, out_projective_dev, (cudaStream_t)stream, false, nullptr, nullptr));
   return ALEO_B200_OK;
@@ -632,7 +869,7 @@ int aleo_b200_srs_msm_dev_profile(const void* handle, void* out_projective_dev, 
                                   void* stream, float* phase_ms3) {
   if (handle == nullptr || out_projective_dev == nullptr || scalars_dev == nullptr || n_used == 0 || phase_ms3 == nullptr)
     return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle);
   if (rc) return rc;
   API_CK(aleo::srs_msm(handle, scalars_dev, n_used, out_projective_dev, (cudaStream_t)stream, false, nullptr, phase_ms3));
   return ALEO_B200_OK;
@@ -641,9 +878,10 @@ int aleo_b200_srs_msm_dev_profile(const void* handle, void* out_projective_dev, 
 // host scalars -> device, run `body` on the staged copy, copy `out_bytes` of result back
 static int srs_host_call(const void* handle, void* out_host, size_t out_bytes, const void* in_host, size_t n, bool montgomery_in) {
   if (handle == nullptr || out_host == nullptr || (n && in_host == nullptr)) return ALEO_B200_EINVAL;
-  int dev = 0;
-  int rc = ensure_ready(&dev);
+  int rc = srs_ready(handle);
   if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
   cudaStream_t s;
   rc = thread_stream(dev, &s);
   if (rc) return rc;
@@ -664,12 +902,14 @@ int aleo_b200_kzg_commit_hiding_dev(const void* handle_beta, const void* handle_
                                     size_t n_random, void* stream) {
   if (handle_beta == nullptr || handle_beta_gamma == nullptr || out_compressed48_dev == nullptr) return ALEO_B200_EINVAL;
   if ((n_coeffs && coeffs_montgomery_dev == nullptr) || (n_random && random_coeffs_montgomery_dev == nullptr)) return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle_beta);
+  if (rc) return rc;
+  rc = srs_ready(handle_beta_gamma);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* d = nullptr;
   const size_t sb = ((n_coeffs > n_random ? n_coeffs : n_random) * 32 + 255) & ~(size_t)255;
-  API_CK(cudaMallocAsync((void**)&d, sb + 512, s));
+  API_CK(aleo::pool_malloc_async((void**)&d, sb + 512, s));
   unsigned char* parts = d + sb;  // two 144-byte partial results, then the sum
   cudaError_t e = aleo::fr_to_bigint(coeffs_montgomery_dev, d, n_coeffs, s);
   if (e == cudaSuccess) e = aleo::srs_msm(handle_beta, d, n_coeffs, parts, s, false, nullptr, nullptr);
@@ -689,7 +929,7 @@ int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_de
   if (out_compressed48_dev == nullptr || coeffs_dev_ptrs_host == nullptr || n_coeffs_host == nullptr || count > 64) return ALEO_B200_EINVAL;
   for (size_t m = 0; m < count; m++)
     if (n_coeffs_host[m] && coeffs_dev_ptrs_host[m] == nullptr) return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle);
   if (rc) return rc;
   API_CK(aleo::srs_msm_batch(handle, coeffs_dev_ptrs_host, n_coeffs_host, count, true, out_compressed48_dev, true, (cudaStream_t)stream));
   return ALEO_B200_OK;
@@ -698,12 +938,12 @@ int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_de
 int aleo_b200_kzg_commit_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                              void* stream) {
   if (handle == nullptr || out_compressed48_dev == nullptr || (n_coeffs && coeffs_montgomery_dev == nullptr)) return ALEO_B200_EINVAL;
-  int rc = ensure_ready(nullptr);
+  int rc = srs_ready(handle);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* d = nullptr;
   const size_t sb = (n_coeffs * 32 + 255) & ~(size_t)255;
-  API_CK(cudaMallocAsync((void**)&d, sb + 256, s));
+  API_CK(aleo::pool_malloc_async((void**)&d, sb + 256, s));
   cudaError_t e = aleo::fr_to_bigint(coeffs_montgomery_dev, d, n_coeffs, s);
   if (e == cudaSuccess) e = aleo::srs_msm(handle, d, n_coeffs, d + sb, s, false, nullptr, nullptr);
   if (e == cudaSuccess) e = aleo::g1_compress(d + sb, out_compressed48_dev, s);

@@ -5,6 +5,38 @@
 #include "platform.cuh"
 
 namespace aleo {
+// A non-blocking stream owned by one host thread for its current device: created on first use, re-created when the
+// thread moves to another device, destroyed when the thread ends (thread_local instances in capi.cu / msm_lib.cu).
+struct ThreadStream {
+  cudaStream_t s = nullptr;
+  int dev = -1;
+  ThreadStream() = default;
+  ThreadStream(const ThreadStream&) = delete;
+  ThreadStream& operator=(const ThreadStream&) = delete;
+  ~ThreadStream() {
+    if (s) cudaStreamDestroy(s);  // fails harmlessly once the runtime is unloading
+  }
+  cudaError_t get(cudaStream_t* out) {
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    if (s == nullptr || dev != d) {
+      if (s) cudaStreamDestroy(s);
+      s = nullptr;
+      e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+      dev = d;
+    }
+    *out = s;
+    return cudaSuccess;
+  }
+};
+
+// capi.cu -- workspace allocator: stream-ordered allocations from a PRIVATE memory pool per device (the process's default
+// pool and its release threshold are left alone: torch's caching allocator and other users of the default pool share
+// the process).  Freed blocks stay in the pool up to ALEO_B200_POOL_KEEP_MB (default 16384) so that the next call does
+// not pay for mapping gigabytes again; aleo_b200_shutdown() trims it.  Free with cudaFreeAsync.
+cudaError_t pool_malloc_async(void** p, size_t bytes, cudaStream_t s);
 // ntt_lib.cu
 cudaError_t ntt_upload_constants();
 cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, bool coset, void* data_dev, cudaStream_t s,
@@ -41,6 +73,8 @@ cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaS
 cudaError_t srs_create(const void* bases_dev, u32 stride, size_t n, cudaStream_t s, void** handle_out);
 void srs_destroy(void* handle);
 void srs_info(const void* handle, size_t* n, int* c, int* W, size_t* bytes);
+int srs_device(const void* handle);  // the device the handle was created on
+bool srs_size_supported(size_t n);   // n * windows must stay below 2^31
 cudaError_t srs_msm(const void* handle, const void* scalars_dev, size_t n_used, void* out144_dev, cudaStream_t s, bool dry,
                     int* launches_out, float* phase_ms);
 cudaError_t srs_msm_batch(const void* handle, const void* const* scalars_dev_ptrs, const size_t* n_each, size_t count,

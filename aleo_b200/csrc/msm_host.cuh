@@ -72,13 +72,13 @@ static inline u32 choose_window_srs(size_t n) {
 }
 
 // Accumulation threads (= equal runs of the sorted entry list) for `n_chunk` points.  At most 16 waves of
-// (148 SMs x 3 CTAs x 128 threads) -- measured best on B200 at n = 2^24: 4 waves 96.1 ms, 16 waves 93.4 ms.  Below
+// (SM count x 3 CTAs x 128 threads; 148 SMs on B200) -- measured best on B200 at n = 2^24: 4 waves 96.1 ms, 16 waves 93.4 ms.  Below
 // that, runs of 64 entries (every run boundary cuts a bucket whose pieces cost two more additions on the latency
 // path: 2^20 runs 3 % faster with 64 than with 32), but never fewer than 4 waves while runs of 32 can fill them.
 static inline u32 lanes_for(size_t n_chunk, u32 W) {
   const size_t entries = (size_t)n_chunk * W;
   static const long waves_env = []() { const char* e = getenv("ALEO_B200_MSM_WAVES"); return e ? atol(e) : 0L; }();
-  const size_t wave = (size_t)148 * 384;
+  const size_t wave = (size_t)dev_props().sms * 384;
   const size_t full = wave * (waves_env > 0 ? (size_t)waves_env : 16);
   size_t lanes = (entries + 63) / 64;
   if (lanes < 4 * wave) {
@@ -273,7 +273,7 @@ struct Session {
         part_nbin = prm.W * part_bps;
         part_wpg = PART_GROUP_BINS / part_bps ? PART_GROUP_BINS / part_bps : 1;
         const size_t ctas = (max_chunk + PART_TPB - 1) / PART_TPB;
-        part_ncta_max = (u32)(ctas < 592 ? ctas : 592);
+        part_ncta_max = (u32)(ctas < (size_t)dev_props().sms * 4 ? ctas : (size_t)dev_props().sms * 4);
         if ((size_t)part_nbin * 4 > (size_t)160 * 1024) part = false;  // histogram of part_count must fit shared memory
       }
       if (part) {
@@ -286,7 +286,7 @@ struct Session {
     }
     bytes = cv.off;
     if (dry) return cudaSuccess;
-    MSM_CK(cudaMallocAsync((void**)&ws, bytes, s));
+    MSM_CK(aleo::pool_malloc_async((void**)&ws, bytes, s));
     MSM_CK(cudaMemsetAsync(at<G1Xyzz>(o_buckets), 0, (size_t)NB * sizeof(G1Xyzz), s));
     return cudaSuccess;
   }
@@ -325,7 +325,7 @@ struct Session {
     if (phase_ev) cudaEventRecord(phase_ev[0], s);
     MSM_CK(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
     MSM_CK(cudaMemsetAsync(meta, 0, 64, s));
-    const u32 g_all = (n + 255) / 256, g_n = g_all < 1184 ? g_all : 1184;  // <= 8 CTAs of 256 per SM and window
+    const u32 g_all = (n + 255) / 256, g_n = g_all < dev_props().sms * 8 ? g_all : dev_props().sms * 8;  // <= 8 CTAs of 256 per SM and window
     TailTrace st;
     st.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
     st.mark("start", s);
@@ -337,7 +337,7 @@ struct Session {
       pa.fb = part_fb;
       pa.bps = part_bps;
       pa.nbin = part_nbin;
-      pa.ncta = g_all < 592 ? g_all : 592;
+      pa.ncta = g_all < dev_props().sms * 4 ? g_all : dev_props().sms * 4;
       pa.wpg = part_wpg;
       u32* pcnt = at<u32>(o_pcnt);
       u32* poffs = at<u32>(o_poffs);
@@ -368,7 +368,7 @@ struct Session {
     // measured on B200 at n = 2^24, c = 20: count 3.3 (scalar) / 4.5 (window) ms, scatter 9.2 / 5.3 ms;
     // at c = 16: count 4.0 / 5.6, scatter 4.2 / 5.8.  ALEO_B200_MSM_SORT = s | w forces one order for both.
     const char* sort_env = getenv("ALEO_B200_MSM_SORT");
-    const bool heads_fit_l2 = (size_t)NB * 32 <= ((size_t)48 << 20);
+    const bool heads_fit_l2 = (size_t)NB * 32 <= l2_resident_budget();
     const bool count_wm = sort_env && sort_env[0] == 'w';
     const bool scatter_wm = sort_env ? sort_env[0] == 'w' : (!heads_fit_l2 && !srs);  // a resident SRS shares one bucket set: nothing to gain
     if (count_wm)
@@ -385,7 +385,7 @@ struct Session {
       // single bucket set (resident SRS) whose heads outgrow L2: bucket-range passes (power of two, <= 8)
       u32 passes = 1;
       if (srs && !prm.nbatch && !sort_env)
-        while (passes < 8 && ((size_t)p.B * 32) / passes > ((size_t)48 << 20) && (p.B / passes) > 1) passes <<= 1;
+        while (passes < 8 && ((size_t)p.B * 32) / passes > l2_resident_budget() && (p.B / passes) > 1) passes <<= 1;
       if (const char* pe = getenv("ALEO_B200_MSM_SRS_PASSES"))  // tests: force the number of bucket-range passes
         if (srs && !prm.nbatch && (atoi(pe) == 2 || atoi(pe) == 4 || atoi(pe) == 8) && p.B >= 8) passes = (u32)atoi(pe);
       LAUNCH_NOSYNC(scatter_kernel_sm, dim3(g_all, passes), dim3(256), 0, s, scalars, n, p, ends, sorted);
@@ -423,7 +423,7 @@ struct Session {
     tr.mark("combine small", s);
     {
       const u32 cl = p.nlanes / SMALL_SPLIT_MAX + 1;
-      const u32 g = cl < 592 ? cl : 592;  // 4 CTAs per SM; the kernel strides over the list
+      const u32 g = cl < dev_props().sms * 4 ? cl : dev_props().sms * 4;  // 4 CTAs per SM; the kernel strides over the list
       LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), 0, s, (const u32*)large_list,
              (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces, (const u32*)piece_bucket,
              buckets);

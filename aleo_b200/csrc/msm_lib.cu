@@ -2,6 +2,9 @@
 #include "internal.h"
 #include "msm_host.cuh"
 #ifndef ALEO_EMU
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <thread>
 #endif
 
@@ -13,28 +16,16 @@ int msm_window_bits(size_t n) { return (int)msm::make_params(n).c; }
 // ---- host-pointer calls: the MSM arrives in point ranges so that the copy of range k + 1 overlaps the
 // accumulation of range k (PCIe moves 136 bytes per point about 2.5x faster than the integer pipe adds it) ----
 namespace {
-thread_local cudaStream_t t_copy_stream = nullptr;
-thread_local int t_copy_dev = -1;
+thread_local ThreadStream t_copy_stream;  // released when the calling thread ends (internal.h)
 
-cudaError_t copy_stream(cudaStream_t* out) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (t_copy_stream == nullptr || t_copy_dev != dev) {
-    e = cudaStreamCreateWithFlags(&t_copy_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return e;
-    t_copy_dev = dev;
-  }
-  *out = t_copy_stream;
-  return cudaSuccess;
-}
+cudaError_t copy_stream(cudaStream_t* out) { return t_copy_stream.get(out); }
 
 // Point ranges of a host-pointer MSM.  The first range is small (its copy is the only one not hidden) and the
 // later ones grow: a range's accumulation must outlast the copy of the next one.
 int chunk_schedule(size_t n, size_t* sizes) {
   const char* env = getenv("ALEO_B200_MSM_CHUNKS");  // read per call: tests and sweeps switch it
   const long k_env = env ? atol(env) : 0L;
-  int k = n < ((size_t)1 << 19) ? 1 : (n < ((size_t)1 << 22) ? 2 : 3);
+  int k = n < ((size_t)1 << 19) ? 1 : (n < ((size_t)1 << 22) ? 2 : 4);
   if (k_env >= 1 && k_env <= 4 && n >= 16) k = (int)k_env;
   // explicit weights, e.g. ALEO_B200_MSM_SPLIT=1,2,4 (sweeps): range i gets w_i / sum(w) of the points
   if (const char* sp = getenv("ALEO_B200_MSM_SPLIT")) {
@@ -56,9 +47,13 @@ int chunk_schedule(size_t n, size_t* sizes) {
   if (k == 1) {
     sizes[0] = n;
   } else if (k == 4) {
-    sizes[0] = n / 16;
-    sizes[1] = (n * 3) / 16;
-    sizes[2] = n / 4;
+    // 3 : 4 : 5 : 7 (default from 2^22 points).  A range may be only ~1.3x its predecessor before the GPU waits for its
+    // copy when the caller's memory is PAGEABLE: staged copies run at 33-46 GB/s on the B200 boxes (tools/feed_probe.cu;
+    // 243-340 Mpts/s at 136 B per point) against 190 Mpts/s of accumulation.  With 1 : 2 : 4 the third range arrived
+    // ~15 ms after the second was done (2^24 pageable: 129 ms, pinned 97.6 ms).
+    sizes[0] = (n * 3) / 19;
+    sizes[1] = (n * 4) / 19;
+    sizes[2] = (n * 5) / 19;
     sizes[3] = n - sizes[0] - sizes[1] - sizes[2];
   } else if (k == 2) {
     sizes[0] = n / 4;
@@ -87,19 +82,20 @@ struct EventSet {
       if (e) cudaEventDestroy(e);
   }
 };
-// ---- host -> device copies of caller memory that may be PAGEABLE (a Rust Vec is) ---------------------------------------
+// ---- host <-> device copies of caller memory that may be PAGEABLE (a Rust Vec is) --------------------------------------
 // Pinned / registered memory goes out as one cudaMemcpyAsync.  A large pageable block would be staged by the driver
-// through one bounce buffer at a few GB/s -- slower than the MSM itself -- so it is staged here instead: FEED_THREADS
-// helper threads memcpy 4 MB slices into their own pinned double buffers and enqueue the DMA from there (the CPU copy
-// of slice i + T overlaps the DMA of slice i).  The call returns when everything is enqueued; `cs` then waits on the
-// helpers' streams.  Staging buffers and streams live per calling thread (8 MB pinned per helper; feed_threads()
-// helpers, ALEO_B200_FEED_THREADS overrides).
+// through one bounce buffer at ~10 GB/s (tools/feed_probe.cu on the B200 box: pinned 55.6 GB/s, driver bounce 10.4 GB/s,
+// cudaHostRegister + copy + unregister 7.3 GB/s) -- slower than the MSM itself -- so it is staged here instead: a
+// Feeder owns feed_threads() PERSISTENT helper threads, each with two pinned 4 MB buffers, a stream and two events;
+// helper t memcpys slices t, t + T, ... into its buffers and enqueues the DMA from there (the CPU copy of the next
+// slice overlaps the DMA of the previous one; measured 42-46 GB/s with 6-12 helpers).  One Feeder per calling thread
+// (thread_local, released by its destructor when the thread ends); it is rebuilt when the thread's device changes.
 #ifndef ALEO_EMU
-constexpr int FEED_THREADS = 8;  // upper bound; feed_threads() of them run
+constexpr int FEED_THREADS = 16;  // upper bound; feed_threads() of them run
 constexpr size_t FEED_SLICE = (size_t)4 << 20;
 constexpr size_t FEED_MIN_BYTES = (size_t)8 << 20;  // below this the plain pageable copy is fine
 
-// helper threads per staged copy: one core copies ~10 GB/s, PCIe takes ~53 GB/s
+// helper threads per staged copy: one core copies ~8 GB/s, PCIe takes ~55 GB/s
 int feed_threads() {
   static const int n = [] {
     const char* env = getenv("ALEO_B200_FEED_THREADS");
@@ -113,27 +109,162 @@ int feed_threads() {
   return n;
 }
 
-struct FeedState {
-  int dev = -1;
-  unsigned char* buf[FEED_THREADS][2] = {};
-  cudaEvent_t ev[FEED_THREADS][2] = {};
-  cudaStream_t st[FEED_THREADS] = {};
-  cudaError_t init(int device) {
-    if (dev == device) return cudaSuccess;
-    for (int t = 0; t < feed_threads(); t++) {
-      cudaError_t e = cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking);
+class Feeder {
+ public:
+  explicit Feeder(int device) : dev_(device), nt_(feed_threads()) {}
+  ~Feeder() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_)
+      if (w.joinable()) w.join();
+    // at process exit the runtime may already be gone: the calls then fail harmlessly
+    for (int t = 0; t < nt_; t++) {
+      for (int b = 0; b < 2; b++) {
+        if (ev_[t][b]) cudaEventDestroy(ev_[t][b]);
+        if (buf_[t][b]) cudaFreeHost(buf_[t][b]);
+      }
+      if (st_[t]) cudaStreamDestroy(st_[t]);
+    }
+  }
+  int device() const { return dev_; }
+
+  cudaError_t init() {
+    for (int t = 0; t < nt_; t++) {
+      cudaError_t e = cudaStreamCreateWithFlags(&st_[t], cudaStreamNonBlocking);
       for (int b = 0; b < 2 && e == cudaSuccess; b++) {
-        e = cudaMallocHost((void**)&buf[t][b], FEED_SLICE);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming);
+        e = cudaMallocHost((void**)&buf_[t][b], FEED_SLICE);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_[t][b], cudaEventDisableTiming);
       }
       if (e != cudaSuccess) return e;
     }
-    dev = device;
+    for (int t = 0; t < nt_; t++) workers_.emplace_back([this, t]() { loop(t); });
     return cudaSuccess;
   }
-};
-thread_local FeedState t_feed;
 
+  // dev <- host: returns when every slice is enqueued; `cs` then waits for the helpers' streams
+  cudaError_t h2d(unsigned char* dst_dev, const unsigned char* src_host, size_t bytes, cudaStream_t cs, cudaEvent_t ready) {
+    cudaError_t e = run(Job{true, dst_dev, const_cast<unsigned char*>(src_host), bytes, ready});
+    for (int t = 0; t < nt_ && e == cudaSuccess; t++)
+      for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaStreamWaitEvent(cs, ev_[t][b], 0);
+    return e;
+  }
+  // host <- dev: `gate` orders the helpers' streams after the producer; returns when the data is in dst_host
+  cudaError_t d2h(unsigned char* dst_host, const unsigned char* src_dev, size_t bytes, cudaEvent_t gate) {
+    return run(Job{false, const_cast<unsigned char*>(src_dev), dst_host, bytes, gate});
+  }
+
+ private:
+  struct Job {
+    bool to_device;
+    unsigned char* dev;
+    unsigned char* host;
+    size_t bytes;
+    cudaEvent_t gate;
+  };
+
+  cudaError_t run(const Job& j) {
+    std::unique_lock<std::mutex> lk(mu_);
+    job_ = j;
+    pending_ = nt_;
+    err_ = cudaSuccess;
+    generation_++;
+    cv_.notify_all();
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    return err_;
+  }
+
+  void loop(int t) {
+    cudaSetDevice(dev_);
+    unsigned long long seen = 0;
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+        j = job_;
+      }
+      const cudaError_t e = j.to_device ? push(t, j) : pull(t, j);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (e != cudaSuccess) err_ = e;
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+
+  cudaError_t push(int t, const Job& j) {
+    const size_t nslices = (j.bytes + FEED_SLICE - 1) / FEED_SLICE;
+    cudaError_t e = cudaStreamWaitEvent(st_[t], j.gate, 0);
+    for (size_t i = (size_t)t, round = 0; i < nslices && e == cudaSuccess; i += (size_t)nt_, round++) {
+      const int b = (int)(round & 1);
+      const size_t off = i * FEED_SLICE, len = (j.bytes - off < FEED_SLICE) ? j.bytes - off : FEED_SLICE;
+      e = cudaEventSynchronize(ev_[t][b]);  // the DMA that last read this buffer is done
+      if (e != cudaSuccess) break;
+      std::memcpy(buf_[t][b], j.host + off, len);
+      e = cudaMemcpyAsync(j.dev + off, buf_[t][b], len, cudaMemcpyHostToDevice, st_[t]);
+      if (e == cudaSuccess) e = cudaEventRecord(ev_[t][b], st_[t]);
+    }
+    return e;
+  }
+
+  cudaError_t pull(int t, const Job& j) {
+    const size_t nslices = (j.bytes + FEED_SLICE - 1) / FEED_SLICE;
+    cudaError_t e = cudaStreamWaitEvent(st_[t], j.gate, 0);
+    for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaEventSynchronize(ev_[t][b]);  // buffers idle
+    size_t prev_off = 0, prev_len = 0;
+    int prev_b = -1;
+    for (size_t i = (size_t)t, round = 0; e == cudaSuccess; i += (size_t)nt_, round++) {
+      const int b = (int)(round & 1);
+      const bool more = i < nslices;
+      size_t off = 0, len = 0;
+      if (more) {
+        off = i * FEED_SLICE;
+        len = (j.bytes - off < FEED_SLICE) ? j.bytes - off : FEED_SLICE;
+        e = cudaMemcpyAsync(buf_[t][b], j.dev + off, len, cudaMemcpyDeviceToHost, st_[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_[t][b], st_[t]);
+      }
+      if (prev_b >= 0 && e == cudaSuccess) {  // copy the previous slice out while this one is in flight
+        e = cudaEventSynchronize(ev_[t][prev_b]);
+        if (e == cudaSuccess) std::memcpy(j.host + prev_off, buf_[t][prev_b], prev_len);
+      }
+      if (!more) break;
+      prev_off = off;
+      prev_len = len;
+      prev_b = b;
+    }
+    return e;
+  }
+
+  const int dev_, nt_;
+  unsigned char* buf_[FEED_THREADS][2] = {};
+  cudaEvent_t ev_[FEED_THREADS][2] = {};
+  cudaStream_t st_[FEED_THREADS] = {};
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  Job job_{};
+  int pending_ = 0;
+  unsigned long long generation_ = 0;
+  cudaError_t err_ = cudaSuccess;
+  bool stop_ = false;
+};
+thread_local std::unique_ptr<Feeder> t_feeder;
+
+cudaError_t feeder_for_current_device(Feeder** out) {
+  int dev = 0;
+  MSM_CK(cudaGetDevice(&dev));
+  if (!t_feeder || t_feeder->device() != dev) {
+    t_feeder.reset();  // a thread that moved to another device drops the old staging context first
+    std::unique_ptr<Feeder> f(new Feeder(dev));
+    MSM_CK(f->init());
+    t_feeder = std::move(f);
+  }
+  *out = t_feeder.get();
+  return cudaSuccess;
+}
 
 bool host_pointer_is_pinned(const void* p) {
   cudaPointerAttributes a;
@@ -154,40 +285,9 @@ cudaError_t feed_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStre
 #ifndef ALEO_EMU
   static const bool force_plain = getenv("ALEO_B200_NO_STAGING") != nullptr;
   if (bytes >= FEED_MIN_BYTES && !force_plain && !host_pointer_is_pinned(src_host)) {
-    int dev = 0;
-    MSM_CK(cudaGetDevice(&dev));
-    MSM_CK(t_feed.init(dev));
-    FeedState* fs = &t_feed;
-    const size_t nslices = (bytes + FEED_SLICE - 1) / FEED_SLICE;
-    const int NT = feed_threads();
-    cudaError_t errs[FEED_THREADS];
-    std::thread workers[FEED_THREADS];
-    for (int t = 0; t < NT; t++) {
-      errs[t] = cudaSuccess;
-      workers[t] = std::thread([=, &errs]() {
-        cudaError_t e = cudaSetDevice(dev);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(fs->st[t], ready, 0);
-        for (size_t i = (size_t)t, round = 0; i < nslices && e == cudaSuccess; i += (size_t)NT, round++) {
-          const int b = (int)(round & 1);
-          const size_t off = i * FEED_SLICE, len = (bytes - off < FEED_SLICE) ? bytes - off : FEED_SLICE;
-          e = cudaEventSynchronize(fs->ev[t][b]);  // the DMA that last read this buffer is done
-          if (e != cudaSuccess) break;
-          std::memcpy(fs->buf[t][b], (const unsigned char*)src_host + off, len);
-          e = cudaMemcpyAsync((unsigned char*)dst_dev + off, fs->buf[t][b], len, cudaMemcpyHostToDevice, fs->st[t]);
-          if (e == cudaSuccess) e = cudaEventRecord(fs->ev[t][b], fs->st[t]);
-        }
-        errs[t] = e;
-      });
-    }
-    cudaError_t e = cudaSuccess;
-    for (int t = 0; t < NT; t++) {
-      workers[t].join();
-      if (errs[t] != cudaSuccess) e = errs[t];
-    }
-    // cs continues after every helper stream's last copy (events of both buffers cover the tail of each stream)
-    for (int t = 0; t < NT && e == cudaSuccess; t++)
-      for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaStreamWaitEvent(cs, fs->ev[t][b], 0);
-    return e;
+    Feeder* f = nullptr;
+    MSM_CK(feeder_for_current_device(&f));
+    return f->h2d((unsigned char*)dst_dev, (const unsigned char*)src_host, bytes, cs, ready);
   }
 #endif
   (void)ready;
@@ -201,52 +301,12 @@ cudaError_t feed_d2h_sync(void* dst_host, const void* src_dev, size_t bytes, cud
 #ifndef ALEO_EMU
   static const bool force_plain = getenv("ALEO_B200_NO_STAGING") != nullptr;
   if (bytes >= FEED_MIN_BYTES && !force_plain && !host_pointer_is_pinned(dst_host)) {
-    int dev = 0;
-    MSM_CK(cudaGetDevice(&dev));
-    MSM_CK(t_feed.init(dev));
-    FeedState* fs = &t_feed;
+    Feeder* f = nullptr;
+    MSM_CK(feeder_for_current_device(&f));
     cudaEvent_t done;
     MSM_CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    MSM_CK(cudaEventRecord(done, s));
-    const size_t nslices = (bytes + FEED_SLICE - 1) / FEED_SLICE;
-    const int NT = feed_threads();
-    cudaError_t errs[FEED_THREADS];
-    std::thread workers[FEED_THREADS];
-    for (int t = 0; t < NT; t++) {
-      errs[t] = cudaSuccess;
-      workers[t] = std::thread([=, &errs]() {
-        cudaError_t e = cudaSetDevice(dev);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(fs->st[t], done, 0);
-        for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaEventSynchronize(fs->ev[t][b]);  // buffers idle
-        size_t prev_off = 0, prev_len = 0;
-        int prev_b = -1;
-        for (size_t i = (size_t)t, round = 0; e == cudaSuccess; i += (size_t)NT, round++) {
-          const int b = (int)(round & 1);
-          const bool more = i < nslices;
-          size_t off = 0, len = 0;
-          if (more) {
-            off = i * FEED_SLICE;
-            len = (bytes - off < FEED_SLICE) ? bytes - off : FEED_SLICE;
-            e = cudaMemcpyAsync(fs->buf[t][b], (const unsigned char*)src_dev + off, len, cudaMemcpyDeviceToHost, fs->st[t]);
-            if (e == cudaSuccess) e = cudaEventRecord(fs->ev[t][b], fs->st[t]);
-          }
-          if (prev_b >= 0 && e == cudaSuccess) {  // copy the previous slice out while this one is in flight
-            e = cudaEventSynchronize(fs->ev[t][prev_b]);
-            if (e == cudaSuccess) std::memcpy((unsigned char*)dst_host + prev_off, fs->buf[t][prev_b], prev_len);
-          }
-          if (!more) break;
-          prev_off = off;
-          prev_len = len;
-          prev_b = b;
-        }
-        errs[t] = e;
-      });
-    }
-    cudaError_t e = cudaSuccess;
-    for (int t = 0; t < NT; t++) {
-      workers[t].join();
-      if (errs[t] != cudaSuccess) e = errs[t];
-    }
+    cudaError_t e = cudaEventRecord(done, s);
+    if (e == cudaSuccess) e = f->d2h((unsigned char*)dst_host, (const unsigned char*)src_dev, bytes, done);
     cudaEventDestroy(done);
     cudaError_t e2 = cudaStreamSynchronize(s);
     return e != cudaSuccess ? e : e2;
@@ -269,7 +329,7 @@ cudaError_t msm_run_host(const void* bases_host, u32 stride, const void* scalars
   unsigned char* d = nullptr;
   const size_t bb = n * stride, sb = n * 32;
   const size_t o_s = (bb + 255) & ~(size_t)255, o_out = o_s + ((sb + 255) & ~(size_t)255);
-  MSM_CK(cudaMallocAsync((void**)&d, o_out + 256, s));
+  MSM_CK(aleo::pool_malloc_async((void**)&d, o_out + 256, s));
   cudaError_t e = cudaSuccess;
   if (n == 0) {
     e = msm::run(nullptr, stride, nullptr, 0, d + o_out, s, false, nullptr);
@@ -371,6 +431,14 @@ void srs_destroy(void* handle) {
   delete h;
 }
 
+int srs_device(const void* handle) { return ((const Srs*)handle)->device; }
+
+bool srs_size_supported(size_t n) {
+  if (n == 0 || n >= ((size_t)1 << 31)) return false;
+  const u32 c = msm::choose_window_srs(n), W = msm::windows_for_srs(c);
+  return W <= msm::SRS_MAX_WINDOWS && (unsigned long long)n * W < (1ull << 31);
+}
+
 void srs_info(const void* handle, size_t* n, int* c, int* W, size_t* bytes) {
   const Srs* h = (const Srs*)handle;
   if (n) *n = h->n;
@@ -408,7 +476,7 @@ cudaError_t srs_msm_host(const void* handle, const void* in_host, size_t n, bool
   msm::SrsView v{h->pre, (u32)h->n, h->c, h->W};
   unsigned char* d = nullptr;
   const size_t sb = (n * 32 + 255) & ~(size_t)255;
-  MSM_CK(cudaMallocAsync((void**)&d, sb + 512, s));
+  MSM_CK(aleo::pool_malloc_async((void**)&d, sb + 512, s));
   cudaError_t e = cudaSuccess;
   if (n == 0) {
     e = msm::run(nullptr, 96, nullptr, 0, d + sb, s, false, nullptr);
@@ -470,7 +538,7 @@ cudaError_t srs_msm_batch(const void* handle, const void* const* scalars_dev_ptr
   msm::SrsView v{h->pre, (u32)h->n, h->c, h->W};
   unsigned char* d = nullptr;
   const size_t sb = ((total ? total : 1) * 32 + 255) & ~(size_t)255, ob = ((count + 1) * 4 + 255) & ~(size_t)255;
-  MSM_CK(cudaMallocAsync((void**)&d, sb + ob, s));
+  MSM_CK(aleo::pool_malloc_async((void**)&d, sb + ob, s));
   u32* off_dev = (u32*)(d + sb);
   cudaError_t e = cudaMemcpyAsync(off_dev, off.data(), (count + 1) * 4, cudaMemcpyHostToDevice, s);
   for (size_t m = 0; m < count && e == cudaSuccess; m++) {

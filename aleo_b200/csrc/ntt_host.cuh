@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <map>
+#include <string>
 #include <tuple>
 #include <vector>
 #include "ntt.cuh"
@@ -409,7 +410,15 @@ class PlanCache {
  public:
   cudaError_t get(int device, u32 log_n, bool inverse, bool coset, cudaStream_t s, const Plan** out, int dist_lg = 0) {
     std::lock_guard<std::mutex> lk(mu_);
-    auto key = std::make_tuple(device, log_n, inverse, coset, dist_lg);
+    // build_plan also reads tuning switches from the environment (sweeps and tests flip them inside one process): they
+    // are part of the key, so a plan built under one setting is never handed out under another
+    std::string env_sig;
+    for (const char* name : {"ALEO_B200_NTT_SPLIT", "ALEO_B200_NTT_DIRECT0", "ALEO_B200_NTT_DIRECT0_MIN"}) {
+      const char* v = getenv(name);
+      env_sig += v ? v : "";
+      env_sig += '|';
+    }
+    auto key = std::make_tuple(device, log_n, inverse, coset, dist_lg, env_sig);
     auto it = plans_.find(key);
     if (it == plans_.end()) {
       Plan p;
@@ -431,7 +440,7 @@ class PlanCache {
 
  private:
   std::mutex mu_;
-  std::map<std::tuple<int, u32, bool, bool, int>, Plan> plans_;
+  std::map<std::tuple<int, u32, bool, bool, int, std::string>, Plan> plans_;
 };
 
 }  // namespace ntt

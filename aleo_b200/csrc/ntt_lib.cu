@@ -26,7 +26,7 @@ cudaError_t ntt_transform(int device, u32 log_n, size_t batch, bool inverse, boo
   if (e != cudaSuccess) return e;
   Fr* scratch = nullptr;
   if (log_n > (u32)ntt::SMALL_MAX_LOG) {
-    e = cudaMallocAsync((void**)&scratch, (sizeof(Fr) << log_n) * ntt::scratch_batch(log_n, batch), s);
+    e = aleo::pool_malloc_async((void**)&scratch, (sizeof(Fr) << log_n) * ntt::scratch_batch(log_n, batch), s);
     if (e != cudaSuccess) return e;
   }
   cudaEvent_t ev[5];
@@ -49,7 +49,7 @@ cudaError_t ntt_bitrev(u32 log_n, size_t batch, void* data_dev, cudaStream_t s) 
   if (log_n < 2 || batch == 0) return cudaSuccess;  // sizes 1 and 2 are their own reversal
   const u64 n = (u64)1 << log_n;
   u64 blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > dev_props().sms * 8) blocks = dev_props().sms * 8;
   for (size_t b0 = 0; b0 < batch; b0 += 65535) {
     const u32 nb = (u32)(batch - b0 < 65535 ? batch - b0 : 65535);
     LAUNCH_NOSYNC(ntt::bitrev_permute_kernel, dim3((u32)blocks, nb), dim3(256), 0, s, (Fr*)data_dev + (b0 << log_n), log_n);
@@ -157,7 +157,7 @@ cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, b
   if (e != cudaSuccess) return e;
   Fr* scratch = nullptr;
   if (plan->npass > 2) {
-    e = cudaMallocAsync((void**)&scratch, (sizeof(Fr) << c->log_n) / (size_t)c->world, s);
+    e = aleo::pool_malloc_async((void**)&scratch, (sizeof(Fr) << c->log_n) / (size_t)c->world, s);
     if (e != cudaSuccess) return e;
   }
   e = ntt::run_dist_stage1(*plan, c->lg, c->rank, (const Fr*)local_in_dev, scratch, c->peers[c->calls & 1], s);

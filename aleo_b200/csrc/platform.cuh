@@ -38,3 +38,30 @@ DEV uint32_t atomic_add_shared_u32(uint32_t* p, uint32_t v) { return atomicAdd(p
 
 typedef uint32_t u32;
 typedef uint64_t u64;
+
+// Part constants of the calling thread's current device, read once per device from the runtime (grids are sized in
+// multiples of the SM count; the sort picks its pass structure from the L2 size).  The emulator reports a B200.
+struct DevProps {
+  u32 sms;
+  size_t l2_bytes;
+};
+#ifndef ALEO_EMU
+static inline DevProps dev_props() {
+  static DevProps cache[64];
+  static bool have[64];  // benign race: every thread computes the same values
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return DevProps{148u, (size_t)126 << 20};
+  if (!have[d]) {
+    int sms = 0, l2 = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || sms <= 0) sms = 148;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, d) != cudaSuccess || l2 <= 0) l2 = 126 << 20;
+    cache[d] = DevProps{(u32)sms, (size_t)l2};
+    have[d] = true;
+  }
+  return cache[d];
+}
+#else
+static inline DevProps dev_props() { return DevProps{148u, (size_t)126 << 20}; }
+#endif
+// bucket heads / tables that should stay L2 resident next to the streaming traffic: 3/8 of the L2 (47 MB on B200)
+static inline size_t l2_resident_budget() { return dev_props().l2_bytes / 8 * 3; }

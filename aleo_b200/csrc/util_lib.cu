@@ -23,8 +23,8 @@ cudaError_t gen_bases(void* bases_dev, size_t n, u32 stride, const void* s0_32, 
   const size_t slab = (size_t)1 << 22;
   Fq* qaff = nullptr;
   G1Xyzz* scratch = nullptr;
-  UT_CK(cudaMallocAsync((void**)&qaff, 2 * sizeof(Fq), s));
-  UT_CK(cudaMallocAsync((void**)&scratch, (n < slab ? n : slab) * sizeof(G1Xyzz), s));
+  UT_CK(aleo::pool_malloc_async((void**)&qaff, 2 * sizeof(Fq), s));
+  UT_CK(aleo::pool_malloc_async((void**)&scratch, (n < slab ? n : slab) * sizeof(G1Xyzz), s));
   LAUNCH_NOSYNC(util::gen_step_point_kernel, dim3(1), dim3(1), 0, s, qaff, d);
   cudaError_t e = cudaGetLastError();
   for (size_t done = 0; done < n && e == cudaSuccess; done += slab) {
@@ -50,9 +50,9 @@ cudaError_t gen_scalars(void* scalars_dev, size_t n, u64 seed, u64 first, bool m
 cudaError_t dlog_dot(void* out_dev, const void* scalars_dev, size_t n, const void* s0_32, const void* d_32, u64 first,
                      cudaStream_t s) {
   const Fr s0 = load_fr(s0_32), d = load_fr(d_32);
-  const u32 nblocks = 592;
+  const u32 nblocks = dev_props().sms * 4;
   Fr* partials = nullptr;
-  UT_CK(cudaMallocAsync((void**)&partials, nblocks * sizeof(Fr), s));
+  UT_CK(aleo::pool_malloc_async((void**)&partials, nblocks * sizeof(Fr), s));
   LAUNCH(util::dlog_dot_kernel, dim3(nblocks), dim3(256), 256 * sizeof(Fr), s, (const Fr*)scalars_dev, (u32)n, s0, d, first,
          partials);
   LAUNCH_NOSYNC(util::dlog_dot_final_kernel, dim3(1), dim3(1), 0, s, (const Fr*)partials, nblocks, (Fr*)out_dev);
@@ -63,7 +63,7 @@ cudaError_t dlog_dot(void* out_dev, const void* scalars_dev, size_t n, const voi
 
 cudaError_t check_on_curve(const void* bases_dev, size_t n, u32 stride, cudaStream_t s, int* ok) {
   u32* bad = nullptr;
-  UT_CK(cudaMallocAsync((void**)&bad, 4, s));
+  UT_CK(aleo::pool_malloc_async((void**)&bad, 4, s));
   cudaMemsetAsync(bad, 0, 4, s);
   LAUNCH_NOSYNC(util::check_on_curve_kernel, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (const unsigned char*)bases_dev,
                 stride, (u32)n, bad);
@@ -87,7 +87,7 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const u32 grid = 148 * 8, block = 256;
+  const u32 grid = dev_props().sms * 8, block = 256;
   const double per_thread[6] = {64.0, 64.0, 64.0, 2.0 * 276.0, 64.0, 64.0};  // kind 5: 64 DFMA + 64 IMAD.WIDE, counted as 64 pairs
   for (int rep = 0; rep < 2; rep++) {  // first launch warms up
     cudaEventRecord(e0, 0);

@@ -164,17 +164,38 @@ class EvaluationDomain:
     def in_order_coset_ifft_in_place_with_pc_dev(self, t, pc=None, batch: int = 1):
         return self._run_dev_ordered(t, _lib.NTT_INVERSE, _lib.NTT_COSET, _lib.NTT_ORDER_II, batch)
 
-    def ntt_host_buffer(self, buf, direction: int, kind: int):
+    def ntt_host_buffer(self, buf, direction: int, kind: int, order: int = _lib.NTT_ORDER_II):
         """in-place transform of a host buffer that already holds `size` elements (numpy array or
-        torch CPU tensor, pinned or pageable) -- the zero-copy form of aleo_b200_ntt_fr"""
+        torch CPU tensor, pinned or pageable) -- the zero-copy form of aleo_b200_ntt_fr / aleo_b200_ntt_fr_ordered"""
         from .msm import _host_ptr
 
         lib = _lib.get_lib()
         ptr, nbytes, _keep = _host_ptr(buf)
         if nbytes != self.size * 32:
             raise ValueError("buffer holds %d bytes, domain needs %d" % (nbytes, self.size * 32))
-        lib.check(lib.ntt_fr(ptr, self.log_size_of_group, direction, kind), "aleo_b200_ntt_fr")
+        if order == _lib.NTT_ORDER_II:
+            lib.check(lib.ntt_fr(ptr, self.log_size_of_group, direction, kind), "aleo_b200_ntt_fr")
+        else:
+            lib.check(lib.ntt_fr_ordered(ptr, self.log_size_of_group, direction, kind, order), "aleo_b200_ntt_fr_ordered")
         return buf
+
+    # host-vector forms of upstream's FFTOrder entry points (the precomputation argument is accepted and ignored)
+    def _run_host_ordered(self, v, direction: int, kind: int, order: int) -> bytearray:
+        lib = _lib.get_lib()
+        buf = self._resize(v)
+        cbuf = (C.c_char * len(buf)).from_buffer(buf)
+        lib.check(lib.ntt_fr_ordered(C.cast(cbuf, C.c_void_p), self.log_size_of_group, direction, kind, order),
+                  "aleo_b200_ntt_fr_ordered")
+        return buf
+
+    def fft_helper_in_place_with_pc(self, v: bytearray, order: int, pc=None) -> bytearray:
+        return self._run_host_ordered(v, _lib.NTT_FORWARD, _lib.NTT_STANDARD, order)
+
+    def ifft_helper_in_place_with_pc(self, v: bytearray, order: int, pc=None) -> bytearray:
+        return self._run_host_ordered(v, _lib.NTT_INVERSE, _lib.NTT_STANDARD, order)
+
+    def out_order_fft_in_place_with_pc(self, v: bytearray, pc=None) -> bytearray:
+        return self._run_host_ordered(v, _lib.NTT_FORWARD, _lib.NTT_STANDARD, _lib.NTT_ORDER_IO)
 
     def launches(self) -> int:
         """kernel launches one transform of this domain issues"""

@@ -148,3 +148,27 @@ class KZG10:
             srs._lib.check(srs._lib.kzg_open_dev(srs._h, out.data_ptr(), coeffs_t.data_ptr(), n, _fr_host(point),
                                                  torch.cuda.current_stream().cuda_stream), "aleo_b200_kzg_open_dev")
         return out
+
+    @staticmethod
+    def open_combinations_dev(srs: ResidentSRS, polys, lc_rows, points, out=None):
+        """m openings in one call (SonicKZG10::open_combinations / batch_open shape): opening k is of the linear
+        combination sum_i lc_rows[k][i] * polys[i] at points[k]; coefficients and points are canonical ints, `polys` a
+        list of CUDA tensors of Montgomery Fr.  -> (m, 48) uint8 CUDA tensor of compressed witness commitments."""
+        import torch
+
+        from .poly import _fr_host
+        m, npoly = len(lc_rows), len(polys)
+        if m != len(points) or any(len(r) != npoly for r in lc_rows):
+            raise ValueError("lc_rows must be m rows of len(polys) coefficients, points m values")
+        dev = polys[0].device
+        if out is None:
+            out = torch.empty((max(m, 1), 48), dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * max(npoly, 1))(*[t.data_ptr() for t in polys])
+        lens = (C.c_size_t * max(npoly, 1))(*[t.numel() * t.element_size() // 32 for t in polys])
+        lc = b"".join(_fr_host(a) for row in lc_rows for a in row)
+        zs = b"".join(_fr_host(z) for z in points)
+        with torch.cuda.device(dev):
+            srs._lib.check(srs._lib.kzg_open_combinations_dev(srs._h, out.data_ptr(), ptrs, lens, npoly, lc, zs, m,
+                                                              torch.cuda.current_stream().cuda_stream),
+                           "aleo_b200_kzg_open_combinations_dev")
+        return out[:m]

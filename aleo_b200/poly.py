@@ -145,3 +145,57 @@ def lagrange_coeffs_dev(log_n: int, tau, device=None):
         lib.check(lib.fr_lagrange_coeffs_dev(out.data_ptr(), log_n, _fr_host(tau), torch.cuda.current_stream().cuda_stream),
                   "aleo_b200_fr_lagrange_coeffs_dev")
     return out
+
+
+class PolyMultiplier:
+    """mirror of snarkVM's ``PolyMultiplier`` (src/fft/polynomial/multiplier.rs [U]; its CUDA arm calls
+    ``snarkvm_polymul``): collect polynomials (coefficient form) and evaluation vectors, then
+    ``multiply`` returns the coefficients of their product over the domain of size 2^log_n -- every operand crosses
+    PCIe once (host form) or not at all (device form)."""
+
+    def __init__(self):
+        self.polynomials, self.evaluations = [], []
+
+    def add_polynomial(self, p):
+        self.polynomials.append(p)
+        return self
+
+    def add_evaluation(self, e):
+        self.evaluations.append(e)
+        return self
+
+    def multiply(self, log_n: int) -> bytes:
+        """host buffers (bytes / bytearray / numpy / CPU tensors of Montgomery Fr) -> n * 32 bytes"""
+        import ctypes as C
+
+        from .msm import _host_ptr
+        lib = _lib.get_lib()
+        ps = [_host_ptr(p) for p in self.polynomials]
+        es = [_host_ptr(e) for e in self.evaluations]
+        out = C.create_string_buffer(32 << log_n)
+        pp = (C.c_void_p * max(len(ps), 1))(*[p[0] for p in ps])
+        pl = (C.c_size_t * max(len(ps), 1))(*[p[1] // 32 for p in ps])
+        ep = (C.c_void_p * max(len(es), 1))(*[e[0] for e in es])
+        el = (C.c_size_t * max(len(es), 1))(*[e[1] // 32 for e in es])
+        lib.check(lib.polymul(C.cast(out, C.c_void_p), len(ps), pp, pl, len(es), ep, el, log_n), "aleo_b200_polymul")
+        return out.raw
+
+    def multiply_dev(self, log_n: int, out=None):
+        """CUDA tensors of Montgomery Fr -> (n, 4) int64 CUDA tensor; asynchronous on torch's current stream"""
+        import ctypes as C
+
+        import torch
+        lib = _lib.get_lib()
+        ts = self.polynomials + self.evaluations
+        dev = ts[0].device
+        if out is None:
+            out = torch.empty((1 << log_n, 4), dtype=torch.int64, device=dev)
+        np_, ne = len(self.polynomials), len(self.evaluations)
+        pp = (C.c_void_p * max(np_, 1))(*[t.data_ptr() for t in self.polynomials])
+        pl = (C.c_size_t * max(np_, 1))(*[t.numel() * t.element_size() // 32 for t in self.polynomials])
+        ep = (C.c_void_p * max(ne, 1))(*[t.data_ptr() for t in self.evaluations])
+        el = (C.c_size_t * max(ne, 1))(*[t.numel() * t.element_size() // 32 for t in self.evaluations])
+        with torch.cuda.device(dev):
+            lib.check(lib.polymul_dev(out.data_ptr(), np_, pp, pl, ne, ep, el, log_n, torch.cuda.current_stream().cuda_stream),
+                      "aleo_b200_polymul_dev")
+        return out

@@ -72,6 +72,23 @@ int aleo_b200_ntt_fr_dev(void* inout_dev, uint32_t log_n, size_t batch, int dire
  *   (out[bitrev(i)] = X[i]);  OI: bit-reversed in, natural out.  Coset scaling always refers to the natural index. */
 enum { ALEO_B200_NTT_ORDER_II = 0, ALEO_B200_NTT_ORDER_IO = 1, ALEO_B200_NTT_ORDER_OI = 2 };
 int aleo_b200_ntt_fr_ordered_dev(void* inout_dev, uint32_t log_n, size_t batch, int direction, int kind, int order, void* stream);
+/* The same on a HOST buffer: the full argument list of upstream's optional FFI `snarkvm_ntt(inout, lg_domain_size, order,
+ * direction, ntt_type)` (upstream's NN / NR / RN are II / IO / OI here).  One H2D, the transform, one D2H. */
+int aleo_b200_ntt_fr_ordered(void* inout_host, uint32_t log_n, int direction, int kind, int order);
+/* Product of polynomials over the domain of size n = 2^log_n, shaped like upstream's `snarkvm_polymul(out, pcount,
+ * polynomials, plens, ecount, evaluations, elens, lg_domain_size)` (the CUDA arm of snarkVM's
+ * PolyMultiplier::multiply, src/fft/polynomial/multiplier.rs [U]):
+ *     out = ifft( prod_i fft(pad_n(polynomials[i])) * prod_j evaluations[j] )          (n coefficients, natural order)
+ * polynomials[i]: plens[i] <= n coefficients; evaluations[j]: elens[j] == n values on the domain; all Montgomery Fr;
+ * pcount + ecount >= 1, each <= 64.  The host call moves every operand over PCIe once and the result back once -- a
+ * prover that called fft / mul / ifft through the host NTT entry would pay 2 (pcount + 1) transfers of n elements instead
+ * (aleo_b200_ntt_fr at 2^24: 23 ms per call against 3.3 ms on the device).  `_dev`: HOST arrays of device pointers,
+ * asynchronous on `stream`; out_dev may not alias an input. */
+int aleo_b200_polymul(void* out_host, size_t pcount, const void* const* polynomials_host, const size_t* plens, size_t ecount,
+                      const void* const* evaluations_host, const size_t* elens, uint32_t log_n);
+int aleo_b200_polymul_dev(void* out_dev, size_t pcount, const void* const* polynomials_dev_ptrs_host, const size_t* plens_host,
+                          size_t ecount, const void* const* evaluations_dev_ptrs_host, const size_t* elens_host, uint32_t log_n,
+                          void* stream);
 /* One transform with CUDA events around every pass: pass_ms4[i] = device time of pass i (unused
  * entries 0).  Synchronises `stream`.  Measurement aid for bench.py's roofline, same kernels. */
 int aleo_b200_ntt_fr_dev_profile(void* inout_dev, uint32_t log_n, int direction, int kind, void* stream, float* pass_ms4);
@@ -218,6 +235,16 @@ int aleo_b200_fr_poly_eval_dev(void* out_dev, const void* coeffs_dev, size_t n, 
 int aleo_b200_fr_divide_by_linear_dev(void* quotient_dev, const void* coeffs_dev, size_t n, const void* z_host, void* stream);
 int aleo_b200_kzg_open_dev(const void* handle, void* out_compressed48_dev, const void* coeffs_montgomery_dev, size_t n_coeffs,
                            const void* z_host, void* stream);
+/* m openings in one call -- the shape of SonicKZG10::open_combinations / kzg10 batch_open (src/polycommit/sonic_pc/mod.rs;
+ * SURVEY.md 8a row 14): opening k is of the linear combination p_k = sum_i lc[k][i] * poly_i at the point z_k, its
+ * witness polynomial (p_k(x) - p_k(z_k)) / (x - z_k) is built on the device, and the m witness commitments go through
+ * ONE launch sequence (the batch path of aleo_b200_kzg_commit_batch_dev).  polys_dev_ptrs_host / n_coeffs_host: HOST
+ * arrays of n_polys device pointers / lengths (Montgomery Fr); lc_coeffs_host: m x n_polys Montgomery Fr on the host,
+ * row-major, a zero coefficient = the polynomial is not part of that combination; points_host: m x 32 bytes;
+ * out_compressed48_dev: m x 48 bytes.  m <= 64, n_polys <= 1024.  (Hiding openings add the caller's random_v.) */
+int aleo_b200_kzg_open_combinations_dev(const void* handle, void* out_compressed48_dev, const void* const* polys_dev_ptrs_host,
+                                        const size_t* n_coeffs_host, size_t n_polys, const void* lc_coeffs_host,
+                                        const void* points_host, size_t m, void* stream);
 
 /* ---- compressed G1 wire format ---------------------------------------------------------
  * snarkVM's CanonicalSerialize / CanonicalDeserialize of G1Affine -- every commitment inside a proof and the points of

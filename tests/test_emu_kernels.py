@@ -559,3 +559,86 @@ def test_emu_divide_by_vanishing_on_coset(emu_lib, log_m, log_n):
             p[i + n] = (p[i + n] + v) % o.R_MOD
             p[i] = (p[i] - v) % o.R_MOD
         assert o.divide_by_vanishing_on_coset(o.coset_fft(p, m), log_n) == o.coset_fft(q, m)
+
+
+def test_emu_host_ordered_ntt_and_polymul(emu_lib):
+    """aleo_b200_ntt_fr_ordered (upstream's snarkvm_ntt argument list on host pointers) and aleo_b200_polymul
+    (snarkvm_polymul's shape): out = ifft(prod fft(p_i) * prod e_j)"""
+    log_n = 9
+    n = 1 << log_n
+    v = o.random_fr_vec(n, 811)
+    buf = C.create_string_buffer(o.fr_vec_to_bytes(v), n * 32)
+    emu_lib.check(emu_lib.ntt_fr_ordered(C.cast(buf, C.c_void_p), log_n, 0, 0, 1), "ordered host IO")
+    assert o.fr_vec_from_bytes(buf.raw) == _bitrev_list(o.fft(v))
+    buf = C.create_string_buffer(o.fr_vec_to_bytes(_bitrev_list(v)), n * 32)
+    emu_lib.check(emu_lib.ntt_fr_ordered(C.cast(buf, C.c_void_p), log_n, 1, 1, 2), "ordered host OI")
+    assert o.fr_vec_from_bytes(buf.raw) == o.coset_ifft(v)
+    assert emu_lib.ntt_fr_ordered(C.cast(buf, C.c_void_p), log_n, 0, 0, 7) == -1
+
+    # polymul: two short polynomials and one evaluation vector
+    a, b = o.random_fr_vec(100, 812), o.random_fr_vec(n // 2 - 3, 813)
+    e = o.random_fr_vec(n, 814)
+    pad = lambda p: p + [0] * (n - len(p))  # noqa: E731
+    fa, fb = o.fft(pad(a)), o.fft(pad(b))
+
+    def polymul(polys, evals):
+        pb = [C.create_string_buffer(o.fr_vec_to_bytes(p), max(1, len(p)) * 32) for p in polys]
+        eb = [C.create_string_buffer(o.fr_vec_to_bytes(x), n * 32) for x in evals]
+        pp = (C.c_void_p * max(1, len(pb)))(*[C.cast(x, C.c_void_p) for x in pb])
+        pl = (C.c_size_t * max(1, len(pb)))(*[len(p) for p in polys])
+        ep = (C.c_void_p * max(1, len(eb)))(*[C.cast(x, C.c_void_p) for x in eb])
+        el = (C.c_size_t * max(1, len(eb)))(*[n for _ in evals])
+        out = C.create_string_buffer(n * 32)
+        emu_lib.check(emu_lib.polymul(C.cast(out, C.c_void_p), len(pb), pp, pl, len(eb), ep, el, log_n), "polymul")
+        out_d = C.create_string_buffer(n * 32)
+        emu_lib.check(emu_lib.polymul_dev(C.cast(out_d, C.c_void_p), len(pb), pp, pl, len(eb), ep, el, log_n, None), "polymul_dev")
+        assert out.raw == out_d.raw
+        return o.fr_vec_from_bytes(out.raw)
+
+    mul = lambda x, y: [p * q % o.R_MOD for p, q in zip(x, y)]  # noqa: E731
+    assert polymul([a, b], [e]) == o.ifft(mul(mul(fa, fb), e))
+    assert polymul([a, b], []) == o.ifft(mul(fa, fb))                      # = the plain product a * b (degree < n)
+    prod = [0] * n
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            prod[i + j] = (prod[i + j] + x * y) % o.R_MOD
+    assert polymul([a, b], []) == prod
+    assert polymul([a], []) == pad(a)
+    assert polymul([], [e]) == o.ifft(e)
+    assert polymul([], [e, fa]) == o.ifft(mul(e, fa))
+    assert polymul([b], [e, fa]) == o.ifft(mul(mul(fb, e), fa))
+    # argument errors: nothing to multiply; polynomial longer than the domain; evaluation vector of the wrong length
+    out = C.create_string_buffer(n * 32)
+    one = (C.c_void_p * 1)(C.cast(out, C.c_void_p))
+    assert emu_lib.polymul(C.cast(out, C.c_void_p), 0, None, None, 0, None, None, log_n) == -1
+    assert emu_lib.polymul(C.cast(out, C.c_void_p), 1, one, (C.c_size_t * 1)(n + 1), 0, None, None, log_n) == -1
+    assert emu_lib.polymul(C.cast(out, C.c_void_p), 0, None, None, 1, one, (C.c_size_t * 1)(n - 1), log_n) == -1
+
+
+def test_emu_kzg_open_combinations(emu_lib):
+    """m openings of linear combinations in one call == the single-opening path on the combined polynomial"""
+    n = 200
+    B = o.synthetic_bases(n, 191)
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    h = C.c_void_p()
+    emu_lib.check(emu_lib.srs_create_dev(C.byref(h), C.cast(bb, C.c_void_p), n, 104, None), "srs_create")
+    polys = [o.random_fr_vec(ln, 300 + ln) for ln in (200, 150, 37, 1)]
+    lc = [[1, 5, 0, 7], [0, 0, 3, 0], [o.R_MOD - 1, 2, 2, 2], [0, 0, 0, 9]]
+    zs = o.random_fr_vec(4, 77)
+    pb = [C.create_string_buffer(o.fr_vec_to_bytes(p), len(p) * 32) for p in polys]
+    pp = (C.c_void_p * 4)(*[C.cast(x, C.c_void_p) for x in pb])
+    pl = (C.c_size_t * 4)(*[len(p) for p in polys])
+    lcb = b"".join(o.int_to_le_bytes(o.fr_to_mont(a), 32) for row in lc for a in row)
+    zb = b"".join(o.int_to_le_bytes(o.fr_to_mont(z), 32) for z in zs)
+    out = C.create_string_buffer(4 * 48)
+    emu_lib.check(emu_lib.kzg_open_combinations_dev(h, C.cast(out, C.c_void_p), pp, pl, 4, lcb, zb, 4, None), "open_combinations")
+    for k in range(4):
+        comb = [0] * n
+        for a, p in zip(lc[k], polys):
+            for i, x in enumerate(p):
+                comb[i] = (comb[i] + a * x) % o.R_MOD
+        ln = max([len(p) for a, p in zip(lc[k], polys) if a] + [0])
+        q = o.divide_by_linear(comb[:ln], zs[k]) if ln > 1 else []
+        want = o.g1_compress(o.msm_pippenger(B[:len(q) - 1], q[:len(q) - 1]) if len(q) > 1 else None)
+        assert out.raw[48 * k:48 * k + 48] == want, k
+    emu_lib.check(emu_lib.srs_destroy(h), "destroy")

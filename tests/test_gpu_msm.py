@@ -162,7 +162,7 @@ def test_error_codes():
     assert lib.msm_g1_dev(p, p, 1 << 40, p, 104, None) == ab._lib.ETOOLARGE
 
 
-@pytest.mark.parametrize("chunks", [1, 2, 3])
+@pytest.mark.parametrize("chunks", [1, 2, 3, 4])
 def test_host_call_streams_point_ranges(chunks, monkeypatch):
     """aleo_b200_msm_g1 copies and accumulates point range by point range (H2D overlapped); the result must
     not depend on the number of ranges.  2^20 points, known discrete logs, witness-like scalars mixed in."""

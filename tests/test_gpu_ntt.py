@@ -254,3 +254,64 @@ def test_host_call_on_pageable_memory_is_staged():
     assert np.array_equal(host, want)
     dom.ntt_host_buffer(host, 1, 1)                     # and back
     assert np.array_equal(host, x.cpu().numpy())
+
+
+@pytest.mark.parametrize("log_n", [3, 12, 16, 21])
+def test_host_pointer_ordered_transform(log_n):
+    """aleo_b200_ntt_fr_ordered: upstream's snarkvm_ntt argument list (order included) on HOST memory -- against the
+    oracle at small sizes, against the device-resident ordered path above that; 2^21 is a pageable 64 MB buffer (staged)"""
+    import torch
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    perm = _bitrev_perm(log_n)
+    if log_n <= 12:
+        v = o.random_fr_vec(n, 4400 + log_n)
+        rev = [v[i] for i in perm]
+        assert bytes(dom.out_order_fft_in_place_with_pc(bytearray(o.fr_vec_to_bytes(v)))) == o.fr_vec_to_bytes([o.fft(v)[i] for i in perm])
+        assert bytes(dom.ifft_helper_in_place_with_pc(bytearray(o.fr_vec_to_bytes(rev)), 2)) == o.fr_vec_to_bytes(o.ifft(v))
+        assert bytes(dom.fft_helper_in_place_with_pc(bytearray(o.fr_vec_to_bytes(v)), 0, pc=object())) == o.fr_vec_to_bytes(o.fft(v))
+    x = ab.gen_scalars_dev(n, 4500 + log_n, 0, True)
+    for direction, kind, order in ((0, 0, 1), (1, 1, 2), (0, 1, 1), (1, 0, 0)):
+        host = x.cpu().numpy().copy()
+        dom.ntt_host_buffer(host, direction, kind, order)
+        want = dom._run_dev_ordered(x.clone(), direction, kind, order)
+        assert np.array_equal(host, want.cpu().numpy()), (direction, kind, order)
+    assert ab.get_lib().ntt_fr_ordered(x.cpu().numpy().ctypes.data, log_n, 0, 0, 9) == -1
+
+
+@pytest.mark.parametrize("log_n", [10, 20])
+def test_polymul_matches_the_transform_pipeline(log_n):
+    """aleo_b200_polymul[_dev] (snarkvm_polymul's shape) = ifft(prod fft(p_i) * prod e_j): against the oracle at 2^10, against
+    the same pipeline built from the already-pinned entry points at 2^20; host form on pageable memory"""
+    import torch
+    n = 1 << log_n
+    dom = ab.EvaluationDomain.new(n)
+    a = ab.gen_scalars_dev(n // 2, 5100 + log_n, 0, True)
+    b = ab.gen_scalars_dev(n // 2 - 5, 5200 + log_n, 0, True)
+    e = ab.gen_scalars_dev(n, 5300 + log_n, 0, True)
+
+    def padded(t):
+        z = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+        z[: t.shape[0]] = t
+        return z
+
+    fa, fb = dom.fft_in_place_dev(padded(a)), dom.fft_in_place_dev(padded(b))
+    want = dom.ifft_in_place_dev(ab.Evaluations.mul(ab.Evaluations.mul(fa, fb), e))
+    got = ab.PolyMultiplier().add_polynomial(a).add_polynomial(b).add_evaluation(e).multiply_dev(log_n)
+    assert torch.equal(got, want)
+    host = ab.PolyMultiplier().add_polynomial(a.cpu().numpy().copy()).add_polynomial(b.cpu().numpy().copy()) \
+        .add_evaluation(e.cpu().numpy().copy()).multiply(log_n)
+    assert host == want.cpu().numpy().tobytes()
+    only_e = ab.PolyMultiplier().add_evaluation(e).multiply_dev(log_n)
+    assert torch.equal(only_e, dom.ifft_in_place_dev(e.clone()))
+    if log_n == 10:
+        av = o.fr_vec_from_bytes(a.cpu().numpy().tobytes())
+        bv = o.fr_vec_from_bytes(b.cpu().numpy().tobytes())
+        prod = [0] * n
+        for i, x in enumerate(av):
+            for j, y in enumerate(bv):
+                prod[i + j] = (prod[i + j] + x * y) % o.R_MOD
+        two = ab.PolyMultiplier().add_polynomial(a).add_polynomial(b).multiply_dev(log_n)
+        assert two.cpu().numpy().tobytes() == o.fr_vec_to_bytes(prod)
+    lib = ab.get_lib()
+    assert lib.polymul_dev(got.data_ptr(), 0, None, None, 0, None, None, log_n, None) == -1

@@ -143,3 +143,45 @@ def test_kzg_open_and_commit_lagrange_wrappers():
     finally:
         srs.close()
         srs_l.close()
+
+
+def test_kzg_open_combinations_equals_single_openings():
+    """aleo_b200_kzg_open_combinations_dev (SonicKZG10::open_combinations / batch_open shape): m openings of linear
+    combinations in one launch sequence == KZG10::open of each combined polynomial; first against the oracle at n = 300,
+    then at proof scale (2^16-point SRS, 6 polynomials, 5 openings) against the single-opening path"""
+    from aleo_b200.kzg import KZG10
+    n = 300
+    B = o.synthetic_bases(n, 291)
+    srs = ab.ResidentSRS.from_host(o.g1_affine_vec_to_bytes(B, 104), 104)
+    try:
+        polys = [o.random_fr_vec(ln, 700 + ln) for ln in (300, 128, 1)]
+        lc = [[3, 0, 1], [1, o.R_MOD - 2, 0], [0, 0, 5]]
+        zs = o.random_fr_vec(3, 78)
+        out = KZG10.open_combinations_dev(srs, [_dev(p) for p in polys], lc, zs).cpu().numpy().tobytes()
+        for k in range(3):
+            comb = [0] * n
+            for a, p in zip(lc[k], polys):
+                for i, x in enumerate(p):
+                    comb[i] = (comb[i] + a * x) % o.R_MOD
+            ln = max([len(p) for a, p in zip(lc[k], polys) if a] + [0])
+            q = o.divide_by_linear(comb[:ln], zs[k]) if ln > 1 else []
+            assert out[48 * k:48 * k + 48] == o.g1_compress(o.msm_pippenger(B[:len(q) - 1], q[:len(q) - 1]) if len(q) > 1 else None), k
+    finally:
+        srs.close()
+    n = 1 << 16
+    s0, d = o.base_dlogs(n, 3131)
+    srs = ab.ResidentSRS.from_device(ab.gen_bases_dev(n, s0, d, 0, 104), n, 104)
+    try:
+        polys = [ab.gen_scalars_dev(ln, 900 + i, 0, True) for i, ln in enumerate((n, n, n // 2, n // 2 + 7, 4096, 1))]
+        lc = [[1, 7, 0, 0, 0, 0], [0, 0, 1, 11, 13, 17], [5, 4, 3, 2, 1, 1], [0, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 3]]
+        zs = o.random_fr_vec(5, 79)
+        got = KZG10.open_combinations_dev(srs, polys, lc, zs)
+        for k in range(5):
+            comb = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+            for a, p in zip(lc[k], polys):
+                if a:
+                    poly.axpy_dev(comb[: p.shape[0]], p, a)
+            ln = max(p.shape[0] for a, p in zip(lc[k], polys) if a)
+            assert torch.equal(got[k], KZG10.open_dev(srs, comb[:ln].contiguous(), zs[k])), k
+    finally:
+        srs.close()
