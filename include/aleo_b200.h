@@ -191,7 +191,8 @@ int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);
 /* The host-pointer entry points (aleo_b200_msm_g1, aleo_b200_srs_msm, aleo_b200_kzg_commit) copy and accumulate
  * the MSM in point ranges so that the host->device copy of range k+1 overlaps the accumulation of range k:
- * how many ranges n points are cut into, and the window size that goes with it. */
+ * how many ranges n points are cut into for PAGEABLE caller memory (what a Rust Vec is; pinned buffers use one range
+ * fewer from 2^22 points), and the window size that goes with it. */
 int aleo_b200_msm_host_plan(size_t n, int* ranges_out, int* window_bits_out);
 
 /* ---- elementwise field arithmetic on device vectors ------------------------------------------------
