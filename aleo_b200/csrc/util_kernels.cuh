@@ -280,8 +280,10 @@ KERNEL void __launch_bounds__(256) imad_bench_kernel(u32* sink, u32 iters, u32 s
 // the IMAD.WIDE counts the roofline arithmetic of DESIGN.md rests on (Fq product 276, dedicated Fq square 210, Fr raw
 // product 120).  The carry chains are separate asm statements that ptxas fuses pairwise into IMAD.WIDE.U32.X; a compiler
 // or source change that breaks the fusion doubles the count and shows up here, on the CPU, before any GPU time is spent.
+#ifndef ALEO_EMU
 extern "C" KERNEL void aleo_probe_fq_mul(Fq* out, const Fq* a, const Fq* b) { out[threadIdx.x] = fp_mul(a[threadIdx.x], b[threadIdx.x]); }
 extern "C" KERNEL void aleo_probe_fq_sqr(Fq* out, const Fq* a) { out[threadIdx.x] = fp_sqr(a[threadIdx.x]); }
 extern "C" KERNEL void aleo_probe_fr_mul_raw(Fr* out, const Fr* a, const Fr* b) { out[threadIdx.x] = lz_mul(a[threadIdx.x], b[threadIdx.x]); }
+#endif
 
 }  // namespace util
