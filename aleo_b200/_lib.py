@@ -42,6 +42,8 @@ SYMBOLS = [
     ("aleo_b200_polymul_dev", _int, [_vp, _sz, C.POINTER(_vp), C.POINTER(_sz), _sz, C.POINTER(_vp), C.POINTER(_sz), _u32, _vp]),
     ("aleo_b200_kzg_open_combinations_dev", _int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _vp, _vp, _sz, _vp]),
     ("aleo_b200_ntt_dist_stage2", _int, [_vp, _vp, _int, _int, _vp]),
+    ("aleo_b200_ntt_dist_transform", _int, [_vp, _vp, _vp, _int, _int, _vp]),
+    ("aleo_b200_ntt_dist_profile", _int, [_vp, _vp, _vp, _int, _int, _vp, C.POINTER(C.c_float)]),
     ("aleo_b200_ntt_dist_destroy", _int, [_vp]),
     ("aleo_b200_msm_g1", _int, [_vp, _vp, _sz, _vp, _sz]),
     ("aleo_b200_msm_g1_multi", _int, [_vp, _vp, _sz, _vp, _sz, _int]),

@@ -293,6 +293,24 @@ int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, int
   return ALEO_B200_OK;
 }
 
+int aleo_b200_ntt_dist_transform(void* ctx, const void* local_in_dev, void* local_out_dev, int direction, int kind, void* stream) {
+  int rc = aleo_b200_ntt_dist_stage1(ctx, local_in_dev, direction, kind, stream);
+  if (rc) return rc;
+  return aleo_b200_ntt_dist_stage2(ctx, local_out_dev, direction, kind, stream);
+}
+
+int aleo_b200_ntt_dist_profile(void* ctx, const void* local_in_dev, void* local_out_dev, int direction, int kind, void* stream,
+                               float* stage_ms4) {
+  if (ctx == nullptr || local_in_dev == nullptr || local_out_dev == nullptr || stage_ms4 == nullptr) return ALEO_B200_EINVAL;
+  if (direction != ALEO_B200_NTT_FORWARD && direction != ALEO_B200_NTT_INVERSE) return ALEO_B200_EINVAL;
+  if (kind != ALEO_B200_NTT_STANDARD && kind != ALEO_B200_NTT_COSET) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::ntt_dist_profile(ctx, local_in_dev, local_out_dev, direction == ALEO_B200_NTT_INVERSE, kind == ALEO_B200_NTT_COSET,
+                                (cudaStream_t)stream, stage_ms4));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_ntt_dist_destroy(void* ctx) {
   aleo::ntt_dist_destroy(ctx);
   return ALEO_B200_OK;

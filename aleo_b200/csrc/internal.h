@@ -51,6 +51,8 @@ cudaError_t ntt_dist_handles(void* ctx, void* handles_out /* 128 bytes */);
 cudaError_t ntt_dist_open(void* ctx, const void* all_handles /* world x 128 bytes */);
 cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, bool coset, cudaStream_t s);
 cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, bool coset, cudaStream_t s);
+cudaError_t ntt_dist_profile(void* ctx, const void* local_in_dev, void* local_out_dev, bool inverse, bool coset, cudaStream_t s,
+                             float* stage_ms4);
 void ntt_dist_destroy(void* ctx);
 int ntt_max_log_n();
 void ntt_clear_plans();

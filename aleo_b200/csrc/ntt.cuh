@@ -251,6 +251,13 @@ struct PassArgs {
   u32 d_rank;
   u32 d_lg;          // log2 of the number of GPUs
   Fr* peer[8];       // receive buffer of every rank (own included), device pointers valid on this GPU
+  // Cross-rank ordering without a collective: the CTA that finishes the exchange pass last stores `d_epoch` into slot
+  // [d_rank] of every rank's flag array (release, system scope, after a system fence); the last pass spins on its own
+  // `world` slots (acquire) before it reads the receive buffer.  nullptr / 0: no signalling / no waiting.
+  u32* d_flag_peer[8];   // &flags_of_rank_r[d_rank]
+  const u32* d_flag_local;  // this rank's slots, one per source rank
+  u32* d_counter;        // CTAs of the exchange pass that are done (reset by the last one)
+  u32 d_epoch;
 };
 
 // global index of the local index i2l of a strided pass: the rank's bits go in above the shortened last digit
@@ -313,6 +320,12 @@ KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(Pas
     ostride_r = (u64)1 << (a.log_n - K);
   }
 
+  if (LAST && a.d_flag_local) {  // every source rank has finished storing into this rank's receive buffer
+    if (tid < (1u << a.d_lg)) {
+      while ((int)(load_acquire_sys_u32(a.d_flag_local + tid) - a.d_epoch) < 0) spin_pause();
+    }
+    SYNC_THREADS();
+  }
   Fr x[8];
   // ---- load + step 1 (radix 8 over the top three bits of r) ------------------------------------
   {
@@ -430,6 +443,27 @@ KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(Pas
       else
         dst[go] = v;
     }
+  }
+  if (!LAST && a.d_exchange && a.d_counter) {
+    // tell the peers: the CTA that finishes last (all earlier CTAs have fenced their remote stores) raises this rank's
+    // slot in every rank's flag array
+    SYNC_THREADS();
+    if (tid == 0) {
+      fence_system();
+      const u32 done = atomic_add_u32(a.d_counter, 1u);
+      if (done + 1u == gridDim.x * gridDim.y) {
+        *a.d_counter = 0;
+        fence_system();
+        for (u32 r = 0; r < (1u << a.d_lg); r++) store_release_sys_u32(a.d_flag_peer[r], a.d_epoch);
+      }
+    }
+  }
+}
+
+// standalone form of the last pass's prologue (profiling: times the cross-rank wait on its own)
+KERNEL void dist_wait_kernel(const u32* flags, u32 world, u32 epoch) {
+  if (threadIdx.x < world) {
+    while ((int)(load_acquire_sys_u32(flags + threadIdx.x) - epoch) < 0) spin_pause();
   }
 }
 

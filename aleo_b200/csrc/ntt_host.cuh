@@ -37,7 +37,19 @@ static inline void set_single_gpu(PassArgs& a) {
   a.d_rank = 0;
   a.d_lg = 0;
   for (int i = 0; i < 8; i++) a.peer[i] = nullptr;
+  for (int i = 0; i < 8; i++) a.d_flag_peer[i] = nullptr;
+  a.d_flag_local = nullptr;
+  a.d_counter = nullptr;
+  a.d_epoch = 0;
 }
+
+// cross-rank flags of one distributed transform (PassArgs d_flag_*): where this rank signals, where it waits
+struct DistFlags {
+  u32* signal[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // slot [rank] of every rank's array
+  const u32* local = nullptr;                                                                  // this rank's slots
+  u32* counter = nullptr;
+  u32 epoch = 0;
+};
 
 // Pass split of a transform spread over 2^lg GPUs (ntt_dist_*): every radix 2^5..2^8, and
 //   K_p + (bits below digit p) - lg >= 11 for every strided pass (its tile is 2^(11 - K_p) local columns wide),
@@ -343,7 +355,7 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
 // barrier stage 2 = the last pass from the receive buffer; rank t ends with X[k], k mod R_0 in its range, as the column
 // block of the (N / R_0) x R_0 matrix.
 static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const Fr* in, Fr* scratch, Fr* const* peers,
-                                          cudaStream_t s) {
+                                          cudaStream_t s, const DistFlags* fl = nullptr, cudaEvent_t* ev2 = nullptr) {
   const u32 L = p.log_n, Ll = L - (u32)lg;
   const u32 klast = (u32)p.K[p.npass - 1];
   u32 log_cur = L;
@@ -370,13 +382,20 @@ static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const
     a.d_exchange = exchange ? 1 : 0;
     a.d_rank = (u32)rank;
     for (int r = 0; r < 8; r++) a.peer[r] = (r < (1 << lg)) ? peers[r] : nullptr;
+    for (int r = 0; r < 8; r++) a.d_flag_peer[r] = (exchange && fl && r < (1 << lg)) ? fl->signal[r] : nullptr;
+    a.d_flag_local = nullptr;
+    a.d_counter = (exchange && fl) ? fl->counter : nullptr;
+    a.d_epoch = fl ? fl->epoch : 0;
+    if (ev2 && i == 0) cudaEventRecord(ev2[0], s);        // profiling: [0] start, [1] before the exchange pass
+    if (ev2 && exchange) cudaEventRecord(ev2[1], s);
     NTT_CK(launch_pass_k<false>(p.K[i], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s));
     log_cur -= (u32)p.K[i];
   }
   return cudaSuccess;
 }
 
-static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const Fr* recv, Fr* out, cudaStream_t s) {
+static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const Fr* recv, Fr* out, cudaStream_t s,
+                                          const DistFlags* fl = nullptr) {
   const u32 L = p.log_n, Ll = L - (u32)lg;
   const int last = p.npass - 1;
   PassArgs a;
@@ -402,6 +421,10 @@ static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const
   a.d_exchange = 0;
   a.d_rank = (u32)rank;
   for (int r = 0; r < 8; r++) a.peer[r] = nullptr;
+  for (int r = 0; r < 8; r++) a.d_flag_peer[r] = nullptr;
+  a.d_flag_local = fl ? fl->local : nullptr;
+  a.d_counter = nullptr;
+  a.d_epoch = fl ? fl->epoch : 0;
   return launch_pass_k<true>(p.K[last], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s);
 }
 

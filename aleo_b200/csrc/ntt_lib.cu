@@ -66,6 +66,17 @@ struct NttDist {
   bool opened[2][8] = {{false}, {false}};
   bool have_peers = false;
   unsigned long long calls = 0;              // parity selects the buffer; every rank issues the same sequence of calls
+  u32* counter = nullptr;                    // "CTAs done" counter of the exchange pass
+  size_t flag_off() const { return (sizeof(Fr) << log_n) / (size_t)world; }  // bytes: 8 flag slots follow the buffer
+  // flags of the transform about to run on buffer b: signal slots in every rank's array, own slots to wait on
+  ntt::DistFlags flags(int b) const {
+    ntt::DistFlags f;
+    for (int r = 0; r < world; r++) f.signal[r] = (u32*)((unsigned char*)peers[b][r] + flag_off()) + rank;
+    f.local = (const u32*)((const unsigned char*)recv[b] + flag_off());
+    f.counter = counter;
+    f.epoch = (u32)(calls + 1);            // every rank issues the same call sequence: the epochs agree
+    return f;
+  }
 };
 
 int ntt_dist_layout(u32 log_n, int world, u32* log_r_first, u32* log_r_last, int* npass) {
@@ -91,9 +102,21 @@ cudaError_t ntt_dist_create(u32 log_n, int rank, int world, void** ctx_out) {
   c->log_n = log_n;
   const size_t bytes = (sizeof(Fr) << log_n) / (size_t)world;
   for (int b = 0; b < 2; b++) {
-    cudaError_t e = cudaMalloc((void**)&c->recv[b], bytes);
+    cudaError_t e = cudaMalloc((void**)&c->recv[b], bytes + 256);  // + the cross-rank flag slots (one u32 per source rank)
+    if (e == cudaSuccess) e = cudaMemset((unsigned char*)c->recv[b] + bytes, 0, 256);
     if (e != cudaSuccess) {
       if (b == 1) cudaFree(c->recv[0]);
+      delete c;
+      return e;
+    }
+  }
+  {
+    cudaError_t e = cudaMalloc((void**)&c->counter, 256);
+    if (e == cudaSuccess) e = cudaMemset(c->counter, 0, 256);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      cudaFree(c->recv[0]);
+      cudaFree(c->recv[1]);
       delete c;
       return e;
     }
@@ -160,7 +183,8 @@ cudaError_t ntt_dist_stage1(void* ctx, const void* local_in_dev, bool inverse, b
     e = aleo::pool_malloc_async((void**)&scratch, (sizeof(Fr) << c->log_n) / (size_t)c->world, s);
     if (e != cudaSuccess) return e;
   }
-  e = ntt::run_dist_stage1(*plan, c->lg, c->rank, (const Fr*)local_in_dev, scratch, c->peers[c->calls & 1], s);
+  const ntt::DistFlags fl = c->flags((int)(c->calls & 1));
+  e = ntt::run_dist_stage1(*plan, c->lg, c->rank, (const Fr*)local_in_dev, scratch, c->peers[c->calls & 1], s, &fl);
   if (scratch) cudaFreeAsync(scratch, s);
   return e;
 }
@@ -171,9 +195,45 @@ cudaError_t ntt_dist_stage2(void* ctx, void* local_out_dev, bool inverse, bool c
   const ntt::Plan* plan = nullptr;
   cudaError_t e = g_plans.get(c->device, c->log_n, inverse, coset, s, &plan, c->lg);
   if (e != cudaSuccess) return e;
-  e = ntt::run_dist_stage2(*plan, c->lg, c->rank, c->recv[c->calls & 1], (Fr*)local_out_dev, s);
+  const ntt::DistFlags fl = c->flags((int)(c->calls & 1));
+  e = ntt::run_dist_stage2(*plan, c->lg, c->rank, c->recv[c->calls & 1], (Fr*)local_out_dev, s, &fl);
   c->calls++;
   return e;
+}
+
+// the whole transform with per-stage events: stage_ms4 = {local passes before the exchange pass, exchange pass (stores
+// into the peers), wait for every peer's flag, last pass}.  Synchronises s.
+cudaError_t ntt_dist_profile(void* ctx, const void* local_in_dev, void* local_out_dev, bool inverse, bool coset, cudaStream_t s,
+                             float* stage_ms4) {
+  NttDist* c = (NttDist*)ctx;
+  if (!c->have_peers) return cudaErrorInvalidValue;
+  const ntt::Plan* plan = nullptr;
+  cudaError_t e = g_plans.get(c->device, c->log_n, inverse, coset, s, &plan, c->lg);
+  if (e != cudaSuccess) return e;
+  Fr* scratch = nullptr;
+  if (plan->npass > 2) {
+    e = aleo::pool_malloc_async((void**)&scratch, (sizeof(Fr) << c->log_n) / (size_t)c->world, s);
+    if (e != cudaSuccess) return e;
+  }
+  cudaEvent_t ev[5];
+  for (auto& x : ev) cudaEventCreate(&x);
+  const int b = (int)(c->calls & 1);
+  const ntt::DistFlags fl = c->flags(b);
+  e = ntt::run_dist_stage1(*plan, c->lg, c->rank, (const Fr*)local_in_dev, scratch, c->peers[b], s, &fl, ev);
+  cudaEventRecord(ev[2], s);
+  LAUNCH_NOSYNC(ntt::dist_wait_kernel, dim3(1), dim3(32), 0, s, fl.local, (u32)c->world, fl.epoch);
+  cudaEventRecord(ev[3], s);
+  if (e == cudaSuccess) e = ntt::run_dist_stage2(*plan, c->lg, c->rank, c->recv[b], (Fr*)local_out_dev, s, &fl);
+  cudaEventRecord(ev[4], s);
+  c->calls++;
+  if (scratch) cudaFreeAsync(scratch, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  for (int i = 0; i < 4; i++) {
+    stage_ms4[i] = 0.f;
+    if (e == cudaSuccess && e2 == cudaSuccess) cudaEventElapsedTime(&stage_ms4[i], ev[i], ev[i + 1]);
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return e != cudaSuccess ? e : e2;
 }
 
 void ntt_dist_destroy(void* ctx) {
@@ -186,6 +246,7 @@ void ntt_dist_destroy(void* ctx) {
 #endif
   cudaFree(c->recv[0]);
   cudaFree(c->recv[1]);
+  cudaFree(c->counter);
   delete c;
 }
 

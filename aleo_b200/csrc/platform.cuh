@@ -31,6 +31,15 @@
 #define SYNC_WARP() __syncwarp()
 DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 DEV uint32_t atomic_add_shared_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+// cross-GPU flags (peer memory over NVLink): release store / acquire load at system scope
+DEV void fence_system() { __threadfence_system(); }
+DEV void store_release_sys_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+DEV uint32_t load_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DEV void spin_pause() { __nanosleep(64); }
 #else
 // ------------------------------------------------------------------------------------------ EMU
 #include "../../tests/emu/emu_runtime.hpp"

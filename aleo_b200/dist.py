@@ -144,8 +144,8 @@ class PeerNTT:
     """One Fr NTT of size 2^log_n spread over the GPUs of a node, one process per GPU (include/aleo_b200.h
     ``aleo_b200_ntt_dist_*``).  The pass split is the single-GPU one; the last-but-one pass stores every result
     element straight into the receive buffer of the rank that needs it (CUDA IPC mapped peer memory), a
-    1-element all-reduce on the same stream is the cross-rank barrier, and the last pass runs from the receive
-    buffer.  Input: this rank's column block of the (N / R_last) x R_last matrix of x; output: its column block
+    flag per source rank in the same peer memory (release store by the exchange pass, acquire spin by the last pass)
+    orders the ranks -- no collective per transform --, and the last pass runs from the receive buffer.  Input: this rank's column block of the (N / R_last) x R_last matrix of x; output: its column block
     of the (N / R_first) x R_first matrix of X (natural order) -- see ``layout``."""
 
     def __init__(self, log_n: int, group=None):
@@ -171,10 +171,8 @@ class PeerNTT:
             allh = torch.empty(128 * self.world, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, t, group=group)
             raw = allh.cpu().numpy().tobytes()
-            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         else:
             raw = mine.raw
-            self._flag = None
         buf = C.create_string_buffer(raw, len(raw))
         self._lib.check(self._lib.ntt_dist_open(self._h, C.cast(buf, C.c_void_p)), "aleo_b200_ntt_dist_open")
 
@@ -195,8 +193,8 @@ class PeerNTT:
         return X_full.reshape(rows, cols * self.world, 4)[:, self.rank * cols:(self.rank + 1) * cols, :].contiguous()
 
     def transform(self, block, out=None, inverse: bool = False, coset: bool = False):
+        """one distributed transform; no collective: the ranks order themselves through flags in peer memory"""
         import torch
-        import torch.distributed as dist
 
         if out is None:
             out = torch.empty_like(block).reshape(-1, 4)
@@ -204,11 +202,29 @@ class PeerNTT:
         kind = _lib.NTT_COSET if coset else _lib.NTT_STANDARD
         with torch.cuda.device(block.device):
             stream = torch.cuda.current_stream().cuda_stream
-            self._lib.check(self._lib.ntt_dist_stage1(self._h, block.data_ptr(), direction, kind, stream), "aleo_b200_ntt_dist_stage1")
-            if self.world > 1:
-                dist.all_reduce(self._flag, group=self.group)      # barrier ordered on the stream: peers' stores are complete
-            self._lib.check(self._lib.ntt_dist_stage2(self._h, out.data_ptr(), direction, kind, stream), "aleo_b200_ntt_dist_stage2")
+            self._lib.check(self._lib.ntt_dist_transform(self._h, block.data_ptr(), out.data_ptr(), direction, kind, stream),
+                            "aleo_b200_ntt_dist_transform")
         return out
+
+    def stage_times(self, block, out, inverse: bool = False, coset: bool = False, reps: int = 5):
+        """per-stage device times of one transform, median of `reps`: dict of ms (local passes before the exchange pass,
+        exchange pass = butterflies + stores into the peers, wait for every peer's flag, last pass)"""
+        import ctypes as C
+
+        import torch
+        direction = _lib.NTT_INVERSE if inverse else _lib.NTT_FORWARD
+        kind = _lib.NTT_COSET if coset else _lib.NTT_STANDARD
+        rows = []
+        ms = (C.c_float * 4)()
+        with torch.cuda.device(block.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for _ in range(reps):
+                self._lib.check(self._lib.ntt_dist_profile(self._h, block.data_ptr(), out.data_ptr(), direction, kind, stream, ms),
+                                "aleo_b200_ntt_dist_profile")
+                rows.append([ms[i] for i in range(4)])
+        med = [sorted(r[i] for r in rows)[len(rows) // 2] for i in range(4)]
+        return {"local_passes": round(med[0], 4), "exchange_pass": round(med[1], 4), "wait_for_peers": round(med[2], 4),
+                "last_pass": round(med[3], 4)}
 
     def close(self):
         if self._h:

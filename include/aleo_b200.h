@@ -107,16 +107,22 @@ int aleo_b200_ntt_twiddle_dev(void* data_dev, uint32_t log_n_global, int directi
  *   output (rank t): column block of the (N / R_0) x R_0 row-major matrix of X (natural order):
  *                    local[a * R_0 / g + b] = X[a * R_0 + t * R_0 / g + b]
  * Usage, every rank, same call sequence:  ctx = create;  gather every rank's 128-byte `handles` (e.g. an
- * all_gather);  open(all handles);  then per transform: stage1(in) -> a cross-rank barrier ordered on the same
- * stream (e.g. a 1-element NCCL all-reduce) -> stage2(out).  Two receive buffers alternate, so the next
- * transform's stage1 may be enqueued at once.  world = 1, 2, 4, 8; all four transform kinds (the coset powers are
- * taken at the global index). */
+ * all_gather);  open(all handles);  then per transform: transform(in, out).  No collective runs per transform: the CTA
+ * that finishes the exchange pass last raises this rank's flag in every rank's receive buffer (st.release.sys after a
+ * system fence, over NVLink) and the last pass spins on its own `world` flags (ld.acquire.sys) before it reads what the
+ * peers stored.  Two receive buffers alternate, so the next transform's first stage may be enqueued at once.
+ * stage1 / stage2 are the two halves of transform() (a caller may put other work between them); profile() is
+ * transform() with events: stage_ms4 = {local passes, exchange pass, wait for the peers' flags, last pass}, synchronises.
+ * world = 1, 2, 4, 8; all four transform kinds (the coset powers are taken at the global index). */
 int aleo_b200_ntt_dist_layout(uint32_t log_n, int world, uint32_t* log_r_first_out, uint32_t* log_r_last_out, int* passes_out);
 int aleo_b200_ntt_dist_create(void** ctx_out, uint32_t log_n, int rank, int world);
 int aleo_b200_ntt_dist_handles(void* ctx, void* handles128_out);
 int aleo_b200_ntt_dist_open(void* ctx, const void* all_handles /* world x 128 bytes, rank-major */);
 int aleo_b200_ntt_dist_stage1(void* ctx, const void* local_in_dev, int direction, int kind, void* stream);
 int aleo_b200_ntt_dist_stage2(void* ctx, void* local_out_dev, int direction, int kind, void* stream);
+int aleo_b200_ntt_dist_transform(void* ctx, const void* local_in_dev, void* local_out_dev, int direction, int kind, void* stream);
+int aleo_b200_ntt_dist_profile(void* ctx, const void* local_in_dev, void* local_out_dev, int direction, int kind, void* stream,
+                               float* stage_ms4);
 int aleo_b200_ntt_dist_destroy(void* ctx);
 /* kernel launches one transform of this size issues (for launch accounting) */
 int aleo_b200_ntt_launches(uint32_t log_n);

@@ -99,6 +99,10 @@ void launch(dim3 grid, dim3 block, size_t smem, bool needs_sync, F body) {
   emu::launch((grid), (block), (smem), false, [=]() { kern(__VA_ARGS__); })
 
 inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void store_release_sys_u32(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline uint32_t load_acquire_sys_u32(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void spin_pause() {}
 inline uint32_t atomic_add_shared_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
@@ -131,6 +135,7 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }

@@ -46,13 +46,14 @@ for log_n in [int(a) for a in sys.argv[1:]] or [16, 20, 24]:
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    stages = p.stage_times(blk, out)
     flags = [None] * world
     dist.all_gather_object(flags, oks)
     good = all(all(f) for f in flags)
     ok_all = ok_all and good
     if rank == 0:
-        print("log_n=%d world=%d passes=%d R_first=2^%d R_last=2^%d parity(fwd,inv,coset fwd,coset inv) per rank=%s  %.3f ms -> %.0f Melem/s" %
-              (log_n, world, p.passes, p.log_r_first, p.log_r_last, flags, ms.item(), n / ms.item() / 1e3), flush=True)
+        print("log_n=%d world=%d passes=%d R_first=2^%d R_last=2^%d parity(fwd,inv,coset fwd,coset inv) per rank=%s  %.3f ms -> %.0f Melem/s  rank-0 stages (ms) %s" %
+              (log_n, world, p.passes, p.log_r_first, p.log_r_last, flags, ms.item(), n / ms.item() / 1e3, stages), flush=True)
     p.close()
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)
