@@ -251,13 +251,16 @@ struct PassArgs {
   u32 d_rank;
   u32 d_lg;          // log2 of the number of GPUs
   Fr* peer[8];       // receive buffer of every rank (own included), device pointers valid on this GPU
-  // Cross-rank ordering without a collective: the CTA that finishes the exchange pass last stores `d_epoch` into slot
+  // Cross-rank ordering without a collective: a one-warp kernel after the exchange pass stores `d_epoch` into slot
   // [d_rank] of every rank's flag array (release, system scope, after a system fence); the last pass spins on its own
   // `world` slots (acquire) before it reads the receive buffer.  nullptr / 0: no signalling / no waiting.
   u32* d_flag_peer[8];   // &flags_of_rank_r[d_rank]
   const u32* d_flag_local;  // this rank's slots, one per source rank
-  u32* d_counter;        // CTAs of the exchange pass that are done (reset by the last one)
   u32 d_epoch;
+  // Exchange pass only: tiles are taken in rotated order, starting with the tiles whose results go to rank d_rank + 1.
+  // All results of a tile go to ONE rank (tile t of T belongs to chunk t / (T / g)), so with the rotation every rank
+  // receives from exactly one sender at a time instead of all g - 1 senders converging on rank 0, then on rank 1, ...
+  u32 d_tile_rot;
 };
 
 // global index of the local index i2l of a strided pass: the rank's bits go in above the shortened last digit
@@ -295,9 +298,14 @@ KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(Pas
   u64 stride_r, stride_g, ostride_r;
   u32 i2_base = 0;
   if (!LAST) {
+    u32 bx = blockIdx.x;
+    if (a.d_exchange) {
+      bx += a.d_tile_rot;
+      if (bx >= gridDim.x) bx -= gridDim.x;
+    }
     const u32 tiles_per_blk = 1u << (log_m - LG);
-    const u32 blk = blockIdx.x / tiles_per_blk;
-    const u32 cg = blockIdx.x % tiles_per_blk;
+    const u32 blk = bx / tiles_per_blk;
+    const u32 cg = bx % tiles_per_blk;
     i2_base = cg << LG;
     in_base = ((u64)blk << a.log_cur) + i2_base;
     out_base = in_base;
@@ -444,20 +452,13 @@ KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(Pas
         dst[go] = v;
     }
   }
-  if (!LAST && a.d_exchange && a.d_counter) {
-    // tell the peers: the CTA that finishes last (all earlier CTAs have fenced their remote stores) raises this rank's
-    // slot in every rank's flag array
-    SYNC_THREADS();
-    if (tid == 0) {
-      fence_system();
-      const u32 done = atomic_add_u32(a.d_counter, 1u);
-      if (done + 1u == gridDim.x * gridDim.y) {
-        *a.d_counter = 0;
-        fence_system();
-        for (u32 r = 0; r < (1u << a.d_lg); r++) store_release_sys_u32(a.d_flag_peer[r], a.d_epoch);
-      }
-    }
-  }
+}
+
+// After the exchange pass (same stream: its stores into the peers are complete when this kernel starts): raise this
+// rank's slot in every rank's flag array.  One warp, lane r signals rank r.
+KERNEL void dist_signal_kernel(PassArgs a) {
+  fence_system();
+  if (threadIdx.x < (1u << a.d_lg)) store_release_sys_u32(a.d_flag_peer[threadIdx.x], a.d_epoch);
 }
 
 // standalone form of the last pass's prologue (profiling: times the cross-rank wait on its own)

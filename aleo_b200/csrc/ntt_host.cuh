@@ -39,15 +39,14 @@ static inline void set_single_gpu(PassArgs& a) {
   for (int i = 0; i < 8; i++) a.peer[i] = nullptr;
   for (int i = 0; i < 8; i++) a.d_flag_peer[i] = nullptr;
   a.d_flag_local = nullptr;
-  a.d_counter = nullptr;
   a.d_epoch = 0;
+  a.d_tile_rot = 0;
 }
 
 // cross-rank flags of one distributed transform (PassArgs d_flag_*): where this rank signals, where it waits
 struct DistFlags {
   u32* signal[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // slot [rank] of every rank's array
   const u32* local = nullptr;                                                                  // this rank's slots
-  u32* counter = nullptr;
   u32 epoch = 0;
 };
 
@@ -384,11 +383,17 @@ static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const
     for (int r = 0; r < 8; r++) a.peer[r] = (r < (1 << lg)) ? peers[r] : nullptr;
     for (int r = 0; r < 8; r++) a.d_flag_peer[r] = (exchange && fl && r < (1 << lg)) ? fl->signal[r] : nullptr;
     a.d_flag_local = nullptr;
-    a.d_counter = (exchange && fl) ? fl->counter : nullptr;
     a.d_epoch = fl ? fl->epoch : 0;
+    const u32 tiles = (u32)(((size_t)1 << Ll) >> TILE_LOG);
+    static const bool no_rot = getenv("ALEO_B200_NTT_DIST_NOROT") != nullptr;  // A/B switch: every rank starts with rank 0's tiles
+    a.d_tile_rot = (exchange && !no_rot) ? (u32)(((u64)((rank + 1) & ((1 << lg) - 1)) * tiles) >> lg) : 0u;
     if (ev2 && i == 0) cudaEventRecord(ev2[0], s);        // profiling: [0] start, [1] before the exchange pass
     if (ev2 && exchange) cudaEventRecord(ev2[1], s);
-    NTT_CK(launch_pass_k<false>(p.K[i], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s));
+    NTT_CK(launch_pass_k<false>(p.K[i], a, tiles, 1, s));
+    if (exchange && fl) {
+      LAUNCH_NOSYNC(dist_signal_kernel, dim3(1), dim3(32), 0, s, a);
+      NTT_CK(cudaGetLastError());
+    }
     log_cur -= (u32)p.K[i];
   }
   return cudaSuccess;
@@ -423,8 +428,8 @@ static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const
   for (int r = 0; r < 8; r++) a.peer[r] = nullptr;
   for (int r = 0; r < 8; r++) a.d_flag_peer[r] = nullptr;
   a.d_flag_local = fl ? fl->local : nullptr;
-  a.d_counter = nullptr;
   a.d_epoch = fl ? fl->epoch : 0;
+  a.d_tile_rot = 0;
   return launch_pass_k<true>(p.K[last], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s);
 }
 

@@ -66,14 +66,12 @@ struct NttDist {
   bool opened[2][8] = {{false}, {false}};
   bool have_peers = false;
   unsigned long long calls = 0;              // parity selects the buffer; every rank issues the same sequence of calls
-  u32* counter = nullptr;                    // "CTAs done" counter of the exchange pass
   size_t flag_off() const { return (sizeof(Fr) << log_n) / (size_t)world; }  // bytes: 8 flag slots follow the buffer
   // flags of the transform about to run on buffer b: signal slots in every rank's array, own slots to wait on
   ntt::DistFlags flags(int b) const {
     ntt::DistFlags f;
     for (int r = 0; r < world; r++) f.signal[r] = (u32*)((unsigned char*)peers[b][r] + flag_off()) + rank;
     f.local = (const u32*)((const unsigned char*)recv[b] + flag_off());
-    f.counter = counter;
     f.epoch = (u32)(calls + 1);            // every rank issues the same call sequence: the epochs agree
     return f;
   }
@@ -111,9 +109,7 @@ cudaError_t ntt_dist_create(u32 log_n, int rank, int world, void** ctx_out) {
     }
   }
   {
-    cudaError_t e = cudaMalloc((void**)&c->counter, 256);
-    if (e == cudaSuccess) e = cudaMemset(c->counter, 0, 256);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaError_t e = cudaDeviceSynchronize();  // the flag slots are zero before any peer can map them
     if (e != cudaSuccess) {
       cudaFree(c->recv[0]);
       cudaFree(c->recv[1]);
@@ -246,7 +242,6 @@ void ntt_dist_destroy(void* ctx) {
 #endif
   cudaFree(c->recv[0]);
   cudaFree(c->recv[1]);
-  cudaFree(c->counter);
   delete c;
 }
 

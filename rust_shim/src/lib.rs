@@ -15,6 +15,42 @@ extern "C" {
     ) -> c_int;
 }
 
+// the full argument lists of upstream's optional FFI (snarkvm_ntt with its `order`, snarkvm_polymul)
+extern "C" {
+    pub fn aleo_b200_ntt_fr_ordered(inout_host: *mut c_void, log_n: u32, direction: c_int, kind: c_int, order: c_int) -> c_int;
+    pub fn aleo_b200_polymul(
+        out_host: *mut c_void,
+        pcount: usize,
+        polynomials_host: *const *const c_void,
+        plens: *const usize,
+        ecount: usize,
+        evaluations_host: *const *const c_void,
+        elens: *const usize,
+        log_n: u32,
+    ) -> c_int;
+}
+pub const NTT_ORDER_II: c_int = 0; // upstream NN
+pub const NTT_ORDER_IO: c_int = 1; // upstream NR
+pub const NTT_ORDER_OI: c_int = 2; // upstream RN
+
+/// Body of `PolyMultiplier::multiply` (src/fft/polynomial/multiplier.rs): coefficients of
+/// `ifft(prod fft(p_i) * prod e_j)` over the domain of size `2^log_n`; every operand crosses PCIe once.
+/// # Safety
+/// `T` must be `Fp256<FrParameters>`; every evaluation vector must hold `2^log_n` elements.
+pub unsafe fn polymul<T: Clone + Default>(polynomials: &[&[T]], evaluations: &[&[T]], log_n: u32) -> Vec<T> {
+    assert_eq!(std::mem::size_of::<T>(), 32);
+    let mut out = vec![T::default(); 1usize << log_n];
+    let pp: Vec<*const c_void> = polynomials.iter().map(|p| p.as_ptr() as *const c_void).collect();
+    let pl: Vec<usize> = polynomials.iter().map(|p| p.len()).collect();
+    let ep: Vec<*const c_void> = evaluations.iter().map(|e| e.as_ptr() as *const c_void).collect();
+    let el: Vec<usize> = evaluations.iter().map(|e| e.len()).collect();
+    let rc = aleo_b200_polymul(out.as_mut_ptr() as *mut c_void, pp.len(), pp.as_ptr(), pl.as_ptr(), ep.len(), ep.as_ptr(), el.as_ptr(), log_n);
+    if rc != 0 {
+        die("PolyMultiplier::multiply", rc);
+    }
+    out
+}
+
 pub const NTT_FORWARD: c_int = 0;
 pub const NTT_INVERSE: c_int = 1;
 pub const NTT_STANDARD: c_int = 0;

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) mix_kernel(u32* sink, u32 iters, u32 seed
           f++;
         }
         if (i * T < s * I) {
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i & 7]) : "r"(m), "r"((u32)(i + 3)));
+          // the second multiplicand changes every iteration: a loop-invariant product would be hoisted into an addition
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i & 7]) : "r"(m), "r"(it + (u32)(i + 3)));
           i++;
         }
         if (a * T < s * A) {
@@ -103,5 +104,7 @@ int main() {
   run<288, 132, 160, 1>("hybrid 24-bit, lean conversions: 288/132/160", sms, ghz);
   run<400, 0, 300, 1>("all-DFMA 48-bit limbs: 400 F + 300 A", sms, ghz);
   run<120, 210, 150, 1>("half hybrid: 120 F + 210 I + 150 A", sms, ghz);
+  run<408, 0, 420, 1>("all-DFMA 48-bit limbs as counted in DESIGN.md: 408 F + 420 A", sms, ghz);
+  run<384, 0, 256, 1>("all-DFMA floor: 384 F + 256 A (no conversions)", sms, ghz);
   return 0;
 }
