@@ -94,8 +94,28 @@ struct EventSet {
 // (thread_local, released by its destructor when the thread ends); it is rebuilt when the thread's device changes.
 #ifndef ALEO_EMU
 constexpr int FEED_THREADS = 16;  // upper bound; feed_threads() of them run
-constexpr size_t FEED_SLICE = (size_t)4 << 20;
 constexpr size_t FEED_MIN_BYTES = (size_t)8 << 20;  // below this the plain pageable copy is fine
+
+// co-located ranks (one process per GPU under torchrun)
+long local_world_size() {
+  const char* lw = getenv("LOCAL_WORLD_SIZE");
+  const long v = lw ? atol(lw) : 1L;
+  return v > 0 ? v : 1L;
+}
+
+// Bytes per staging slice (two per helper).  One process on the host: 4 MB (fewest synchronisations: 42.5 GB/s against
+// 35 GB/s with 1 MB, tools/feed_probe.cu).  Several ranks share the host's memory bandwidth, and every staged byte is
+// read, written and read again by the DMA: slices small enough to stay in the last-level cache between the CPU's copy
+// and the DMA's read take the second and third pass off the DRAM (ALEO_B200_FEED_SLICE_KB overrides).
+size_t feed_slice_bytes() {
+  static const size_t v = [] {
+    const char* env = getenv("ALEO_B200_FEED_SLICE_KB");
+    long kb = env ? atol(env) : 0L;
+    if (kb < 64 || kb > 65536) kb = local_world_size() > 1 ? 1024 : 4096;
+    return (size_t)kb << 10;
+  }();
+  return v;
+}
 
 // helper threads per staged copy: one core copies ~8 GB/s, PCIe takes ~55 GB/s
 int feed_threads() {
@@ -106,8 +126,7 @@ int feed_threads() {
       // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): the ranks of a box share its cores -- 8 ranks x 6 helpers
       // on 32 cores ran the staged copies slower than 3 helpers each
       unsigned hc = std::thread::hardware_concurrency();
-      const char* lw = getenv("LOCAL_WORLD_SIZE");
-      const long ranks = lw ? atol(lw) : 1L;
+      const long ranks = local_world_size();
       if (ranks > 1 && hc > 0) hc = hc / (unsigned)ranks > 0 ? hc / (unsigned)ranks : 1u;
       v = hc >= 12 ? 6 : (hc >= 4 ? 4 : (hc >= 3 ? 3 : 2));
     }
@@ -118,7 +137,7 @@ int feed_threads() {
 
 class Feeder {
  public:
-  explicit Feeder(int device) : dev_(device), nt_(feed_threads()) {}
+  explicit Feeder(int device) : dev_(device), nt_(feed_threads()), slice_(feed_slice_bytes()) {}
   ~Feeder() {
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -142,7 +161,7 @@ class Feeder {
     for (int t = 0; t < nt_; t++) {
       cudaError_t e = cudaStreamCreateWithFlags(&st_[t], cudaStreamNonBlocking);
       for (int b = 0; b < 2 && e == cudaSuccess; b++) {
-        e = cudaMallocHost((void**)&buf_[t][b], FEED_SLICE);
+        e = cudaMallocHost((void**)&buf_[t][b], slice_);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_[t][b], cudaEventDisableTiming);
       }
       if (e != cudaSuccess) return e;
@@ -203,11 +222,11 @@ class Feeder {
   }
 
   cudaError_t push(int t, const Job& j) {
-    const size_t nslices = (j.bytes + FEED_SLICE - 1) / FEED_SLICE;
+    const size_t nslices = (j.bytes + slice_ - 1) / slice_;
     cudaError_t e = cudaStreamWaitEvent(st_[t], j.gate, 0);
     for (size_t i = (size_t)t, round = 0; i < nslices && e == cudaSuccess; i += (size_t)nt_, round++) {
       const int b = (int)(round & 1);
-      const size_t off = i * FEED_SLICE, len = (j.bytes - off < FEED_SLICE) ? j.bytes - off : FEED_SLICE;
+      const size_t off = i * slice_, len = (j.bytes - off < slice_) ? j.bytes - off : slice_;
       e = cudaEventSynchronize(ev_[t][b]);  // the DMA that last read this buffer is done
       if (e != cudaSuccess) break;
       std::memcpy(buf_[t][b], j.host + off, len);
@@ -218,7 +237,7 @@ class Feeder {
   }
 
   cudaError_t pull(int t, const Job& j) {
-    const size_t nslices = (j.bytes + FEED_SLICE - 1) / FEED_SLICE;
+    const size_t nslices = (j.bytes + slice_ - 1) / slice_;
     cudaError_t e = cudaStreamWaitEvent(st_[t], j.gate, 0);
     for (int b = 0; b < 2 && e == cudaSuccess; b++) e = cudaEventSynchronize(ev_[t][b]);  // buffers idle
     size_t prev_off = 0, prev_len = 0;
@@ -228,8 +247,8 @@ class Feeder {
       const bool more = i < nslices;
       size_t off = 0, len = 0;
       if (more) {
-        off = i * FEED_SLICE;
-        len = (j.bytes - off < FEED_SLICE) ? j.bytes - off : FEED_SLICE;
+        off = i * slice_;
+        len = (j.bytes - off < slice_) ? j.bytes - off : slice_;
         e = cudaMemcpyAsync(buf_[t][b], j.dev + off, len, cudaMemcpyDeviceToHost, st_[t]);
         if (e == cudaSuccess) e = cudaEventRecord(ev_[t][b], st_[t]);
       }
@@ -246,6 +265,7 @@ class Feeder {
   }
 
   const int dev_, nt_;
+  const size_t slice_;
   unsigned char* buf_[FEED_THREADS][2] = {};
   cudaEvent_t ev_[FEED_THREADS][2] = {};
   cudaStream_t st_[FEED_THREADS] = {};
