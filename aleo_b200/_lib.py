@@ -80,6 +80,7 @@ SYMBOLS = [
     ("aleo_b200_gen_scalars_dev", _int, [_vp, _sz, _u64, _u64, _int, _vp]),
     ("aleo_b200_dlog_dot_dev", _int, [_vp, _vp, _sz, _vp, _vp, _u64, _vp]),
     ("aleo_b200_check_on_curve_dev", _int, [_vp, _sz, _sz, _vp]),
+    ("aleo_b200_fq_mul_fp64_dev", _int, [_vp, _vp, _vp, _sz, _int, _vp]),
     ("aleo_b200_bench_imad", _int, [_int, _int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 

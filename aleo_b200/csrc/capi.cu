@@ -816,8 +816,17 @@ int aleo_b200_g1_compress_dev(void* out48_dev, const void* affine_dev, size_t af
   return ALEO_B200_OK;
 }
 
+int aleo_b200_fq_mul_fp64_dev(void* out_dev, const void* a_dev, const void* b_dev, size_t n, int square, void* stream) {
+  if (n == 0) return ALEO_B200_OK;
+  if (out_dev == nullptr || a_dev == nullptr || (!square && b_dev == nullptr) || n >= ((size_t)1 << 32)) return ALEO_B200_EINVAL;
+  int rc = ensure_ready(nullptr);
+  if (rc) return rc;
+  API_CK(aleo::fq_mul_fp64(out_dev, a_dev, b_dev, n, square != 0, (cudaStream_t)stream));
+  return ALEO_B200_OK;
+}
+
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
-  if (kind < 0 || kind > 5 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
+  if (kind < 0 || kind > 8 || iters <= 0 || ms_out == nullptr || ops_out == nullptr) return ALEO_B200_EINVAL;
   int rc = ensure_ready(nullptr);
   if (rc) return rc;
   API_CK(aleo::bench_imad(kind, iters, ms_out, ops_out));

@@ -101,4 +101,5 @@ cudaError_t gen_scalars(void* scalars_dev, size_t n, u64 seed, u64 first, bool m
 cudaError_t dlog_dot(void* out_dev, const void* scalars_dev, size_t n, const void* s0_32, const void* d_32, u64 first, cudaStream_t s);
 cudaError_t check_on_curve(const void* bases_dev, size_t n, u32 stride, cudaStream_t s, int* ok);
 cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out);
+cudaError_t fq_mul_fp64(void* out_dev, const void* a_dev, const void* b_dev, size_t n, bool square, cudaStream_t s);
 }  // namespace aleo

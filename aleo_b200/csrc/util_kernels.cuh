@@ -3,6 +3,7 @@
 // depends on these).
 #pragma once
 #include "g1.cuh"
+#include "mont_fp64.cuh"
 
 namespace util {
 
@@ -257,6 +258,8 @@ KERNEL void __launch_bounds__(256) imad_bench_kernel(u32* sink, u32 iters, u32 s
     }
     if (sd == 0.12345678 || s == 0x12345678u) sink[0] = (u32)s;
   } else {
+    // KIND 3: dependent Fq products on IMAD.WIDE; KIND 6: the same chains through the FP64-pipe multiplier
+    // (mont_fp64.cuh); KIND 7: FP64-pipe squares
     Fq a = fp_zero<FqParams>(), b = fp_zero<FqParams>();
 #pragma unroll
     for (int k = 0; k < 11; k++) {
@@ -265,8 +268,19 @@ KERNEL void __launch_bounds__(256) imad_bench_kernel(u32* sink, u32 iters, u32 s
     }
     const Fq c = fp_const<FqParams, FqParams::GX_M>();
     for (u32 it = 0; it < iters; it++) {
-      a = fp_mul(a, c);
-      b = fp_mul(b, c);
+      if (KIND == 6) {
+        a = fq_mul_fp64(a, c);
+        b = fq_mul_fp64(b, c);
+      } else if (KIND == 7) {
+        a = fq_sqr_fp64(a);
+        b = fq_sqr_fp64(b);
+      } else if (KIND == 8) {
+        a = fp_sqr(a);
+        b = fp_sqr(b);
+      } else {
+        a = fp_mul(a, c);
+        b = fp_mul(b, c);
+      }
     }
     u32 s = 0;
 #pragma unroll
@@ -280,7 +294,16 @@ KERNEL void __launch_bounds__(256) imad_bench_kernel(u32* sink, u32 iters, u32 s
 // the IMAD.WIDE counts the roofline arithmetic of DESIGN.md rests on (Fq product 276, dedicated Fq square 210, Fr raw
 // product 120).  The carry chains are separate asm statements that ptxas fuses pairwise into IMAD.WIDE.U32.X; a compiler
 // or source change that breaks the fusion doubles the count and shows up here, on the CPU, before any GPU time is spent.
+// out[i] = a[i] * b[i] (or a[i]^2) over Fq through the FP64-pipe multiplier: parity of the experiment with fp_mul
+KERNEL void __launch_bounds__(128) fq_mul_fp64_kernel(Fq* out, const Fq* a, const Fq* b, u32 n, u32 square) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = square ? fq_sqr_fp64(a[i]) : fq_mul_fp64(a[i], b[i]);
+}
+
 #ifndef ALEO_EMU
+extern "C" KERNEL void aleo_probe_fq_mul_fp64(Fq* out, const Fq* a, const Fq* b) { out[threadIdx.x] = fq_mul_fp64(a[threadIdx.x], b[threadIdx.x]); }
+extern "C" KERNEL void aleo_probe_fq_sqr_fp64(Fq* out, const Fq* a) { out[threadIdx.x] = fq_sqr_fp64(a[threadIdx.x]); }
 extern "C" KERNEL void aleo_probe_fq_mul(Fq* out, const Fq* a, const Fq* b) { out[threadIdx.x] = fp_mul(a[threadIdx.x], b[threadIdx.x]); }
 extern "C" KERNEL void aleo_probe_fq_sqr(Fq* out, const Fq* a) { out[threadIdx.x] = fp_sqr(a[threadIdx.x]); }
 extern "C" KERNEL void aleo_probe_fr_mul_raw(Fr* out, const Fr* a, const Fr* b) { out[threadIdx.x] = lz_mul(a[threadIdx.x], b[threadIdx.x]); }

@@ -75,6 +75,13 @@ cudaError_t check_on_curve(const void* bases_dev, size_t n, u32 stride, cudaStre
   return e;
 }
 
+cudaError_t fq_mul_fp64(void* out_dev, const void* a_dev, const void* b_dev, size_t n, bool square, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  LAUNCH_NOSYNC(util::fq_mul_fp64_kernel, dim3((u32)((n + 127) / 128)), dim3(128), 0, s, (Fq*)out_dev, (const Fq*)a_dev, (const Fq*)b_dev,
+                (u32)n, (u32)(square ? 1 : 0));
+  return cudaGetLastError();
+}
+
 cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
 #ifdef ALEO_EMU
   (void)kind; (void)iters;
@@ -88,7 +95,7 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const u32 grid = dev_props().sms * 8, block = 256;
-  const double per_thread[6] = {64.0, 64.0, 64.0, 2.0 * 276.0, 64.0, 64.0};  // kind 5: 64 DFMA + 64 IMAD.WIDE, counted as 64 pairs
+  const double per_thread[9] = {64.0, 64.0, 64.0, 2.0 * 276.0, 64.0, 64.0, 2.0 * 276.0, 2.0 * 276.0, 2.0 * 276.0};  // kinds 6-8: counted as 276-MAC products  // kind 5: 64 DFMA + 64 IMAD.WIDE, counted as 64 pairs
   for (int rep = 0; rep < 2; rep++) {  // first launch warms up
     cudaEventRecord(e0, 0);
     switch (kind) {
@@ -97,6 +104,9 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
       case 2: util::imad_bench_kernel<2><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       case 4: util::imad_bench_kernel<4><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       case 5: util::imad_bench_kernel<5><<<grid, block>>>(sink, (u32)iters, 12345u); break;
+      case 6: util::imad_bench_kernel<6><<<grid, block>>>(sink, (u32)iters, 12345u); break;
+      case 7: util::imad_bench_kernel<7><<<grid, block>>>(sink, (u32)iters, 12345u); break;
+      case 8: util::imad_bench_kernel<8><<<grid, block>>>(sink, (u32)iters, 12345u); break;
       default: util::imad_bench_kernel<3><<<grid, block>>>(sink, (u32)iters, 12345u); break;
     }
     cudaEventRecord(e1, 0);
@@ -109,7 +119,7 @@ cudaError_t bench_imad(int kind, int iters, double* ms_out, double* ops_out) {
   cudaEventDestroy(e1);
   cudaFree(sink);
   *ms_out = ms;
-  *ops_out = per_thread[(kind >= 0 && kind < 6) ? kind : 3] * (double)iters * (double)grid * (double)block;
+  *ops_out = per_thread[(kind >= 0 && kind < 9) ? kind : 3] * (double)iters * (double)grid * (double)block;
   return e;
 #endif
 }

@@ -284,8 +284,14 @@ int aleo_b200_check_on_curve_dev(const void* bases_dev, size_t n, size_t affine_
  * `iters` x 64 chains per thread on a full-chip grid, and the op count through *ops_out.
  * kind 0 = mad.lo (IMAD), 1 = 32x32+64 (IMAD.WIDE), 2 = mad.lo.cc/madc.hi.cc carry chains (IMAD.WIDE.U32.X),
  * 3 = dependent Fq products, 4 = DFMA chains (FP64 pipe), 5 = DFMA and IMAD.WIDE interleaved one to one
- * (ops = pairs): do the two pipes overlap? */
+ * (ops = pairs): do the two pipes overlap?  6 / 7 = the dependent Fq product / square chains of kind 3 through the
+ * FP64-pipe multiplier (csrc/mont_fp64.cuh; ops counted as 276-MAC products, so the rates compare directly), 8 = dedicated
+ * IMAD.WIDE squares. */
 int aleo_b200_bench_imad(int kind, int iters, double* ms_out, double* ops_out);
+/* EXPERIMENT: out[i] = a[i] * b[i] (square != 0: a[i]^2) over Fq, 48-byte Montgomery images, through
+ * the FP64-pipe (DFMA, 48-bit limbs) multiplier -- bit-identical to aleo_b200_field_op_dev(FQ, MUL / SQR); parity tests
+ * and the A/B measurement use it. */
+int aleo_b200_fq_mul_fp64_dev(void* out_dev, const void* a_dev, const void* b_dev, size_t n, int square, void* stream);
 
 #ifdef __cplusplus
 }

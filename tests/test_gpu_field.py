@@ -81,3 +81,37 @@ def test_empty_and_bad_arguments():
     assert lib.field_op_dev(0, 9, None, None, None, 1, None) == -1
     x = torch.zeros(32, dtype=torch.uint8, device="cuda")
     assert lib.field_op_dev(0, 2, x.data_ptr(), x.data_ptr(), None, 1, None) == -1     # MUL needs b
+
+
+def test_fp64_pipe_multiplier_is_bit_identical():
+    """EXPERIMENT (csrc/mont_fp64.cuh): the Fq product / square on the FP64 pipe (DFMA, 48-bit limbs,
+    exact hi / lo halves through fma_rz) against big integers and against the IMAD.WIDE multiplier: edge values whose
+    48-bit limbs are all ones / zero / single bits (every hi / lo split and every column carry saturates somewhere) and
+    2 * 10^5 random pairs"""
+    mod = o.P_MOD
+    rng = random.Random(4848)
+    a = _edge_values(mod, 12) + [rng.randrange(mod) for _ in range(2000)]
+    b = list(reversed(_edge_values(mod, 12))) + [rng.randrange(mod) for _ in range(2000)]
+    for _ in range(3000):
+        limbs = [rng.choice([0, (1 << 48) - 1, (1 << 48) - 2, 1, 1 << 47, (1 << 47) - 1, rng.getrandbits(48)]) for _ in range(8)]
+        # as Montgomery IMAGES: the multiplier sees exactly these limb patterns
+        a.append(sum(v << (48 * i) for i, v in enumerate(limbs)) % mod * pow(1 << 384, -1, mod) % mod)
+        b.append(rng.randrange(mod))
+    A, B = _enc(poly.FQ, a), _enc(poly.FQ, b)
+    lib = ab.get_lib()
+    out = torch.empty_like(A)
+    lib.check(lib.fq_mul_fp64_dev(out.data_ptr(), A.data_ptr(), B.data_ptr(), len(a), 0, None), "fq_mul_fp64")
+    assert _dec(poly.FQ, out) == [(x * y) % mod for x, y in zip(a, b)]
+    lib.check(lib.fq_mul_fp64_dev(out.data_ptr(), A.data_ptr(), None, len(a), 1, None), "fq_sqr_fp64")
+    assert _dec(poly.FQ, out) == [(x * x) % mod for x in a]
+    # at scale against the IMAD.WIDE multiplier (raw 48-byte images, any bit pattern below p)
+    n = 200000
+    raw = np.random.default_rng(5).integers(0, 2**63, size=(n, 6), dtype=np.int64)
+    raw[:, 5] &= (1 << 55) - 1                       # < 2^375 < p
+    X = torch.from_numpy(raw).cuda()
+    Y = torch.from_numpy(np.roll(raw, 1, axis=0).copy()).cuda()
+    got = torch.empty_like(X)
+    lib.check(lib.fq_mul_fp64_dev(got.data_ptr(), X.data_ptr(), Y.data_ptr(), n, 0, None), "fq_mul_fp64")
+    assert torch.equal(got, poly.field_op_dev(poly.FQ, poly.MUL, X, Y))
+    lib.check(lib.fq_mul_fp64_dev(got.data_ptr(), X.data_ptr(), None, n, 1, None), "fq_sqr_fp64")
+    assert torch.equal(got, poly.field_op_dev(poly.FQ, poly.SQR, X))

@@ -10,7 +10,8 @@ import aleo_b200 as ab  # noqa: E402
 lib = ab.get_lib()
 lib.check(lib.init(0), "init")
 names = ["IMAD (mad.lo)", "IMAD.WIDE 32x32+64", "IMAD.WIDE.U32.X carry chains", "dependent Fq products (wide MACs)",
-         "DFMA", "DFMA + IMAD.WIDE interleaved 1:1 (pairs)"]
+         "DFMA", "DFMA + IMAD.WIDE interleaved 1:1 (pairs)", "dependent Fq products on the FP64 pipe (as wide MACs)",
+         "dependent Fq squares on the FP64 pipe (as wide MACs)", "dependent Fq squares, dedicated IMAD.WIDE square (as wide MACs)"]
 for kind, name in enumerate(names):
     ms, ops = C.c_double(), C.c_double()
     lib.check(lib.bench_imad(kind, 4096, C.byref(ms), C.byref(ops)), "bench_imad")
