@@ -261,6 +261,9 @@ struct PassArgs {
   // All results of a tile go to ONE rank (tile t of T belongs to chunk t / (T / g)), so with the rotation every rank
   // receives from exactly one sender at a time instead of all g - 1 senders converging on rank 0, then on rank 1, ...
   u32 d_tile_rot;
+  // Single-GPU passes: while a tile's results are being stored, its CTA prefetches into L2 the inputs of the tile
+  // `pf_ahead` blocks further on (the tile some SM starts about when this one ends).  0 = off.
+  u32 pf_ahead;
 };
 
 // global index of the local index i2l of a strided pass: the rank's bits go in above the shortened last digit
@@ -416,6 +419,32 @@ KERNEL void __launch_bounds__((1 << TL) / 8, (TL >= 11) ? 2 : 4) pass_kernel(Pas
       for (int k = 0; k < PTS; k++) smem_put(plane0, plane1, tile_phys<K, LAST, TL>(bp + k, tg), x[h * PTS + k]);
     }
     SYNC_THREADS();
+  }
+  // ---- L2 prefetch of a later tile's inputs (same thread -> element mapping as the load phase above) ------------
+  if (a.pf_ahead && a.d_k2l >= 31u && blockIdx.x + a.pf_ahead < gridDim.x) {
+    const u32 bx = blockIdx.x + a.pf_ahead;
+    u64 pbase, pstride_r, pstride_g;
+    if (!LAST) {
+      const u32 tiles_per_blk = 1u << (log_m - LG);
+      pbase = ((u64)(bx / tiles_per_blk) << a.log_cur) + ((bx % tiles_per_blk) << LG);
+      pstride_r = (u64)1 << log_m;
+      pstride_g = 1;
+    } else {
+      const u32 log_s = a.log_r2 + a.log_r3;
+      pbase = (((u64)((bx >> log_s) << LG) << log_s) + (bx & ((1u << log_s) - 1u))) << K;
+      pstride_r = 1;
+      pstride_g = ((u64)1 << log_s) << K;
+    }
+    constexpr u32 C1 = R >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const Fr* ptr = src + pbase + (j * C1 + tr) * pstride_r + tg * pstride_g;
+#ifndef ALEO_EMU
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+      (void)ptr;
+#endif
+    }
   }
   // ---- store: thread takes outputs kappa = j*RT + sr for its column sg (lanes along g) ------------
   // Rolled on purpose (2 iterations per trip): nothing here indexes the register array, and 8 inlined copies of

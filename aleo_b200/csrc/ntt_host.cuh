@@ -41,6 +41,7 @@ static inline void set_single_gpu(PassArgs& a) {
   a.d_flag_local = nullptr;
   a.d_epoch = 0;
   a.d_tile_rot = 0;
+  a.pf_ahead = 0;
 }
 
 // cross-rank flags of one distributed transform (PassArgs d_flag_*): where this rank signals, where it waits
@@ -338,6 +339,11 @@ static inline cudaError_t run(const Plan& p, Fr* data, size_t batch, Fr* scratch
       const u32 grid = (u32)(n >> tl);
       a.use_pre = ((i == 0) && p.coset && !p.inverse) ? 1 : 0;
       a.use_post = (last && p.coset && p.inverse) ? 1 : 0;
+      {
+        // ALEO_B200_NTT_PREFETCH = tiles ahead (experiment); read per call: sweeps flip it
+        const char* pe = getenv("ALEO_B200_NTT_PREFETCH");
+        a.pf_ahead = pe ? (u32)atoi(pe) : 0u;
+      }
       if (pass_ev && i == 0) cudaEventRecord(pass_ev[0], s);
       NTT_CK(last ? launch_pass_k<true>(p.K[i], a, grid, nb, s, tl) : launch_pass_k<false>(p.K[i], a, grid, nb, s, tl));
       if (pass_ev) cudaEventRecord(pass_ev[i + 1], s);
@@ -386,6 +392,7 @@ static inline cudaError_t run_dist_stage1(const Plan& p, int lg, int rank, const
     a.d_epoch = fl ? fl->epoch : 0;
     const u32 tiles = (u32)(((size_t)1 << Ll) >> TILE_LOG);
     static const bool no_rot = getenv("ALEO_B200_NTT_DIST_NOROT") != nullptr;  // A/B switch: every rank starts with rank 0's tiles
+    a.pf_ahead = 0;
     a.d_tile_rot = (exchange && !no_rot) ? (u32)(((u64)((rank + 1) & ((1 << lg) - 1)) * tiles) >> lg) : 0u;
     if (ev2 && i == 0) cudaEventRecord(ev2[0], s);        // profiling: [0] start, [1] before the exchange pass
     if (ev2 && exchange) cudaEventRecord(ev2[1], s);
@@ -430,6 +437,7 @@ static inline cudaError_t run_dist_stage2(const Plan& p, int lg, int rank, const
   a.d_flag_local = fl ? fl->local : nullptr;
   a.d_epoch = fl ? fl->epoch : 0;
   a.d_tile_rot = 0;
+  a.pf_ahead = 0;
   return launch_pass_k<true>(p.K[last], a, (u32)(((size_t)1 << Ll) >> TILE_LOG), 1, s);
 }
 

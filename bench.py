@@ -9,8 +9,10 @@ A step = one G1 MSM over 2^log_n points per GPU (the rank's point range of an N*
 BASELINE.json config 4's decomposition) followed, for N > 1, by the single final combine (all-gather
 of the 144-byte partials + g1_sum).  `value` = total points / max-over-ranks device time, inputs
 resident in HBM.  `e2e` = the same work through the host-pointer C-ABI entry point
-aleo_b200_msm_g1 (pinned host buffers, H2D of bases + scalars and D2H of the result inside the timed
-region).  The JSON line also carries the NTT figures, both rooflines and the CPU baseline.
+aleo_b200_msm_g1 on PAGEABLE host buffers (what a Rust Vec is; H2D of bases + scalars and D2H of the
+result inside the timed region), with the same call on pinned buffers beside it.  The JSON line also
+carries the NTT figures, both rooflines, BASELINE configs[3] (fixed 2^26 MSM + NTT over the N GPUs)
+and the CPU baseline; `roofline.secondary` mirrors the secondary results compactly.
 The oracle (oracle/) is used here only as the checker and as the timed CPU baseline.
 """
 import argparse
