@@ -6,6 +6,10 @@
 // point returns ALEO_B200_ENODEVICE.
 #include "../../include/aleo_b200.h"
 #include <cstdlib>
+#ifndef ALEO_EMU
+#include <condition_variable>
+#include <functional>
+#endif
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -83,6 +87,60 @@ int thread_stream(int dev, cudaStream_t* out) {
 }
 
 bool stride_ok(size_t s) { return s == 96 || s == 104; }
+
+#ifndef ALEO_EMU
+// One persistent host thread per device for the single-process multi-GPU entry point.  Created on first use and never
+// destroyed (a leaked singleton: no ordering problems against the CUDA runtime's own teardown at process exit); calls
+// are serialised.
+class DeviceWorkers {
+ public:
+  static DeviceWorkers& get() {
+    static DeviceWorkers* p = new DeviceWorkers();
+    return *p;
+  }
+  // fn(d) for d = 0 .. nd - 1, each on device d's worker thread; returns when all of them are done
+  void run(int nd, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> call(call_mu_);
+    std::unique_lock<std::mutex> lk(mu_);
+    while ((int)threads_.size() < nd) {
+      const int d = (int)threads_.size();
+      threads_.emplace_back([this, d]() { loop(d); });
+      threads_.back().detach();
+    }
+    fn_ = &fn;
+    active_ = nd;
+    pending_ = nd;
+    generation_++;
+    cv_.notify_all();
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int d) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (d >= active_) continue;
+        fn = fn_;
+      }
+      (*fn)(d);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> threads_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int active_ = 0, pending_ = 0;
+  unsigned long long generation_ = 0;
+};
+#endif
 
 // a resident-SRS handle lives on the device it was created on: using it from a thread whose current device differs
 // would fault on the device instead of failing here
@@ -542,22 +600,19 @@ int aleo_b200_msm_g1_multi(void* out_projective_host, const void* bases_host, si
   cudaGetDevice(&home);
   std::vector<unsigned char> partials((size_t)n_devices * 144);
   std::vector<int> rcs(n_devices, ALEO_B200_OK);
-  std::vector<std::thread> workers;
   const size_t base = n / n_devices, rem = n % n_devices;
-  size_t first = 0;
-  for (int d = 0; d < n_devices; d++) {
+  // one PERSISTENT worker thread per device (DeviceWorkers): its stream, staging buffers and helper threads are created
+  // once and reused by every later call instead of being rebuilt (tens of MB of pinned memory per device) per call
+  DeviceWorkers::get().run(n_devices, [&](int d) {
+    size_t first = 0;
+    for (int k = 0; k < d; k++) first += base + ((size_t)k < rem ? 1 : 0);
     const size_t cnt = base + ((size_t)d < rem ? 1 : 0);
-    const unsigned char* b = (const unsigned char*)bases_host + first * affine_stride;
-    const unsigned char* sc = (const unsigned char*)scalars_host + first * 32;
-    unsigned char* out = partials.data() + (size_t)d * 144;
-    workers.emplace_back([=, &rcs]() {
-      int rc = aleo_b200_init(d);  // selects device d for this thread and prepares it
-      if (rc == ALEO_B200_OK) rc = aleo_b200_msm_g1(out, b, cnt, sc, affine_stride);
-      rcs[d] = rc;
-    });
-    first += cnt;
-  }
-  for (auto& w : workers) w.join();
+    int rc = aleo_b200_init(d);  // selects device d for the worker thread and prepares it
+    if (rc == ALEO_B200_OK)
+      rc = aleo_b200_msm_g1(partials.data() + (size_t)d * 144, (const unsigned char*)bases_host + first * affine_stride, cnt,
+                            (const unsigned char*)scalars_host + first * 32, affine_stride);
+    rcs[d] = rc;
+  });
   cudaSetDevice(home);
   for (int rc : rcs)
     if (rc) return rc;
