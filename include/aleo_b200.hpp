@@ -74,11 +74,43 @@ class EvaluationDomain {
   std::vector<Fr> coset_fft(const std::vector<Fr>& c) const { auto v = c; coset_fft_in_place(v); return v; }
   std::vector<Fr> coset_ifft(const std::vector<Fr>& e) const { auto v = e; coset_ifft_in_place(v); return v; }
 
+  // FFTOrder variants (fft_helper_in_place_with_pc & co.): II natural in / natural out, IO bit-reversed out, OI
+  // bit-reversed in.  The FFTPrecomputation argument of upstream is dropped: twiddle tables are cached in the library.
+  enum class FFTOrder : int { II = ALEO_B200_NTT_ORDER_II, IO = ALEO_B200_NTT_ORDER_IO, OI = ALEO_B200_NTT_ORDER_OI };
+  void fft_helper_in_place(std::vector<Fr>& v, FFTOrder order) const { run_ordered(v, ALEO_B200_NTT_FORWARD, ALEO_B200_NTT_STANDARD, order); }
+  void ifft_helper_in_place(std::vector<Fr>& v, FFTOrder order) const { run_ordered(v, ALEO_B200_NTT_INVERSE, ALEO_B200_NTT_STANDARD, order); }
+  void out_order_fft_in_place(std::vector<Fr>& v) const { fft_helper_in_place(v, FFTOrder::IO); }
+
  private:
+  void run_ordered(std::vector<Fr>& v, int direction, int kind, FFTOrder order) const {
+    v.resize(size, Fr{{0, 0, 0, 0}});
+    check(aleo_b200_ntt_fr_ordered(v.data(), log_size_of_group, direction, kind, (int)order), "EvaluationDomain::fft_helper");
+  }
   void run(std::vector<Fr>& v, int direction, int kind) const {
     v.resize(size, Fr{{0, 0, 0, 0}});
     check(aleo_b200_ntt_fr(v.data(), log_size_of_group, direction, kind), "EvaluationDomain::fft");
   }
+};
+
+// PolyMultiplier (src/fft/polynomial/multiplier.rs): collect polynomials and evaluation vectors, multiply() returns the
+// coefficients of ifft(prod fft(p_i) * prod e_j) over `domain` -- every operand crosses PCIe once (aleo_b200_polymul).
+class PolyMultiplier {
+ public:
+  void add_polynomial(const std::vector<Fr>& p) { polys_.push_back(&p); }
+  void add_evaluation(const std::vector<Fr>& e) { evals_.push_back(&e); }
+  std::vector<Fr> multiply(const EvaluationDomain& domain) const {
+    std::vector<const void*> pp, ep;
+    std::vector<size_t> pl, el;
+    for (auto* p : polys_) { pp.push_back(p->data()); pl.push_back(p->size()); }
+    for (auto* e : evals_) { ep.push_back(e->data()); el.push_back(e->size()); }
+    std::vector<Fr> out(domain.size);
+    check(aleo_b200_polymul(out.data(), pp.size(), pp.data(), pl.data(), ep.size(), ep.data(), el.data(), domain.log_size_of_group),
+          "PolyMultiplier::multiply");
+    return out;
+  }
+
+ private:
+  std::vector<const std::vector<Fr>*> polys_, evals_;
 };
 
 // Commitment as it appears in a proof: compressed G1 (x little-endian | bit 383: larger y | bit 382: infinity)

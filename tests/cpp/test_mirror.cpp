@@ -55,6 +55,36 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 4; k++) REQUIRE(w[i].v[k] == (i < 5 ? v[i].v[k] : 0));
   std::vector<Fr> c = dom.coset_ifft(dom.coset_fft(v));
   for (size_t i = 0; i < 5; i++) REQUIRE(c[i].v[0] == v[i].v[0]);
+  // FFTOrder: IO followed by OI of the inverse is the identity (the bit-reversed intermediate is consumed as it is)
+  {
+    std::vector<Fr> u = v;
+    dom.out_order_fft_in_place(u);
+    dom.ifft_helper_in_place(u, EvaluationDomain::FFTOrder::OI);
+    for (size_t i = 0; i < 8; i++) REQUIRE(u[i].v[0] == (i < 5 ? v[i].v[0] : 0));
+  }
+  // PolyMultiplier: one polynomial and no evaluations gives the polynomial back, zero padded to the domain
+  {
+    PolyMultiplier pm;
+    pm.add_polynomial(v);
+    std::vector<Fr> p1 = pm.multiply(dom);
+    REQUIRE(p1.size() == 8);
+    for (size_t i = 0; i < 8; i++)
+      for (int k = 0; k < 4; k++) REQUIRE(p1[i].v[k] == (i < 5 ? v[i].v[k] : 0));
+    // (p * p) evaluated on the domain == pointwise square of fft(p): multiply, then transform both ways
+    auto dom16 = *EvaluationDomain::new_(16);
+    PolyMultiplier sq;
+    sq.add_polynomial(v);
+    sq.add_polynomial(v);
+    std::vector<Fr> pp = sq.multiply(dom16);
+    PolyMultiplier viaev;
+    std::vector<Fr> e = dom16.fft(v);
+    viaev.add_polynomial(v);
+    viaev.add_evaluation(e);
+    std::vector<Fr> pe = viaev.multiply(dom16);
+    for (size_t i = 0; i < 16; i++)
+      for (int k = 0; k < 4; k++) REQUIRE(pp[i].v[k] == pe[i].v[k]);
+    for (size_t i = 9; i < 16; i++) REQUIRE((pp[i].v[0] | pp[i].v[1] | pp[i].v[2] | pp[i].v[3]) == 0);   // degree 8
+  }
   // KZG10::commit against resident powers: all-identity powers commit to the identity (flag bit 382 set, x = 0),
   // and a handle serves any prefix length
   {
