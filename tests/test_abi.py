@@ -75,3 +75,33 @@ def test_product_package_never_touches_oracle_or_emulator():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "libaleo_b200_emu" not in src, f
+
+
+def test_header_is_valid_c_and_cpp(tmp_path):
+    """include/aleo_b200.h is what a bindgen / cgo / ctypes binding consumes: it must compile as plain C99 and as C++"""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "aleo_b200.h"\nint main(void) { return aleo_b200_strerror(ALEO_B200_OK) == 0; }\n')
+    inc = "-I" + os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", inc, str(src)], check=True)
+
+
+def test_argument_validation_of_the_round_two_entry_points(product_lib_path):
+    lib = _lib.Lib(product_lib_path)
+    buf = C.create_string_buffer(1024)
+    p = C.cast(buf, C.c_void_p)
+    assert lib.ntt_fr_ordered(p, 3, 0, 0, 5) == _lib.EINVAL and lib.ntt_fr_ordered(None, 3, 0, 0, 1) == _lib.EINVAL
+    assert lib.ntt_fr_ordered(p, 40, 0, 0, 1) == _lib.ETOOLARGE
+    one = (C.c_void_p * 1)(p)
+    assert lib.polymul(p, 0, None, None, 0, None, None, 3) == _lib.EINVAL                       # nothing to multiply
+    assert lib.polymul(p, 1, one, (C.c_size_t * 1)(9), 0, None, None, 3) == _lib.EINVAL         # longer than the domain
+    assert lib.polymul(p, 0, None, None, 1, one, (C.c_size_t * 1)(7), 3) == _lib.EINVAL         # evaluations != domain size
+    assert lib.polymul(p, 65, one, (C.c_size_t * 1)(1), 0, None, None, 3) == _lib.EINVAL
+    assert lib.polymul_dev(p, 1, one, (C.c_size_t * 1)(1), 0, None, None, 40, None) == _lib.ETOOLARGE
+    assert lib.kzg_open_combinations_dev(None, p, one, (C.c_size_t * 1)(1), 1, p, p, 1, None) == _lib.EINVAL
+    assert lib.kzg_open_combinations_dev(None, p, one, (C.c_size_t * 1)(1), 1, p, p, 0, None) == _lib.EINVAL   # no handle
+    assert lib.fq_mul_fp64_dev(None, None, None, 0, 0, None) == 0 and lib.fq_mul_fp64_dev(None, p, p, 1, 0, None) == _lib.EINVAL
+    assert lib.g1_decompress_unchecked_dev(p, 100, p, 1, None) == _lib.EINVAL
+    assert lib.ntt_dist_transform(None, p, p, 0, 0, None) == _lib.EINVAL
+    assert lib.ntt_dist_profile(None, p, p, 0, 0, None, None) == _lib.EINVAL
