@@ -6,7 +6,7 @@ Aleo SDK 0.5.1) holds no golden vector for `VariableBase::msm` or `EvaluationDom
 the algorithm lives in the crates.io dependencies snarkvm-algorithms / -curves / -fields /
 -utilities, all pinned "=0.14.5" (reference Cargo.toml:28-53, Cargo.lock:2200-2203, 2637-2640,
 2652-2655, 2860-2863) whose sources are absent from this environment.  What the reference DOES
-pin and this file is checked against (tests/test_oracle_fixtures.py):
+pin and this file is checked against (tests/test_oracle.py):
   * the real proof string in wasm/src/programs/transaction.rs:100 -> 13 compressed G1 points that
     must decompress onto y^2 = x^3 + 1 and lie in the r-torsion, Fr evaluations < r;
   * the curve/field parameters (re-derived from the BLS12 family parameter x).
