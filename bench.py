@@ -544,7 +544,7 @@ def run_ours(args):
                 "frac": macs / acc / 1e6 / peak_gmac,
                 "pipe_frac": n * windows * ISSUED_MACS_PER_MIXED_ADD / acc / 1e6 / peak_gmac,
                 "issued_macs_per_mixed_add": ISSUED_MACS_PER_MIXED_ADD, "traffic": (prof["msm_accumulate_dram_bytes_per_entry"] * n * windows) if "msm_accumulate_dram_bytes_per_entry" in prof else None,
-                "traffic_source": "ncu --set full at n=2^22 (profiles/r01c_ncu_hot_kernels.md): DRAM bytes per sorted entry x n x windows",
+                "traffic_source": "ncu --set full at n=2^22 (profiles/r02_ncu_hot_kernels.md via profiles/ncu_traffic.json): DRAM bytes per sorted entry x n x windows",
                 "algorithmic_bytes_per_launch": n * windows * 108,
                 "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows,
                 "kernel_ms": acc, "kernel_share_of_step": acc / (sum(sort_ms) / len(sort_ms) + acc + sum(tail_ms) / len(tail_ms)),
