@@ -638,6 +638,63 @@ KERNEL void __launch_bounds__(128) reduce_level_kernel(ReduceArgs a) {
   a.P_out[(size_t)w * a.T_out + t] = acc;
 }
 
+// The same level computed by a whole CTA per chunk (blockDim.x = chunk size Kc <= 256, one thread per element): a
+// log-depth suffix scan gives the running sums, a tree adds them up, thread 0 scales and joins the previous level's plain
+// sums.  Depth 2 log2(Kc) + scale_log additions instead of 2 Kc + scale_log, for (log2(Kc) + 1) / 2 times the work: used
+// while the whole level is small (proof-sized commitments: a 2^16-point KZG commit spent 1.0 of its 1.66 ms in three
+// serial chunk levels and the scan stage, profiles/r02_small_msm_trace.log).
+KERNEL void __launch_bounds__(SCAN_MAX) reduce_level_cta_kernel(ReduceArgs a) {
+  DYN_SMEM(G1Xyzz, sh);
+  const u32 w = blockIdx.x / a.T_out, t = blockIdx.x % a.T_out;
+  const u32 j = threadIdx.x, kc = blockDim.x;
+  const G1Xyzz* x = a.X + (size_t)w * a.x_stride + a.x_off;
+  const u32 idx = t * kc + j;
+  G1Xyzz mine = xyzz_identity();
+  if (idx < a.m) mine = x[idx];
+  sh[j] = mine;
+  SYNC_THREADS();
+  // suffix scan over the chunk (Hillis-Steele): mine = sum of the chunk's elements at positions >= j
+  for (u32 off = 1; off < kc; off <<= 1) {
+    const bool take = (j + off < kc);
+    G1Xyzz other;
+    if (take) other = sh[j + off];
+    SYNC_THREADS();
+    if (take) {
+      xyzz_add_ni(mine, other);
+      sh[j] = mine;
+    }
+    SYNC_THREADS();
+  }
+  if (j == 0) a.R_out[(size_t)w * a.T_out + t] = mine;  // the chunk's plain sum
+  // WS = sum of the suffix sums = sum (local index + 1) * X
+  for (u32 off = kc >> 1; off > 0; off >>= 1) {
+    if (j < off) {
+      xyzz_add_ni(mine, sh[j + off]);
+      sh[j] = mine;
+    }
+    SYNC_THREADS();
+  }
+  G1Xyzz acc = mine;  // thread 0: WS
+  if (j == 0)
+    for (u32 i = 0; i < a.scale_log; i++) acc = xyzz_double(acc);
+  if (a.P) {  // uniform branch: the previous level's plain sums of this chunk join through a second tree
+    G1Xyzz pj = xyzz_identity();
+    if (idx < a.T_in) pj = a.P[(size_t)w * a.T_in + idx];
+    SYNC_THREADS();
+    sh[j] = pj;
+    SYNC_THREADS();
+    for (u32 off = kc >> 1; off > 0; off >>= 1) {
+      if (j < off) {
+        xyzz_add_ni(pj, sh[j + off]);
+        sh[j] = pj;
+      }
+      SYNC_THREADS();
+    }
+    if (j == 0) xyzz_add_ni(acc, pj);
+  }
+  if (j == 0) a.P_out[(size_t)w * a.T_out + t] = acc;
+}
+
 // Last reduction stage, one CTA per window: S_w = 2^scale_log * f(X[0..m)) + sum P[0..T_in), m, T_in <= blockDim.x.
 struct ScanArgs {
   const G1Xyzz* X;

@@ -158,7 +158,13 @@ struct TailTrace {
 
 struct RedLevel {
   u32 m, T, log_kc, scale_log;  // weighted input length per window, chunks out per window, chunk size, weight of WS
+  bool cta;                     // computed by a CTA per chunk (reduce_level_cta_kernel) instead of a thread per chunk
 };
+
+// A level whose whole input (all bucket sets) has at most this many elements is computed CTA-cooperatively: the extra
+// additions (about 4.5x) are cheaper than the serial chain of a chunk level while they still fit a fraction of a
+// millisecond of the chip (2^17 elements x 9 additions ~ 0.5 ms).  ALEO_B200_MSM_REDUCE = chunk | cta | ctaK (chunks of at most 2^K: tests) forces one.
+constexpr u64 CTA_LEVEL_MAX_ELEMS = (u64)1 << 17;
 
 static inline u32 ceil_log2(u32 v) {
   u32 l = 0;
@@ -220,7 +226,21 @@ struct Session {
         if (need <= SCAN_MAX) break;
         RedLevel l;
         l.m = m;
+        const char* renv = getenv("ALEO_B200_MSM_REDUCE");  // read per call: tests force both paths
+        l.cta = renv ? (renv[0] == 'c' && renv[1] == 't') : ((u64)nwin * need <= CTA_LEVEL_MAX_ELEMS);
         l.log_kc = ceil_log2((need + SCAN_MAX - 1) / SCAN_MAX);
+        if (l.cta) {
+          if (l.log_kc > 8) l.log_kc = 8;  // one thread per element, at most SCAN_MAX threads
+          if (renv && renv[3] >= '1' && renv[3] <= '8' && l.log_kc > (u32)(renv[3] - '0')) l.log_kc = (u32)(renv[3] - '0');  // tests: "cta2" caps the chunk at 4
+          if (l.log_kc < 1) l.log_kc = 1;
+          l.scale_log = scale_log;
+          l.T = (need + (1u << l.log_kc) - 1) >> l.log_kc;
+          lv.push_back(l);
+          scale_log += l.log_kc;
+          t_prev = l.T;
+          m = l.T - 1;
+          continue;
+        }
         // a chunk is serial inside its thread (2 * Kc additions): chunks of 16 while they still fill the chip, chunks of
         // 4 once a level would run on a few warps per SM and its time is the chain, not the work (ncu at 2^22: the second
         // level of 16 ran 3840 threads for 0.82 ms at 26 % of the pipe -- as long as the first with 1/16 of its work)
@@ -458,8 +478,14 @@ struct Session {
       ra.T_out = lv[l].T;
       ra.nwin = nwin;
       const u32 threads = nwin * lv[l].T;
-      LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra);
-      tr.mark("chunk level", s);
+      if (lv[l].cta) {
+        const u32 kc = 1u << lv[l].log_kc;
+        LAUNCH(reduce_level_cta_kernel, dim3(threads), dim3(kc), kc * sizeof(G1Xyzz), s, ra);
+        tr.mark("cta level", s);
+      } else {
+        LAUNCH_NOSYNC(reduce_level_kernel, dim3((threads + 127) / 128), dim3(128), 0, s, ra);
+        tr.mark("chunk level", s);
+      }
     }
     G1Xyzz* S = at<G1Xyzz>(o_D);
     {

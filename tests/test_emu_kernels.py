@@ -211,11 +211,14 @@ def test_emu_host_calls_stream_point_ranges(emu_lib, chunks, monkeypatch):
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
 
 
+@pytest.mark.parametrize("mode", ["chunk", "cta", "cta2"])   # cta2: CTA levels of 4 elements -> several levels, the later ones join plain sums
 @pytest.mark.parametrize("c", [5, 12, 14])
-def test_emu_msm_reduction_stages(emu_lib, c, monkeypatch):
-    """forced window sizes: c = 5 -> scan stage only, 12 -> one chunk level + scan, 14 -> two chunk levels + scan;
+def test_emu_msm_reduction_stages(emu_lib, c, mode, monkeypatch):
+    """forced window sizes: c = 5 -> scan stage only, 12 -> one level + scan, 14 -> two levels + scan, each with the
+    serial chunk levels (a thread per chunk) and with the CTA-cooperative levels (a CTA per chunk: suffix scan + tree);
     also exercises the quad-cooperative doubling tail over 51 / 22 / 19 windows and the binary-GCD inversion"""
     monkeypatch.setenv("ALEO_B200_MSM_C", str(c))
+    monkeypatch.setenv("ALEO_B200_MSM_REDUCE", mode)
     n = 200
     assert emu_lib.msm_window_bits(n) == c
     B = o.synthetic_bases(n, 41)

@@ -201,3 +201,30 @@ def test_single_process_multi_gpu_msm():
         assert ab.VariableBase.msm_multi(hb, hs, k, 104) == want, k
     assert ab.get_lib().msm_g1_multi(None, None, 10, None, 104, 0) == -1
     assert ab.get_lib().msm_g1_multi(hb.ctypes.data, hb.ctypes.data, n, hs.ctypes.data, 104, ndev + 1) == -3
+
+
+@pytest.mark.parametrize("mode", ["chunk", "cta", "cta3"])
+def test_reduction_level_variants_agree(c_oracle, mode, monkeypatch):
+    """bucket reduction with serial chunk levels (a thread per chunk) and with CTA-cooperative levels (a CTA per chunk:
+    suffix scan + tree; cta3 = chunks of 8, several levels joining plain sums): plain MSM against the C oracle at 2^15,
+    resident-SRS MSM and a batch of commitments against the plain path"""
+    import torch
+    monkeypatch.setenv("ALEO_B200_MSM_REDUCE", mode)
+    n = 1 << 15
+    s0, d = o.base_dlogs(n, 6100)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, 6200)
+    hb, hs = bases.cpu().numpy(), sc.cpu().numpy()
+    want = C.create_string_buffer(144)
+    c_oracle.oracle_msm_g1(want, hb.ctypes.data, n, hs.ctypes.data, 104, os.cpu_count() or 1)
+    assert ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes() == want.raw
+    srs = ab.ResidentSRS.from_device(bases, n, 104)
+    try:
+        assert srs.msm_dev(sc, n).cpu().numpy().tobytes() == want.raw
+        scm = ab.gen_scalars_dev(n, 6200, 0, True)             # the same values in Montgomery form
+        one = ab.KZG10.commit_dev(srs, scm, n)
+        batch = ab.KZG10.commit_batch_dev(srs, [scm, scm[: n // 2].contiguous(), scm])
+        assert torch.equal(batch[0], one) and torch.equal(batch[2], one)
+        assert torch.equal(batch[1], ab.KZG10.commit_dev(srs, scm[: n // 2].contiguous(), n // 2))
+    finally:
+        srs.close()
