@@ -364,12 +364,15 @@ DEV u32 block_inclusive_scan(u32 v, u32* sh /* >= blockDim.x */) {
   return sh[t];
 }
 
-KERNEL void scan_block_sums_kernel(const u32* in, u32 n, u32* block_sums) {
+// shift != 0: the scanned value is ceil(in / 2^shift) -- the bucket sizes after `shift` pair-tree levels (msm_ba.cuh)
+DEV u32 scan_value(u32 v, u32 shift) { return (v + ((1u << shift) - 1u)) >> shift; }
+
+KERNEL void scan_block_sums_kernel(const u32* in, u32 n, u32* block_sums, u32 shift) {
   SHARED u32 sh[SCAN_TPB];
   const u32 base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   u32 sum = 0;
   for (u32 k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < n) sum += in[base + k];
+    if (base + k < n) sum += scan_value(in[base + k], shift);
   const u32 incl = block_inclusive_scan(sum, sh);
   if (threadIdx.x == blockDim.x - 1) block_sums[blockIdx.x] = incl;
 }
@@ -393,13 +396,14 @@ KERNEL void scan_sums_kernel(u32* block_sums, u32 nblocks, u32* total) {
   if (threadIdx.x == 0) *total = running;
 }
 
-KERNEL void scan_apply_kernel(const u32* in, u32 n, const u32* block_sums, u32* out, u32* out_copy) {
+// out = exclusive offsets; out_copy (optional) = the same (a cursor for the scatter) or, with copy_end, offset + value
+KERNEL void scan_apply_kernel(const u32* in, u32 n, const u32* block_sums, u32* out, u32* out_copy, u32 shift, u32 copy_end) {
   SHARED u32 sh[SCAN_TPB];
   const u32 base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   u32 v[SCAN_ITEMS];
   u32 sum = 0;
   for (u32 k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = (base + k < n) ? in[base + k] : 0u;
+    v[k] = (base + k < n) ? scan_value(in[base + k], shift) : 0u;
     sum += v[k];
   }
   const u32 incl = block_inclusive_scan(sum, sh);
@@ -407,7 +411,7 @@ KERNEL void scan_apply_kernel(const u32* in, u32 n, const u32* block_sums, u32* 
   for (u32 k = 0; k < SCAN_ITEMS; k++) {
     if (base + k < n) {
       out[base + k] = run;
-      if (out_copy) out_copy[base + k] = run;
+      if (out_copy) out_copy[base + k] = copy_end ? run + v[k] : run;
     }
     run += v[k];
   }
@@ -476,7 +480,9 @@ DEV void prefetch_base(const unsigned char* bases, size_t stride, u32 idx) {
 #endif
 }
 
-template <bool CALL, bool PREFETCH = false>
+// DIRECT: the entries ARE the points -- position pos of the (dense, bucket-ordered) packed affine array `bases` that the
+// batch-affine levels left (msm_ba.cuh); `sorted` is not read and there is no sign.
+template <bool CALL, bool PREFETCH = false, bool DIRECT = false>
 KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
@@ -518,12 +524,12 @@ KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bas
         else
           acc = xyzz_identity();
       }
-      const u32 e = sorted[pos];
+      const u32 e = DIRECT ? pos : sorted[pos];
       pos++;
       G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
-      if (PREFETCH && pos < end) prefetch_base(bases, stride, sorted[pos] & 0x7fffffffu);  // the next gather, while this addition runs
+      if (PREFETCH && !DIRECT && pos < end) prefetch_base(bases, stride, sorted[pos] & 0x7fffffffu);  // the next gather, while this addition runs
       if (p.inf) continue;
-      if (e >> 31) p.y = fp_neg(p.y);
+      if (!DIRECT && (e >> 31)) p.y = fp_neg(p.y);
       px = p.x;
       py = p.y;
       have = true;

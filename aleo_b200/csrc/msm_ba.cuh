@@ -1,0 +1,257 @@
+// msm_ba.cuh -- batch-affine pair-tree levels in front of the XYZZ bucket accumulation (msm.cuh step 5).
+//
+// The sorted entry list holds, bucket by bucket, the points a bucket has to sum.  Summing them one after the other
+// into an XYZZ accumulator costs 8 products + 2 squares per point (madd-2008-s).  An AFFINE addition costs
+// 2 products + 1 square + one inversion, and inversions can be shared (Montgomery's trick: 3 products per
+// member and ONE inversion per batch) -- but only between INDEPENDENT additions.  A pair-tree makes them so:
+//
+//   level l holds, per bucket, ceil(m / 2^l) affine points (level 0 = the gathered bases, sign applied);
+//   level l + 1 is built by adding the points of every bucket two by two: positions (s + 2i, s + 2i + 1) of a bucket
+//   whose level-l points start at s give output slot s' + i; an odd last point is copied.
+//
+// Every addition of a level is independent of every other one, so a thread takes a contiguous run of input positions
+// (all threads the same length, whatever the bucket sizes are: the flat scheme of the XYZZ kernel), and shares one
+// inversion over ALL additions of its run (up to a few hundred):
+//   pass 1 (forward)   walks the run, copies single points, and for every pair stores the running product of the
+//                      denominators BEFORE it (48 B) and a record {input position, output slot | doubling flag} (8 B)
+//                      in scratch memory (planes of 16-byte words, coalesced across the warp);
+//   inversion          one binary-GCD inversion per thread, all lanes of a warp busy;
+//   pass 2 (backward)  unwinds: 1 / den_i = inv * prefix_{i-1}, inv *= den_i; lambda = num_i / den_i;
+//                      x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1; stores the sum.
+// 5 products + 1 square per addition (1590 IMAD.WIDE against 2628) plus 1 / k of an inversion that runs on the ALU
+// pipe.  Exceptional pairs never enter the batch: a point at infinity (packed (0, 0)) or P + (-P) is resolved in
+// pass 1; P + P joins the batch with den = 2 y, num = 3 x^2.  Level sizes need no per-level bookkeeping beyond an
+// exclusive scan of ceil(count / 2^l) (scan_value in msm.cuh).  After L levels the buckets' remaining
+// ceil(m / 2^L) points are summed by the XYZZ kernel reading the level array directly (accumulate_kernel<.., DIRECT>).
+// The result is the same group element as before, so the normalised output is bit-identical.
+//
+// Stands in for the same reference function as msm.cuh (snarkvm-algorithms 0.14.5 src/msm/variable_base/batched.rs
+// uses batched affine additions on the CPU for the same reason; this is not a port of it -- SURVEY.md 8a row 7).
+#pragma once
+#include "g1.cuh"
+
+namespace msm {
+namespace ba {
+
+constexpr u32 TPB = 128;
+
+struct LevelArgs {
+  // level 0 input: bases gathered through the sorted entry list (index | sign << 31)
+  const unsigned char* bases;
+  u32 stride;
+  const u32* sorted;
+  // level >= 1 input: packed affine points (96 B, infinity = (0, 0))
+  const unsigned char* in;
+  const u32* start_in;   // per bucket: first input position
+  const u32* cnt0;       // per bucket: level-0 size; the size at level l is ceil(cnt0 / 2^l)
+  u32 level;             // l
+  const u32* start_out;  // per bucket: first output slot = exclusive scan of ceil(cnt0 / 2^(l + 1))
+  unsigned char* out;    // packed affine points of level l + 1
+  u32 nb;                // buckets
+  u32 nthreads;          // runs the input positions are cut into (a multiple of TPB)
+  uint4* pre;            // scratch: prefix products, plane (op * 3 + j) * nthreads + thread
+  uint2* rec;            // scratch: records, op * nthreads + thread
+};
+
+DEV Fq fq_load16(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint4 v = q[i];
+    r.l[4 * i] = v.x;
+    r.l[4 * i + 1] = v.y;
+    r.l[4 * i + 2] = v.z;
+    r.l[4 * i + 3] = v.w;
+  }
+  return r;
+}
+DEV void fq_store16(void* p, const Fq& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; i++) q[i] = make_uint4(v.l[4 * i], v.l[4 * i + 1], v.l[4 * i + 2], v.l[4 * i + 3]);
+}
+
+// One input point of a level.  x first (pass 1 needs nothing else for an ordinary pair); y on demand.
+// Infinity: level >= 1 and packed bases: (0, 0); Rust-layout bases (stride 104): the flag byte, read when x = 0
+// (snarkVM's Affine::zero() is (0, 1, true): an infinity flag never comes with x != 0).
+template <bool LEVEL0>
+struct PointRef {
+  const unsigned char* p;
+  u32 neg;
+  bool rust;
+  DEV PointRef(const LevelArgs& a, u32 pos) {
+    if (LEVEL0) {
+      const u32 e = a.sorted[pos];
+      p = a.bases + (size_t)(e & 0x7fffffffu) * a.stride;
+      neg = e >> 31;
+      rust = a.stride >= 97;
+    } else {
+      p = a.in + (size_t)pos * 96;
+      neg = 0;
+      rust = false;
+    }
+  }
+  DEV Fq x() const { return LEVEL0 ? fq_load8(p) : fq_load16(p); }
+  DEV Fq y() const {
+    Fq v = LEVEL0 ? fq_load8(p + 48) : fq_load16(p + 48);
+    if (LEVEL0 && neg) v = fp_neg(v);
+    return v;
+  }
+  // x is this point's x coordinate (already loaded)
+  DEV bool is_infinity(const Fq& xv) const {
+    if (!fp_is_zero(xv)) return false;
+    if (LEVEL0 && rust) return p[96] != 0;
+    return fp_is_zero(LEVEL0 ? fq_load8(p + 48) : fq_load16(p + 48));
+  }
+};
+
+DEV void store_point(unsigned char* out, u32 slot, const Fq& x, const Fq& y) {
+  unsigned char* q = out + (size_t)slot * 96;
+  fq_store16(q, x);
+  fq_store16(q + 48, y);
+}
+DEV void store_infinity(unsigned char* out, u32 slot) {
+  const Fq z = fp_zero<FqParams>();
+  store_point(out, slot, z, z);
+}
+
+DEV u32 level_count(const u32* cnt0, u32 g, u32 level) { return (cnt0[g] + ((1u << level) - 1u)) >> level; }
+
+template <bool LEVEL0>
+KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nthreads) return;
+  const u32 first = a.start_in[0];
+  const u32 total = a.start_in[a.nb - 1] + level_count(a.cnt0, a.nb - 1, a.level) - first;
+  if (total == 0) return;
+  const u32 L = (total + a.nthreads - 1) / a.nthreads;
+  if ((u64)t * L >= total) return;
+  const u32 begin = first + t * L;
+  const u32 end = ((u64)t * L + L < total) ? begin + L : first + total;
+  // bucket that holds position `begin`
+  u32 g;
+  {
+    u32 lo = 0, hi = a.nb - 1;
+    while (lo < hi) {
+      const u32 mid = (lo + hi + 1) >> 1;
+      if (a.start_in[mid] <= begin)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    g = lo;
+  }
+  u32 s = a.start_in[g], e = s + level_count(a.cnt0, g, a.level);
+  u32 so = a.start_out[g];
+  // ---- pass 1: singles and exceptional pairs are resolved here; ordinary pairs join the batch
+  Fq prefix = fp_one<FqParams>();
+  u32 nops = 0;
+  u32 pos = begin;
+  for (;;) {
+    bool have = false;
+    Fq den;
+    u32 r_pos = 0, r_out = 0;
+    while (pos < end) {
+      while (pos >= e) {  // next non-empty bucket (pos < first + total bounds the walk)
+        g++;
+        s = a.start_in[g];
+        e = s + level_count(a.cnt0, g, a.level);
+        so = a.start_out[g];
+      }
+      const u32 off = pos - s;
+      if (off & 1u) {  // second point of a pair that belongs to the run before this one
+        pos++;
+        continue;
+      }
+      const u32 slot = so + (off >> 1);
+      const PointRef<LEVEL0> p1(a, pos);
+      const Fq x1 = p1.x();
+      if (pos + 1 >= e) {  // odd last point of its bucket: copied
+        if (p1.is_infinity(x1))
+          store_infinity(a.out, slot);
+        else
+          store_point(a.out, slot, x1, p1.y());
+        pos++;
+        continue;
+      }
+      const PointRef<LEVEL0> p2(a, pos + 1);
+      const Fq x2 = p2.x();
+      pos += 2;
+      const bool inf1 = p1.is_infinity(x1), inf2 = p2.is_infinity(x2);
+      if (inf1 || inf2) {
+        if (inf1 && inf2)
+          store_infinity(a.out, slot);
+        else if (inf1)
+          store_point(a.out, slot, x2, p2.y());
+        else
+          store_point(a.out, slot, x1, p1.y());
+        continue;
+      }
+      den = fp_sub(x2, x1);
+      u32 dbl = 0;
+      if (fp_is_zero(den)) {  // same x: P + P or P + (-P)
+        const Fq y1 = p1.y();
+        if (!fp_eq(y1, p2.y()) || fp_is_zero(y1)) {
+          store_infinity(a.out, slot);
+          continue;
+        }
+        den = fp_dbl(y1);
+        dbl = 1;
+      }
+      r_pos = pos - 2;
+      r_out = slot | (dbl << 31);
+      have = true;
+      break;
+    }
+    if (!have) break;
+    {
+      const size_t o = (size_t)nops * 3 * a.nthreads + t;
+      a.pre[o] = make_uint4(prefix.l[0], prefix.l[1], prefix.l[2], prefix.l[3]);
+      a.pre[o + a.nthreads] = make_uint4(prefix.l[4], prefix.l[5], prefix.l[6], prefix.l[7]);
+      a.pre[o + 2 * (size_t)a.nthreads] = make_uint4(prefix.l[8], prefix.l[9], prefix.l[10], prefix.l[11]);
+      a.rec[(size_t)nops * a.nthreads + t] = make_uint2(r_pos, r_out);
+    }
+    prefix = fq_mul_v(prefix, den);
+    nops++;
+  }
+  if (nops == 0) return;
+  // ---- one inversion for the whole run
+  Fq inv = fq_inv_ni(prefix);
+  // ---- pass 2: unwind
+  for (u32 i = nops; i-- > 0;) {
+    const uint2 r = a.rec[(size_t)i * a.nthreads + t];
+    const size_t o = (size_t)i * 3 * a.nthreads + t;
+    Fq pre;
+    {
+      const uint4 v0 = a.pre[o], v1 = a.pre[o + a.nthreads], v2 = a.pre[o + 2 * (size_t)a.nthreads];
+      pre.l[0] = v0.x; pre.l[1] = v0.y; pre.l[2] = v0.z; pre.l[3] = v0.w;
+      pre.l[4] = v1.x; pre.l[5] = v1.y; pre.l[6] = v1.z; pre.l[7] = v1.w;
+      pre.l[8] = v2.x; pre.l[9] = v2.y; pre.l[10] = v2.z; pre.l[11] = v2.w;
+    }
+    const u32 dbl = r.y >> 31, slot = r.y & 0x7fffffffu;
+    const PointRef<LEVEL0> p1(a, r.x);
+    const Fq x1 = p1.x(), y1 = p1.y();
+    Fq x2, num, den;
+    if (dbl) {
+      x2 = x1;
+      den = fp_dbl(y1);
+      const Fq xx = fq_sqr_v(x1);
+      num = fp_add(fp_dbl(xx), xx);
+    } else {
+      const PointRef<LEVEL0> p2(a, r.x + 1);
+      x2 = p2.x();
+      den = fp_sub(x2, x1);
+      num = fp_sub(p2.y(), y1);
+    }
+    const Fq inv_den = fq_mul_v(inv, pre);
+    inv = fq_mul_v(inv, den);
+    const Fq lam = fq_mul_v(num, inv_den);
+    const Fq x3 = fp_sub(fp_sub(fq_sqr_v(lam), x1), x2);
+    const Fq y3 = fp_sub(fq_mul_v(lam, fp_sub(x1, x3)), y1);
+    store_point(a.out, slot, x3, y3);
+  }
+}
+
+}  // namespace ba
+}  // namespace msm

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <vector>
 #include "msm.cuh"
+#include "msm_ba.cuh"
 
 namespace msm {
 
@@ -75,8 +76,7 @@ static inline u32 choose_window_srs(size_t n) {
 // (SM count x 3 CTAs x 128 threads; 148 SMs on B200) -- measured best on B200 at n = 2^24: 4 waves 96.1 ms, 16 waves 93.4 ms.  Below
 // that, runs of 64 entries (every run boundary cuts a bucket whose pieces cost two more additions on the latency
 // path: 2^20 runs 3 % faster with 64 than with 32), but never fewer than 4 waves while runs of 32 can fill them.
-static inline u32 lanes_for(size_t n_chunk, u32 W) {
-  const size_t entries = (size_t)n_chunk * W;
+static inline u32 lanes_for_entries(size_t entries) {
   static const long waves_env = []() { const char* e = getenv("ALEO_B200_MSM_WAVES"); return e ? atol(e) : 0L; }();
   const size_t wave = (size_t)dev_props().sms * 384;
   const size_t full = wave * (waves_env > 0 ? (size_t)waves_env : 16);
@@ -88,6 +88,56 @@ static inline u32 lanes_for(size_t n_chunk, u32 W) {
   if (lanes > full) lanes = full;
   if (lanes < 128) lanes = 128;
   return (u32)((lanes + 127) / 128 * 128);
+}
+static inline u32 lanes_for(size_t n_chunk, u32 W) { return lanes_for_entries((size_t)n_chunk * W); }
+
+// ---- batch-affine pair-tree levels (msm_ba.cuh) in front of the XYZZ accumulation ------------------------------------
+// How many levels: after L levels a bucket that received m entries holds ceil(m / 2^L) points; the levels stop once the
+// average bucket is down to about two points (the XYZZ kernel then does what is left, and it is the stage that copes
+// with buckets cut by run boundaries).  Off below 2^20 entries per bucket set group: the levels cost launches and a
+// per-thread inversion latency that proof-sized MSMs cannot amortise.  ALEO_B200_MSM_BA = 0 | levels overrides.
+static inline u32 ba_levels_for(size_t entries, size_t buckets) {
+  const char* env = getenv("ALEO_B200_MSM_BA");  // read per call: tests and sweeps switch it
+  if (env) {
+    const long v = atol(env);
+    return v < 0 ? 0u : (v > 12 ? 12u : (u32)v);
+  }
+  if (entries < ((size_t)1 << 22)) return 0;
+  const size_t load = entries / (buckets ? buckets : 1);  // average entries per bucket (uniform scalars)
+  u32 l = 0;
+  while (((size_t)4 << l) <= load) l++;  // load 32 -> 4 levels (two points left per bucket on average)
+  return l;
+}
+// additions one thread shares an inversion over, at most (ALEO_B200_MSM_BA_K)
+static inline u32 ba_kmax() {
+  const char* env = getenv("ALEO_B200_MSM_BA_K");
+  const long v = env ? atol(env) : 0L;
+  return (v >= 1 && v <= 4096) ? (u32)v : 256u;
+}
+// workspace the levels may take, in bytes (ALEO_B200_MSM_BA_MB): about 100 bytes per sorted entry of a group
+static inline size_t ba_budget_bytes() {
+  const char* env = getenv("ALEO_B200_MSM_BA_MB");
+  const long v = env ? atol(env) : 0L;
+  return (v > 0 ? (size_t)v : (size_t)32768) << 20;
+}
+struct BaLevelPlan {
+  u32 k, nthreads;
+};
+// level l of a group with at most `entries` sorted entries over `nb` buckets: its input has at most
+// (entries >> l) + nb points (sum of ceil(m / 2^l)); a thread takes 2 k positions = at most k additions
+static inline BaLevelPlan ba_level_plan(size_t entries, u32 nb, u32 l) {
+  const size_t slots = (entries >> l) + (l ? nb : 0);
+  const size_t target = (size_t)dev_props().sms * 384 * 4;  // four waves of 3 CTAs of 128 per SM
+  size_t k = slots / 2 / target;
+  const u32 kmax = ba_kmax();
+  if (k > kmax) k = kmax;
+  if (k < 16) k = 16 < kmax ? 16 : kmax;
+  BaLevelPlan pl;
+  pl.k = (u32)k;
+  const size_t th = (slots + 2 * k - 1) / (2 * k);
+  pl.nthreads = (u32)((th + ba::TPB - 1) / ba::TPB * ba::TPB);
+  if (pl.nthreads == 0) pl.nthreads = ba::TPB;
+  return pl;
 }
 
 // n: points of the whole MSM (decides the window); chunks: how many point ranges it arrives in
@@ -122,11 +172,11 @@ struct Carver {
 };
 
 static inline cudaError_t exclusive_scan(const u32* in, u32 n, u32* block_sums, u32* out, u32* out_copy, u32* total,
-                                         cudaStream_t s, int& launches) {
+                                         cudaStream_t s, int& launches, u32 shift = 0, u32 copy_end = 0) {
   const u32 nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  LAUNCH(scan_block_sums_kernel, dim3(nblocks), dim3(SCAN_TPB), 0, s, in, n, block_sums);
+  LAUNCH(scan_block_sums_kernel, dim3(nblocks), dim3(SCAN_TPB), 0, s, in, n, block_sums, shift);
   LAUNCH(scan_sums_kernel, dim3(1), dim3(SCAN_TPB), 0, s, block_sums, nblocks, total);
-  LAUNCH(scan_apply_kernel, dim3(nblocks), dim3(SCAN_TPB), 0, s, in, n, (const u32*)block_sums, out, out_copy);
+  LAUNCH(scan_apply_kernel, dim3(nblocks), dim3(SCAN_TPB), 0, s, in, n, (const u32*)block_sums, out, out_copy, shift, copy_end);
   launches += 3;
   return cudaGetLastError();
 }
@@ -191,6 +241,9 @@ struct Session {
   size_t o_counts = 0, o_starts = 0, o_ends = 0, o_piece_bucket = 0, o_bsums = 0, o_meta = 0, o_sorted = 0, o_small = 0,
          o_large = 0, o_buckets = 0, o_pieces = 0, o_D = 0, bytes = 0;
   std::vector<size_t> o_R, o_P;
+  // batch-affine levels: L levels per group of `ba_wpg` bucket sets (the workspace bounds a group's entries)
+  u32 ba_L = 0, ba_wpg = 0;
+  size_t o_baA = 0, o_baB = 0, o_ba_pre = 0, o_ba_rec = 0, o_ba_s0 = 0, o_ba_s1 = 0, o_ba_e = 0, o_meta2 = 0;
   unsigned char* ws = nullptr;
   bool dry = false;
   int launches = 0;
@@ -304,6 +357,40 @@ struct Session {
         if (sb > scan_blocks + 1) o_bsums = cv.take(sb * 4);  // the scan of cnt needs more block sums than the bucket scan
       }
     }
+    {
+      // a group = whole bucket sets whose entries fit the budget; the shared set of a resident SRS and the member sets
+      // of a batch (whose sizes the host does not know) form one group
+      const size_t total_entries = (size_t)max_chunk * prm.W;
+      const size_t cap_entries = ba_budget_bytes() / 100;
+      ba_L = ba_levels_for(total_entries, NB);
+      size_t ge = total_entries;
+      if (srs) {
+        ba_wpg = nwin;
+        if (ge > cap_entries) ba_L = 0;
+      } else {
+        const size_t fit = cap_entries / (max_chunk ? max_chunk : 1);
+        ba_wpg = fit < nwin ? (u32)fit : nwin;
+        if (ba_wpg == 0) ba_L = 0;
+        ge = (size_t)max_chunk * ba_wpg;
+      }
+      if (ba_L) {
+        const u32 gnb = ba_wpg * prm.B;
+        size_t scratch_ops = 0;
+        for (u32 l = 0; l < ba_L; l++) {
+          const BaLevelPlan pl = ba_level_plan(ge, gnb, l);
+          const size_t ops = (size_t)pl.nthreads * pl.k;
+          if (ops > scratch_ops) scratch_ops = ops;
+        }
+        o_baA = cv.take(((ge >> 1) + gnb + 1) * 96);
+        o_baB = ba_L > 1 ? cv.take(((ge >> 2) + gnb + 1) * 96) : 0;
+        o_ba_pre = cv.take(scratch_ops * 48);
+        o_ba_rec = cv.take(scratch_ops * 8);
+        o_ba_s0 = cv.take((size_t)gnb * 4);
+        o_ba_s1 = cv.take((size_t)gnb * 4);
+        o_ba_e = cv.take((size_t)gnb * 4);
+        o_meta2 = cv.take(64);
+      }
+    }
     bytes = cv.off;
     if (dry) return cudaSuccess;
     MSM_CK(aleo::pool_malloc_async((void**)&ws, bytes, s));
@@ -329,7 +416,12 @@ struct Session {
     }
     const u32 into = chunks_done > 0 ? 1u : 0u;  // later chunks start every bucket from its stored sum
     chunks_done++;
-    launches += part ? 10 : 9;
+    {
+      // sort (count, 3 scan kernels, scatter; the partitioned sort has one more) + per accumulation: plan, XYZZ kernel,
+      // two combine kernels; with batch-affine levels every group of bucket sets adds (3 scan kernels + 1 level) per level
+      const u32 groups = ba_L ? (nwin + ba_wpg - 1) / ba_wpg : 1;
+      launches += (part ? 6 : 5) + (int)groups * (4 + 4 * (int)ba_L);
+    }
     if (dry) return cudaSuccess;
     u32* counts = at<u32>(o_counts);
     u32* starts = at<u32>(o_starts);
@@ -412,42 +504,89 @@ struct Session {
     }
     }
     st.mark("scatter", s);
-    LAUNCH_NOSYNC(plan_pieces_kernel, dim3((NB + 255) / 256), dim3(256), 0, s, (const u32*)starts, (const u32*)ends, NB, p.nlanes,
-                  small_list, large_list, cap_small, cap_large, meta);
-    st.mark("plan", s);
     st.report(s);
     if (phase_ev) cudaEventRecord(phase_ev[1], s);
     // ALEO_B200_MSM_ACC=i: inlined field products instead of the two out-of-line functions (A/B switch behind the
-    // I-cache finding of DESIGN.md: 85.0 against 72.9 ms at 2^24)
+    // I-cache finding of DESIGN.md: 85.0 against 72.9 ms at 2^24); n: no prefetch of the next base (73.00 -> 72.71 ms)
     static const bool acc_inline = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return e && e[0] == 'i'; }();
-#define ACC_LAUNCH(CALLV)                                                                                              \
-  LAUNCH_NOSYNC((accumulate_kernel<CALLV>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted, \
-                (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into)
-    // next base prefetched into L1 while the current addition runs: 73.00 -> 72.71 ms at 2^24 (n = no prefetch)
     static const bool acc_prefetch = []() { const char* e = getenv("ALEO_B200_MSM_ACC"); return !(e && e[0] == 'n'); }();
-    if (acc_inline)
-      ACC_LAUNCH(false);
-    else if (acc_prefetch)
-      LAUNCH_NOSYNC((accumulate_kernel<true, true>), dim3(p.nlanes / 128), dim3(128), 0, s, bases, stride, (const u32*)sorted,
-                    (const u32*)starts, (const u32*)ends, NB, p.nlanes, (const u32*)meta, buckets, pieces, piece_bucket, into);
-    else
-      ACC_LAUNCH(true);
-#undef ACC_LAUNCH
-    if (phase_ev) cudaEventRecord(phase_ev[2], s);
     TailTrace tr;
-    tr.on = getenv("ALEO_B200_MSM_TRACE") != nullptr;
+    tr.on = st.on;
     tr.mark("start", s);
-    LAUNCH_NOSYNC(combine_small_kernel, dim3((p.nlanes + 1 + 127) / 128), dim3(128), 0, s, (const u32*)small_list,
-                  (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces,
-                  (const u32*)piece_bucket, buckets);
-    tr.mark("combine small", s);
-    {
-      const u32 cl = p.nlanes / SMALL_SPLIT_MAX + 1;
+    // plan + XYZZ accumulation + combine over one bucket range: `pts` / `ent` are the bases and the sorted entry list,
+    // or (direct) the dense level array the batch-affine levels left and no entry list
+    auto flat = [&](const unsigned char* pts, u32 pstride, const u32* ent, const u32* st_, const u32* en_, u32 nb, u32 lanes,
+                    u32* mt, G1Xyzz* bk, bool direct) -> cudaError_t {
+      LAUNCH_NOSYNC(plan_pieces_kernel, dim3((nb + 255) / 256), dim3(256), 0, s, st_, en_, nb, lanes, small_list, large_list, cap_small,
+                    cap_large, mt);
+#define ACC_LAUNCH(...)                                                                                                   \
+  LAUNCH_NOSYNC((accumulate_kernel<__VA_ARGS__>), dim3(lanes / 128), dim3(128), 0, s, pts, pstride, ent, st_, en_, nb, lanes, \
+                (const u32*)mt, bk, pieces, piece_bucket, into)
+      if (direct)
+        ACC_LAUNCH(true, false, true);
+      else if (acc_inline)
+        ACC_LAUNCH(false);
+      else if (acc_prefetch)
+        ACC_LAUNCH(true, true);
+      else
+        ACC_LAUNCH(true);
+#undef ACC_LAUNCH
+      tr.mark(direct ? "xyzz (direct)" : "accumulate", s);
+      LAUNCH_NOSYNC(combine_small_kernel, dim3((lanes + 1 + 127) / 128), dim3(128), 0, s, (const u32*)small_list, st_, en_, lanes,
+                    (const u32*)mt, (const G1Xyzz*)pieces, (const u32*)piece_bucket, bk);
+      tr.mark("combine small", s);
+      const u32 cl = lanes / SMALL_SPLIT_MAX + 1;
       const u32 g = cl < dev_props().sms * 4 ? cl : dev_props().sms * 4;  // 4 CTAs per SM; the kernel strides over the list
-      LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), 0, s, (const u32*)large_list,
-             (const u32*)starts, (const u32*)ends, p.nlanes, (const u32*)meta, (const G1Xyzz*)pieces, (const u32*)piece_bucket,
-             buckets);
+      LAUNCH(combine_large_kernel, dim3(g), dim3(COMBINE_TPB), 0, s, (const u32*)large_list, st_, en_, lanes, (const u32*)mt,
+             (const G1Xyzz*)pieces, (const u32*)piece_bucket, bk);
       tr.mark("combine large", s);
+      return cudaGetLastError();
+    };
+    if (!ba_L) {
+      MSM_CK(flat(bases, stride, sorted, starts, ends, NB, p.nlanes, meta, buckets, false));
+      if (phase_ev) cudaEventRecord(phase_ev[2], s);
+    } else {
+      u32* meta2 = at<u32>(o_meta2);
+      u32* sa[2] = {at<u32>(o_ba_s0), at<u32>(o_ba_s1)};
+      u32* e_out = at<u32>(o_ba_e);
+      unsigned char* lvbuf[2] = {at<unsigned char>(o_baA), o_baB ? at<unsigned char>(o_baB) : nullptr};
+      for (u32 w0 = 0; w0 < nwin; w0 += ba_wpg) {
+        const u32 nw = (w0 + ba_wpg <= nwin) ? ba_wpg : nwin - w0;
+        const u32 g0 = w0 * p.B, nb = nw * p.B;
+        const size_t ge = srs ? (size_t)n * p.W : (size_t)n * nw;  // entries of this group, at most
+        MSM_CK(cudaMemsetAsync(meta2, 0, 64, s));
+        ba::LevelArgs la;
+        la.bases = bases;
+        la.stride = stride;
+        la.sorted = sorted;
+        la.in = nullptr;
+        la.start_in = starts + g0;
+        la.cnt0 = counts + g0;
+        la.nb = nb;
+        la.pre = at<uint4>(o_ba_pre);
+        la.rec = at<uint2>(o_ba_rec);
+        for (u32 l = 0; l < ba_L; l++) {
+          const bool last = (l + 1 == ba_L);
+          int sl = 0;
+          MSM_CK(exclusive_scan(counts + g0, nb, at<u32>(o_bsums), sa[l & 1], last ? e_out : nullptr, meta2 + 0, s, sl, l + 1,
+                                last ? 1u : 0u));
+          const BaLevelPlan pl = ba_level_plan(ge, nb, l);
+          la.level = l;
+          la.start_out = sa[l & 1];
+          la.out = lvbuf[l & 1];
+          la.nthreads = pl.nthreads;
+          if (l == 0)
+            LAUNCH_NOSYNC(ba::level_kernel<true>, dim3(pl.nthreads / ba::TPB), dim3(ba::TPB), 0, s, la);
+          else
+            LAUNCH_NOSYNC(ba::level_kernel<false>, dim3(pl.nthreads / ba::TPB), dim3(ba::TPB), 0, s, la);
+          tr.mark("affine level", s);
+          la.in = la.out;
+          la.start_in = la.start_out;
+        }
+        const u32 lanes = lanes_for_entries((ge >> ba_L) + nb);
+        MSM_CK(flat(lvbuf[(ba_L - 1) & 1], 96, nullptr, sa[(ba_L - 1) & 1], e_out, nb, lanes, meta2, buckets + g0, true));
+      }
+      if (phase_ev) cudaEventRecord(phase_ev[2], s);
     }
     tr.report(s);
     return cudaGetLastError();

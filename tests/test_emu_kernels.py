@@ -668,3 +668,50 @@ def test_emu_kzg_open_combinations(emu_lib):
         want = o.g1_compress(o.msm_pippenger(B[:len(q) - 1], q[:len(q) - 1]) if len(q) > 1 else None)
         assert out.raw[48 * k:48 * k + 48] == want, k
     emu_lib.check(emu_lib.srs_destroy(h), "destroy")
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 6])
+@pytest.mark.parametrize("c", [4, 7])
+def test_emu_msm_batch_affine_levels(emu_lib, c, levels, monkeypatch):
+    """batch-affine pair-tree levels (msm_ba.cuh) forced in front of the XYZZ accumulation: small windows make crowded
+    buckets (c = 4: ~60 entries per bucket, c = 7: ~8), so pairs, odd leftovers, buckets cut by run boundaries and the
+    direct XYZZ stage are all hit; K = 3 makes many short batches.  Edge cases: P + P, P + (-P), infinity bases."""
+    monkeypatch.setenv("ALEO_B200_MSM_C", str(c))
+    monkeypatch.setenv("ALEO_B200_MSM_BA", str(levels))
+    monkeypatch.setenv("ALEO_B200_MSM_BA_K", "3")
+    n = 480
+    B = o.synthetic_bases(n, 51)
+    s = o.random_fr_vec(n, 52)
+    s[0], s[1], s[2] = o.R_MOD - 1, 1, 0
+
+    def ok(bases, scalars, stride=104):
+        return _msm(emu_lib, bases, scalars, stride) == o.g1_projective_to_bytes(o.msm_pippenger(bases, scalars))
+
+    assert ok(B, s, 104) and ok(B, s, 96)
+    assert ok([B[0]] * n, s)                                                     # every pair is a doubling
+    assert ok([B[i // 2] if i % 2 == 0 else o.g1_neg(B[i // 2]) for i in range(n)], [s[i // 2] for i in range(n)])  # cancellations
+    Binf = [None if i % 5 == 0 else B[i] for i in range(n)]
+    assert ok(Binf, s, 104) and ok(Binf, s, 96) and ok([None] * n, s)
+    assert ok(B, [1] * n) and ok(B, [1 if i % 4 else 0 for i in range(n)])       # one huge bucket: deep tree, then cut pieces
+    assert ok(B[:1], s[:1]) and ok(B[:2], [5, 5])
+
+
+def test_emu_msm_batch_affine_groups_and_ranges(emu_lib, monkeypatch):
+    """a workspace budget of 1 MB splits the bucket sets into several groups; three host point ranges accumulate into
+    the same buckets (`into`); the resident SRS (one shared set) and a batch of commitments go through the levels too"""
+    monkeypatch.setenv("ALEO_B200_MSM_C", "6")
+    monkeypatch.setenv("ALEO_B200_MSM_BA", "2")
+    monkeypatch.setenv("ALEO_B200_MSM_BA_K", "5")
+    n = 600
+    B = o.synthetic_bases(n, 61)
+    s = o.random_fr_vec(n, 62)
+    want = o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+    assert _msm(emu_lib, B, s, 104) == want
+    monkeypatch.setenv("ALEO_B200_MSM_BA_MB", "1")     # 1 MB / 100 B = 10 485 entries: 17 windows of 600 entries per group
+    assert _msm(emu_lib, B, s, 104) == want
+    monkeypatch.setenv("ALEO_B200_MSM_CHUNKS", "3")
+    bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
+    sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), n * 32)
+    out = C.create_string_buffer(144)
+    emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), 104), "msm_g1")
+    assert out.raw == want

@@ -228,3 +228,51 @@ def test_reduction_level_variants_agree(c_oracle, mode, monkeypatch):
         assert torch.equal(batch[1], ab.KZG10.commit_dev(srs, scm[: n // 2].contiguous(), n // 2))
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("levels,k", [(1, 3), (3, 7), (6, 256)])
+def test_batch_affine_levels_edge_cases(levels, k, monkeypatch):
+    """batch-affine pair-tree levels (csrc/msm_ba.cuh) forced on crowded buckets (c = 5: ~40 entries per bucket): ordinary
+    pairs, P + P, P + (-P), infinity bases, odd leftovers, one huge bucket -- against the big-integer oracle"""
+    monkeypatch.setenv("ALEO_B200_MSM_C", "5")
+    monkeypatch.setenv("ALEO_B200_MSM_BA", str(levels))
+    monkeypatch.setenv("ALEO_B200_MSM_BA_K", str(k))
+    n = 700
+    B = o.synthetic_bases(n, 71)
+    s = o.random_fr_vec(n, 72)
+    s[0], s[1], s[2] = o.R_MOD - 1, 1, 0
+
+    def check(bases, scalars, stride=104):
+        assert _host(bases, scalars, stride) == o.g1_projective_to_bytes(o.msm_pippenger(bases, scalars))
+
+    check(B, s, 104)
+    check(B, s, 96)
+    check([B[0]] * n, s)
+    check([B[0]] * n, [s[0]] * n)
+    check([B[i // 2] if i % 2 == 0 else o.g1_neg(B[i // 2]) for i in range(n)], [s[i // 2] for i in range(n)])
+    Binf = [None if i % 5 == 0 else B[i] for i in range(n)]
+    check(Binf, s, 104)
+    check(Binf, s, 96)
+    check([None] * n, s)
+    check(B, [1] * n)
+    check(B, [0 if i % 2 == 0 else (1 if i % 4 == 1 else s[i]) for i in range(n)])
+
+
+@pytest.mark.parametrize("levels", [0, 2, 5])
+@pytest.mark.parametrize("log_n", [16, 18])
+def test_batch_affine_levels_match_c_oracle(c_oracle, log_n, levels, monkeypatch):
+    """the same MSM with 0 / 2 / 5 batch-affine levels in front of the XYZZ kernel and a 1 MB..64 MB workspace budget
+    (several bucket-set groups): bytes equal to the C oracle's"""
+    monkeypatch.setenv("ALEO_B200_MSM_BA", str(levels))
+    monkeypatch.setenv("ALEO_B200_MSM_BA_MB", "64")
+    monkeypatch.setenv("ALEO_B200_MSM_C", "10")
+    n = 1 << log_n
+    s0, d = o.base_dlogs(n, 7000 + log_n)
+    bases = ab.gen_bases_dev(n, s0, d, 0, 104)
+    sc = ab.gen_scalars_dev(n, 1999 + log_n)
+    got = ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes()
+    hb, hs = bases.cpu().numpy(), sc.cpu().numpy()
+    out = C.create_string_buffer(144)
+    c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, 104, os.cpu_count() or 1)
+    assert got == out.raw
+    assert ab.VariableBase.msm(hb, hs, 104) == out.raw      # host ranges accumulate into the same buckets

@@ -45,6 +45,30 @@ if mode == "phases":
         best = min(res[1:], key=sum)
         print("log_n=%d c=%d sort/acc/tail ms: %.2f/%.2f/%.2f total %.2f same_result=%s" %
               (log_n, lib.msm_window_bits(n), best[0], best[1], best[2], sum(best), raw == ref), flush=True)
+elif mode == "ba":  # ba LOG_N  SPEC ...   SPEC = levels[:k[:c]] (batch-affine levels, additions per inversion, window bits); 0 = off
+    log_n = int(sys.argv[2])
+    n, bases, sc = setup(log_n)
+    out = torch.empty(144, dtype=torch.uint8, device="cuda")
+    ph = (C.c_float * 3)()
+    ref = None
+    for spec in sys.argv[3:]:
+        f = spec.split(":")
+        os.environ["ALEO_B200_MSM_BA"] = f[0]
+        os.environ.pop("ALEO_B200_MSM_BA_K", None)
+        os.environ.pop("ALEO_B200_MSM_C", None)
+        if len(f) > 1 and f[1]:
+            os.environ["ALEO_B200_MSM_BA_K"] = f[1]
+        if len(f) > 2 and f[2]:
+            os.environ["ALEO_B200_MSM_C"] = f[2]
+        res = []
+        for _ in range(4):
+            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), 104, stream(), ph), "p")
+            res.append((ph[0], ph[1], ph[2]))
+        raw = out.cpu().numpy().tobytes()
+        ref = ref or raw
+        best = min(res[1:], key=sum)
+        print("log_n=%d ba=%s c=%d sort/acc/tail ms: %.2f/%.2f/%.2f total %.2f -> %.1f Mpts/s same_result=%s" %
+              (log_n, spec, lib.msm_window_bits(n), best[0], best[1], best[2], sum(best), n / sum(best) / 1e3, raw == ref), flush=True)
 elif mode == "host":
     log_n = int(sys.argv[2])
     n, bases, sc = setup(log_n)
