@@ -13,7 +13,7 @@
 // (all threads the same length, whatever the bucket sizes are: the flat scheme of the XYZZ kernel), and shares one
 // inversion over ALL additions of its run (up to a few hundred):
 //   pass 1 (forward)   walks the run, copies single points, and for every pair stores the running product of the
-//                      denominators BEFORE it (48 B) and a record {input position, output slot | doubling flag} (8 B)
+//                      denominators BEFORE it (48 B) and a record {the two points, output slot | doubling flag} (16 B)
 //                      in scratch memory (planes of 16-byte words, coalesced across the warp);
 //   inversion          one binary-GCD inversion per thread, all lanes of a warp busy;
 //   pass 2 (backward)  unwinds: 1 / den_i = inv * prefix_{i-1}, inv *= den_i; lambda = num_i / den_i;
@@ -50,8 +50,21 @@ struct LevelArgs {
   u32 nb;                // buckets
   u32 nthreads;          // runs the input positions are cut into (a multiple of TPB)
   uint4* pre;            // scratch: prefix products, plane (op * 3 + j) * nthreads + thread
-  uint2* rec;            // scratch: records, op * nthreads + thread
+  uint4* rec;            // scratch: records {first point, second point, output slot | doubling << 31, -}, op * nthreads + thread;
+                         // a point is named by its sorted entry (index | sign << 31) at level 0, by its position above
+  u32 lookahead;         // prefetch distance in additions (0: none); bit 8: into L1 instead of L2
 };
+
+DEV void prefetch_line(const void* p, bool l1) {
+#ifndef ALEO_EMU
+  if (l1)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p; (void)l1;
+#endif
+}
 
 DEV Fq fq_load16(const void* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -80,17 +93,23 @@ struct PointRef {
   const unsigned char* p;
   u32 neg;
   bool rust;
-  DEV PointRef(const LevelArgs& a, u32 pos) {
+  // name: the sorted entry (level 0) or the position (above)
+  DEV PointRef(const LevelArgs& a, u32 name) {
     if (LEVEL0) {
-      const u32 e = a.sorted[pos];
-      p = a.bases + (size_t)(e & 0x7fffffffu) * a.stride;
-      neg = e >> 31;
+      p = a.bases + (size_t)(name & 0x7fffffffu) * a.stride;
+      neg = name >> 31;
       rust = a.stride >= 97;
     } else {
-      p = a.in + (size_t)pos * 96;
+      p = a.in + (size_t)name * 96;
       neg = 0;
       rust = false;
     }
+  }
+  DEV static u32 name_of(const LevelArgs& a, u32 pos) { return LEVEL0 ? a.sorted[pos] : pos; }
+  // pulls the point towards the SM ahead of its use; x_only: pass 1 reads nothing else of an ordinary pair
+  DEV void prefetch(bool x_only, bool l1) const {
+    prefetch_line(p, l1);
+    prefetch_line(p + (x_only ? 40 : 88), l1);
   }
   DEV Fq x() const { return LEVEL0 ? fq_load8(p) : fq_load16(p); }
   DEV Fq y() const {
@@ -121,17 +140,18 @@ DEV u32 level_count(const u32* cnt0, u32 g, u32 level) { return (cnt0[g] + ((1u 
 template <bool LEVEL0>
 KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.nthreads) return;
+  if (t >= a.nthreads) return;  // nthreads is a multiple of the CTA size: whole warps leave
   const u32 first = a.start_in[0];
   const u32 total = a.start_in[a.nb - 1] + level_count(a.cnt0, a.nb - 1, a.level) - first;
   if (total == 0) return;
   const u32 L = (total + a.nthreads - 1) / a.nthreads;
-  if ((u64)t * L >= total) return;
-  const u32 begin = first + t * L;
-  const u32 end = ((u64)t * L + L < total) ? begin + L : first + total;
+  // a lane whose run lies beyond the end has nothing to do but stays for the warp's shared inversion
+  const bool active = (u64)t * L < total;
+  const u32 begin = active ? first + t * L : 0u;
+  const u32 end = active ? (((u64)t * L + L < total) ? begin + L : first + total) : 0u;
   // bucket that holds position `begin`
-  u32 g;
-  {
+  u32 g = 0;
+  if (active) {
     u32 lo = 0, hi = a.nb - 1;
     while (lo < hi) {
       const u32 mid = (lo + hi + 1) >> 1;
@@ -144,6 +164,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   }
   u32 s = a.start_in[g], e = s + level_count(a.cnt0, g, a.level);
   u32 so = a.start_out[g];
+  const u32 la = a.lookahead & 0xffu;
+  const bool l1 = (a.lookahead & 0x100u) != 0;
   // ---- pass 1: singles and exceptional pairs are resolved here; ordinary pairs join the batch
   Fq prefix = fp_one<FqParams>();
   u32 nops = 0;
@@ -151,7 +173,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   for (;;) {
     bool have = false;
     Fq den;
-    u32 r_pos = 0, r_out = 0;
+    u32 r_n1 = 0, r_n2 = 0, r_out = 0;
     while (pos < end) {
       while (pos >= e) {  // next non-empty bucket (pos < first + total bounds the walk)
         g++;
@@ -165,7 +187,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
         continue;
       }
       const u32 slot = so + (off >> 1);
-      const PointRef<LEVEL0> p1(a, pos);
+      const u32 name1 = PointRef<LEVEL0>::name_of(a, pos);
+      const PointRef<LEVEL0> p1(a, name1);
       const Fq x1 = p1.x();
       if (pos + 1 >= e) {  // odd last point of its bucket: copied
         if (p1.is_infinity(x1))
@@ -175,7 +198,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
         pos++;
         continue;
       }
-      const PointRef<LEVEL0> p2(a, pos + 1);
+      const u32 name2 = PointRef<LEVEL0>::name_of(a, pos + 1);
+      const PointRef<LEVEL0> p2(a, name2);
       const Fq x2 = p2.x();
       pos += 2;
       const bool inf1 = p1.is_infinity(x1), inf2 = p2.is_infinity(x2);
@@ -199,7 +223,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
         den = fp_dbl(y1);
         dbl = 1;
       }
-      r_pos = pos - 2;
+      r_n1 = name1;
+      r_n2 = name2;
       r_out = slot | (dbl << 31);
       have = true;
       break;
@@ -210,18 +235,72 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       a.pre[o] = make_uint4(prefix.l[0], prefix.l[1], prefix.l[2], prefix.l[3]);
       a.pre[o + a.nthreads] = make_uint4(prefix.l[4], prefix.l[5], prefix.l[6], prefix.l[7]);
       a.pre[o + 2 * (size_t)a.nthreads] = make_uint4(prefix.l[8], prefix.l[9], prefix.l[10], prefix.l[11]);
-      a.rec[(size_t)nops * a.nthreads + t] = make_uint2(r_pos, r_out);
+      a.rec[(size_t)nops * a.nthreads + t] = make_uint4(r_n1, r_n2, r_out, 0u);
+    }
+    // the x coordinates `la` pairs ahead (as if the run went on two by two: right inside a bucket, harmless otherwise)
+    u32 pf1 = 0, pf2 = 0;
+    const bool pf = la != 0 && pos + 2 * la - 1 < end;
+    if (pf) {
+      pf1 = PointRef<LEVEL0>::name_of(a, pos + 2 * la - 2);
+      pf2 = PointRef<LEVEL0>::name_of(a, pos + 2 * la - 1);
     }
     prefix = fq_mul_v(prefix, den);
+    if (pf) {
+      PointRef<LEVEL0>(a, pf1).prefetch(true, l1);
+      PointRef<LEVEL0>(a, pf2).prefetch(true, l1);
+    }
     nops++;
   }
+  // ---- ONE inversion per warp.  A binary-GCD inversion is a few ten thousand data-dependent shift / subtract steps:
+  // run by 32 lanes at once it diverges into several hundred thousand warp instructions (ncu: it was half of the
+  // kernel's instructions even at 256 additions per lane), run by one lane it is a tenth of that.  So the lanes' run
+  // products are multiplied up across the warp (prefix and suffix scans over shuffles, 5 products each), lane 0
+  // inverts the warp's total, and lane j gets 1 / P_j = (1 / total) * prod_{i < j} P_i * prod_{i > j} P_i.
+  Fq inv;
+#ifndef ALEO_EMU
+  {
+    const u32 lane = threadIdx.x & 31u;
+    Fq incl = prefix, sfx = prefix;
+#pragma unroll 1
+    for (u32 d = 1; d < 32; d <<= 1) {
+      Fq up, dn;
+#pragma unroll
+      for (int k = 0; k < FqParams::N; k++) {
+        up.l[k] = __shfl_up_sync(0xffffffffu, incl.l[k], d);
+        dn.l[k] = __shfl_down_sync(0xffffffffu, sfx.l[k], d);
+      }
+      const Fq a1 = fq_mul_v(incl, up), a2 = fq_mul_v(sfx, dn);
+      if (lane >= d) incl = a1;
+      if (lane + d < 32) sfx = a2;
+    }
+    Fq tot, ex, sx;
+#pragma unroll
+    for (int k = 0; k < FqParams::N; k++) {
+      tot.l[k] = __shfl_sync(0xffffffffu, incl.l[k], 31);
+      ex.l[k] = __shfl_up_sync(0xffffffffu, incl.l[k], 1);
+      sx.l[k] = __shfl_down_sync(0xffffffffu, sfx.l[k], 1);
+    }
+    if (lane == 0) ex = fp_one<FqParams>();
+    if (lane == 31) sx = fp_one<FqParams>();
+    Fq tinv = tot;
+    if (lane == 0) tinv = fq_inv_ni(tot);
+#pragma unroll
+    for (int k = 0; k < FqParams::N; k++) tinv.l[k] = __shfl_sync(0xffffffffu, tinv.l[k], 0);
+    inv = fq_mul_v(fq_mul_v(tinv, ex), sx);
+  }
+#else
+  inv = fq_inv_ni(prefix);  // the emulator runs CUDA threads one after the other: every thread inverts its own product
+#endif
   if (nops == 0) return;
-  // ---- one inversion for the whole run
-  Fq inv = fq_inv_ni(prefix);
-  // ---- pass 2: unwind
+  // ---- pass 2: unwind.  The operands of addition i - la are prefetched while addition i is computed.
+  uint4 r = a.rec[(size_t)(nops - 1) * a.nthreads + t];
   for (u32 i = nops; i-- > 0;) {
-    const uint2 r = a.rec[(size_t)i * a.nthreads + t];
     const size_t o = (size_t)i * 3 * a.nthreads + t;
+    const bool pf = la != 0 && i >= la;
+    uint4 rp = r;
+    if (pf) rp = a.rec[(size_t)(i - la) * a.nthreads + t];
+    uint4 rn = r;
+    if (i) rn = a.rec[(size_t)(i - 1) * a.nthreads + t];
     Fq pre;
     {
       const uint4 v0 = a.pre[o], v1 = a.pre[o + a.nthreads], v2 = a.pre[o + 2 * (size_t)a.nthreads];
@@ -229,7 +308,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       pre.l[4] = v1.x; pre.l[5] = v1.y; pre.l[6] = v1.z; pre.l[7] = v1.w;
       pre.l[8] = v2.x; pre.l[9] = v2.y; pre.l[10] = v2.z; pre.l[11] = v2.w;
     }
-    const u32 dbl = r.y >> 31, slot = r.y & 0x7fffffffu;
+    const u32 dbl = r.z >> 31, slot = r.z & 0x7fffffffu;
     const PointRef<LEVEL0> p1(a, r.x);
     const Fq x1 = p1.x(), y1 = p1.y();
     Fq x2, num, den;
@@ -239,17 +318,26 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       const Fq xx = fq_sqr_v(x1);
       num = fp_add(fp_dbl(xx), xx);
     } else {
-      const PointRef<LEVEL0> p2(a, r.x + 1);
+      const PointRef<LEVEL0> p2(a, r.y);
       x2 = p2.x();
       den = fp_sub(x2, x1);
       num = fp_sub(p2.y(), y1);
     }
     const Fq inv_den = fq_mul_v(inv, pre);
+    if (pf) {
+      PointRef<LEVEL0>(a, rp.x).prefetch(false, l1);
+      PointRef<LEVEL0>(a, rp.y).prefetch(false, l1);
+      const size_t op = (size_t)(i - la) * 3 * a.nthreads + t;
+      prefetch_line(&a.pre[op], l1);
+      prefetch_line(&a.pre[op + a.nthreads], l1);
+      prefetch_line(&a.pre[op + 2 * (size_t)a.nthreads], l1);
+    }
     inv = fq_mul_v(inv, den);
     const Fq lam = fq_mul_v(num, inv_den);
     const Fq x3 = fp_sub(fp_sub(fq_sqr_v(lam), x1), x2);
     const Fq y3 = fp_sub(fq_mul_v(lam, fp_sub(x1, x3)), y1);
     store_point(a.out, slot, x3, y3);
+    r = rn;
   }
 }
 

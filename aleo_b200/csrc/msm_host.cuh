@@ -114,11 +114,17 @@ static inline u32 ba_kmax() {
   const long v = env ? atol(env) : 0L;
   return (v >= 1 && v <= 4096) ? (u32)v : 256u;
 }
-// workspace the levels may take, in bytes (ALEO_B200_MSM_BA_MB): about 100 bytes per sorted entry of a group
+// workspace the levels may take, in bytes (ALEO_B200_MSM_BA_MB): about 104 bytes per sorted entry of a group
 static inline size_t ba_budget_bytes() {
   const char* env = getenv("ALEO_B200_MSM_BA_MB");
   const long v = env ? atol(env) : 0L;
   return (v > 0 ? (size_t)v : (size_t)32768) << 20;
+}
+// prefetch distance of the level kernel, in additions (ALEO_B200_MSM_BA_PF; + 256: into L1)
+static inline u32 ba_lookahead() {
+  const char* env = getenv("ALEO_B200_MSM_BA_PF");
+  const long v = env ? atol(env) : 0L;  // measured on B200 at 2^24: 75.6 ms without, 85.1 / 85.3 / 87.6 ms with distance 1 / 2 / 4
+  return (v >= 0 && v < 512) ? (u32)v : 0u;
 }
 struct BaLevelPlan {
   u32 k, nthreads;
@@ -127,16 +133,25 @@ struct BaLevelPlan {
 // (entries >> l) + nb points (sum of ceil(m / 2^l)); a thread takes 2 k positions = at most k additions
 static inline BaLevelPlan ba_level_plan(size_t entries, u32 nb, u32 l) {
   const size_t slots = (entries >> l) + (l ? nb : 0);
-  const size_t target = (size_t)dev_props().sms * 384 * 4;  // four waves of 3 CTAs of 128 per SM
-  size_t k = slots / 2 / target;
+  // whole waves of 3 CTAs of 128 threads per SM (all runs take the same time: a partial last wave idles the chip), as
+  // few as keep a run at <= kmax additions but at least 4 while runs of 16 additions can fill them
+  const size_t wave = (size_t)dev_props().sms * 3 * ba::TPB;
   const u32 kmax = ba_kmax();
-  if (k > kmax) k = kmax;
-  if (k < 16) k = 16 < kmax ? 16 : kmax;
+  size_t waves = (slots / 2 + wave * kmax - 1) / (wave * kmax);
+  const size_t kmin = kmax < 32 ? kmax : 32;
+  if (waves < 4) {
+    const size_t by16 = (slots / 2 + wave * kmin - 1) / (wave * kmin);
+    waves = by16 < 4 ? by16 : 4;
+  }
   BaLevelPlan pl;
-  pl.k = (u32)k;
-  const size_t th = (slots + 2 * k - 1) / (2 * k);
-  pl.nthreads = (u32)((th + ba::TPB - 1) / ba::TPB * ba::TPB);
-  if (pl.nthreads == 0) pl.nthreads = ba::TPB;
+  pl.nthreads = (u32)(waves * wave);
+  if (slots / 2 < wave * kmin) {  // not even one wave of 16-addition runs: as many threads as there are such runs
+    const size_t th = (slots / 2 + kmin - 1) / kmin;
+    pl.nthreads = (u32)((th + ba::TPB - 1) / ba::TPB * ba::TPB);
+    if (pl.nthreads == 0) pl.nthreads = ba::TPB;
+  }
+  const size_t run = (slots + pl.nthreads - 1) / pl.nthreads;  // positions per thread
+  pl.k = (u32)((run + 1) / 2 + 1);                              // additions per thread, at most
   return pl;
 }
 
@@ -243,6 +258,7 @@ struct Session {
   std::vector<size_t> o_R, o_P;
   // batch-affine levels: L levels per group of `ba_wpg` bucket sets (the workspace bounds a group's entries)
   u32 ba_L = 0, ba_wpg = 0;
+  size_t ba_scratch_ops = 0;
   size_t o_baA = 0, o_baB = 0, o_ba_pre = 0, o_ba_rec = 0, o_ba_s0 = 0, o_ba_s1 = 0, o_ba_e = 0, o_meta2 = 0;
   unsigned char* ws = nullptr;
   bool dry = false;
@@ -361,7 +377,7 @@ struct Session {
       // a group = whole bucket sets whose entries fit the budget; the shared set of a resident SRS and the member sets
       // of a batch (whose sizes the host does not know) form one group
       const size_t total_entries = (size_t)max_chunk * prm.W;
-      const size_t cap_entries = ba_budget_bytes() / 100;
+      const size_t cap_entries = ba_budget_bytes() / 104;
       ba_L = ba_levels_for(total_entries, NB);
       size_t ge = total_entries;
       if (srs) {
@@ -376,15 +392,19 @@ struct Session {
       if (ba_L) {
         const u32 gnb = ba_wpg * prm.B;
         size_t scratch_ops = 0;
-        for (u32 l = 0; l < ba_L; l++) {
-          const BaLevelPlan pl = ba_level_plan(ge, gnb, l);
-          const size_t ops = (size_t)pl.nthreads * pl.k;
-          if (ops > scratch_ops) scratch_ops = ops;
+        for (u32 w0 = 0; w0 < nwin; w0 += ba_wpg) {  // the groups add_chunk() will form (the last one may be smaller)
+          const u32 nw = (w0 + ba_wpg <= nwin) ? ba_wpg : nwin - w0;
+          for (u32 l = 0; l < ba_L; l++) {
+            const BaLevelPlan pl = ba_level_plan(srs ? ge : (size_t)max_chunk * nw, nw * prm.B, l);
+            const size_t ops = (size_t)pl.nthreads * pl.k;
+            if (ops > scratch_ops) scratch_ops = ops;
+          }
         }
         o_baA = cv.take(((ge >> 1) + gnb + 1) * 96);
         o_baB = ba_L > 1 ? cv.take(((ge >> 2) + gnb + 1) * 96) : 0;
+        ba_scratch_ops = scratch_ops;
         o_ba_pre = cv.take(scratch_ops * 48);
-        o_ba_rec = cv.take(scratch_ops * 8);
+        o_ba_rec = cv.take(scratch_ops * 16);
         o_ba_s0 = cv.take((size_t)gnb * 4);
         o_ba_s1 = cv.take((size_t)gnb * 4);
         o_ba_e = cv.take((size_t)gnb * 4);
@@ -564,13 +584,15 @@ struct Session {
         la.cnt0 = counts + g0;
         la.nb = nb;
         la.pre = at<uint4>(o_ba_pre);
-        la.rec = at<uint2>(o_ba_rec);
+        la.rec = at<uint4>(o_ba_rec);
+        la.lookahead = ba_lookahead();
         for (u32 l = 0; l < ba_L; l++) {
           const bool last = (l + 1 == ba_L);
           int sl = 0;
           MSM_CK(exclusive_scan(counts + g0, nb, at<u32>(o_bsums), sa[l & 1], last ? e_out : nullptr, meta2 + 0, s, sl, l + 1,
                                 last ? 1u : 0u));
           const BaLevelPlan pl = ba_level_plan(ge, nb, l);
+          if ((size_t)pl.nthreads * pl.k > ba_scratch_ops) return cudaErrorInvalidValue;  // cannot happen: begin() sized it over these groups
           la.level = l;
           la.start_out = sa[l & 1];
           la.out = lvbuf[l & 1];

@@ -45,7 +45,7 @@ if mode == "phases":
         best = min(res[1:], key=sum)
         print("log_n=%d c=%d sort/acc/tail ms: %.2f/%.2f/%.2f total %.2f same_result=%s" %
               (log_n, lib.msm_window_bits(n), best[0], best[1], best[2], sum(best), raw == ref), flush=True)
-elif mode == "ba":  # ba LOG_N  SPEC ...   SPEC = levels[:k[:c]] (batch-affine levels, additions per inversion, window bits); 0 = off
+elif mode == "ba":  # ba LOG_N  SPEC ...   SPEC = levels[:k[:c[:pf]]] (batch-affine levels, additions per inversion, window bits, prefetch distance); 0 = off
     log_n = int(sys.argv[2])
     n, bases, sc = setup(log_n)
     out = torch.empty(144, dtype=torch.uint8, device="cuda")
@@ -60,6 +60,9 @@ elif mode == "ba":  # ba LOG_N  SPEC ...   SPEC = levels[:k[:c]] (batch-affine l
             os.environ["ALEO_B200_MSM_BA_K"] = f[1]
         if len(f) > 2 and f[2]:
             os.environ["ALEO_B200_MSM_C"] = f[2]
+        os.environ.pop("ALEO_B200_MSM_BA_PF", None)
+        if len(f) > 3 and f[3]:
+            os.environ["ALEO_B200_MSM_BA_PF"] = f[3]
         res = []
         for _ in range(4):
             lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), 104, stream(), ph), "p")
