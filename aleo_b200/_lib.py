@@ -74,6 +74,7 @@ SYMBOLS = [
     ("aleo_b200_g1_decompress_unchecked_dev", _int, [_vp, _sz, _vp, _sz, _vp]),
     ("aleo_b200_g1_compress_dev", _int, [_vp, _vp, _sz, _sz, _vp]),
     ("aleo_b200_msm_window_bits", _int, [_sz]),
+    ("aleo_b200_msm_ba_levels", _int, [_sz]),
     ("aleo_b200_msm_launches", _int, [_sz]),
     ("aleo_b200_msm_host_plan", _int, [_sz, C.POINTER(_int), C.POINTER(_int)]),
     ("aleo_b200_gen_bases_dev", _int, [_vp, _sz, _sz, _vp, _vp, _u64, _vp]),

@@ -546,6 +546,7 @@ int aleo_b200_polymul(void* out_host, size_t pcount, const void* const* polynomi
 
 // ------------------------------------------------------------------------------------------ MSM
 int aleo_b200_msm_window_bits(size_t n) { return aleo::msm_window_bits(n); }
+int aleo_b200_msm_ba_levels(size_t n) { return aleo::msm_ba_levels(n); }
 
 int aleo_b200_msm_launches(size_t n) {
   int launches = 0;

@@ -71,6 +71,7 @@ cudaError_t feed_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStre
 cudaError_t feed_d2h_sync(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
 bool msm_size_supported(size_t n);
 int msm_window_bits(size_t n);
+int msm_ba_levels(size_t n);
 cudaError_t g1_sum(const void* points144_dev, u32 count, void* out144_dev, cudaStream_t s);
 cudaError_t srs_create(const void* bases_dev, u32 stride, size_t n, cudaStream_t s, void** handle_out);
 void srs_destroy(void* handle);

@@ -52,19 +52,7 @@ struct LevelArgs {
   uint4* pre;            // scratch: prefix products, plane (op * 3 + j) * nthreads + thread
   uint4* rec;            // scratch: records {first point, second point, output slot | doubling << 31, -}, op * nthreads + thread;
                          // a point is named by its sorted entry (index | sign << 31) at level 0, by its position above
-  u32 lookahead;         // prefetch distance in additions (0: none); bit 8: into L1 instead of L2
 };
-
-DEV void prefetch_line(const void* p, bool l1) {
-#ifndef ALEO_EMU
-  if (l1)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-  else
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p; (void)l1;
-#endif
-}
 
 DEV Fq fq_load16(const void* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -106,11 +94,6 @@ struct PointRef {
     }
   }
   DEV static u32 name_of(const LevelArgs& a, u32 pos) { return LEVEL0 ? a.sorted[pos] : pos; }
-  // pulls the point towards the SM ahead of its use; x_only: pass 1 reads nothing else of an ordinary pair
-  DEV void prefetch(bool x_only, bool l1) const {
-    prefetch_line(p, l1);
-    prefetch_line(p + (x_only ? 40 : 88), l1);
-  }
   DEV Fq x() const { return LEVEL0 ? fq_load8(p) : fq_load16(p); }
   DEV Fq y() const {
     Fq v = LEVEL0 ? fq_load8(p + 48) : fq_load16(p + 48);
@@ -137,8 +120,121 @@ DEV void store_infinity(unsigned char* out, u32 slot) {
 
 DEV u32 level_count(const u32* cnt0, u32 g, u32 level) { return (cnt0[g] + ((1u << level) - 1u)) >> level; }
 
-template <bool LEVEL0>
+// ---- operand staging -------------------------------------------------------------------------------------------
+// A thread's operands (two 96-byte points and a 48-byte prefix per addition) are gathered from all over HBM, and with
+// 168 registers per thread an SM holds 12 warps: too few to hide the gathers behind other warps' arithmetic (ncu on the
+// first version: long_scoreboard 2.7 warps per issue, heavy pipe at 56 %), and prefetch instructions made it worse.
+// So the operands of the NEXT addition travel global -> shared memory asynchronously (cp.async: no registers, no
+// warp stall) while the current one is computed from the other half of a double buffer.  Shared layout: 16-byte word j
+// of thread t at (j * TPB + t) * 16 (conflict-free LDS.128); words 0-2 x1, 3-5 y1, 6-8 x2, 9-11 y2, 12-14 prefix.
+constexpr u32 STAGE_WORDS = 15;
+constexpr u32 STAGE_BYTES = 2 * STAGE_WORDS * 16 * TPB;  // dynamic shared memory of a CTA (61 440 B; 3 CTAs per SM)
+
+#ifndef ALEO_EMU
+struct AsyncStager {
+  static constexpr bool ASYNC = true;
+  u32 base;  // shared-memory address of word 0 of this thread, buffer 0
+  DEV explicit AsyncStager(unsigned char* smem) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
+  DEV u32 word(u32 buf, u32 j) const { return base + (buf * STAGE_WORDS + j) * (16u * TPB); }
+  // 48 bytes, 16-byte aligned source
+  DEV void fq16(u32 buf, u32 j, const void* src) const {
+#pragma unroll
+    for (u32 k = 0; k < 3; k++)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, j + k)), "l"((const unsigned char*)src + 16 * k) : "memory");
+  }
+  // 48 bytes, 8-byte aligned source (caller-owned bases)
+  DEV void fq8(u32 buf, u32 j, const void* src) const {
+#pragma unroll
+    for (u32 k = 0; k < 6; k++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(word(buf, j + (k >> 1)) + 8u * (k & 1u)), "l"((const unsigned char*)src + 8 * k) : "memory");
+  }
+  DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  DEV void wait_all_but_last() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  DEV Fq get(u32 buf, u32 j) const {
+    Fq r;
+#pragma unroll
+    for (u32 k = 0; k < 3; k++) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(word(buf, j + k)) : "memory");
+      r.l[4 * k] = v.x;
+      r.l[4 * k + 1] = v.y;
+      r.l[4 * k + 2] = v.z;
+      r.l[4 * k + 3] = v.w;
+    }
+    return r;
+  }
+  DEV void stage_pre(u32 buf, const uint4* p0, size_t plane) const {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 12)), "l"(p0) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 13)), "l"(p0 + plane) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 14)), "l"(p0 + 2 * plane) : "memory");
+  }
+  DEV Fq get_pre(u32 buf, const uint4*, size_t) const { return get(buf, 12); }
+};
+#endif
+// No staging: the "stage" only remembers the source addresses and get() loads from them.  Used for level 0, whose
+// operands sit in caller-owned bases with 8-byte alignment (8-byte asynchronous copies, 48 per addition, throttle the
+// memory-instruction queue: 35.1 ms direct against 42.2 ms staged at 2^24), and by the emulator.
+struct DirectStager {
+  static constexpr bool ASYNC = false;
+  const unsigned char *a1, *a2, *b1, *b2;  // first / second point of buffer 0 (a) and 1 (b); y lies 48 bytes after x
+  DEV explicit DirectStager(unsigned char*) : a1(nullptr), a2(nullptr), b1(nullptr), b2(nullptr) {}
+  DEV void note(u32 buf, u32 j, const void* p) {
+    const unsigned char* q = (const unsigned char*)p;
+    if (j == 0) {
+      if (buf) b1 = q; else a1 = q;
+    } else if (j == 6) {
+      if (buf) b2 = q; else a2 = q;
+    }
+  }
+  DEV void fq16(u32 buf, u32 j, const void* p) { note(buf, j, p); }
+  DEV void fq8(u32 buf, u32 j, const void* p) { note(buf, j, p); }
+  DEV void commit() const {}
+  DEV void wait_all_but_last() const {}
+  DEV Fq get(u32 buf, u32 j) const {
+    const unsigned char* q = (j < 6) ? (buf ? b1 : a1) : (buf ? b2 : a2);
+    return fq_load8(q + ((j == 3 || j == 9) ? 48 : 0));
+  }
+  DEV void stage_pre(u32, const uint4*, size_t) const {}
+  DEV Fq get_pre(u32, const uint4* p0, size_t plane) const {
+    const uint4 v0 = p0[0], v1 = p0[plane], v2 = p0[2 * plane];
+    Fq pre;
+    pre.l[0] = v0.x; pre.l[1] = v0.y; pre.l[2] = v0.z; pre.l[3] = v0.w;
+    pre.l[4] = v1.x; pre.l[5] = v1.y; pre.l[6] = v1.z; pre.l[7] = v1.w;
+    pre.l[8] = v2.x; pre.l[9] = v2.y; pre.l[10] = v2.z; pre.l[11] = v2.w;
+    return pre;
+  }
+};
+#ifdef ALEO_EMU
+typedef DirectStager AsyncStager;  // the emulator has no asynchronous copies
+#endif
+
+constexpr u32 REC_DOUBLE = 1u << 31;    // record flag: P + P (den = 2 y, num = 3 x^2)
+constexpr u32 REC_RESOLVED = 1u << 30;  // record flag: exceptional pair, result already stored by pass 1
+constexpr u32 REC_SLOT = REC_RESOLVED - 1u;
+
+template <bool LEVEL0, class ST>
+DEV void stage_points(ST& st, u32 buf, const LevelArgs& a, const uint4& r, bool with_y) {
+  const PointRef<LEVEL0> p1(a, r.x), p2(a, r.y);
+  if (LEVEL0) {
+    st.fq8(buf, 0, p1.p);
+    st.fq8(buf, 6, p2.p);
+    if (with_y) {
+      st.fq8(buf, 3, p1.p + 48);
+      st.fq8(buf, 9, p2.p + 48);
+    }
+  } else {
+    st.fq16(buf, 0, p1.p);
+    st.fq16(buf, 6, p2.p);
+    if (with_y) {
+      st.fq16(buf, 3, p1.p + 48);
+      st.fq16(buf, 9, p2.p + 48);
+    }
+  }
+}
+
+template <bool LEVEL0, class ST>
 KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
+  DYN_SMEM(unsigned char, smem);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nthreads) return;  // nthreads is a multiple of the CTA size: whole warps leave
   const u32 first = a.start_in[0];
@@ -149,31 +245,25 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   const bool active = (u64)t * L < total;
   const u32 begin = active ? first + t * L : 0u;
   const u32 end = active ? (((u64)t * L + L < total) ? begin + L : first + total) : 0u;
-  // bucket that holds position `begin`
-  u32 g = 0;
-  if (active) {
-    u32 lo = 0, hi = a.nb - 1;
-    while (lo < hi) {
-      const u32 mid = (lo + hi + 1) >> 1;
-      if (a.start_in[mid] <= begin)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    g = lo;
-  }
-  u32 s = a.start_in[g], e = s + level_count(a.cnt0, g, a.level);
-  u32 so = a.start_out[g];
-  const u32 la = a.lookahead & 0xffu;
-  const bool l1 = (a.lookahead & 0x100u) != 0;
-  // ---- pass 1: singles and exceptional pairs are resolved here; ordinary pairs join the batch
-  Fq prefix = fp_one<FqParams>();
+  const size_t NT = a.nthreads;
+  // ---- pass 1a: index walk.  Pairs become records, odd last points of a bucket are copied.
   u32 nops = 0;
-  u32 pos = begin;
-  for (;;) {
-    bool have = false;
-    Fq den;
-    u32 r_n1 = 0, r_n2 = 0, r_out = 0;
+  if (active) {
+    u32 g;
+    {
+      u32 lo = 0, hi = a.nb - 1;
+      while (lo < hi) {  // bucket that holds position `begin`
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (a.start_in[mid] <= begin)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      g = lo;
+    }
+    u32 s = a.start_in[g], e = s + level_count(a.cnt0, g, a.level);
+    u32 so = a.start_out[g];
+    u32 pos = begin;
     while (pos < end) {
       while (pos >= e) {  // next non-empty bucket (pos < first + total bounds the walk)
         g++;
@@ -188,9 +278,9 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       }
       const u32 slot = so + (off >> 1);
       const u32 name1 = PointRef<LEVEL0>::name_of(a, pos);
-      const PointRef<LEVEL0> p1(a, name1);
-      const Fq x1 = p1.x();
       if (pos + 1 >= e) {  // odd last point of its bucket: copied
+        const PointRef<LEVEL0> p1(a, name1);
+        const Fq x1 = p1.x();
         if (p1.is_infinity(x1))
           store_infinity(a.out, slot);
         else
@@ -198,58 +288,70 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
         pos++;
         continue;
       }
-      const u32 name2 = PointRef<LEVEL0>::name_of(a, pos + 1);
-      const PointRef<LEVEL0> p2(a, name2);
-      const Fq x2 = p2.x();
+      a.rec[(size_t)nops * NT + t] = make_uint4(name1, PointRef<LEVEL0>::name_of(a, pos + 1), slot, 0u);
+      nops++;
       pos += 2;
-      const bool inf1 = p1.is_infinity(x1), inf2 = p2.is_infinity(x2);
-      if (inf1 || inf2) {
-        if (inf1 && inf2)
-          store_infinity(a.out, slot);
-        else if (inf1)
-          store_point(a.out, slot, x2, p2.y());
-        else
-          store_point(a.out, slot, x1, p1.y());
-        continue;
+    }
+  }
+  ST st(smem);
+  // ---- pass 1b: running product of the denominators; exceptional pairs are resolved here and leave the batch
+  Fq prefix = fp_one<FqParams>();
+  {
+    uint4 r = make_uint4(0, 0, 0, 0), rn = r;
+    if (nops) {
+      r = a.rec[t];
+      stage_points<LEVEL0, ST>(st, 0, a, r, false);
+      if (nops > 1) rn = a.rec[NT + t];
+    }
+    st.commit();
+    for (u32 j = 0; j < nops; j++) {
+      const u32 buf = j & 1u;
+      uint4 rnn = rn;
+      if (j + 1 < nops) {
+        stage_points<LEVEL0, ST>(st, buf ^ 1u, a, rn, false);
+        if (j + 2 < nops) rnn = a.rec[(size_t)(j + 2) * NT + t];
       }
-      den = fp_sub(x2, x1);
-      u32 dbl = 0;
-      if (fp_is_zero(den)) {  // same x: P + P or P + (-P)
-        const Fq y1 = p1.y();
-        if (!fp_eq(y1, p2.y()) || fp_is_zero(y1)) {
-          store_infinity(a.out, slot);
-          continue;
+      st.commit();
+      st.wait_all_but_last();
+      const Fq x1 = st.get(buf, 0), x2 = st.get(buf, 6);
+      Fq den = fp_sub(x2, x1);
+      u32 flag = 0;
+      const bool z1 = fp_is_zero(x1), z2 = fp_is_zero(x2);
+      if (z1 || z2 || fp_is_zero(den)) {  // rare: a point at infinity, or the same x twice
+        const PointRef<LEVEL0> p1(a, r.x), p2(a, r.y);
+        const bool inf1 = p1.is_infinity(x1), inf2 = p2.is_infinity(x2);
+        const u32 slot = r.z & REC_SLOT;
+        if (inf1 || inf2) {
+          flag = REC_RESOLVED;
+          if (inf1 && inf2)
+            store_infinity(a.out, slot);
+          else if (inf1)
+            store_point(a.out, slot, x2, p2.y());
+          else
+            store_point(a.out, slot, x1, p1.y());
+        } else if (fp_is_zero(den)) {  // P + P or P + (-P)
+          const Fq y1 = p1.y();
+          if (!fp_eq(y1, p2.y()) || fp_is_zero(y1)) {
+            flag = REC_RESOLVED;
+            store_infinity(a.out, slot);
+          } else {
+            flag = REC_DOUBLE;
+            den = fp_dbl(y1);
+          }
         }
-        den = fp_dbl(y1);
-        dbl = 1;
+        if (flag) a.rec[(size_t)j * NT + t] = make_uint4(r.x, r.y, r.z | flag, 0u);
+        if (flag & REC_RESOLVED) den = fp_one<FqParams>();
       }
-      r_n1 = name1;
-      r_n2 = name2;
-      r_out = slot | (dbl << 31);
-      have = true;
-      break;
+      {
+        const size_t o = (size_t)j * 3 * NT + t;
+        a.pre[o] = make_uint4(prefix.l[0], prefix.l[1], prefix.l[2], prefix.l[3]);
+        a.pre[o + NT] = make_uint4(prefix.l[4], prefix.l[5], prefix.l[6], prefix.l[7]);
+        a.pre[o + 2 * NT] = make_uint4(prefix.l[8], prefix.l[9], prefix.l[10], prefix.l[11]);
+      }
+      prefix = fq_mul_v(prefix, den);
+      r = rn;
+      rn = rnn;
     }
-    if (!have) break;
-    {
-      const size_t o = (size_t)nops * 3 * a.nthreads + t;
-      a.pre[o] = make_uint4(prefix.l[0], prefix.l[1], prefix.l[2], prefix.l[3]);
-      a.pre[o + a.nthreads] = make_uint4(prefix.l[4], prefix.l[5], prefix.l[6], prefix.l[7]);
-      a.pre[o + 2 * (size_t)a.nthreads] = make_uint4(prefix.l[8], prefix.l[9], prefix.l[10], prefix.l[11]);
-      a.rec[(size_t)nops * a.nthreads + t] = make_uint4(r_n1, r_n2, r_out, 0u);
-    }
-    // the x coordinates `la` pairs ahead (as if the run went on two by two: right inside a bucket, harmless otherwise)
-    u32 pf1 = 0, pf2 = 0;
-    const bool pf = la != 0 && pos + 2 * la - 1 < end;
-    if (pf) {
-      pf1 = PointRef<LEVEL0>::name_of(a, pos + 2 * la - 2);
-      pf2 = PointRef<LEVEL0>::name_of(a, pos + 2 * la - 1);
-    }
-    prefix = fq_mul_v(prefix, den);
-    if (pf) {
-      PointRef<LEVEL0>(a, pf1).prefetch(true, l1);
-      PointRef<LEVEL0>(a, pf2).prefetch(true, l1);
-    }
-    nops++;
   }
   // ---- ONE inversion per warp.  A binary-GCD inversion is a few ten thousand data-dependent shift / subtract steps:
   // run by 32 lanes at once it diverges into several hundred thousand warp instructions (ncu: it was half of the
@@ -292,52 +394,53 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   inv = fq_inv_ni(prefix);  // the emulator runs CUDA threads one after the other: every thread inverts its own product
 #endif
   if (nops == 0) return;
-  // ---- pass 2: unwind.  The operands of addition i - la are prefetched while addition i is computed.
-  uint4 r = a.rec[(size_t)(nops - 1) * a.nthreads + t];
-  for (u32 i = nops; i-- > 0;) {
-    const size_t o = (size_t)i * 3 * a.nthreads + t;
-    const bool pf = la != 0 && i >= la;
-    uint4 rp = r;
-    if (pf) rp = a.rec[(size_t)(i - la) * a.nthreads + t];
-    uint4 rn = r;
-    if (i) rn = a.rec[(size_t)(i - 1) * a.nthreads + t];
-    Fq pre;
-    {
-      const uint4 v0 = a.pre[o], v1 = a.pre[o + a.nthreads], v2 = a.pre[o + 2 * (size_t)a.nthreads];
-      pre.l[0] = v0.x; pre.l[1] = v0.y; pre.l[2] = v0.z; pre.l[3] = v0.w;
-      pre.l[4] = v1.x; pre.l[5] = v1.y; pre.l[6] = v1.z; pre.l[7] = v1.w;
-      pre.l[8] = v2.x; pre.l[9] = v2.y; pre.l[10] = v2.z; pre.l[11] = v2.w;
+  // ---- pass 2: unwind, last addition first
+  {
+    uint4 r = a.rec[(size_t)(nops - 1) * NT + t], rn = r;
+    stage_points<LEVEL0, ST>(st, (nops - 1) & 1u, a, r, true);
+    // the prefix planes are NT * 16 bytes apart: staged word by word
+    st.stage_pre((nops - 1) & 1u, &a.pre[(size_t)(nops - 1) * 3 * NT + t], NT);
+    if (nops > 1) rn = a.rec[(size_t)(nops - 2) * NT + t];
+    st.commit();
+    for (u32 i = nops; i-- > 0;) {
+      const u32 buf = i & 1u;
+      uint4 rnn = rn;
+      if (i) {
+        stage_points<LEVEL0, ST>(st, buf ^ 1u, a, rn, true);
+        st.stage_pre(buf ^ 1u, &a.pre[(size_t)(i - 1) * 3 * NT + t], NT);
+        if (i > 1) rnn = a.rec[(size_t)(i - 2) * NT + t];
+      }
+      st.commit();
+      st.wait_all_but_last();
+      if (!(r.z & REC_RESOLVED)) {
+        const u32 dbl = r.z >> 31, slot = r.z & REC_SLOT;
+        const Fq x1 = st.get(buf, 0);
+        Fq y1 = st.get(buf, 3);
+        if (LEVEL0 && (r.x >> 31)) y1 = fp_neg(y1);
+        const Fq pre = st.get_pre(buf, &a.pre[(size_t)i * 3 * NT + t], NT);
+        Fq x2, num, den;
+        if (dbl) {
+          x2 = x1;
+          den = fp_dbl(y1);
+          const Fq xx = fq_sqr_v(x1);
+          num = fp_add(fp_dbl(xx), xx);
+        } else {
+          x2 = st.get(buf, 6);
+          Fq y2 = st.get(buf, 9);
+          if (LEVEL0 && (r.y >> 31)) y2 = fp_neg(y2);
+          den = fp_sub(x2, x1);
+          num = fp_sub(y2, y1);
+        }
+        const Fq inv_den = fq_mul_v(inv, pre);
+        inv = fq_mul_v(inv, den);
+        const Fq lam = fq_mul_v(num, inv_den);
+        const Fq x3 = fp_sub(fp_sub(fq_sqr_v(lam), x1), x2);
+        const Fq y3 = fp_sub(fq_mul_v(lam, fp_sub(x1, x3)), y1);
+        store_point(a.out, slot, x3, y3);
+      }
+      r = rn;
+      rn = rnn;
     }
-    const u32 dbl = r.z >> 31, slot = r.z & 0x7fffffffu;
-    const PointRef<LEVEL0> p1(a, r.x);
-    const Fq x1 = p1.x(), y1 = p1.y();
-    Fq x2, num, den;
-    if (dbl) {
-      x2 = x1;
-      den = fp_dbl(y1);
-      const Fq xx = fq_sqr_v(x1);
-      num = fp_add(fp_dbl(xx), xx);
-    } else {
-      const PointRef<LEVEL0> p2(a, r.y);
-      x2 = p2.x();
-      den = fp_sub(x2, x1);
-      num = fp_sub(p2.y(), y1);
-    }
-    const Fq inv_den = fq_mul_v(inv, pre);
-    if (pf) {
-      PointRef<LEVEL0>(a, rp.x).prefetch(false, l1);
-      PointRef<LEVEL0>(a, rp.y).prefetch(false, l1);
-      const size_t op = (size_t)(i - la) * 3 * a.nthreads + t;
-      prefetch_line(&a.pre[op], l1);
-      prefetch_line(&a.pre[op + a.nthreads], l1);
-      prefetch_line(&a.pre[op + 2 * (size_t)a.nthreads], l1);
-    }
-    inv = fq_mul_v(inv, den);
-    const Fq lam = fq_mul_v(num, inv_den);
-    const Fq x3 = fp_sub(fp_sub(fq_sqr_v(lam), x1), x2);
-    const Fq y3 = fp_sub(fq_mul_v(lam, fp_sub(x1, x3)), y1);
-    store_point(a.out, slot, x3, y3);
-    r = rn;
   }
 }
 

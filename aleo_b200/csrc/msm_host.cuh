@@ -23,22 +23,39 @@ static inline u32 floor_log2(size_t n) {
 // windows of c bits: W(c) = 253 / c + 1 (the +1 absorbs the signed-recoding carry)
 static inline u32 windows_for(u32 c) { return SCALAR_BITS / c + 1; }
 
+// Batch-affine levels (msm_ba.cuh) run in front of the XYZZ kernel from this many points on (ALEO_B200_MSM_BA = 0: never).
+// Measured on B200 (profiles/r03e_ba_sweep_*.log): 2^20 9.18 ms without / 9.61 ms with, 2^22 26.8 / 24.9, 2^24 88.2 / 79.8.
+static inline bool ba_enabled_for(size_t n_points) {
+  const char* env = getenv("ALEO_B200_MSM_BA");  // read per call: tests and sweeps switch it
+  if (env) return atol(env) > 0;
+  return n_points >= ((size_t)1 << 22);
+}
+
 // Window bits by cost model, in Fq products: n * W(c) mixed additions (10 each) of bucket accumulation
 // against W(c) * 2^(c-1) buckets * 2 full additions (14 each, x1.5: the reduction runs at lower
-// occupancy).  2^16 -> 12, 2^20 -> 16, 2^24 -> 20, 2^26 -> 20.  ALEO_B200_MSM_C overrides (sweeps).
+// occupancy).  2^16 -> 12, 2^20 -> 16.  With the batch-affine levels an entry costs less and a bucket more (every
+// bucket is copied through the levels and finished by an XYZZ stage of short runs): fitted on B200 at 2^24,
+// 0.262 ns per entry + 1.18 ns per bucket in the accumulation and 1.3 .. 2.4 ns per bucket in the reduction = about 11
+// entries per bucket: 2^22 -> 16, 2^24 -> 18 (79.8 ms against 81.2 / 81.0 ms for c = 17 / 20), 2^26 -> 20.
+// ALEO_B200_MSM_C overrides (sweeps).
 static inline u32 choose_window(size_t n, u32 chunks = 1) {
   const char* env = getenv("ALEO_B200_MSM_C");  // read per call: sweeps switch it
   const long c_env = env ? atol(env) : 0L;
   if (c_env >= 4 && c_env <= 22) return (u32)c_env;
   if (n < 2) return 4;
+  const bool ba = ba_enabled_for(n / chunks);
+  const double per_bucket = ba ? 110.0 : 2.0 * 14.0 * 1.5;
   u32 best_c = 4;
   double best = 0;
   for (u32 c = 4; c <= 22; c++) {
     const double W = (double)windows_for(c);
+    // half-range scalars have 252 bits: only ceil(252 / c) windows receive entries, the one above holds the recoding
+    // carry alone (c = 18: 14 windows of entries, c = 17: 15 -- why 18 beats 17 at 2^24); counted in the fitted model only
+    const double We = ba ? (double)((SCALAR_BITS - 1 + c - 1) / c) : W;
     // an MSM that arrives in `chunks` point ranges re-opens every bucket once per extra range: one more
     // mixed addition per bucket and range (the first addition into an empty bucket is a copy); weighted 5 rather
     // than 10: measured on B200 at 2^24 in 3 ranges, c = 20 runs 102.3 ms against 105.5 ms for c = 19
-    const double cost = (double)n * W * 10.0 + W * (double)(1u << (c - 1)) * (2.0 * 14.0 * 1.5 + 5.0 * (chunks - 1));
+    const double cost = (double)n * We * 10.0 + W * (double)(1u << (c - 1)) * (per_bucket + 5.0 * (chunks - 1));
     if (c == 4 || cost < best) {
       best = cost;
       best_c = c;
@@ -92,20 +109,22 @@ static inline u32 lanes_for_entries(size_t entries) {
 static inline u32 lanes_for(size_t n_chunk, u32 W) { return lanes_for_entries((size_t)n_chunk * W); }
 
 // ---- batch-affine pair-tree levels (msm_ba.cuh) in front of the XYZZ accumulation ------------------------------------
-// How many levels: after L levels a bucket that received m entries holds ceil(m / 2^L) points; the levels stop once the
-// average bucket is down to about two points (the XYZZ kernel then does what is left, and it is the stage that copes
-// with buckets cut by run boundaries).  Off below 2^20 entries per bucket set group: the levels cost launches and a
-// per-thread inversion latency that proof-sized MSMs cannot amortise.  ALEO_B200_MSM_BA = 0 | levels overrides.
-static inline u32 ba_levels_for(size_t entries, size_t buckets) {
+// How many levels: after L levels a bucket that received m entries holds ceil(m / 2^L) points, which the XYZZ kernel
+// sums (it is the stage that copes with buckets cut by run boundaries).  A level costs 0.26 .. 0.30 ns per addition
+// against 0.33 ns in the XYZZ kernel, plus its scans and launch: measured flat within 1 % between log2(load) - 3 and
+// log2(load) - 1 levels (load = average entries per bucket; 2^24: c = 20 (load 32) 3 / 4 levels 69.7 / 69.8 ms,
+// c = 18 (load 128) 5 / 6 levels 68.3 / 69.3 ms; 2^22, c = 17 (load 64) 3 / 4 / 5 levels 19.6 / 19.8 / 20.0 ms).
+// ALEO_B200_MSM_BA = 0 | levels overrides.
+static inline u32 ba_levels_for(size_t points, size_t entries, size_t buckets) {
   const char* env = getenv("ALEO_B200_MSM_BA");  // read per call: tests and sweeps switch it
   if (env) {
     const long v = atol(env);
     return v < 0 ? 0u : (v > 12 ? 12u : (u32)v);
   }
-  if (entries < ((size_t)1 << 22)) return 0;
-  const size_t load = entries / (buckets ? buckets : 1);  // average entries per bucket (uniform scalars)
+  if (!ba_enabled_for(points)) return 0;
+  const size_t load = entries / (buckets ? buckets : 1);
   u32 l = 0;
-  while (((size_t)4 << l) <= load) l++;  // load 32 -> 4 levels (two points left per bucket on average)
+  while (((size_t)8 << l) <= load) l++;  // load 32 -> 3, 64 -> 4, 128 -> 5
   return l;
 }
 // additions one thread shares an inversion over, at most (ALEO_B200_MSM_BA_K)
@@ -119,12 +138,6 @@ static inline size_t ba_budget_bytes() {
   const char* env = getenv("ALEO_B200_MSM_BA_MB");
   const long v = env ? atol(env) : 0L;
   return (v > 0 ? (size_t)v : (size_t)32768) << 20;
-}
-// prefetch distance of the level kernel, in additions (ALEO_B200_MSM_BA_PF; + 256: into L1)
-static inline u32 ba_lookahead() {
-  const char* env = getenv("ALEO_B200_MSM_BA_PF");
-  const long v = env ? atol(env) : 0L;  // measured on B200 at 2^24: 75.6 ms without, 85.1 / 85.3 / 87.6 ms with distance 1 / 2 / 4
-  return (v >= 0 && v < 512) ? (u32)v : 0u;
 }
 struct BaLevelPlan {
   u32 k, nthreads;
@@ -378,7 +391,7 @@ struct Session {
       // of a batch (whose sizes the host does not know) form one group
       const size_t total_entries = (size_t)max_chunk * prm.W;
       const size_t cap_entries = ba_budget_bytes() / 104;
-      ba_L = ba_levels_for(total_entries, NB);
+      ba_L = ba_levels_for(max_chunk, total_entries, NB);
       size_t ge = total_entries;
       if (srs) {
         ba_wpg = nwin;
@@ -566,6 +579,20 @@ struct Session {
       MSM_CK(flat(bases, stride, sorted, starts, ends, NB, p.nlanes, meta, buckets, false));
       if (phase_ev) cudaEventRecord(phase_ev[2], s);
     } else {
+#ifndef ALEO_EMU
+      {  // the staging buffers of the level kernel need the large shared-memory carve-out (once per device and thread)
+        static thread_local int attr_dev = -1;
+        int devnow = 0;
+        MSM_CK(cudaGetDevice(&devnow));
+        if (attr_dev != devnow) {
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStager>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStager>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          attr_dev = devnow;
+        }
+      }
+#endif
       u32* meta2 = at<u32>(o_meta2);
       u32* sa[2] = {at<u32>(o_ba_s0), at<u32>(o_ba_s1)};
       u32* e_out = at<u32>(o_ba_e);
@@ -585,7 +612,6 @@ struct Session {
         la.nb = nb;
         la.pre = at<uint4>(o_ba_pre);
         la.rec = at<uint4>(o_ba_rec);
-        la.lookahead = ba_lookahead();
         for (u32 l = 0; l < ba_L; l++) {
           const bool last = (l + 1 == ba_L);
           int sl = 0;
@@ -597,10 +623,20 @@ struct Session {
           la.start_out = sa[l & 1];
           la.out = lvbuf[l & 1];
           la.nthreads = pl.nthreads;
-          if (l == 0)
-            LAUNCH_NOSYNC(ba::level_kernel<true>, dim3(pl.nthreads / ba::TPB), dim3(ba::TPB), 0, s, la);
+          // level 0 gathers caller-owned bases with plain loads; above, the operands are staged through shared memory
+          // (ALEO_B200_MSM_BA_STAGE = 0: plain loads everywhere, 2: staged everywhere -- A/B switch)
+          const char* stage_env = getenv("ALEO_B200_MSM_BA_STAGE");
+          const int stage_mode = stage_env ? atoi(stage_env) : 1;
+          const bool staged = stage_mode == 2 || (stage_mode == 1 && l > 0);
+          const dim3 grid(pl.nthreads / ba::TPB), block(ba::TPB);
+          if (l == 0 && staged)
+            LAUNCH_NOSYNC((ba::level_kernel<true, ba::AsyncStager>), grid, block, ba::STAGE_BYTES, s, la);
+          else if (l == 0)
+            LAUNCH_NOSYNC((ba::level_kernel<true, ba::DirectStager>), grid, block, 0, s, la);
+          else if (staged)
+            LAUNCH_NOSYNC((ba::level_kernel<false, ba::AsyncStager>), grid, block, ba::STAGE_BYTES, s, la);
           else
-            LAUNCH_NOSYNC(ba::level_kernel<false>, dim3(pl.nthreads / ba::TPB), dim3(ba::TPB), 0, s, la);
+            LAUNCH_NOSYNC((ba::level_kernel<false, ba::DirectStager>), grid, block, 0, s, la);
           tr.mark("affine level", s);
           la.in = la.out;
           la.start_in = la.start_out;

@@ -12,6 +12,12 @@ namespace aleo {
 cudaError_t msm_upload_constants() { return aleo_upload_field_constants(); }
 bool msm_size_supported(size_t n) { return msm::size_supported(n); }
 int msm_window_bits(size_t n) { return (int)msm::make_params(n).c; }
+int msm_ba_levels(size_t n) {
+  if (n == 0) return 0;
+  msm::Session ss;
+  ss.begin(n, n, 1, nullptr, nullptr, true);  // dry: plans only
+  return (int)ss.ba_L;
+}
 
 // ---- host-pointer calls: the MSM arrives in point ranges so that the copy of range k + 1 overlaps the
 // accumulation of range k (PCIe moves 136 bytes per point about 2.5x faster than the integer pipe adds it) ----

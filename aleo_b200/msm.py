@@ -90,6 +90,11 @@ class VariableBase:
         return _lib.get_lib().msm_window_bits(n)
 
     @staticmethod
+    def batch_affine_levels(n: int) -> int:
+        """pair-tree levels of batch-affine additions in front of the XYZZ accumulation (0 below 2^22 points)"""
+        return _lib.get_lib().msm_ba_levels(n)
+
+    @staticmethod
     def launches(n: int) -> int:
         return _lib.get_lib().msm_launches(n)
 

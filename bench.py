@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 MACS_PER_MIXED_ADD = 3000          # 10 Fq products x (2*12^2 + 12) 32x32->64 MACs (algorithmic)
 ISSUED_MACS_PER_MIXED_ADD = 8 * 276 + 2 * 210   # IMAD.WIDE actually issued: 8 products + 2 dedicated squares (cuobjdump)
+ISSUED_MACS_PER_AFFINE_ADD = 5 * 276 + 210      # batch-affine addition (csrc/msm_ba.cuh): 5 products + 1 square, inversion shared
 NTT_BYTES_PER_ELEM_PER_PASS = 64   # 32 B read + 32 B write
 
 
@@ -532,7 +533,11 @@ def run_ours(args):
     acc = sum(acc_ms) / len(acc_ms)
     c_bits = ab.VariableBase.window_bits(n)
     windows = 253 // c_bits + 1
-    macs = n * windows * MACS_PER_MIXED_ADD
+    entry_windows = -(-252 // c_bits)      # half-range scalars have 252 bits: the window above only holds the recoding carry
+    ba_levels = ab.VariableBase.batch_affine_levels(n)
+    ba_share = 1.0 - 0.5 ** ba_levels       # additions done by the batch-affine levels (uniform scalars)
+    issued_per_add = ba_share * ISSUED_MACS_PER_AFFINE_ADD + (1.0 - ba_share) * ISSUED_MACS_PER_MIXED_ADD
+    macs = n * entry_windows * MACS_PER_MIXED_ADD
     ms_i, ops_i = C.c_double(), C.c_double()
     lib.check(lib.bench_imad(2, 4096, C.byref(ms_i), C.byref(ops_i)), "bench_imad")
     peak_gmac = ops_i.value / ms_i.value / 1e6          # IMAD.WIDE.U32.X issue rate, measured live
@@ -540,20 +545,24 @@ def run_ours(args):
     ppath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(ppath):
         prof = json.load(open(ppath))
-    roofline = {"kernel": "msm::accumulate_kernel", "bound": "int", "achieved": macs / acc / 1e6, "peak": peak_gmac, "unit": "GMAC/s",
+    roofline = {"kernel": "MSM accumulation phase: msm::ba::level_kernel x %d + msm::accumulate_kernel" % ba_levels if ba_levels else "msm::accumulate_kernel",
+                "bound": "int", "achieved": macs / acc / 1e6, "peak": peak_gmac, "unit": "GMAC/s",
                 "frac": macs / acc / 1e6 / peak_gmac,
-                "pipe_frac": n * windows * ISSUED_MACS_PER_MIXED_ADD / acc / 1e6 / peak_gmac,
-                "issued_macs_per_mixed_add": ISSUED_MACS_PER_MIXED_ADD, "traffic": (prof["msm_accumulate_dram_bytes_per_entry"] * n * windows) if "msm_accumulate_dram_bytes_per_entry" in prof else None,
-                "traffic_source": "ncu --set full at n=2^22 (profiles/r02_ncu_hot_kernels.md via profiles/ncu_traffic.json): DRAM bytes per sorted entry x n x windows",
-                "algorithmic_bytes_per_launch": n * windows * 108,
-                "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows,
+                "pipe_frac": n * entry_windows * issued_per_add / acc / 1e6 / peak_gmac,
+                "issued_macs_per_mixed_add": ISSUED_MACS_PER_MIXED_ADD, "issued_macs_per_affine_add": ISSUED_MACS_PER_AFFINE_ADD,
+                "batch_affine_levels": ba_levels, "batch_affine_share_of_additions": ba_share, "issued_macs_per_addition": issued_per_add,
+                "traffic": (prof["msm_accumulate_dram_bytes_per_entry"] * n * entry_windows) if "msm_accumulate_dram_bytes_per_entry" in prof else None,
+                "traffic_source": prof.get("msm_accumulate_source", "ncu --set full at n=2^22 via profiles/ncu_traffic.json: DRAM bytes per sorted entry x n x windows with entries"),
+                "algorithmic_bytes_per_launch": n * entry_windows * 108,
+                "algorithmic_macs_per_launch": macs, "window_bits": c_bits, "windows": windows, "windows_with_entries": entry_windows,
                 "kernel_ms": acc, "kernel_share_of_step": acc / (sum(sort_ms) / len(sort_ms) + acc + sum(tail_ms) / len(tail_ms)),
                 "phases_ms": {"recode_sort_plan": sum(sort_ms) / len(sort_ms), "accumulate": acc, "combine_reduce_final": sum(tail_ms) / len(tail_ms)},
                 "peak_source": "measured live: carry-chained IMAD.WIDE.U32.X microbenchmark in this library (MEASURED_PEAKS.json "
                                "has no integer-pipe figure); 32-bit MAC = one IMAD.WIDE",
                 "note": "MSM is integer-pipe bound (SURVEY.md 8d); the schema's hbm/tensor bounds do not apply to this kernel. "
-                        "frac counts SURVEY's ALGORITHMIC 3000 MACs per mixed addition; the kernel issues fewer (dedicated "
-                        "squaring, modulus limb 0 = 1), so frac can exceed the share of the pipe it occupies: pipe_frac"}
+                        "frac counts SURVEY's ALGORITHMIC 3000 MACs per bucket addition (n x windows that receive entries); the "
+                        "kernels issue fewer (batch-affine additions with a shared inversion: 1590; XYZZ mixed additions with a "
+                        "dedicated squaring: 2628), so frac exceeds the share of the pipe they occupy: pipe_frac"}
 
     # ---- skewed scalars (real KZG witnesses are full of 0 / 1 / small and "negative small" values) -------
     witness = None

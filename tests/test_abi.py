@@ -62,7 +62,7 @@ def test_argument_validation_precedes_device_use(product_lib_path):
     assert lib.kzg_commit_batch_dev(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), None, None, 65, None) == _lib.EINVAL
     assert lib.ntt_dist_layout(12, 8, None, None, None) == _lib.EINVAL          # 2^12 cannot be spread over 8 GPUs
     assert lib.ntt_dist_layout(27, 8, None, None, None) == 0 and lib.ntt_dist_layout(24, 3, None, None, None) == _lib.EINVAL
-    assert lib.msm_window_bits(1 << 24) == 20 and lib.msm_window_bits(1 << 16) == 12 and lib.msm_window_bits(1) == 4
+    assert lib.msm_window_bits(1 << 24) == 18 and lib.msm_window_bits(1 << 20) == 16 and lib.msm_window_bits(1 << 16) == 12 and lib.msm_window_bits(1) == 4
     assert lib.ntt_launches(24) == 3 and lib.ntt_launches(16) == 2 and lib.ntt_launches(8) == 1 and lib.ntt_launches(26) == 3 and lib.ntt_launches(28) == 4
 
 
