@@ -183,7 +183,7 @@ cudaError_t pool_malloc_async(void** p, size_t bytes, cudaStream_t s) {
         return e;
       }
       const char* env = getenv("ALEO_B200_POOL_KEEP_MB");
-      unsigned long long keep = (env && atoll(env) >= 0 ? (unsigned long long)atoll(env) : 16384ull) << 20;
+      unsigned long long keep = (env && atoll(env) >= 0 ? (unsigned long long)atoll(env) : 65536ull) << 20;  // above the largest MSM workspace (sorted list + buckets + 40 GB of batch-affine levels at 2^26): a pool trimmed below what every call needs re-maps gigabytes per call (measured: 146 instead of 80 ms per 2^24 MSM)
       cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
     }
     pool = g_pool[dev];

@@ -48,7 +48,9 @@ struct LevelArgs {
   const u32* start_out;  // per bucket: first output slot = exclusive scan of ceil(cnt0 / 2^(l + 1))
   unsigned char* out;    // packed affine points of level l + 1
   u32 nb;                // buckets
-  u32 nthreads;          // runs the input positions are cut into (a multiple of TPB)
+  u32 nthreads;          // runs the input positions are cut into, at most (a multiple of TPB; the stride of the scratch planes)
+  u32 run_target;        // positions per run the host planned for (2 k); with fewer positions than planned (zero digits,
+  u32 wave;              // witness-like scalars) fewer threads work, in whole waves of `wave`, so that runs keep that length
   uint4* pre;            // scratch: prefix products, plane (op * 3 + j) * nthreads + thread
   uint4* rec;            // scratch: records {first point, second point, output slot | doubling << 31, -}, op * nthreads + thread;
                          // a point is named by its sorted entry (index | sign << 31) at level 0, by its position above
@@ -127,73 +129,81 @@ DEV u32 level_count(const u32* cnt0, u32 g, u32 level) { return (cnt0[g] + ((1u 
 // So the operands of the NEXT addition travel global -> shared memory asynchronously (cp.async: no registers, no
 // warp stall) while the current one is computed from the other half of a double buffer.  Shared layout: 16-byte word j
 // of thread t at (j * TPB + t) * 16 (conflict-free LDS.128); words 0-2 x1, 3-5 y1, 6-8 x2, 9-11 y2, 12-14 prefix.
-constexpr u32 STAGE_WORDS = 15;
-constexpr u32 STAGE_BYTES = 2 * STAGE_WORDS * 16 * TPB;  // dynamic shared memory of a CTA (61 440 B; 3 CTAs per SM)
+constexpr u32 STAGE_POINT_WORDS = 7;                                  // a 96-byte point that starts 8 bytes into a 16-byte word
+constexpr u32 STAGE_WORDS = 2 * STAGE_POINT_WORDS + 3;               // two points + the prefix
+constexpr u32 STAGE_BYTES = 2 * STAGE_WORDS * 16 * TPB;              // dynamic shared memory of a CTA (69 632 B; 3 CTAs per SM)
 
 #ifndef ALEO_EMU
-struct AsyncStager {
+// SHIFTED: the points may start 8 bytes into a 16-byte word (caller-owned bases at stride 104 from a 16-byte aligned
+// array: every odd index).  The copy then takes the ENCLOSING aligned 16-byte words -- [p - 8, p + 104) is still inside
+// the array: the 8 bytes in front belong to the previous point -- and the reader adds the shift.  A first version copied
+// such points in 8-byte pieces: 48 copies per addition throttled the memory-instruction queue (ncu: mio_throttle 1.5,
+// lg_throttle 0.8 warps per issue; level 0 at 2^24 42.2 ms against 35.1 ms with plain loads).
+template <bool SHIFTED>
+struct AsyncStagerT {
   static constexpr bool ASYNC = true;
   u32 base;  // shared-memory address of word 0 of this thread, buffer 0
-  DEV explicit AsyncStager(unsigned char* smem) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
+  DEV explicit AsyncStagerT(unsigned char* smem) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
   DEV u32 word(u32 buf, u32 j) const { return base + (buf * STAGE_WORDS + j) * (16u * TPB); }
-  // 48 bytes, 16-byte aligned source
-  DEV void fq16(u32 buf, u32 j, const void* src) const {
-#pragma unroll
-    for (u32 k = 0; k < 3; k++)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, j + k)), "l"((const unsigned char*)src + 16 * k) : "memory");
+  DEV static void copy16(u32 dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
-  // 48 bytes, 8-byte aligned source (caller-owned bases)
-  DEV void fq8(u32 buf, u32 j, const void* src) const {
+  // point `which` (0 / 1) of the addition staged in `buf`; with_y = false: the x coordinate only
+  DEV void stage_point(u32 buf, u32 which, const unsigned char* p, bool with_y) const {
+    const u32 shift = SHIFTED ? (u32)((size_t)p & 8u) : 0u;
+    const unsigned char* a = p - shift;
+    const u32 n16 = ((with_y ? 96u : 48u) + shift + 15u) >> 4;  // 3 / 4 words for x, 6 / 7 for the point
+    const u32 w0 = which * STAGE_POINT_WORDS;
 #pragma unroll
-    for (u32 k = 0; k < 6; k++)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(word(buf, j + (k >> 1)) + 8u * (k & 1u)), "l"((const unsigned char*)src + 8 * k) : "memory");
+    for (u32 k = 0; k < STAGE_POINT_WORDS; k++)
+      if (k < n16) copy16(word(buf, w0 + k), a + 16 * k);
   }
-  DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-  DEV void wait_all_but_last() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-  DEV Fq get(u32 buf, u32 j) const {
+  // coordinate at byte offset `off` (0: x, 48: y) of that point
+  DEV Fq get_fq(u32 buf, u32 which, const unsigned char* p, u32 off) const {
     Fq r;
+    const u32 w0 = which * STAGE_POINT_WORDS;
+    if (SHIFTED) {
+      const u32 o = (u32)((size_t)p & 8u) + off;
 #pragma unroll
-    for (u32 k = 0; k < 3; k++) {
-      uint4 v;
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(word(buf, j + k)) : "memory");
-      r.l[4 * k] = v.x;
-      r.l[4 * k + 1] = v.y;
-      r.l[4 * k + 2] = v.z;
-      r.l[4 * k + 3] = v.w;
+      for (u32 i = 0; i < 6; i++) {
+        const u32 byte = o + 8 * i;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.l[2 * i]), "=r"(r.l[2 * i + 1]) : "r"(word(buf, w0 + (byte >> 4)) + (byte & 8u)) : "memory");
+      }
+    } else {
+#pragma unroll
+      for (u32 k = 0; k < 3; k++)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4 * k]), "=r"(r.l[4 * k + 1]), "=r"(r.l[4 * k + 2]), "=r"(r.l[4 * k + 3]) : "r"(word(buf, w0 + off / 16 + k)) : "memory");
     }
     return r;
   }
+  DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  DEV void wait_all_but_last() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  // the prefix planes are `plane` 16-byte words apart
   DEV void stage_pre(u32 buf, const uint4* p0, size_t plane) const {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 12)), "l"(p0) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 13)), "l"(p0 + plane) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(word(buf, 14)), "l"(p0 + 2 * plane) : "memory");
+    copy16(word(buf, 2 * STAGE_POINT_WORDS), p0);
+    copy16(word(buf, 2 * STAGE_POINT_WORDS + 1), p0 + plane);
+    copy16(word(buf, 2 * STAGE_POINT_WORDS + 2), p0 + 2 * plane);
   }
-  DEV Fq get_pre(u32 buf, const uint4*, size_t) const { return get(buf, 12); }
+  DEV Fq get_pre(u32 buf, const uint4*, size_t) const {
+    Fq r;
+#pragma unroll
+    for (u32 k = 0; k < 3; k++)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4 * k]), "=r"(r.l[4 * k + 1]), "=r"(r.l[4 * k + 2]), "=r"(r.l[4 * k + 3]) : "r"(word(buf, 2 * STAGE_POINT_WORDS + k)) : "memory");
+    return r;
+  }
 };
+typedef AsyncStagerT<false> AsyncStager;         // levels >= 1: packed 96-byte records
+typedef AsyncStagerT<true> AsyncStagerShifted;   // level 0
 #endif
-// No staging: the "stage" only remembers the source addresses and get() loads from them.  Used for level 0, whose
-// operands sit in caller-owned bases with 8-byte alignment (8-byte asynchronous copies, 48 per addition, throttle the
-// memory-instruction queue: 35.1 ms direct against 42.2 ms staged at 2^24), and by the emulator.
+// No staging: plain loads at the point of use.  The fallback for bases that are not 16-byte aligned, the A/B switch
+// (ALEO_B200_MSM_BA_STAGE), and what the emulator runs.
 struct DirectStager {
   static constexpr bool ASYNC = false;
-  const unsigned char *a1, *a2, *b1, *b2;  // first / second point of buffer 0 (a) and 1 (b); y lies 48 bytes after x
-  DEV explicit DirectStager(unsigned char*) : a1(nullptr), a2(nullptr), b1(nullptr), b2(nullptr) {}
-  DEV void note(u32 buf, u32 j, const void* p) {
-    const unsigned char* q = (const unsigned char*)p;
-    if (j == 0) {
-      if (buf) b1 = q; else a1 = q;
-    } else if (j == 6) {
-      if (buf) b2 = q; else a2 = q;
-    }
-  }
-  DEV void fq16(u32 buf, u32 j, const void* p) { note(buf, j, p); }
-  DEV void fq8(u32 buf, u32 j, const void* p) { note(buf, j, p); }
+  DEV explicit DirectStager(unsigned char*) {}
+  DEV void stage_point(u32, u32, const unsigned char*, bool) const {}
+  DEV Fq get_fq(u32, u32, const unsigned char* p, u32 off) const { return fq_load8(p + off); }
   DEV void commit() const {}
   DEV void wait_all_but_last() const {}
-  DEV Fq get(u32 buf, u32 j) const {
-    const unsigned char* q = (j < 6) ? (buf ? b1 : a1) : (buf ? b2 : a2);
-    return fq_load8(q + ((j == 3 || j == 9) ? 48 : 0));
-  }
   DEV void stage_pre(u32, const uint4*, size_t) const {}
   DEV Fq get_pre(u32, const uint4* p0, size_t plane) const {
     const uint4 v0 = p0[0], v1 = p0[plane], v2 = p0[2 * plane];
@@ -206,6 +216,7 @@ struct DirectStager {
 };
 #ifdef ALEO_EMU
 typedef DirectStager AsyncStager;  // the emulator has no asynchronous copies
+typedef DirectStager AsyncStagerShifted;
 #endif
 
 constexpr u32 REC_DOUBLE = 1u << 31;    // record flag: P + P (den = 2 y, num = 3 x^2)
@@ -214,22 +225,8 @@ constexpr u32 REC_SLOT = REC_RESOLVED - 1u;
 
 template <bool LEVEL0, class ST>
 DEV void stage_points(ST& st, u32 buf, const LevelArgs& a, const uint4& r, bool with_y) {
-  const PointRef<LEVEL0> p1(a, r.x), p2(a, r.y);
-  if (LEVEL0) {
-    st.fq8(buf, 0, p1.p);
-    st.fq8(buf, 6, p2.p);
-    if (with_y) {
-      st.fq8(buf, 3, p1.p + 48);
-      st.fq8(buf, 9, p2.p + 48);
-    }
-  } else {
-    st.fq16(buf, 0, p1.p);
-    st.fq16(buf, 6, p2.p);
-    if (with_y) {
-      st.fq16(buf, 3, p1.p + 48);
-      st.fq16(buf, 9, p2.p + 48);
-    }
-  }
+  st.stage_point(buf, 0, PointRef<LEVEL0>(a, r.x).p, with_y);
+  st.stage_point(buf, 1, PointRef<LEVEL0>(a, r.y).p, with_y);
 }
 
 template <bool LEVEL0, class ST>
@@ -240,7 +237,15 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   const u32 first = a.start_in[0];
   const u32 total = a.start_in[a.nb - 1] + level_count(a.cnt0, a.nb - 1, a.level) - first;
   if (total == 0) return;
-  const u32 L = (total + a.nthreads - 1) / a.nthreads;
+  u32 nt = a.nthreads;
+  {
+    const u32 want = (total + a.run_target - 1) / a.run_target;      // threads that give runs of the planned length
+    const u32 unit = want >= a.wave ? a.wave : TPB;
+    const u64 rounded = ((u64)want + unit - 1) / unit * unit;
+    if (rounded < nt) nt = (u32)rounded;
+  }
+  if (t >= nt) return;  // whole warps again
+  const u32 L = (total + nt - 1) / nt;
   // a lane whose run lies beyond the end has nothing to do but stays for the warp's shared inversion
   const bool active = (u64)t * L < total;
   const u32 begin = active ? first + t * L : 0u;
@@ -313,7 +318,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       }
       st.commit();
       st.wait_all_but_last();
-      const Fq x1 = st.get(buf, 0), x2 = st.get(buf, 6);
+      const Fq x1 = st.get_fq(buf, 0, PointRef<LEVEL0>(a, r.x).p, 0), x2 = st.get_fq(buf, 1, PointRef<LEVEL0>(a, r.y).p, 0);
       Fq den = fp_sub(x2, x1);
       u32 flag = 0;
       const bool z1 = fp_is_zero(x1), z2 = fp_is_zero(x2);
@@ -414,8 +419,9 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       st.wait_all_but_last();
       if (!(r.z & REC_RESOLVED)) {
         const u32 dbl = r.z >> 31, slot = r.z & REC_SLOT;
-        const Fq x1 = st.get(buf, 0);
-        Fq y1 = st.get(buf, 3);
+        const unsigned char* q1 = PointRef<LEVEL0>(a, r.x).p;
+        const Fq x1 = st.get_fq(buf, 0, q1, 0);
+        Fq y1 = st.get_fq(buf, 0, q1, 48);
         if (LEVEL0 && (r.x >> 31)) y1 = fp_neg(y1);
         const Fq pre = st.get_pre(buf, &a.pre[(size_t)i * 3 * NT + t], NT);
         Fq x2, num, den;
@@ -425,8 +431,9 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
           const Fq xx = fq_sqr_v(x1);
           num = fp_add(fp_dbl(xx), xx);
         } else {
-          x2 = st.get(buf, 6);
-          Fq y2 = st.get(buf, 9);
+          const unsigned char* q2 = PointRef<LEVEL0>(a, r.y).p;
+          x2 = st.get_fq(buf, 1, q2, 0);
+          Fq y2 = st.get_fq(buf, 1, q2, 48);
           if (LEVEL0 && (r.y >> 31)) y2 = fp_neg(y2);
           den = fp_sub(x2, x1);
           num = fp_sub(y2, y1);

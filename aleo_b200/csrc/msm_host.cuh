@@ -137,10 +137,10 @@ static inline u32 ba_kmax() {
 static inline size_t ba_budget_bytes() {
   const char* env = getenv("ALEO_B200_MSM_BA_MB");
   const long v = env ? atol(env) : 0L;
-  return (v > 0 ? (size_t)v : (size_t)32768) << 20;
+  return (v > 0 ? (size_t)v : (size_t)40960) << 20;
 }
 struct BaLevelPlan {
-  u32 k, nthreads;
+  u32 k, nthreads, run, wave;  // additions per thread at most, threads, positions per thread, threads per wave
 };
 // level l of a group with at most `entries` sorted entries over `nb` buckets: its input has at most
 // (entries >> l) + nb points (sum of ceil(m / 2^l)); a thread takes 2 k positions = at most k additions
@@ -165,6 +165,8 @@ static inline BaLevelPlan ba_level_plan(size_t entries, u32 nb, u32 l) {
   }
   const size_t run = (slots + pl.nthreads - 1) / pl.nthreads;  // positions per thread
   pl.k = (u32)((run + 1) / 2 + 1);                              // additions per thread, at most
+  pl.run = (u32)(run ? run : 1);
+  pl.wave = (u32)wave;
   return pl;
 }
 
@@ -309,8 +311,11 @@ struct Session {
         RedLevel l;
         l.m = m;
         const char* renv = getenv("ALEO_B200_MSM_REDUCE");  // read per call: tests force both paths
-        l.cta = renv ? (renv[0] == 'c' && renv[1] == 't') : ((u64)nwin * need <= CTA_LEVEL_MAX_ELEMS);
         l.log_kc = ceil_log2((need + SCAN_MAX - 1) / SCAN_MAX);
+        // ... and only with chunks of >= 32 elements: a CTA of 8 threads still costs whole warp instructions (plain MSM at
+        // 2^16, 22 windows x 256 chunks of 8: 0.61 ms against 0.24 ms for the serial chunk levels; the resident SRS's
+        // single set of 2^14 .. 2^16 buckets makes chunks of 64 .. 256: 2^16 commit 1.67 -> 1.28 ms, 2^18 3.13 -> 2.86 ms)
+        l.cta = renv ? (renv[0] == 'c' && renv[1] == 't') : ((u64)nwin * need <= CTA_LEVEL_MAX_ELEMS && l.log_kc >= 5);
         if (l.cta) {
           if (l.log_kc > 8) l.log_kc = 8;  // one thread per element, at most SCAN_MAX threads
           if (renv && renv[3] >= '1' && renv[3] <= '8' && l.log_kc > (u32)(renv[3] - '0')) l.log_kc = (u32)(renv[3] - '0');  // tests: "cta2" caps the chunk at 4
@@ -400,6 +405,9 @@ struct Session {
         const size_t fit = cap_entries / (max_chunk ? max_chunk : 1);
         ba_wpg = fit < nwin ? (u32)fit : nwin;
         if (ba_wpg == 0) ba_L = 0;
+        // as few groups as fit, of equal size (one group at 2^24; 13 windows at 2^26 that fit 6 by 6 become 5 + 5 + 3):
+        // every group pays its levels' launches and partial last waves (2^24 in two groups: accumulate 68.3 -> 72.9 ms)
+        else ba_wpg = (nwin + ((nwin + ba_wpg - 1) / ba_wpg) - 1) / ((nwin + ba_wpg - 1) / ba_wpg);
         ge = (size_t)max_chunk * ba_wpg;
       }
       if (ba_L) {
@@ -585,9 +593,9 @@ struct Session {
         int devnow = 0;
         MSM_CK(cudaGetDevice(&devnow));
         if (attr_dev != devnow) {
-          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStager>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStagerShifted>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
-          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStager>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStagerShifted>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           attr_dev = devnow;
         }
@@ -623,14 +631,18 @@ struct Session {
           la.start_out = sa[l & 1];
           la.out = lvbuf[l & 1];
           la.nthreads = pl.nthreads;
-          // level 0 gathers caller-owned bases with plain loads; above, the operands are staged through shared memory
-          // (ALEO_B200_MSM_BA_STAGE = 0: plain loads everywhere, 2: staged everywhere -- A/B switch)
+          la.run_target = pl.run;
+          la.wave = pl.wave;
+          // operands staged through shared memory (cp.async); level 0 too when the bases allow whole 16-byte words to be
+          // copied (array 16-byte aligned, stride a multiple of 8).  ALEO_B200_MSM_BA_STAGE = 0: plain loads everywhere,
+          // 1: plain loads at level 0 only -- A/B switch
           const char* stage_env = getenv("ALEO_B200_MSM_BA_STAGE");
-          const int stage_mode = stage_env ? atoi(stage_env) : 1;
-          const bool staged = stage_mode == 2 || (stage_mode == 1 && l > 0);
+          const int stage_mode = stage_env ? atoi(stage_env) : 2;
+          const bool bases_ok = ((size_t)bases & 15u) == 0 && (stride & 7u) == 0;
+          const bool staged = l > 0 ? stage_mode >= 1 : (stage_mode >= 2 && bases_ok);
           const dim3 grid(pl.nthreads / ba::TPB), block(ba::TPB);
           if (l == 0 && staged)
-            LAUNCH_NOSYNC((ba::level_kernel<true, ba::AsyncStager>), grid, block, ba::STAGE_BYTES, s, la);
+            LAUNCH_NOSYNC((ba::level_kernel<true, ba::AsyncStagerShifted>), grid, block, ba::STAGE_BYTES, s, la);
           else if (l == 0)
             LAUNCH_NOSYNC((ba::level_kernel<true, ba::DirectStager>), grid, block, 0, s, la);
           else if (staged)

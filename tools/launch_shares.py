@@ -13,7 +13,7 @@ for r in rows:
     tot[name] = tot.get(name, 0) + int(r[-1])
     cnt[name] += 1
 allt = sum(tot.values())
-is_msm = lambda k: k.startswith(("msm::", "void msm::"))  # noqa: E731
+is_msm = lambda k: k.startswith(("msm::", "void msm::", "ba::", "void ba::"))  # noqa: E731  (ncu prints msm::ba:: kernels as ba::)
 msm = sum(v for k, v in tot.items() if is_msm(k))
 for h in sys.argv[2:]:
     print("# " + h)
