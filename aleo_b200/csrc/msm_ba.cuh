@@ -51,6 +51,7 @@ struct LevelArgs {
   u32 nthreads;          // runs the input positions are cut into, at most (a multiple of TPB; the stride of the scratch planes)
   u32 run_target;        // positions per run the host planned for (2 k); with fewer positions than planned (zero digits,
   u32 wave;              // witness-like scalars) fewer threads work, in whole waves of `wave`, so that runs keep that length
+  u32 copy_via_l1;       // asynchronous copies allocate in L1 (cp.async.ca) instead of bypassing it (.cg)
   uint4* pre;            // scratch: prefix products, plane (op * 3 + j) * nthreads + thread
   uint4* rec;            // scratch: records {first point, second point, output slot | doubling << 31, -}, op * nthreads + thread;
                          // a point is named by its sorted entry (index | sign << 31) at level 0, by its position above
@@ -136,17 +137,20 @@ constexpr u32 STAGE_BYTES = 2 * STAGE_WORDS * 16 * TPB;              // dynamic 
 #ifndef ALEO_EMU
 // SHIFTED: the points may start 8 bytes into a 16-byte word (caller-owned bases at stride 104 from a 16-byte aligned
 // array: every odd index).  The copy then takes the ENCLOSING aligned 16-byte words -- [p - 8, p + 104) is still inside
-// the array: the 8 bytes in front belong to the previous point -- and the reader adds the shift.  A first version copied
-// such points in 8-byte pieces: 48 copies per addition throttled the memory-instruction queue (ncu: mio_throttle 1.5,
-// lg_throttle 0.8 warps per issue; level 0 at 2^24 42.2 ms against 35.1 ms with plain loads).
+// the array: the 8 bytes in front belong to the previous point -- and the reader adds the shift.  EXPERIMENT, not the
+// default: level 0 is faster with plain loads (msm_host.cuh, where the level kernels are launched, has the figures).
 template <bool SHIFTED>
 struct AsyncStagerT {
   static constexpr bool ASYNC = true;
   u32 base;  // shared-memory address of word 0 of this thread, buffer 0
-  DEV explicit AsyncStagerT(unsigned char* smem) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
+  bool ca;
+  DEV AsyncStagerT(unsigned char* smem, u32 via_l1) : ca(via_l1 != 0) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
   DEV u32 word(u32 buf, u32 j) const { return base + (buf * STAGE_WORDS + j) * (16u * TPB); }
-  DEV static void copy16(u32 dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  DEV void copy16(u32 dst, const void* src) const {
+    if (ca)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
   // point `which` (0 / 1) of the addition staged in `buf`; with_y = false: the x coordinate only
   DEV void stage_point(u32 buf, u32 which, const unsigned char* p, bool with_y) const {
@@ -199,7 +203,7 @@ typedef AsyncStagerT<true> AsyncStagerShifted;   // level 0
 // (ALEO_B200_MSM_BA_STAGE), and what the emulator runs.
 struct DirectStager {
   static constexpr bool ASYNC = false;
-  DEV explicit DirectStager(unsigned char*) {}
+  DEV DirectStager(unsigned char*, u32) {}
   DEV void stage_point(u32, u32, const unsigned char*, bool) const {}
   DEV Fq get_fq(u32, u32, const unsigned char* p, u32 off) const { return fq_load8(p + off); }
   DEV void commit() const {}
@@ -298,7 +302,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       pos += 2;
     }
   }
-  ST st(smem);
+  ST st(smem, a.copy_via_l1);
   // ---- pass 1b: running product of the denominators; exceptional pairs are resolved here and leave the batch
   Fq prefix = fp_one<FqParams>();
   {

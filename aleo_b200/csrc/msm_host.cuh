@@ -632,12 +632,20 @@ struct Session {
           la.out = lvbuf[l & 1];
           la.nthreads = pl.nthreads;
           la.run_target = pl.run;
+          {
+            const char* ce = getenv("ALEO_B200_MSM_BA_CA");  // bit 0: level 0, bit 1: levels >= 1 (A/B switch)
+            const int cm = ce ? atoi(ce) : 0;
+            la.copy_via_l1 = (l == 0) ? (cm & 1) : ((cm >> 1) & 1);
+          }
           la.wave = pl.wave;
-          // operands staged through shared memory (cp.async); level 0 too when the bases allow whole 16-byte words to be
-          // copied (array 16-byte aligned, stride a multiple of 8).  ALEO_B200_MSM_BA_STAGE = 0: plain loads everywhere,
-          // 1: plain loads at level 0 only -- A/B switch
+          // levels >= 1: operands staged through shared memory (cp.async.cg); level 0 gathers the caller's bases with plain
+          // loads -- staged it is slower whichever way (2^24, accumulate phase: 67.9 ms plain; 84.4 ms with 16-byte .cg
+          // copies of the enclosing words, 77.9 ms with .ca, 42.2 ms for the level alone with 8-byte copies against 35.1:
+          // a gathered 96-byte point is two L1 lines that plain loads fetch once, an L2-only copy asks for every 16 bytes).
+          // ALEO_B200_MSM_BA_STAGE = 0: plain loads everywhere, 2: staged everywhere (bases 16-byte aligned) -- A/B switch;
+          // ALEO_B200_MSM_BA_CA bit 0 / 1: .ca copies at level 0 / above (levels >= 1: 70.7 ms against 67.9 with .cg)
           const char* stage_env = getenv("ALEO_B200_MSM_BA_STAGE");
-          const int stage_mode = stage_env ? atoi(stage_env) : 2;
+          const int stage_mode = stage_env ? atoi(stage_env) : 1;
           const bool bases_ok = ((size_t)bases & 15u) == 0 && (stride & 7u) == 0;
           const bool staged = l > 0 ? stage_mode >= 1 : (stage_mode >= 2 && bases_ok);
           const dim3 grid(pl.nthreads / ba::TPB), block(ba::TPB);
