@@ -180,6 +180,8 @@ struct AsyncStagerT {
     }
     return r;
   }
+  DEV void advance() const {}
+  DEV void end_pass1() const {}
   DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
   DEV void wait_all_but_last() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
   // the prefix planes are `plane` 16-byte words apart
@@ -201,11 +203,25 @@ typedef AsyncStagerT<true> AsyncStagerShifted;   // level 0
 #endif
 // No staging: plain loads at the point of use.  The fallback for bases that are not 16-byte aligned, the A/B switch
 // (ALEO_B200_MSM_BA_STAGE), and what the emulator runs.
+// Pass 1b holds few registers, so there the x coordinates of the NEXT pair are loaded into registers while the current
+// product runs (`nxt`, rotated by advance()); pass 2 has no registers to spare and loads at the point of use.
 struct DirectStager {
   static constexpr bool ASYNC = false;
-  DEV DirectStager(unsigned char*, u32) {}
-  DEV void stage_point(u32, u32, const unsigned char*, bool) const {}
-  DEV Fq get_fq(u32, u32, const unsigned char* p, u32 off) const { return fq_load8(p + off); }
+  Fq cur[2], nxt[2];
+  bool x_ahead;
+  DEV DirectStager(unsigned char*, u32) : x_ahead(true) {}
+  DEV void stage_point(u32, u32 which, const unsigned char* p, bool with_y) {
+    if (!with_y) nxt[which] = fq_load8(p);
+  }
+  DEV void advance() {
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
+  }
+  DEV void end_pass1() { x_ahead = false; }
+  DEV Fq get_fq(u32, u32 which, const unsigned char* p, u32 off) const {
+    if (x_ahead && off == 0) return cur[which];
+    return fq_load8(p + off);
+  }
   DEV void commit() const {}
   DEV void wait_all_but_last() const {}
   DEV void stage_pre(u32, const uint4*, size_t) const {}
@@ -313,6 +329,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       if (nops > 1) rn = a.rec[NT + t];
     }
     st.commit();
+    st.advance();
     for (u32 j = 0; j < nops; j++) {
       const u32 buf = j & 1u;
       uint4 rnn = rn;
@@ -358,10 +375,12 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
         a.pre[o + 2 * NT] = make_uint4(prefix.l[8], prefix.l[9], prefix.l[10], prefix.l[11]);
       }
       prefix = fq_mul_v(prefix, den);
+      st.advance();
       r = rn;
       rn = rnn;
     }
   }
+  st.end_pass1();
   // ---- ONE inversion per warp.  A binary-GCD inversion is a few ten thousand data-dependent shift / subtract steps:
   // run by 32 lanes at once it diverges into several hundred thousand warp instructions (ncu: it was half of the
   // kernel's instructions even at 256 additions per lane), run by one lane it is a tenth of that.  So the lanes' run
