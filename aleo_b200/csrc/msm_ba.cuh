@@ -180,6 +180,15 @@ struct AsyncStagerT {
     }
     return r;
   }
+  template <bool LEVEL0>
+  DEV void stage_op(u32 buf, const LevelArgs& a, const uint4& r, u32, u32, size_t, bool with_y) const {
+    stage_point(buf, 0, PointRef<LEVEL0>(a, r.x).p, with_y);
+    stage_point(buf, 1, PointRef<LEVEL0>(a, r.y).p, with_y);
+  }
+  template <bool LEVEL0>
+  DEV Fq get(u32 buf, u32 which, const LevelArgs& a, const uint4& r, u32, u32, size_t, u32 off) const {
+    return get_fq(buf, which, PointRef<LEVEL0>(a, which ? r.y : r.x).p, off);
+  }
   DEV void advance() const {}
   DEV void end_pass1() const {}
   DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -218,6 +227,15 @@ struct DirectStager {
     cur[1] = nxt[1];
   }
   DEV void end_pass1() { x_ahead = false; }
+  template <bool LEVEL0>
+  DEV void stage_op(u32 buf, const LevelArgs& a, const uint4& r, u32, u32, size_t, bool with_y) {
+    stage_point(buf, 0, PointRef<LEVEL0>(a, r.x).p, with_y);
+    stage_point(buf, 1, PointRef<LEVEL0>(a, r.y).p, with_y);
+  }
+  template <bool LEVEL0>
+  DEV Fq get(u32 buf, u32 which, const LevelArgs& a, const uint4& r, u32, u32, size_t, u32 off) const {
+    return get_fq(buf, which, PointRef<LEVEL0>(a, which ? r.y : r.x).p, off);
+  }
   DEV Fq get_fq(u32, u32 which, const unsigned char* p, u32 off) const {
     if (x_ahead && off == 0) return cur[which];
     return fq_load8(p + off);
@@ -242,12 +260,6 @@ typedef DirectStager AsyncStagerShifted;
 constexpr u32 REC_DOUBLE = 1u << 31;    // record flag: P + P (den = 2 y, num = 3 x^2)
 constexpr u32 REC_RESOLVED = 1u << 30;  // record flag: exceptional pair, result already stored by pass 1
 constexpr u32 REC_SLOT = REC_RESOLVED - 1u;
-
-template <bool LEVEL0, class ST>
-DEV void stage_points(ST& st, u32 buf, const LevelArgs& a, const uint4& r, bool with_y) {
-  st.stage_point(buf, 0, PointRef<LEVEL0>(a, r.x).p, with_y);
-  st.stage_point(buf, 1, PointRef<LEVEL0>(a, r.y).p, with_y);
-}
 
 // 3 CTAs per SM (168 registers, no spills).  4 (128 registers, ~150 bytes of spills) was measured for level 0, whose gathers
 // would like more warps in flight: accumulate 69.8 against 67.3 ms at 2^24.
@@ -327,7 +339,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
     uint4 r = make_uint4(0, 0, 0, 0), rn = r;
     if (nops) {
       r = a.rec[t];
-      stage_points<LEVEL0, ST>(st, 0, a, r, false);
+      st.template stage_op<LEVEL0>(0, a, r, 0, t, NT, false);
       if (nops > 1) rn = a.rec[NT + t];
     }
     st.commit();
@@ -336,12 +348,12 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       const u32 buf = j & 1u;
       uint4 rnn = rn;
       if (j + 1 < nops) {
-        stage_points<LEVEL0, ST>(st, buf ^ 1u, a, rn, false);
+        st.template stage_op<LEVEL0>(buf ^ 1u, a, rn, j + 1, t, NT, false);
         if (j + 2 < nops) rnn = a.rec[(size_t)(j + 2) * NT + t];
       }
       st.commit();
       st.wait_all_but_last();
-      const Fq x1 = st.get_fq(buf, 0, PointRef<LEVEL0>(a, r.x).p, 0), x2 = st.get_fq(buf, 1, PointRef<LEVEL0>(a, r.y).p, 0);
+      const Fq x1 = st.template get<LEVEL0>(buf, 0, a, r, j, t, NT, 0), x2 = st.template get<LEVEL0>(buf, 1, a, r, j, t, NT, 0);
       Fq den = fp_sub(x2, x1);
       u32 flag = 0;
       const bool z1 = fp_is_zero(x1), z2 = fp_is_zero(x2);
@@ -427,7 +439,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   // ---- pass 2: unwind, last addition first
   {
     uint4 r = a.rec[(size_t)(nops - 1) * NT + t], rn = r;
-    stage_points<LEVEL0, ST>(st, (nops - 1) & 1u, a, r, true);
+    st.template stage_op<LEVEL0>((nops - 1) & 1u, a, r, nops - 1, t, NT, true);
     // the prefix planes are NT * 16 bytes apart: staged word by word
     st.stage_pre((nops - 1) & 1u, &a.pre[(size_t)(nops - 1) * 3 * NT + t], NT);
     if (nops > 1) rn = a.rec[(size_t)(nops - 2) * NT + t];
@@ -436,7 +448,7 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       const u32 buf = i & 1u;
       uint4 rnn = rn;
       if (i) {
-        stage_points<LEVEL0, ST>(st, buf ^ 1u, a, rn, true);
+        st.template stage_op<LEVEL0>(buf ^ 1u, a, rn, i - 1, t, NT, true);
         st.stage_pre(buf ^ 1u, &a.pre[(size_t)(i - 1) * 3 * NT + t], NT);
         if (i > 1) rnn = a.rec[(size_t)(i - 2) * NT + t];
       }
@@ -444,9 +456,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
       st.wait_all_but_last();
       if (!(r.z & REC_RESOLVED)) {
         const u32 dbl = r.z >> 31, slot = r.z & REC_SLOT;
-        const unsigned char* q1 = PointRef<LEVEL0>(a, r.x).p;
-        const Fq x1 = st.get_fq(buf, 0, q1, 0);
-        Fq y1 = st.get_fq(buf, 0, q1, 48);
+        const Fq x1 = st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 0);
+        Fq y1 = st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 48);
         if (LEVEL0 && (r.x >> 31)) y1 = fp_neg(y1);
         const Fq pre = st.get_pre(buf, &a.pre[(size_t)i * 3 * NT + t], NT);
         Fq x2, num, den;
@@ -456,9 +467,8 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
           const Fq xx = fq_sqr_v(x1);
           num = fp_add(fp_dbl(xx), xx);
         } else {
-          const unsigned char* q2 = PointRef<LEVEL0>(a, r.y).p;
-          x2 = st.get_fq(buf, 1, q2, 0);
-          Fq y2 = st.get_fq(buf, 1, q2, 48);
+          x2 = st.template get<LEVEL0>(buf, 1, a, r, i, t, NT, 0);
+          Fq y2 = st.template get<LEVEL0>(buf, 1, a, r, i, t, NT, 48);
           if (LEVEL0 && (r.y >> 31)) y2 = fp_neg(y2);
           den = fp_sub(x2, x1);
           num = fp_sub(y2, y1);

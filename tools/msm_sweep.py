@@ -22,9 +22,12 @@ lib.check(lib.init(0), "init")
 stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
 
 
+STRIDE = int(os.environ.get("MSM_SWEEP_STRIDE", "104"))  # 104: Rust G1Affine layout, 96: packed (modes ba / phases / sizes)
+
+
 def setup(log_n):
     n = 1 << log_n
-    return n, ab.gen_bases_dev(n, 12345, 67891, 0, 104), ab.gen_scalars_dev(n, 1)
+    return n, ab.gen_bases_dev(n, 12345, 67891, 0, STRIDE), ab.gen_scalars_dev(n, 1)
 
 
 if mode == "phases":
@@ -38,7 +41,7 @@ if mode == "phases":
             os.environ["ALEO_B200_MSM_C"] = str(c)
         res = []
         for _ in range(4):
-            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), 104, stream(), ph), "p")
+            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), STRIDE, stream(), ph), "p")
             res.append((ph[0], ph[1], ph[2]))
         raw = out.cpu().numpy().tobytes()
         ref = ref or raw
@@ -65,7 +68,7 @@ elif mode == "ba":  # ba LOG_N  SPEC ...   SPEC = levels[:k[:c[:pf]]] (batch-aff
             os.environ["ALEO_B200_MSM_BA_PF"] = f[3]
         res = []
         for _ in range(4):
-            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), 104, stream(), ph), "p")
+            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), STRIDE, stream(), ph), "p")
             res.append((ph[0], ph[1], ph[2]))
         raw = out.cpu().numpy().tobytes()
         ref = ref or raw
@@ -132,7 +135,7 @@ elif mode == "sizes":
         ph = (C.c_float * 3)()
         res = []
         for _ in range(4):
-            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), 104, stream(), ph), "p")
+            lib.check(lib.msm_g1_dev_profile(out.data_ptr(), bases.data_ptr(), n, sc.data_ptr(), STRIDE, stream(), ph), "p")
             res.append((ph[0], ph[1], ph[2]))
         best = min(res[1:], key=sum)
         print("log_n=%d c=%d sort/acc/tail ms: %.3f/%.3f/%.3f total %.3f -> %.1f Mpts/s" %
