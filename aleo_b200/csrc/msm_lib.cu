@@ -31,9 +31,11 @@ cudaError_t copy_stream(cudaStream_t* out) { return t_copy_stream.get(out); }
 int chunk_schedule(size_t n, size_t* sizes, bool pinned = false) {
   const char* env = getenv("ALEO_B200_MSM_CHUNKS");  // read per call: tests and sweeps switch it
   const long k_env = env ? atol(env) : 0L;
-  // from 2^22 points: 4 ranges 3 : 4 : 5 : 7 for pageable caller memory (the default: a Rust Vec), 3 ranges 1 : 2 : 4
-  // when the caller's buffers are pinned (copies at the full 55 GB/s: 2^24 measured 97.6 ms against 102.9 ms with 4)
-  int k = n < ((size_t)1 << 19) ? 1 : (n < ((size_t)1 << 22) ? 2 : (pinned ? 3 : 4));
+  // from 2^22 points: 4 ranges, 1 : 2 : 3 : 5 for pageable caller memory (the default: a Rust Vec), 1 : 2 : 4 : 8 when the
+  // caller's buffers are pinned (copies at the full 55 GB/s).  Re-swept after the batch-affine levels made the
+  // accumulation faster (2^24, profiles/r03k_*: pageable 3:4:5:7 98.4 ms, 2:3:5:9 97.0, 1:2:3:5 95.7, 1:2:4:8 97.2;
+  // pinned 1:2:4 94.1 ms, 1:2:4:8 93.1, 1:3:6 93.8): the first range's copy is the only one that is exposed.
+  int k = n < ((size_t)1 << 19) ? 1 : (n < ((size_t)1 << 22) ? 2 : 4);
   if (k_env >= 1 && k_env <= 4 && n >= 16) k = (int)k_env;
   // explicit weights, e.g. ALEO_B200_MSM_SPLIT=1,2,4 (sweeps): range i gets w_i / sum(w) of the points
   if (const char* sp = getenv("ALEO_B200_MSM_SPLIT")) {
@@ -55,13 +57,14 @@ int chunk_schedule(size_t n, size_t* sizes, bool pinned = false) {
   if (k == 1) {
     sizes[0] = n;
   } else if (k == 4) {
-    // 3 : 4 : 5 : 7 (default from 2^22 points).  A range may be only ~1.3x its predecessor before the GPU waits for its
-    // copy when the caller's memory is PAGEABLE: staged copies run at 33-46 GB/s on the B200 boxes (tools/feed_probe.cu;
-    // 243-340 Mpts/s at 136 B per point) against 190 Mpts/s of accumulation.  With 1 : 2 : 4 the third range arrived
-    // ~15 ms after the second was done (2^24 pageable: 129 ms, pinned 97.6 ms).
-    sizes[0] = (n * 3) / 19;
-    sizes[1] = (n * 4) / 19;
-    sizes[2] = (n * 5) / 19;
+    // A range may be about 1.5x its predecessor before the GPU waits for its copy when the caller's memory is PAGEABLE
+    // (staged copies run at 33-46 GB/s on the B200 boxes, tools/feed_probe.cu: 243-340 Mpts/s at 136 B per point against
+    // 210 Mpts/s of accumulation), about twice when it is pinned.
+    const size_t w[4] = {1, 2, pinned ? (size_t)4 : 3, pinned ? (size_t)8 : 5};
+    const size_t tot = w[0] + w[1] + w[2] + w[3];
+    sizes[0] = (n * w[0]) / tot;
+    sizes[1] = (n * w[1]) / tot;
+    sizes[2] = (n * w[2]) / tot;
     sizes[3] = n - sizes[0] - sizes[1] - sizes[2];
   } else if (k == 2) {
     sizes[0] = n / 4;
