@@ -276,3 +276,24 @@ def test_batch_affine_levels_match_c_oracle(c_oracle, log_n, levels, monkeypatch
     c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, 104, os.cpu_count() or 1)
     assert got == out.raw
     assert ab.VariableBase.msm(hb, hs, 104) == out.raw      # host ranges accumulate into the same buckets
+
+
+@pytest.mark.parametrize("stage,ca", [(0, 0), (1, 0), (1, 2), (2, 0), (2, 1)])
+def test_batch_affine_operand_staging_variants(c_oracle, stage, ca, monkeypatch):
+    """the level kernel's operand paths -- plain loads, cp.async staging above level 0 (the default), staging of level 0
+    through the enclosing 16-byte words of stride-104 bases, .cg / .ca copies -- give the same bytes as the C oracle"""
+    monkeypatch.setenv("ALEO_B200_MSM_BA", "3")
+    monkeypatch.setenv("ALEO_B200_MSM_BA_STAGE", str(stage))
+    monkeypatch.setenv("ALEO_B200_MSM_BA_CA", str(ca))
+    monkeypatch.setenv("ALEO_B200_MSM_C", "9")
+    n = 1 << 16
+    s0, d = o.base_dlogs(n, 8100)
+    sc = ab.gen_scalars_dev(n, 2100)
+    hs = sc.cpu().numpy()
+    for stride in (104, 96):
+        bases = ab.gen_bases_dev(n, s0, d, 0, stride)
+        got = ab.VariableBase.msm_dev(bases, sc, n, stride).cpu().numpy().tobytes()
+        hb = bases.cpu().numpy()
+        out = C.create_string_buffer(144)
+        c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, stride, os.cpu_count() or 1)
+        assert got == out.raw, stride
