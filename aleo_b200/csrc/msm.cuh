@@ -31,7 +31,9 @@
 namespace msm {
 
 constexpr u32 SCALAR_BITS = 253;
-constexpr u32 SMALL_SPLIT_MAX = 64;      // split buckets with <= 64 tasks are combined by one thread
+constexpr u32 SMALL_SPLIT_MAX = 8;       // buckets cut into <= 8 pieces are combined by one thread, the others by a CTA each (a narrow top
+                                         // window -- GLV at c = 12: 70 buckets of 1900 entries -- makes buckets of ~60 pieces: 60 serial
+                                         // additions in combine_small doubled the 2^16 accumulation phase, 0.9 -> 1.8 ms)
 constexpr u32 COMBINE_TPB = 128;
 
 struct Params {
@@ -54,6 +56,13 @@ struct Params {
   // and MSM m owns the bucket set m (a "window" of the reduction kernels).  nbatch = 0: a single MSM.
   const u32* batch_off;
   u32 nbatch;
+  // GLV (plain MSM below the batch-affine threshold): the scalars were split k = k1 + k2 u^2 (glv_split_kernel) and the
+  // MSM runs over 2 n "virtual" points with 127-bit scalars -- virtual point i < glv_n is P_i, virtual point
+  // glv_n + i is [u^2] P_i = (beta x_i, -y_i), whose x coordinates lie in `glv_bx` (48 bytes each).  Half as many
+  // windows: half as many buckets to reduce and half the doubling chain of the tail, which is what a proof-sized MSM
+  // spends most of its time in.  glv_n = 0: off.
+  u32 glv_n;
+  const unsigned char* glv_bx;
 };
 
 // which MSM of a batch scalar i belongs to (nbatch <= 64: a short walk), and its index inside that MSM
@@ -482,11 +491,18 @@ DEV void prefetch_base(const unsigned char* bases, size_t stride, u32 idx) {
 
 // DIRECT: the entries ARE the points -- position pos of the (dense, bucket-ordered) packed affine array `bases` that the
 // batch-affine levels left (msm_ba.cuh); `sorted` is not read and there is no sign.
+// virtual point of a GLV entry -> base index; returns true for the endomorphism image ([u^2] P = (beta x, -y))
+DEV bool glv_map(u32& idx, u32 glv_n) {
+  if (glv_n == 0 || idx < glv_n) return false;
+  idx -= glv_n;
+  return true;
+}
+
 template <bool CALL, bool PREFETCH = false, bool DIRECT = false>
 KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bases, u32 stride, const u32* sorted,
                                                       const u32* starts, const u32* ends, u32 nb, u32 nlanes,
                                                       const u32* meta, G1Xyzz* buckets, G1Xyzz* pieces,
-                                                      u32* piece_bucket, u32 into) {
+                                                      u32* piece_bucket, u32 into, u32 glv_n, const unsigned char* glv_bx) {
   const u32 lane = blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= nlanes) return;
   piece_bucket[2 * lane] = NO_BUCKET;
@@ -526,10 +542,29 @@ KERNEL void __launch_bounds__(128, 3) accumulate_kernel(const unsigned char* bas
       }
       const u32 e = DIRECT ? pos : sorted[pos];
       pos++;
-      G1Affine p = affine_load(bases, stride, e & 0x7fffffffu);
-      if (PREFETCH && !DIRECT && pos < end) prefetch_base(bases, stride, sorted[pos] & 0x7fffffffu);  // the next gather, while this addition runs
+      u32 idx = e & 0x7fffffffu;
+      const bool phi = !DIRECT && glv_map(idx, glv_n);
+      G1Affine p;
+      if (phi) {  // x from the beta x array, y and the flag from the base: one round of loads, not two
+        const unsigned char* pb = bases + (size_t)idx * stride;
+        p.x = fq_load8(glv_bx + (size_t)idx * 48);
+        p.y = fq_load8(pb + 48);
+        p.inf = (stride >= 97) ? (pb[96] != 0) : (fp_is_zero(p.x) && fp_is_zero(p.y));  // beta x of a packed identity is 0
+      } else {
+        p = affine_load(bases, stride, idx);
+      }
+      if (PREFETCH && !DIRECT && pos < end) {  // the next gather, while this addition runs
+        u32 nidx = sorted[pos] & 0x7fffffffu;
+        const bool nphi = glv_map(nidx, glv_n);
+        prefetch_base(bases, stride, nidx);
+#ifndef ALEO_EMU
+        if (nphi) asm volatile("prefetch.global.L1 [%0];" ::"l"(glv_bx + (size_t)nidx * 48));
+#else
+        (void)nphi;
+#endif
+      }
       if (p.inf) continue;
-      if (!DIRECT && (e >> 31)) p.y = fp_neg(p.y);
+      if (!DIRECT && ((e >> 31) != (phi ? 1u : 0u))) p.y = fp_neg(p.y);
       px = p.x;
       py = p.y;
       have = true;
@@ -920,6 +955,94 @@ KERNEL void __launch_bounds__(128) srs_expand_kernel(const unsigned char* bases,
     }
     affine_store(pre, 96, (size_t)w * n + i, a);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GLV split.  On G1 the endomorphism phi(x, y) = (beta x, y) is multiplication by -u^2 (poly.cuh uses the same fact
+// for its subgroup test), so for k < r:  k P = k1 P + k2 [u^2] P = k1 P + k2 (beta x, -y)  with k2 = k div u^2,
+// k1 = k mod u^2, both below 2^127 -- no lattice rounding: r = u^4 - u^2 + 1 makes plain division by u^2 a balanced
+// split.  Holds for points of the prime-order subgroup, which is what a snarkVM G1Affine is (deserialisation checks
+// it and the group law preserves it).  out: 2 n scalars of 8 limbs (k1 of point i at i, k2 at n + i); bx: beta x_i.
+// ---------------------------------------------------------------------------------------------
+KERNEL void glv_split_kernel(const u32* scalars, u32 n, const unsigned char* bases, u32 stride, u32* out, unsigned char* bx) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 k[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = scalars[(size_t)i * 8 + j];
+  // q = floor(k * BARRETT / 2^384): limbs 12 .. 15 of the 17-limb product (column sums; q <= floor(k / u^2) <= q + 2)
+  u32 q[4] = {0, 0, 0, 0};
+  {
+    u64 carry = 0;
+    for (int col = 0; col < 16; col++) {
+      u64 lo = carry & 0xffffffffull, hi = carry >> 32;  // running column sum in two halves so that nothing overflows
+      for (int a = 0; a < 8; a++) {
+        const int b = col - a;
+        if (b < 0 || b > 8) continue;
+        const u64 prod = (u64)k[a] * GlvParams::BARRETT(b);
+        lo += prod & 0xffffffffull;
+        hi += prod >> 32;
+      }
+      hi += lo >> 32;
+      if (col >= 12) q[col - 12] = (u32)lo;
+      carry = hi;
+    }
+  }
+  // rem = k - q * u^2 (fits 5 limbs: < 3 u^2), then at most two corrections
+  u32 rem[5];
+  {
+    u32 qd[5] = {0, 0, 0, 0, 0};  // low 5 limbs of q * u^2
+    u64 carry = 0;
+    for (int col = 0; col < 5; col++) {
+      u64 lo = carry & 0xffffffffull, hi = carry >> 32;
+      for (int a = 0; a < 4; a++) {
+        const int b = col - a;
+        if (b < 0 || b > 3) continue;
+        const u64 prod = (u64)q[a] * GlvParams::U2(b);
+        lo += prod & 0xffffffffull;
+        hi += prod >> 32;
+      }
+      hi += lo >> 32;
+      qd[col] = (u32)lo;
+      carry = hi;
+    }
+    u64 borrow = 0;
+    for (int j = 0; j < 5; j++) {
+      const u64 d = (u64)k[j] - qd[j] - borrow;
+      rem[j] = (u32)d;
+      borrow = (d >> 32) & 1ull;
+    }
+  }
+  for (int round = 0; round < 3; round++) {
+    bool ge = rem[4] != 0;
+    if (!ge) {
+      ge = true;
+      for (int j = 3; j >= 0; j--) {
+        if (rem[j] != GlvParams::U2(j)) {
+          ge = rem[j] > GlvParams::U2(j);
+          break;
+        }
+      }
+    }
+    if (!ge) break;
+    u64 borrow = 0;
+    for (int j = 0; j < 5; j++) {
+      const u64 d = (u64)rem[j] - (j < 4 ? GlvParams::U2(j) : 0u) - borrow;
+      rem[j] = (u32)d;
+      borrow = (d >> 32) & 1ull;
+    }
+    for (int j = 0; j < 4; j++) {
+      q[j] += 1u;
+      if (q[j] != 0) break;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    out[(size_t)i * 8 + j] = j < 4 ? rem[j] : 0u;
+    out[(size_t)(n + i) * 8 + j] = j < 4 ? q[j] : 0u;
+  }
+  const G1Affine p = affine_load(bases, stride, i);
+  fq_store8(bx + (size_t)i * 48, p.inf ? fp_zero<FqParams>() : fq_mul_ni(fp_const<FqParams, FqParams::BETA_M>(), p.x));
 }
 
 // Montgomery Fr -> canonical BigInteger256 (PrimeField::to_bigint), the first step of KZG10::commit

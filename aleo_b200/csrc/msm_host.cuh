@@ -31,6 +31,20 @@ static inline bool ba_enabled_for(size_t n_points) {
   return n_points >= ((size_t)1 << 22);
 }
 
+// GLV split (msm.cuh glv_split_kernel): plain MSMs below the batch-affine threshold run over 2 n virtual points with
+// 127-bit scalars -- half the windows, so half the buckets to reduce and half the doubling chain of the tail, which is
+// most of a proof-sized MSM (2^16: 1.65 of 2.6 ms).  Above the threshold the accumulation dominates and the levels
+// gather the bases themselves.  ALEO_B200_MSM_GLV = 0 | 1 overrides.
+constexpr u32 GLV_BITS = 127;
+static inline bool glv_enabled_for(size_t n_points) {
+  const char* env = getenv("ALEO_B200_MSM_GLV");  // read per call: tests switch it
+  if (env) return atol(env) > 0 && !ba_enabled_for(n_points);
+  // measured on B200 (profiles/r03r_glv_sizes.log, with / without): 2^12 1.45 / 1.99 ms, 2^16 2.25 / 2.62, 2^18 3.71 / 4.23,
+  // 2^20 8.69 / 8.74, 2^21 15.19 / 14.61 -- the split doubles the points the sort and the gathers see
+  return n_points <= ((size_t)1 << 20) && !ba_enabled_for(n_points);
+}
+static inline u32 windows_for_glv(u32 c) { return GLV_BITS / c + 1; }
+
 // Window bits by cost model, in Fq products: n * W(c) mixed additions (10 each) of bucket accumulation
 // against W(c) * 2^(c-1) buckets * 2 full additions (14 each, x1.5: the reduction runs at lower
 // occupancy).  2^16 -> 12, 2^20 -> 16.  With the batch-affine levels an entry costs less and a bucket more (every
@@ -44,18 +58,21 @@ static inline u32 choose_window(size_t n, u32 chunks = 1) {
   if (c_env >= 4 && c_env <= 22) return (u32)c_env;
   if (n < 2) return 4;
   const bool ba = ba_enabled_for(n / chunks);
-  const double per_bucket = ba ? 110.0 : 2.0 * 14.0 * 1.5;
+  const bool glv = glv_enabled_for(n / chunks);
+  // GLV sizes are latency bound in the reduction: 2.7 ns per bucket against 0.38 ns per entry (r03r: tails of 1.88 / 1.28 ms
+  // for 262 k / 41 k buckets)
+  const double per_bucket = ba ? 110.0 : (glv ? 80.0 : 2.0 * 14.0 * 1.5);
   u32 best_c = 4;
   double best = 0;
   for (u32 c = 4; c <= 22; c++) {
-    const double W = (double)windows_for(c);
+    const double W = glv ? (double)windows_for_glv(c) : (double)windows_for(c);
     // half-range scalars have 252 bits: only ceil(252 / c) windows receive entries, the one above holds the recoding
     // carry alone (c = 18: 14 windows of entries, c = 17: 15 -- why 18 beats 17 at 2^24); counted in the fitted model only
     const double We = ba ? (double)((SCALAR_BITS - 1 + c - 1) / c) : W;
     // an MSM that arrives in `chunks` point ranges re-opens every bucket once per extra range: one more
     // mixed addition per bucket and range (the first addition into an empty bucket is a copy); weighted 5 rather
     // than 10: measured on B200 at 2^24 in 3 ranges, c = 20 runs 102.3 ms against 105.5 ms for c = 19
-    const double cost = (double)n * We * 10.0 + W * (double)(1u << (c - 1)) * (per_bucket + 5.0 * (chunks - 1));
+    const double cost = (glv ? 2.0 : 1.0) * (double)n * We * 10.0 + W * (double)(1u << (c - 1)) * (per_bucket + 5.0 * (chunks - 1));
     if (c == 4 || cost < best) {
       best = cost;
       best_c = c;
@@ -173,15 +190,18 @@ static inline BaLevelPlan ba_level_plan(size_t entries, u32 nb, u32 l) {
 // n: points of the whole MSM (decides the window); chunks: how many point ranges it arrives in
 static inline Params make_params(size_t n, const SrsView* srs = nullptr, u32 chunks = 1) {
   Params p;
+  const bool glv = !srs && n > 0 && glv_enabled_for(n / (chunks ? chunks : 1));
   p.c = srs ? srs->c : choose_window(n, chunks);
-  p.W = srs ? srs->W : windows_for(p.c);
-  p.half_range = 1u;
+  p.W = srs ? srs->W : (glv ? windows_for_glv(p.c) : windows_for(p.c));
+  p.half_range = glv ? 0u : 1u;  // split scalars are not residues mod r
+  p.glv_n = glv ? 1u : 0u;       // Session::add_chunk sets the range's point count
+  p.glv_bx = nullptr;
   p.batch_off = nullptr;
   p.nbatch = 0;
   p.B = 1u << (p.c - 1);
   p.n_stride = srs ? srs->n_total : 0;
   p.first = 0;
-  p.nlanes = lanes_for(n, p.W);
+  p.nlanes = lanes_for(glv ? 2 * n : n, p.W);
   return p;
 }
 
@@ -274,6 +294,8 @@ struct Session {
   // batch-affine levels: L levels per group of `ba_wpg` bucket sets (the workspace bounds a group's entries)
   u32 ba_L = 0, ba_wpg = 0;
   size_t ba_scratch_ops = 0;
+  bool glv = false;  // scalars split by u^2, 2 n virtual points (make_params)
+  size_t o_glv_sc = 0, o_glv_bx = 0;
   size_t o_baA = 0, o_baB = 0, o_ba_pre = 0, o_ba_rec = 0, o_ba_s0 = 0, o_ba_s1 = 0, o_ba_e = 0, o_meta2 = 0;
   unsigned char* ws = nullptr;
   bool dry = false;
@@ -294,9 +316,10 @@ struct Session {
     prm = make_params(n_total, srs, chunks);
     prm.nbatch = nbatch;
     prm.batch_off = batch_off;
+    glv = prm.glv_n != 0;
     nwin = nbatch ? nbatch : (srs ? 1u : prm.W);  // bucket sets (the resident SRS shares one across all windows)
     NB = nwin * prm.B;
-    max_lanes = lanes_for(max_chunk, prm.W);
+    max_lanes = lanes_for(glv ? 2 * max_chunk : max_chunk, prm.W);
     cap_small = max_lanes + 1;  // every run boundary cuts at most one bucket
     cap_large = max_lanes / SMALL_SPLIT_MAX + 1;
     scan_blocks = (NB + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -353,7 +376,11 @@ struct Session {
     o_piece_bucket = cv.take((size_t)max_lanes * 2 * 4);
     o_bsums = cv.take((size_t)(scan_blocks + 1) * 4);
     o_meta = cv.take(64);
-    o_sorted = cv.take((size_t)max_chunk * prm.W * 4);
+    o_sorted = cv.take((size_t)max_chunk * (glv ? 2 : 1) * prm.W * 4);
+    if (glv) {
+      o_glv_sc = cv.take((size_t)max_chunk * 2 * 32);
+      o_glv_bx = cv.take((size_t)max_chunk * 48);
+    }
     o_small = cv.take((size_t)cap_small * 4);
     o_large = cv.take((size_t)cap_large * 4);
     o_buckets = cv.take((size_t)NB * sizeof(G1Xyzz));
@@ -379,14 +406,14 @@ struct Session {
         part_bps = prm.B >> part_fb;
         part_nbin = prm.W * part_bps;
         part_wpg = PART_GROUP_BINS / part_bps ? PART_GROUP_BINS / part_bps : 1;
-        const size_t ctas = (max_chunk + PART_TPB - 1) / PART_TPB;
+        const size_t ctas = ((glv ? 2 : 1) * max_chunk + PART_TPB - 1) / PART_TPB;  // scalars the sort sees (GLV: 2 n)
         part_ncta_max = (u32)(ctas < (size_t)dev_props().sms * 4 ? ctas : (size_t)dev_props().sms * 4);
         if ((size_t)part_nbin * 4 > (size_t)160 * 1024) part = false;  // histogram of part_count must fit shared memory
       }
       if (part) {
         o_pcnt = cv.take((size_t)part_nbin * part_ncta_max * 4);
         o_poffs = cv.take((size_t)part_nbin * part_ncta_max * 4);
-        o_part = cv.take((size_t)max_chunk * prm.W * sizeof(PartRecord));
+        o_part = cv.take((size_t)max_chunk * (glv ? 2 : 1) * prm.W * sizeof(PartRecord));
         const size_t sb = ((size_t)part_nbin * part_ncta_max + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
         if (sb > scan_blocks + 1) o_bsums = cv.take(sb * 4);  // the scan of cnt needs more block sums than the bucket scan
       }
@@ -395,8 +422,9 @@ struct Session {
       // a group = whole bucket sets whose entries fit the budget; the shared set of a resident SRS and the member sets
       // of a batch (whose sizes the host does not know) form one group
       const size_t total_entries = (size_t)max_chunk * prm.W;
-      const size_t cap_entries = ba_budget_bytes() / 104;
-      ba_L = ba_levels_for(max_chunk, total_entries, NB);
+      size_t cap_entries = ba_budget_bytes() / 104;
+      if (cap_entries > ((size_t)3 << 29)) cap_entries = (size_t)3 << 29;  // output slots of a level are 30-bit fields of its records
+      ba_L = glv ? 0u : ba_levels_for(max_chunk, total_entries, NB);  // the level kernel does not know GLV's virtual points
       size_t ge = total_entries;
       if (srs) {
         ba_wpg = nwin;
@@ -447,10 +475,10 @@ struct Session {
                         cudaStream_t s, cudaEvent_t* phase_ev = nullptr) {
     if (n_chunk == 0) return cudaSuccess;
     if (n_chunk > max_chunk) return cudaErrorInvalidValue;
-    const u32 n = (u32)n_chunk;
+    u32 n = (u32)n_chunk;
     Params p = prm;
     p.first = (u32)first;
-    p.nlanes = lanes_for(n_chunk, p.W);
+    p.nlanes = lanes_for(glv ? 2 * n_chunk : n_chunk, p.W);
     if (srs) {
       bases = srs->pre;
       stride = 96;
@@ -461,9 +489,19 @@ struct Session {
       // sort (count, 3 scan kernels, scatter; the partitioned sort has one more) + per accumulation: plan, XYZZ kernel,
       // two combine kernels; with batch-affine levels every group of bucket sets adds (3 scan kernels + 1 level) per level
       const u32 groups = ba_L ? (nwin + ba_wpg - 1) / ba_wpg : 1;
-      launches += (part ? 6 : 5) + (int)groups * (4 + 4 * (int)ba_L);
+      launches += (part ? 6 : 5) + (int)groups * (4 + 4 * (int)ba_L) + (glv ? 1 : 0);
     }
     if (dry) return cudaSuccess;
+    if (phase_ev) cudaEventRecord(phase_ev[0], s);
+    if (glv) {  // k = k1 + k2 u^2: from here on the MSM has 2 n virtual points and 127-bit scalars
+      u32* sc2 = at<u32>(o_glv_sc);
+      unsigned char* bx = at<unsigned char>(o_glv_bx);
+      LAUNCH_NOSYNC(glv_split_kernel, dim3((n + 127) / 128), dim3(128), 0, s, scalars, n, bases, stride, sc2, bx);
+      p.glv_n = n;
+      p.glv_bx = bx;
+      scalars = sc2;
+      n *= 2;
+    }
     u32* counts = at<u32>(o_counts);
     u32* starts = at<u32>(o_starts);
     u32* ends = at<u32>(o_ends);
@@ -475,7 +513,6 @@ struct Session {
     G1Xyzz* buckets = at<G1Xyzz>(o_buckets);
     G1Xyzz* pieces = at<G1Xyzz>(o_pieces);
     const u32 NB = this->NB, cap_small = this->cap_small, cap_large = this->cap_large;  // plain values for the launch macros
-    if (phase_ev) cudaEventRecord(phase_ev[0], s);
     MSM_CK(cudaMemsetAsync(counts, 0, (size_t)NB * 4, s));
     MSM_CK(cudaMemsetAsync(meta, 0, 64, s));
     const u32 g_all = (n + 255) / 256, g_n = g_all < dev_props().sms * 8 ? g_all : dev_props().sms * 8;  // <= 8 CTAs of 256 per SM and window
@@ -562,7 +599,7 @@ struct Session {
                     cap_large, mt);
 #define ACC_LAUNCH(...)                                                                                                   \
   LAUNCH_NOSYNC((accumulate_kernel<__VA_ARGS__>), dim3(lanes / 128), dim3(128), 0, s, pts, pstride, ent, st_, en_, nb, lanes, \
-                (const u32*)mt, bk, pieces, piece_bucket, into)
+                (const u32*)mt, bk, pieces, piece_bucket, into, direct ? 0u : p.glv_n, p.glv_bx)
       if (direct)
         ACC_LAUNCH(true, false, true);
       else if (acc_inline)

@@ -715,3 +715,23 @@ def test_emu_msm_batch_affine_groups_and_ranges(emu_lib, monkeypatch):
     out = C.create_string_buffer(144)
     emu_lib.check(emu_lib.msm_g1(C.cast(out, C.c_void_p), C.cast(bb, C.c_void_p), n, C.cast(sb, C.c_void_p), 104), "msm_g1")
     assert out.raw == want
+
+
+@pytest.mark.parametrize("glv", ["0", "1"])
+def test_emu_msm_with_and_without_glv_split(emu_lib, glv, monkeypatch):
+    """plain MSMs below the batch-affine threshold split their scalars k = k1 + k2 u^2 and run over 2 n virtual points
+    ((beta x, -y) for the second half) with half the windows; ALEO_B200_MSM_GLV = 0 keeps the 253-bit path.  Scalars at
+    the split's edges: multiples of u^2, u^2 - 1, r - 1, values just below / above 2^126."""
+    monkeypatch.setenv("ALEO_B200_MSM_GLV", glv)
+    u2 = 0x8508c00000000001 ** 2
+    n = 300
+    B = o.synthetic_bases(n, 81)
+    s = o.random_fr_vec(n, 82)
+    s[:12] = [0, 1, u2 - 1, u2, u2 + 1, 2 * u2, (o.R_MOD - 1) // u2 * u2, o.R_MOD - 1, (1 << 126) - 1, 1 << 126, (1 << 127) - 1, (1 << 252) + 12345]
+    want = o.g1_projective_to_bytes(o.msm_pippenger(B, s))
+    for stride in (104, 96):
+        assert _msm(emu_lib, B, s, stride) == want, stride
+    Binf = [None if i % 3 == 0 else B[i] for i in range(n)]
+    assert _msm(emu_lib, Binf, s, 104) == o.g1_projective_to_bytes(o.msm_pippenger(Binf, s))
+    assert _msm(emu_lib, [B[0]] * n, s, 104) == o.g1_projective_to_bytes(o.msm_pippenger([B[0]] * n, s))
+    assert emu_lib.msm_window_bits(1 << 18) == 13 and emu_lib.msm_window_bits(1 << 12) == (8 if glv == "1" else 8)

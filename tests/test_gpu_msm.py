@@ -297,3 +297,30 @@ def test_batch_affine_operand_staging_variants(c_oracle, stage, ca, monkeypatch)
         out = C.create_string_buffer(144)
         c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, stride, os.cpu_count() or 1)
         assert got == out.raw, stride
+
+
+@pytest.mark.parametrize("glv", ["0", "1"])
+def test_glv_split_on_and_off(c_oracle, glv, monkeypatch):
+    """proof-sized plain MSMs with and without the GLV split (scalars k = k1 + k2 u^2, 2 n virtual points, half the windows):
+    edge scalars against the big-integer oracle, 2^16 / 2^18 against the C oracle, device and host entry points"""
+    monkeypatch.setenv("ALEO_B200_MSM_GLV", glv)
+    u2 = 0x8508c00000000001 ** 2
+    n = 400
+    B = o.synthetic_bases(n, 91)
+    s = o.random_fr_vec(n, 92)
+    s[:12] = [0, 1, u2 - 1, u2, u2 + 1, 2 * u2, (o.R_MOD - 1) // u2 * u2, o.R_MOD - 1, (1 << 126) - 1, 1 << 126, (1 << 127) - 1, (1 << 252) + 12345]
+    Binf = [None if i % 3 == 0 else B[i] for i in range(n)]
+    for bases in (B, Binf, [B[0]] * n):
+        for stride in (104, 96):
+            assert _host(bases, s, stride) == o.g1_projective_to_bytes(o.msm_pippenger(bases, s))
+    for log_n in (16, 18):
+        m = 1 << log_n
+        s0, d = o.base_dlogs(m, 9000 + log_n)
+        bases = ab.gen_bases_dev(m, s0, d, 0, 104)
+        sc = ab.gen_scalars_dev(m, 3000 + log_n)
+        got = ab.VariableBase.msm_dev(bases, sc, m, 104).cpu().numpy().tobytes()
+        hb, hs = bases.cpu().numpy(), sc.cpu().numpy()
+        out = C.create_string_buffer(144)
+        c_oracle.oracle_msm_g1(out, hb.ctypes.data, m, hs.ctypes.data, 104, os.cpu_count() or 1)
+        assert got == out.raw
+        assert ab.VariableBase.msm(hb, hs, 104) == out.raw

@@ -59,3 +59,23 @@ def test_host_pointer_helper_accepts_numpy_and_torch():
 def test_package_surface():
     for name in ("EvaluationDomain", "VariableBase", "AleoB200Error", "gen_bases_dev", "gen_scalars_dev"):
         assert hasattr(aleo_b200, name)
+
+
+def test_glv_constants_in_the_generated_header():
+    """u^2 and floor(2^384 / u^2) of the GLV split (csrc/msm.cuh glv_split_kernel) against big integers; r = u^4 - u^2 + 1"""
+    import os
+    import re
+    from oracle import bls12_377 as o
+    src = open(os.path.join(os.path.dirname(__file__), "..", "aleo_b200", "csrc", "bls12_377_constants.cuh")).read()
+    body = src[src.index("struct GlvParams"):]
+
+    def limbs(name):
+        m = re.search(name + r"\(int i\) \{\s*constexpr u32 t\[\d+\] = \{([^}]*)\}", body)
+        return sum(int(x.strip().rstrip("u"), 16) << (32 * i) for i, x in enumerate(m.group(1).split(",")))
+
+    u = 0x8508c00000000001
+    assert u ** 4 - u ** 2 + 1 == o.R_MOD
+    assert limbs("U2") == u * u and limbs("BARRETT") == (1 << 384) // (u * u)
+    # the endomorphism's eigenvalue on G1 is -u^2: lambda^2 + lambda + 1 = 0 mod r
+    lam = (-u * u) % o.R_MOD
+    assert (lam * lam + lam + 1) % o.R_MOD == 0
