@@ -327,14 +327,23 @@ struct Session {
       // chunk level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out; the
       // plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too.  Chunk
       // levels run until the scan stage (<= SCAN_MAX elements per window) can take over.
+      // Small bucket sets (proof-sized MSMs) are latency bound: the last stage runs ONE CTA per window, and with 256
+      // elements its 8 warps share one SM's multiplier (16 steps x 8 warps x 14 products: 0.35 ms at 2^16); handing it
+      // 64 elements and the CTA-cooperative levels the rest spreads the same additions over the chip.
+      // ALEO_B200_MSM_SCAN_TARGET = 32 .. 256 overrides.
+      u32 scan_target = ((u64)nwin * prm.B <= CTA_LEVEL_MAX_ELEMS && prm.B > SCAN_MAX) ? 64u : SCAN_MAX;
+      if (const char* te = getenv("ALEO_B200_MSM_SCAN_TARGET")) {
+        const long v = atol(te);
+        if (v == 32 || v == 64 || v == 128 || v == 256) scan_target = (u32)v;
+      }
       u32 m = prm.B, t_prev = 0, scale_log = 0;
       for (;;) {
         const u32 need = t_prev > m ? t_prev : m;
-        if (need <= SCAN_MAX) break;
+        if (need <= scan_target) break;
         RedLevel l;
         l.m = m;
         const char* renv = getenv("ALEO_B200_MSM_REDUCE");  // read per call: tests force both paths
-        l.log_kc = ceil_log2((need + SCAN_MAX - 1) / SCAN_MAX);
+        l.log_kc = ceil_log2((need + scan_target - 1) / scan_target);
         // ... and only with chunks of >= 32 elements: a CTA of 8 threads still costs whole warp instructions (plain MSM at
         // 2^16, 22 windows x 256 chunks of 8: 0.61 ms against 0.24 ms for the serial chunk levels; the resident SRS's
         // single set of 2^14 .. 2^16 buckets makes chunks of 64 .. 256: 2^16 commit 1.67 -> 1.28 ms, 2^18 3.13 -> 2.86 ms)

@@ -131,7 +131,10 @@ int aleo_b200_ntt_launches(uint32_t log_n);
  * Stands in for snarkvm_algorithms::msm::VariableBase::msm::<G1Affine>(bases, scalars)
  * (snarkvm-algorithms 0.14.5 src/msm/variable_base/mod.rs) as called by KZG10::commit /
  * commit_lagrange / open (src/polycommit/kzg10/mod.rs), reached from the same reference call sites.
- * Like upstream the two slices are zipped: n is the shorter length.  n = 0 gives the identity. */
+ * Like upstream the two slices are zipped: n is the shorter length.  n = 0 gives the identity.
+ * The bases are points of the prime-order subgroup G1, which is what a snarkVM G1Affine is (deserialisation checks it,
+ * the group law preserves it): up to 2^20 points the scalars are split with the curve's endomorphism (GLV), which is
+ * multiplication by -u^2 on G1 only.  ALEO_B200_MSM_GLV=0 turns the split off for arbitrary curve points. */
 int aleo_b200_msm_g1(void* out_projective_host, const void* bases_host, size_t n, const void* scalars_host,
                      size_t affine_stride);
 /* The same MSM spread over the first `n_devices` GPUs of the node from ONE process (how a single prover process uses
