@@ -327,11 +327,11 @@ struct Session {
       // chunk level l: weighted input of length m (buckets, then R[1..) of the level below), T chunks out; the
       // plain input P of the level below has T_prev entries and needs ceil(T_prev / Kc) chunks too.  Chunk
       // levels run until the scan stage (<= SCAN_MAX elements per window) can take over.
-      // Small bucket sets (proof-sized MSMs) are latency bound: the last stage runs ONE CTA per window, and with 256
-      // elements its 8 warps share one SM's multiplier (16 steps x 8 warps x 14 products: 0.35 ms at 2^16); handing it
-      // 64 elements and the CTA-cooperative levels the rest spreads the same additions over the chip.
-      // ALEO_B200_MSM_SCAN_TARGET = 32 .. 256 overrides.
-      u32 scan_target = ((u64)nwin * prm.B <= CTA_LEVEL_MAX_ELEMS && prm.B > SCAN_MAX) ? 64u : SCAN_MAX;
+      // Elements per window the last stage (one CTA per window) takes.  64 instead of 256 for small bucket sets -- the
+      // CTA-cooperative levels would spread the additions of that stage over more SMs -- measured a wash on B200
+      // (profiles/r03v_scan_target.log: 2^16 2.08 against 2.17 ms, 2^15 1.89 against 1.76, resident-SRS commit 2^18 3.04
+      // against 2.89): 256 stays.  ALEO_B200_MSM_SCAN_TARGET = 32 | 64 | 128 | 256 overrides.
+      u32 scan_target = SCAN_MAX;
       if (const char* te = getenv("ALEO_B200_MSM_SCAN_TARGET")) {
         const long v = atol(te);
         if (v == 32 || v == 64 || v == 128 || v == 256) scan_target = (u32)v;
