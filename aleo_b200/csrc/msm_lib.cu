@@ -103,7 +103,16 @@ struct EventSet {
 // (thread_local, released by its destructor when the thread ends); it is rebuilt when the thread's device changes.
 #ifndef ALEO_EMU
 constexpr int FEED_THREADS = 16;  // upper bound; feed_threads() of them run
-constexpr size_t FEED_MIN_BYTES = (size_t)8 << 20;  // below this the plain pageable copy is fine
+// below this the driver's own pageable copy is used (ALEO_B200_FEED_MIN_KB overrides)
+static size_t feed_min_bytes() {
+  static const size_t v = [] {
+    const char* env = getenv("ALEO_B200_FEED_MIN_KB");
+    const long kb = env ? atol(env) : 0L;
+    return (kb >= 64 && kb <= (1 << 20)) ? (size_t)kb << 10 : (size_t)8 << 20;
+  }();
+  return v;
+}
+#define FEED_MIN_BYTES feed_min_bytes()
 
 // co-located ranks (one process per GPU under torchrun)
 long local_world_size() {
