@@ -142,6 +142,7 @@ constexpr u32 STAGE_BYTES = 2 * STAGE_WORDS * 16 * TPB;              // dynamic 
 template <bool SHIFTED>
 struct AsyncStagerT {
   static constexpr bool ASYNC = true;
+  static constexpr bool REREAD = false;
   u32 base;  // shared-memory address of word 0 of this thread, buffer 0
   bool ca;
   DEV AsyncStagerT(unsigned char* smem, u32 via_l1) : ca(via_l1 != 0) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
@@ -216,6 +217,7 @@ typedef AsyncStagerT<true> AsyncStagerShifted;   // level 0
 // product runs (`nxt`, rotated by advance()); pass 2 has no registers to spare and loads at the point of use.
 struct DirectStager {
   static constexpr bool ASYNC = false;
+  static constexpr bool REREAD = false;
   Fq cur[2], nxt[2];
   bool x_ahead;
   DEV DirectStager(unsigned char*, u32) : x_ahead(true) {}
@@ -252,6 +254,72 @@ struct DirectStager {
     return pre;
   }
 };
+// Levels >= 1 at FOUR CTAs per SM.  The level kernel is bound by the dependency stalls of its multiplier chains with 12
+// warps per SM (ncu: `wait` 3.4 of 7 warp-cycles per issue, heavy pipe 74 % busy); a fourth CTA needs <= 128 registers
+// and <= 56 KB of shared memory.  Registers: pass 2 re-reads its operands from the staging buffer right before each use
+// (REREAD) instead of holding x1, y1, x2, y2 and the prefix across five products.  Shared memory: the two points stay
+// double-buffered (12 words per buffer), the prefix gets ONE slot that is refilled as soon as the current prefix has
+// been read -- 27 words per thread, 55 296 B per CTA.
+#ifndef ALEO_EMU
+constexpr u32 COMPACT_WORDS = 27;
+constexpr u32 COMPACT_BYTES = COMPACT_WORDS * 16 * TPB;
+struct CompactStager {
+  static constexpr bool ASYNC = true;
+  static constexpr bool REREAD = true;
+  u32 base;
+  DEV CompactStager(unsigned char* smem, u32) { base = (u32)__cvta_generic_to_shared(smem) + threadIdx.x * 16u; }
+  DEV u32 word(u32 j) const { return base + j * (16u * TPB); }
+  DEV static void copy16(u32 dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+  template <bool LEVEL0>
+  DEV void stage_op(u32 buf, const LevelArgs& a, const uint4& r, u32, u32, size_t, bool with_y) const {
+    const unsigned char* p1 = PointRef<LEVEL0>(a, r.x).p;
+    const unsigned char* p2 = PointRef<LEVEL0>(a, r.y).p;
+    const u32 n16 = with_y ? 6u : 3u;
+#pragma unroll
+    for (u32 k = 0; k < 6; k++) {
+      if (k < n16) {
+        copy16(word(buf * 12 + k), p1 + 16 * k);
+        copy16(word(buf * 12 + 6 + k), p2 + 16 * k);
+      }
+    }
+  }
+  DEV Fq ld3(u32 w) const {
+    Fq r;
+#pragma unroll
+    for (u32 k = 0; k < 3; k++)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4 * k]), "=r"(r.l[4 * k + 1]), "=r"(r.l[4 * k + 2]), "=r"(r.l[4 * k + 3]) : "r"(word(w + k)) : "memory");
+    return r;
+  }
+  template <bool LEVEL0>
+  DEV Fq get(u32 buf, u32 which, const LevelArgs&, const uint4&, u32, u32, size_t, u32 off) const {
+    return ld3(buf * 12 + which * 6 + off / 16);
+  }
+  DEV void stage_pre(u32, const uint4* p0, size_t plane) const {
+    copy16(word(24), p0);
+    copy16(word(25), p0 + plane);
+    copy16(word(26), p0 + 2 * plane);
+  }
+  DEV Fq get_pre(u32, const uint4*, size_t) const { return ld3(24); }
+  DEV void advance() const {}
+  DEV void end_pass1() const {}
+  DEV void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  DEV void wait_all_but_last() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  DEV void wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+};
+#endif
+// The same re-read order with plain loads: what the emulator runs in place of CompactStager.  (Measured for level 0 at
+// four CTAs per SM, 128 registers, no spills: 40.4 against 35.0 ms -- level 0 wants fewer gathers in flight, not more.)
+struct DirectRereadStager : DirectStager {
+  static constexpr bool REREAD = true;
+  DEV DirectRereadStager(unsigned char* smem, u32 f) : DirectStager(smem, f) {}
+  DEV void wait_all() const {}
+};
+#ifdef ALEO_EMU
+typedef DirectRereadStager CompactStager;
+constexpr u32 COMPACT_BYTES = 0;
+#endif
 #ifdef ALEO_EMU
 typedef DirectStager AsyncStager;  // the emulator has no asynchronous copies
 typedef DirectStager AsyncStagerShifted;
@@ -263,8 +331,8 @@ constexpr u32 REC_SLOT = REC_RESOLVED - 1u;
 
 // 3 CTAs per SM (168 registers, no spills).  4 (128 registers, ~150 bytes of spills) was measured for level 0, whose gathers
 // would like more warps in flight: accumulate 69.8 against 67.3 ms at 2^24.
-template <bool LEVEL0, class ST>
-KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
+template <bool LEVEL0, class ST, int MINB = 3>
+KERNEL void __launch_bounds__(TPB, MINB) level_kernel(LevelArgs a) {
   DYN_SMEM(unsigned char, smem);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nthreads) return;  // nthreads is a multiple of the CTA size: whole warps leave
@@ -436,6 +504,63 @@ KERNEL void __launch_bounds__(TPB, 3) level_kernel(LevelArgs a) {
   inv = fq_inv_ni(prefix);  // the emulator runs CUDA threads one after the other: every thread inverts its own product
 #endif
   if (nops == 0) return;
+  // ---- pass 2 (REREAD stagers): the same unwinding with every operand read from the staging buffer right before its use
+  if constexpr (ST::REREAD) {
+    uint4 r = a.rec[(size_t)(nops - 1) * NT + t], rn = r;
+    st.template stage_op<LEVEL0>((nops - 1) & 1u, a, r, nops - 1, t, NT, true);
+    st.stage_pre(0, &a.pre[(size_t)(nops - 1) * 3 * NT + t], NT);
+    if (nops > 1) rn = a.rec[(size_t)(nops - 2) * NT + t];
+    st.commit();
+    for (u32 i = nops; i-- > 0;) {
+      const u32 buf = i & 1u;
+      uint4 rnn = rn;
+      if (i > 1) rnn = a.rec[(size_t)(i - 2) * NT + t];
+      st.wait_all();
+      const bool live = !(r.z & REC_RESOLVED);
+      const u32 dbl = r.z >> 31, slot = r.z & REC_SLOT;
+      const uint4* pre_i = &a.pre[(size_t)i * 3 * NT + t];
+      Fq inv_den;
+      if (live) {
+        Fq den;
+        if (dbl) {
+          Fq y1 = st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 48);
+          if (LEVEL0 && (r.x >> 31)) y1 = fp_neg(y1);
+          den = fp_dbl(y1);
+        } else {
+          den = fp_sub(st.template get<LEVEL0>(buf, 1, a, r, i, t, NT, 0), st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 0));
+        }
+        inv_den = fq_mul_v(inv, st.get_pre(buf, pre_i, NT));
+        inv = fq_mul_v(inv, den);
+      }
+      if (i) {  // the prefix slot is free again: the next addition's operands set out now
+        st.template stage_op<LEVEL0>(buf ^ 1u, a, rn, i - 1, t, NT, true);
+        st.stage_pre(0, &a.pre[(size_t)(i - 1) * 3 * NT + t], NT);
+      }
+      st.commit();
+      if (live) {
+        Fq y1 = st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 48);
+        if (LEVEL0 && (r.x >> 31)) y1 = fp_neg(y1);
+        Fq num;
+        if (dbl) {
+          const Fq xx = fq_sqr_v(st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 0));
+          num = fp_add(fp_dbl(xx), xx);
+        } else {
+          Fq y2 = st.template get<LEVEL0>(buf, 1, a, r, i, t, NT, 48);
+          if (LEVEL0 && (r.y >> 31)) y2 = fp_neg(y2);
+          num = fp_sub(y2, y1);
+        }
+        const Fq lam = fq_mul_v(num, inv_den);
+        const Fq x1 = st.template get<LEVEL0>(buf, 0, a, r, i, t, NT, 0);
+        Fq x3 = fp_sub(fq_sqr_v(lam), x1);
+        x3 = fp_sub(x3, dbl ? x1 : st.template get<LEVEL0>(buf, 1, a, r, i, t, NT, 0));
+        const Fq y3 = fp_sub(fq_mul_v(lam, fp_sub(x1, x3)), y1);
+        store_point(a.out, slot, x3, y3);
+      }
+      r = rn;
+      rn = rnn;
+    }
+    return;
+  }
   // ---- pass 2: unwind, last addition first
   {
     uint4 r = a.rec[(size_t)(nops - 1) * NT + t], rn = r;

@@ -144,6 +144,11 @@ static inline u32 ba_levels_for(size_t points, size_t entries, size_t buckets) {
   while (((size_t)8 << l) <= load) l++;  // load 32 -> 3, 64 -> 4, 128 -> 5
   return l;
 }
+// levels >= 1 at four CTAs per SM (ba::CompactStager: operands re-read from the staging buffer; ALEO_B200_MSM_BA_COMPACT)
+static inline bool ba_compact() {
+  const char* env = getenv("ALEO_B200_MSM_BA_COMPACT");
+  return env ? atoi(env) != 0 : true;  // 2^24: accumulate 67.7 -> 66.2 ms, 2^22: 20.6 -> 20.1 ms (profiles/r03z_ba_compact_sweep.log)
+}
 // additions one thread shares an inversion over, at most (ALEO_B200_MSM_BA_K)
 static inline u32 ba_kmax() {
   const char* env = getenv("ALEO_B200_MSM_BA_K");
@@ -165,7 +170,7 @@ static inline BaLevelPlan ba_level_plan(size_t entries, u32 nb, u32 l) {
   const size_t slots = (entries >> l) + (l ? nb : 0);
   // whole waves of 3 CTAs of 128 threads per SM (all runs take the same time: a partial last wave idles the chip), as
   // few as keep a run at <= kmax additions but at least 4 while runs of 16 additions can fill them
-  const size_t wave = (size_t)dev_props().sms * 3 * ba::TPB;
+  const size_t wave = (size_t)dev_props().sms * ((l > 0 && ba_compact()) ? 4 : 3) * ba::TPB;
   const u32 kmax = ba_kmax();
   size_t waves = (slots / 2 + wave * kmax - 1) / (wave * kmax);
   const size_t kmin = kmax < 32 ? kmax : 32;
@@ -641,6 +646,8 @@ struct Session {
         if (attr_dev != devnow) {
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStagerShifted>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::STAGE_BYTES));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::CompactStager, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::COMPACT_BYTES));
+          MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::CompactStager, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<true, ba::AsyncStagerShifted>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           MSM_CK(cudaFuncSetAttribute(ba::level_kernel<false, ba::AsyncStager>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           attr_dev = devnow;
@@ -699,6 +706,8 @@ struct Session {
             LAUNCH_NOSYNC((ba::level_kernel<true, ba::AsyncStagerShifted>), grid, block, ba::STAGE_BYTES, s, la);
           else if (l == 0)
             LAUNCH_NOSYNC((ba::level_kernel<true, ba::DirectStager>), grid, block, 0, s, la);
+          else if (staged && ba_compact())
+            LAUNCH_NOSYNC((ba::level_kernel<false, ba::CompactStager, 4>), grid, block, ba::COMPACT_BYTES, s, la);
           else if (staged)
             LAUNCH_NOSYNC((ba::level_kernel<false, ba::AsyncStager>), grid, block, ba::STAGE_BYTES, s, la);
           else
