@@ -24,11 +24,12 @@ static inline u32 floor_log2(size_t n) {
 static inline u32 windows_for(u32 c) { return SCALAR_BITS / c + 1; }
 
 // Batch-affine levels (msm_ba.cuh) run in front of the XYZZ kernel from this many points on (ALEO_B200_MSM_BA = 0: never).
-// Measured on B200 (profiles/r03e_ba_sweep_*.log): 2^20 9.18 ms without / 9.61 ms with, 2^22 26.8 / 24.9, 2^24 88.2 / 79.8.
+// Measured on B200 (profiles/r03e_ba_sweep_*.log): 2^20 9.18 ms without / 9.61 ms with, 2^22 26.8 / 24.9, 2^24 88.2 / 79.8;
+// with the final level kernels 2^21 14.79 / 14.15 (profiles/r04c_ba_2p21.log).
 static inline bool ba_enabled_for(size_t n_points) {
   const char* env = getenv("ALEO_B200_MSM_BA");  // read per call: tests and sweeps switch it
   if (env) return atol(env) > 0;
-  return n_points >= ((size_t)1 << 22);
+  return n_points >= ((size_t)1 << 21);
 }
 
 // GLV split (msm.cuh glv_split_kernel): plain MSMs below the batch-affine threshold run over 2 n virtual points with

@@ -199,7 +199,7 @@ int aleo_b200_kzg_commit_batch_dev(const void* handle, void* out_compressed48_de
 int aleo_b200_msm_window_bits(size_t n);
 int aleo_b200_msm_launches(size_t n);
 /* batch-affine pair-tree levels (csrc/msm_ba.cuh) the MSM runs in front of its XYZZ accumulation for n device-resident
- * points (0 below 2^22 points): after L levels 1 - 2^-L of the additions were done at 5 products + 1 square instead of
+ * points (0 below 2^21 points): after L levels 1 - 2^-L of the additions were done at 5 products + 1 square instead of
  * 8 + 2 -- bench.py needs it to count the multiplies the accumulation phase issues */
 int aleo_b200_msm_ba_levels(size_t n);
 /* The host-pointer entry points (aleo_b200_msm_g1, aleo_b200_srs_msm, aleo_b200_kzg_commit) copy and accumulate
