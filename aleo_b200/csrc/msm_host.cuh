@@ -301,6 +301,7 @@ struct Session {
   u32 ba_L = 0, ba_wpg = 0;
   size_t ba_scratch_ops = 0;
   bool glv = false;  // scalars split by u^2, 2 n virtual points (make_params)
+  bool ba_denied = false;  // the levels' workspace did not fit the device: this session runs the XYZZ kernel alone
   size_t o_glv_sc = 0, o_glv_bx = 0;
   size_t o_baA = 0, o_baB = 0, o_ba_pre = 0, o_ba_rec = 0, o_ba_s0 = 0, o_ba_s1 = 0, o_ba_e = 0, o_meta2 = 0;
   unsigned char* ws = nullptr;
@@ -439,7 +440,7 @@ struct Session {
       const size_t total_entries = (size_t)max_chunk * prm.W;
       size_t cap_entries = ba_budget_bytes() / 104;
       if (cap_entries > ((size_t)3 << 29)) cap_entries = (size_t)3 << 29;  // output slots of a level are 30-bit fields of its records
-      ba_L = glv ? 0u : ba_levels_for(max_chunk, total_entries, NB);  // the level kernel does not know GLV's virtual points
+      ba_L = (glv || ba_denied) ? 0u : ba_levels_for(max_chunk, total_entries, NB);  // the level kernel does not know GLV's virtual points
       size_t ge = total_entries;
       if (srs) {
         ba_wpg = nwin;
@@ -477,7 +478,22 @@ struct Session {
     }
     bytes = cv.off;
     if (dry) return cudaSuccess;
-    MSM_CK(aleo::pool_malloc_async((void**)&ws, bytes, s));
+    {
+      // ALEO_B200_TEST_DENY_BA_ALLOC: the tests' stand-in for a device without room for the levels' workspace
+      const bool deny = ba_L > 0 && getenv("ALEO_B200_TEST_DENY_BA_ALLOC") != nullptr;
+      cudaError_t ea = deny ? cudaErrorMemoryAllocation : aleo::pool_malloc_async((void**)&ws, bytes, s);
+      if (ea == cudaErrorMemoryAllocation && ba_L > 0) {
+        // the batch-affine levels want ~104 bytes per sorted entry; on a device that cannot spare them the MSM still runs,
+        // on the XYZZ kernel alone (same result, the round-1 speed), instead of failing
+        (void)cudaGetLastError();
+        ws = nullptr;
+        ba_denied = true;
+        lv.clear();
+        launches = 0;
+        return begin(n_total, max_chunk_, chunks, srs_, s, dry_, nbatch, batch_off);
+      }
+      MSM_CK(ea);
+    }
     MSM_CK(cudaMemsetAsync(at<G1Xyzz>(o_buckets), 0, (size_t)NB * sizeof(G1Xyzz), s));
     return cudaSuccess;
   }

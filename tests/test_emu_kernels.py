@@ -709,6 +709,9 @@ def test_emu_msm_batch_affine_groups_and_ranges(emu_lib, monkeypatch):
     assert _msm(emu_lib, B, s, 104) == want
     monkeypatch.setenv("ALEO_B200_MSM_BA_MB", "1")     # 1 MB / 100 B = 10 485 entries: 17 windows of 600 entries per group
     assert _msm(emu_lib, B, s, 104) == want
+    monkeypatch.setenv("ALEO_B200_TEST_DENY_BA_ALLOC", "1")   # no room for the levels' workspace: the XYZZ kernel alone
+    assert _msm(emu_lib, B, s, 104) == want
+    monkeypatch.delenv("ALEO_B200_TEST_DENY_BA_ALLOC")
     monkeypatch.setenv("ALEO_B200_MSM_CHUNKS", "3")
     bb = C.create_string_buffer(o.g1_affine_vec_to_bytes(B, 104), n * 104)
     sb = C.create_string_buffer(o.fr_vec_to_bytes(s, mont=False), n * 32)

@@ -276,6 +276,9 @@ def test_batch_affine_levels_match_c_oracle(c_oracle, log_n, levels, monkeypatch
     c_oracle.oracle_msm_g1(out, hb.ctypes.data, n, hs.ctypes.data, 104, os.cpu_count() or 1)
     assert got == out.raw
     assert ab.VariableBase.msm(hb, hs, 104) == out.raw      # host ranges accumulate into the same buckets
+    if levels:
+        monkeypatch.setenv("ALEO_B200_TEST_DENY_BA_ALLOC", "1")   # a device without room for the levels: XYZZ kernel alone
+        assert ab.VariableBase.msm_dev(bases, sc, n, 104).cpu().numpy().tobytes() == out.raw
 
 
 @pytest.mark.parametrize("stage,ca", [(0, 0), (1, 0), (1, 2), (2, 0), (2, 1)])
