@@ -119,6 +119,17 @@ static inline u32 lanes_for_entries(size_t entries) {
   if (lanes < 4 * wave) {
     const size_t by32 = (entries + 31) / 32;
     lanes = by32 < 4 * wave ? by32 : 4 * wave;
+    // ... in WHOLE waves: every lane does the same number of additions, so 1.44 waves of 32-entry runs take as long as
+    // two full waves would (2^17: 82 k lanes); k = ceil(entries / (32 wave)) full waves of shorter runs take
+    // entries / (k wave) instead.  Not below runs of 12: runs of 8 cut every bucket of 2^14's 64 entries into 8 pieces and the
+    // combine doubles the phase (0.55 -> 1.15 ms).  Measured (profiles/r04g_whole_waves.log): 2^16 2.17 -> 2.07 ms, 2^17 2.89 ->
+    // 2.81, 13 batched 2^18 commitments 20.5 -> 18.7 ms.  ALEO_B200_MSM_WHOLE_WAVES = 0 switches off.
+    static const bool whole = []() { const char* e = getenv("ALEO_B200_MSM_WHOLE_WAVES"); return !(e && e[0] == '0'); }();
+    if (whole && by32 > 0 && by32 < 4 * wave) {
+      const size_t k = (by32 + wave - 1) / wave;
+      const size_t aligned = k * wave;
+      if ((entries + aligned - 1) / aligned >= 12) lanes = aligned;
+    }
   }
   if (lanes > full) lanes = full;
   if (lanes < 128) lanes = 128;
@@ -510,6 +521,7 @@ struct Session {
     Params p = prm;
     p.first = (u32)first;
     p.nlanes = lanes_for(glv ? 2 * n_chunk : n_chunk, p.W);
+    if (p.nlanes > max_lanes) p.nlanes = max_lanes;  // whole-wave rounding is not monotone in the range size; the piece arrays are sized for max_lanes
     if (srs) {
       bases = srs->pre;
       stride = 96;
@@ -733,7 +745,8 @@ struct Session {
           la.in = la.out;
           la.start_in = la.start_out;
         }
-        const u32 lanes = lanes_for_entries((ge >> ba_L) + nb);
+        u32 lanes = lanes_for_entries((ge >> ba_L) + nb);
+        if (lanes > max_lanes) lanes = max_lanes;
         MSM_CK(flat(lvbuf[(ba_L - 1) & 1], 96, nullptr, sa[(ba_L - 1) & 1], e_out, nb, lanes, meta2, buckets + g0, true));
       }
       if (phase_ev) cudaEventRecord(phase_ev[2], s);
